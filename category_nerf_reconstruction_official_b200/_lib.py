@@ -1,0 +1,159 @@
+"""ctypes binding of the C-ABI library ``csrc/libcnf_sm100.so`` (declared in ``include/cnf.h``).
+
+The library is built in-tree with nvcc for sm_100a (``build()``), loaded with ctypes and called with raw
+device pointers + the current CUDA stream.  There is NO CPU fallback: every op raises if the library is
+missing or the device is not an sm_100 part.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+from ctypes import c_char_p, c_float, c_int, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libcnf_sm100.so")
+SOURCES = ["cnf_api.cu", "cnf_sampler.cu", "cnf_embed.cu", "cnf_composite.cu", "cnf_mlp_simt.cu",
+           "cnf_selftest.cu", "cnf_fused.cu"]
+HEADERS = ["cnf_common.cuh", "cnf_umma.cuh", os.path.join("..", "..", "include", "cnf.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC"]
+
+_lock = threading.Lock()
+_lib = None
+
+
+class CnfError(RuntimeError):
+    pass
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    for f in SOURCES + HEADERS:
+        p = os.path.join(CSRC, f)
+        if os.path.exists(p) and os.path.getmtime(p) > t:
+            return True
+    return False
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu for sm_100a and link libcnf_sm100.so in-tree (nvcc cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(CSRC, "build"), exist_ok=True)
+    for src in SOURCES:
+        obj = os.path.join(CSRC, "build", src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise CnfError("nvcc failed for %s:\n%s" % (src, out))
+        if verbose and out:
+            print(out)
+    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-cudart", "static"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise CnfError("link failed:\n" + r.stdout)
+    return LIB_PATH
+
+
+# name -> (restype, argtypes); must list every symbol declared in include/cnf.h
+P = c_void_p
+SIGNATURES = {
+    "cnf_version": (c_int, []),
+    "cnf_last_error_string": (c_char_p, []),
+    "cnf_device_check": (c_int, [c_int]),
+    "cnf_sample_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "cnf_sample_fwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P,
+                               c_float, c_float, c_float, c_int, P, P, P, P, P, P, c_size_t, P]),
+    "cnf_stratified_bins": (c_int, [c_int, c_int, P, c_int, P, c_int, P, P, P, P]),
+    "cnf_embed_fwd": (c_int, [c_int, c_int, P, P, P, P, P]),
+    "cnf_embed_bwd": (c_int, [c_int, c_int, P, P, P, P, P, P, P]),
+    "cnf_codenerf_param_count": (c_size_t, [c_int, c_int]),
+    "cnf_codenerf_workspace_floats": (c_size_t, [c_int, c_int, c_int]),
+    "cnf_codenerf_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
+    "cnf_codenerf_bwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_size_t,
+                                 P, P, P, P, P]),
+    "cnf_occmap_param_count": (c_size_t, [c_int]),
+    "cnf_occmap_workspace_floats": (c_size_t, [c_int, c_int]),
+    "cnf_occmap_fwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, c_size_t, P]),
+    "cnf_occmap_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, c_size_t, P, P, P]),
+    "cnf_termination_fwd": (c_int, [c_int, c_int, P, P, P]),
+    "cnf_mask_counts": (c_int, [c_int, c_int, P, P, P, P]),
+    "cnf_composite_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "cnf_composite_loss_fwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_float, c_float, P, P, P,
+                                       c_size_t, P]),
+    "cnf_composite_loss_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_float, c_float, P, P, P, P]),
+    "cnf_code_reg": (c_int, [c_int, c_int, P, c_float, P, P, P]),
+    "cnf_train_step_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "cnf_train_step": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P, P,
+                               c_float, c_float, c_float, c_int, P, P, P, P, P, P, c_size_t, P]),
+    "cnf_umma_selftest": (c_int, [c_int, c_int, c_int, P, P, P, P]),
+    "cnf_adamw_step": (c_int, [c_size_t, P, P, P, P, c_float, c_float, c_float, c_float, c_float, c_int, P]),
+}
+
+
+def load(auto_build: bool = True):
+    """dlopen the library (building it first if sources are newer). Raises CnfError if impossible."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if auto_build and _stale():
+            build()
+        if not os.path.exists(LIB_PATH):
+            raise CnfError("libcnf_sm100.so is missing (%s): run __graft_entry__.build(); there is no fallback path"
+                           % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)       # AttributeError if a declared symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+_checked_devices = set()
+
+
+def lib_for(t: torch.Tensor):
+    """Library handle for an op on tensor ``t``; enforces CUDA + sm_100."""
+    if not t.is_cuda:
+        raise CnfError("cnf ops run only on CUDA (sm_100a) tensors; got device %s. There is no CPU fallback." % t.device)
+    lib = load()
+    dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if dev not in _checked_devices:
+        check(lib.cnf_device_check(dev))
+        _checked_devices.add(dev)
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().cnf_last_error_string()
+        raise CnfError("libcnf error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """data pointer of a contiguous tensor (or NULL for None)."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "cnf: tensor must be contiguous"
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,62 @@
+// Shared helpers for libcnf_sm100.so (sm_100a only; no CPU fallback anywhere in this library).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/cnf.h"
+
+namespace cnf {
+
+void set_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return CNF_OK;
+}
+
+#define CNF_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      cnf::set_error(__VA_ARGS__);        \
+      return CNF_ERR_ARG;                 \
+    }                                     \
+  } while (0)
+
+#define CNF_CUDA(call)                                                     \
+  do {                                                                     \
+    cudaError_t e__ = (call);                                              \
+    if (e__ != cudaSuccess) {                                              \
+      cnf::set_error("%s failed: %s", #call, cudaGetErrorString(e__));     \
+      return (int)e__;                                                     \
+    }                                                                      \
+  } while (0)
+
+inline cudaStream_t as_stream(cnf_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+}  // namespace cnf

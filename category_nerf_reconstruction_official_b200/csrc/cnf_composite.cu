@@ -1,0 +1,352 @@
+// Occupancy -> termination compositing and the depth / colour / opacity losses, forward and backward.
+// Reference: src/render_rays.py:3-95 (occupancy_activation, occupancy_to_termination, render, render_loss,
+// reduce_batch_loss) and src/loss.py:5-74 (step_batch_loss, step_batch_loss_reg); math in SURVEY appendix A.
+//
+// One ray occupies a power-of-two segment of a warp (G = 16 lanes for S = 10/14); the exclusive cumprod of
+// the free-space factors and the reverse (suffix) sum of the backward are warp-shuffle scans.  S > 32 runs
+// the segment over 32-sample chunks with a carry.  HBM-bound: 20 B/sample in, 24 B/ray out (fwd).
+#include "cnf_common.cuh"
+
+namespace cnf {
+
+constexpr int CT = 256;  // threads per block
+
+__device__ __forceinline__ float seg_sum(float v, int G) {
+  for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// inclusive product scan inside a G-lane segment
+__device__ __forceinline__ float seg_scan_mul(float v, int G, int sl) {
+  for (int o = 1; o < G; o <<= 1) {
+    const float n = __shfl_up_sync(0xffffffffu, v, o);
+    if (sl >= o) v *= n;
+  }
+  return v;
+}
+// inclusive suffix-sum scan inside a G-lane segment
+__device__ __forceinline__ float seg_scan_add_rev(float v, int G, int sl) {
+  for (int o = 1; o < G; o <<= 1) {
+    const float n = __shfl_down_sync(0xffffffffu, v, o);
+    if (sl + o < G) v += n;
+  }
+  return v;
+}
+__device__ __forceinline__ float sigmoid_acc(float a) { return 1.0f / (1.0f + expf(-a)); }
+
+struct RayOut { float D, var, C0, C1, C2, O; };
+
+// Forward quantities of one ray held by a G-lane segment.  Returns totals in every lane of the segment.
+__device__ __forceinline__ RayOut ray_forward(const float* __restrict__ alpha, const float* __restrict__ color,
+                                              const float* __restrict__ z, int S, int G, int sl) {
+  RayOut o{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float carry = 1.0f;
+  for (int c0 = 0; c0 < S; c0 += G) {
+    const int i = c0 + sl;
+    const bool act = i < S;
+    const float occ = act ? sigmoid_acc(alpha[i]) : 0.f;
+    const float f = act ? __fadd_rn(__fsub_rn(1.0f, occ), 1e-10f) : 1.0f;   // render_rays.py:28
+    const float incl = seg_scan_mul(f, G, sl);
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (sl == 0) excl = 1.0f;
+    const float T = carry * excl;
+    const float w = occ * T;                                                // render_rays.py:33
+    carry *= __shfl_sync(0xffffffffu, incl, G - 1, G);
+    if (act) {
+      o.D += w * z[i]; o.O += w;
+      o.C0 += w * color[i * 3 + 0]; o.C1 += w * color[i * 3 + 1]; o.C2 += w * color[i * 3 + 2];
+    }
+  }
+  o.D = seg_sum(o.D, G); o.O = seg_sum(o.O, G);
+  o.C0 = seg_sum(o.C0, G); o.C1 = seg_sum(o.C1, G); o.C2 = seg_sum(o.C2, G);
+  // variance needs D: second pass (loss.py:45)
+  carry = 1.0f;
+  for (int c0 = 0; c0 < S; c0 += G) {
+    const int i = c0 + sl;
+    const bool act = i < S;
+    const float occ = act ? sigmoid_acc(alpha[i]) : 0.f;
+    const float f = act ? __fadd_rn(__fsub_rn(1.0f, occ), 1e-10f) : 1.0f;
+    const float incl = seg_scan_mul(f, G, sl);
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (sl == 0) excl = 1.0f;
+    const float w = occ * carry * excl;
+    carry *= __shfl_sync(0xffffffffu, incl, G - 1, G);
+    if (act) { const float dz = z[i] - o.D; o.var += w * dz * dz; }
+  }
+  o.var = seg_sum(o.var, G);
+  return o;
+}
+
+__device__ __forceinline__ int seg_width(int S) {
+  int G = 1;
+  while (G < S && G < 32) G <<= 1;
+  return G;
+}
+
+__global__ void mask_counts_kernel(int R, const uint8_t* __restrict__ labels, const uint8_t* __restrict__ mask_depth,
+                                   int32_t* __restrict__ counts) {
+  const int k = blockIdx.y;
+  int cd = 0, co = 0, cs = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
+    const uint8_t lab = labels[(size_t)k * R + r];
+    const bool mo = lab != 0, ms = lab != 2, md = mask_depth[(size_t)k * R + r] != 0;
+    cd += (md && mo); co += mo; cs += ms;
+  }
+  cd = warp_sum_i(cd); co = warp_sum_i(co); cs = warp_sum_i(cs);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&counts[k * 4 + 0], cd); atomicAdd(&counts[k * 4 + 1], co); atomicAdd(&counts[k * 4 + 2], cs);
+  }
+}
+
+// flags: term t (0 depth,1 obj,2 sem) is empty in ANY category -> that loss term is 0 everywhere (render_rays.py:67-72)
+__device__ __forceinline__ void empty_flags(int K, const int32_t* __restrict__ counts, bool& e0, bool& e1, bool& e2) {
+  e0 = e1 = e2 = false;
+  for (int k = 0; k < K; ++k) {
+    e0 |= counts[k * 4 + 0] == 0; e1 |= counts[k * 4 + 1] == 0; e2 |= counts[k * 4 + 2] == 0;
+  }
+}
+
+__global__ void __launch_bounds__(CT)
+composite_fwd_kernel(int K, int R, int S, const float* __restrict__ alpha, const float* __restrict__ color,
+                     const float* __restrict__ z, const float* __restrict__ gt_depth, const float* __restrict__ gt_color,
+                     const uint8_t* __restrict__ labels, const uint8_t* __restrict__ mask_depth,
+                     float* __restrict__ out_rays, float* __restrict__ partial) {
+  const int k = blockIdx.y;
+  const int G = seg_width(S), rpw = 32 / G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = lane / G, sl = lane - seg * G;
+  const int rays_per_block = (CT / 32) * rpw;
+  float ld = 0.f, lc = 0.f, lo = 0.f;
+  for (int rb = blockIdx.x * rays_per_block; rb < R; rb += gridDim.x * rays_per_block) {
+    const int r = rb + warp * rpw + seg;
+    const int rr = min(r, R - 1);                 // keep all lanes in the shuffles
+    const size_t g = (size_t)k * R + rr;
+    const RayOut o = ray_forward(alpha + g * S, color + g * S * 3, z + g * S, S, G, sl);
+    if (r < R && sl == 0) {
+      float* orow = out_rays + g * 6;
+      orow[0] = o.D; orow[1] = o.var; orow[2] = o.C0; orow[3] = o.C1; orow[4] = o.C2; orow[5] = o.O;
+      const uint8_t lab = labels[g];
+      const float mo = (lab != 0) ? 1.f : 0.f, ms = (lab != 2) ? 1.f : 0.f;
+      const float md = (mask_depth[g] != 0 && lab != 0) ? 1.f : 0.f;
+      const float info = 1.0f / (sqrtf(o.var) + 1e-4f);                       // render_rays.py:73-80
+      ld += fabsf(o.D - gt_depth[g]) * md * info;                             // loss.py:52-54
+      lc += (fabsf(o.C0 - gt_color[g * 3]) + fabsf(o.C1 - gt_color[g * 3 + 1]) + fabsf(o.C2 - gt_color[g * 3 + 2])) * mo;
+      lo += fabsf(o.O - mo) * ms;                                             // loss.py:64-66
+    }
+  }
+  __shared__ float s_p[CT / 32][3];
+  ld = warp_sum(ld); lc = warp_sum(lc); lo = warp_sum(lo);
+  if (lane == 0) { s_p[warp][0] = ld; s_p[warp][1] = lc; s_p[warp][2] = lo; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int i = 0; i < CT / 32; ++i) t += s_p[i][threadIdx.x];
+    partial[((size_t)k * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = t;    // deterministic 2-stage reduce
+  }
+}
+
+// out_loss = {loss, e_depth, e_obj, e_sem, depth[K], color[K], opacity[K]}
+__global__ void composite_finalize_kernel(int K, int nblk, const float* __restrict__ partial,
+                                          const int32_t* __restrict__ counts, float cs, float os,
+                                          float* __restrict__ out_loss) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  bool e0, e1, e2;
+  empty_flags(K, counts, e0, e1, e2);
+  float total = 0.f;
+  for (int k = 0; k < K; ++k) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int b = 0; b < nblk; ++b) {
+      const float* p = partial + ((size_t)k * nblk + b) * 3;
+      s0 += p[0]; s1 += p[1]; s2 += p[2];
+    }
+    const float d = e0 ? 0.f : s0 / ((float)counts[k * 4 + 0] + 1e-10f);      // render_rays.py:86
+    const float c = e1 ? 0.f : s1 / ((float)counts[k * 4 + 1] + 1e-10f);
+    const float o = e2 ? 0.f : s2 / ((float)counts[k * 4 + 2] + 1e-10f);
+    out_loss[4 + k] = d; out_loss[4 + K + k] = c; out_loss[4 + 2 * K + k] = o;
+    total += d + c * cs + o * os;                                             // loss.py:69-70
+  }
+  out_loss[0] = total; out_loss[1] = e0; out_loss[2] = e1; out_loss[3] = e2;
+}
+
+__global__ void __launch_bounds__(CT)
+composite_bwd_kernel(int K, int R, int S, const float* __restrict__ alpha, const float* __restrict__ color,
+                     const float* __restrict__ z, const float* __restrict__ gt_depth, const float* __restrict__ gt_color,
+                     const uint8_t* __restrict__ labels, const uint8_t* __restrict__ mask_depth,
+                     const int32_t* __restrict__ counts, float cs, float os, const float* __restrict__ g_loss,
+                     float* __restrict__ g_alpha, float* __restrict__ g_color) {
+  const int k = blockIdx.y;
+  const int G = seg_width(S), rpw = 32 / G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = lane / G, sl = lane - seg * G;
+  const int rays_per_block = (CT / 32) * rpw;
+  bool e0, e1, e2;
+  empty_flags(K, counts, e0, e1, e2);
+  const float gl = g_loss ? g_loss[0] : 1.0f;
+  const float iNd = e0 ? 0.f : gl / ((float)counts[k * 4 + 0] + 1e-10f);
+  const float iNo = e1 ? 0.f : gl * cs / ((float)counts[k * 4 + 1] + 1e-10f);
+  const float iNs = e2 ? 0.f : gl * os / ((float)counts[k * 4 + 2] + 1e-10f);
+  const int nchunk = (S + G - 1) / G;
+  for (int rb = blockIdx.x * rays_per_block; rb < R; rb += gridDim.x * rays_per_block) {
+    const int r = rb + warp * rpw + seg;
+    const int rr = min(r, R - 1);
+    const size_t g = (size_t)k * R + rr;
+    const float* al = alpha + g * S; const float* co = color + g * S * 3; const float* zz = z + g * S;
+    const RayOut o = ray_forward(al, co, zz, S, G, sl);
+    const uint8_t lab = labels[g];
+    const float mo = (lab != 0) ? 1.f : 0.f, ms = (lab != 2) ? 1.f : 0.f;
+    const float md = (mask_depth[g] != 0 && lab != 0) ? 1.f : 0.f;
+    auto sgn = [](float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); };
+    const float gD = sgn(o.D - gt_depth[g]) * md * (1.0f / (sqrtf(o.var) + 1e-4f)) * iNd;
+    const float gC0 = sgn(o.C0 - gt_color[g * 3 + 0]) * mo * iNo;
+    const float gC1 = sgn(o.C1 - gt_color[g * 3 + 1]) * mo * iNo;
+    const float gC2 = sgn(o.C2 - gt_color[g * 3 + 2]) * mo * iNo;
+    const float gO = sgn(o.O - mo) * ms * iNs;
+    // total free-space product of whole chunks before each chunk, walking chunks in reverse with a suffix carry
+    float suffix_carry = 0.f;
+    for (int ch = nchunk - 1; ch >= 0; --ch) {
+      // transmittance carry into this chunk = product of f over all earlier chunks
+      float carry = 1.0f;
+      for (int c2 = 0; c2 < ch; ++c2) {
+        const int i2 = c2 * G + sl;
+        const float f2 = (i2 < S) ? __fadd_rn(__fsub_rn(1.0f, sigmoid_acc(al[i2])), 1e-10f) : 1.0f;
+        const float inc2 = seg_scan_mul(f2, G, sl);
+        carry *= __shfl_sync(0xffffffffu, inc2, G - 1, G);
+      }
+      const int i = ch * G + sl;
+      const bool act = i < S;
+      const float occ = act ? sigmoid_acc(al[i]) : 0.f;
+      const float f = act ? __fadd_rn(__fsub_rn(1.0f, occ), 1e-10f) : 1.0f;
+      const float incl = seg_scan_mul(f, G, sl);
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (sl == 0) excl = 1.0f;
+      const float T = carry * excl;
+      const float w = occ * T;
+      float c0 = 0.f, c1 = 0.f, c2v = 0.f, zi = 0.f;
+      if (act) { c0 = co[i * 3]; c1 = co[i * 3 + 1]; c2v = co[i * 3 + 2]; zi = zz[i]; }
+      const float Gi = act ? (gD * zi + gC0 * c0 + gC1 * c1 + gC2 * c2v + gO) : 0.f;
+      const float Gw = Gi * w;
+      const float incl_s = seg_scan_add_rev(Gw, G, sl);
+      const float suffix = (incl_s - Gw) + suffix_carry;                     // sum_{i>j} G_i w_i
+      suffix_carry += __shfl_sync(0xffffffffu, incl_s, 0, G);
+      if (act && r < R) {
+        const float docc = Gi * T - suffix / f;
+        g_alpha[g * S + i] = docc * occ * (1.0f - occ);
+        g_color[(g * S + i) * 3 + 0] = w * gC0;
+        g_color[(g * S + i) * 3 + 1] = w * gC1;
+        g_color[(g * S + i) * 3 + 2] = w * gC2;
+      }
+    }
+  }
+}
+
+__global__ void termination_kernel(int n_rays, int S, const float* __restrict__ occ_in, float* __restrict__ w_out) {
+  const int G = seg_width(S), rpw = 32 / G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = lane / G, sl = lane - seg * G;
+  const int rays_per_block = (blockDim.x / 32) * rpw;
+  for (int rb = blockIdx.x * rays_per_block; rb < n_rays; rb += gridDim.x * rays_per_block) {
+    const int r = rb + warp * rpw + seg;
+    const int rr = min(r, n_rays - 1);
+    float carry = 1.0f;
+    for (int c0 = 0; c0 < S; c0 += G) {
+      const int i = c0 + sl;
+      const bool act = i < S;
+      const float occ = act ? occ_in[(size_t)rr * S + i] : 0.f;
+      const float f = act ? __fadd_rn(__fsub_rn(1.0f, occ), 1e-10f) : 1.0f;
+      const float incl = seg_scan_mul(f, G, sl);
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (sl == 0) excl = 1.0f;
+      if (act && r < n_rays) w_out[(size_t)rr * S + i] = occ * (carry * excl);
+      carry *= __shfl_sync(0xffffffffu, incl, G - 1, G);
+    }
+  }
+}
+
+// one block; warp per code row
+__global__ void code_reg_kernel(int n_obj, int L, const float* __restrict__ codes, float weight,
+                                float* __restrict__ out, float* __restrict__ g_codes) {
+  __shared__ float s_n[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float acc = 0.f;
+  for (int i = warp; i < n_obj; i += nw) {
+    float s = 0.f;
+    for (int j = lane; j < L; j += 32) { const float v = codes[(size_t)i * L + j]; s += v * v; }
+    s = warp_sum(s);
+    const float nrm = sqrtf(s);
+    acc += nrm;
+    if (g_codes && n_obj > 1) {
+      const float inv = nrm > 0.f ? weight / nrm : 0.f;
+      for (int j = lane; j < L; j += 32) g_codes[(size_t)i * L + j] += inv * codes[(size_t)i * L + j];
+    }
+  }
+  if (lane == 0) s_n[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < nw; ++i) t += s_n[i];
+    out[0] = (n_obj > 1) ? t : 0.f;                                          // loss.py:12
+  }
+}
+
+}  // namespace cnf
+
+using namespace cnf;
+
+static int comp_blocks(int R, int S) {
+  int G = 1; while (G < S && G < 32) G <<= 1;
+  const int rpb = (CT / 32) * (32 / G);
+  int nb = (R + rpb - 1) / rpb;
+  if (nb > 1184) nb = 1184;      // 8 x 148 SMs, grid-stride beyond
+  return nb < 1 ? 1 : nb;
+}
+
+extern "C" int cnf_termination_fwd(int n_rays, int S, const float* occ, float* w, cnf_stream_t stream) {
+  CNF_REQUIRE(n_rays >= 0 && S > 0 && occ && w, "cnf_termination_fwd: bad arguments");
+  if (n_rays == 0) return CNF_OK;
+  termination_kernel<<<comp_blocks(n_rays, S), CT, 0, as_stream(stream)>>>(n_rays, S, occ, w);
+  return check_launch("cnf_termination_fwd");
+}
+
+extern "C" int cnf_mask_counts(int K, int R, const uint8_t* labels, const uint8_t* mask_depth, int32_t* counts,
+                               cnf_stream_t stream) {
+  CNF_REQUIRE(K > 0 && R > 0 && labels && mask_depth && counts, "cnf_mask_counts: bad arguments");
+  CNF_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * 4 * K, as_stream(stream)));
+  int nb = (R + 255) / 256; if (nb > 296) nb = 296;
+  mask_counts_kernel<<<dim3(nb, K), 256, 0, as_stream(stream)>>>(R, labels, mask_depth, counts);
+  return check_launch("cnf_mask_counts");
+}
+
+extern "C" size_t cnf_composite_workspace_bytes(int K, int R) { return (size_t)K * 1184 * 3 * sizeof(float); }
+
+extern "C" int cnf_composite_loss_fwd(int K, int R, int S, const float* alpha, const float* color, const float* z,
+                                      const float* gt_depth, const float* gt_color, const uint8_t* labels,
+                                      const uint8_t* mask_depth, const int32_t* counts, float cs, float os,
+                                      float* out_rays, float* out_loss, void* ws, size_t ws_bytes, cnf_stream_t stream) {
+  CNF_REQUIRE(K > 0 && R > 0 && S > 0, "cnf_composite_loss_fwd: bad sizes");
+  CNF_REQUIRE(alpha && color && z && gt_depth && gt_color && labels && mask_depth && counts && out_rays && out_loss && ws,
+              "cnf_composite_loss_fwd: null pointer");
+  if (ws_bytes < cnf_composite_workspace_bytes(K, R)) { set_error("cnf_composite_loss_fwd: workspace too small"); return CNF_ERR_WORKSPACE; }
+  const int nb = comp_blocks(R, S);
+  composite_fwd_kernel<<<dim3(nb, K), CT, 0, as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels,
+                                                                  mask_depth, out_rays, (float*)ws);
+  composite_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(K, nb, (const float*)ws, counts, cs, os, out_loss);
+  return check_launch("cnf_composite_loss_fwd");
+}
+
+extern "C" int cnf_composite_loss_bwd(int K, int R, int S, const float* alpha, const float* color, const float* z,
+                                      const float* gt_depth, const float* gt_color, const uint8_t* labels,
+                                      const uint8_t* mask_depth, const int32_t* counts, float cs, float os,
+                                      const float* g_loss, float* g_alpha, float* g_color, cnf_stream_t stream) {
+  CNF_REQUIRE(K > 0 && R > 0 && S > 0, "cnf_composite_loss_bwd: bad sizes");
+  CNF_REQUIRE(alpha && color && z && gt_depth && gt_color && labels && mask_depth && counts && g_alpha && g_color,
+              "cnf_composite_loss_bwd: null pointer");
+  composite_bwd_kernel<<<dim3(comp_blocks(R, S), K), CT, 0, as_stream(stream)>>>(
+      K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth, counts, cs, os, g_loss, g_alpha, g_color);
+  return check_launch("cnf_composite_loss_bwd");
+}
+
+extern "C" int cnf_code_reg(int n_obj, int L, const float* codes, float weight, float* out, float* g_codes,
+                            cnf_stream_t stream) {
+  CNF_REQUIRE(n_obj > 0 && L > 0 && codes && out, "cnf_code_reg: bad arguments");
+  code_reg_kernel<<<1, 256, 0, as_stream(stream)>>>(n_obj, L, codes, weight, out, g_codes);
+  return check_launch("cnf_code_reg");
+}

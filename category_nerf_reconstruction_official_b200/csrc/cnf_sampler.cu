@@ -1,0 +1,250 @@
+// Depth-guided ray sampler: sceneCategory.sample_3d_points / stratified_bins / normal_bins_sampling
+// (reference src/scene_cateogries.py:51-96, 453-546).  Bit-exact against the reference: every fp32 op is
+// separately rounded (__fmul_rn/__fadd_rn/__fdiv_rn, no FMA contraction), linspace tables and random
+// draws are inputs, and rows of the random tensors are consumed by rank-within-case in ray order.
+//
+// HBM-bound.  Three launches: (A) per-block case counts + max depth, (B) per-category exclusive scan of
+// the block counts, (C) emit: thread-per-ray rank computation, then thread-per-sample coalesced writes.
+#include "cnf_common.cuh"
+
+namespace cnf {
+
+constexpr int SB = 256;  // rays per block
+
+struct SampleCase { int c; };  // 0 invalid, 1 valid&this-object, 2 valid&other
+
+__device__ __forceinline__ int ray_case(float d, uint8_t label, float min_bound, int this_obj) {
+  if (d <= min_bound) return 0;
+  return (label == this_obj) ? 1 : 2;
+}
+
+// (A) counts per block: {nI, nV, nO, nT} plus loss-mask counts {Nd, No, Ns} and block max depth.
+__global__ void sample_count_kernel(int R, const uint8_t* __restrict__ rgbs, const float* __restrict__ depth,
+                                    float min_bound, int this_obj, int* __restrict__ blk_counts,
+                                    float* __restrict__ blk_max) {
+  const int k = blockIdx.y, nb = gridDim.x, b = blockIdx.x;
+  const int r = b * SB + threadIdx.x;
+  int cI = 0, cO = 0, cT = 0, cD = 0, cObj = 0, cSem = 0;
+  float mx = -INFINITY;
+  if (r < R) {
+    const float d = depth[(size_t)k * R + r];
+    const uint8_t lab = rgbs[((size_t)k * R + r) * 4 + 3];
+    const int c = ray_case(d, lab, min_bound, this_obj);
+    cI = (c == 0); cO = (c == 1); cT = (c == 2);
+    const bool mo = lab != 0, ms = lab != 2;
+    cD = (c != 0) && mo; cObj = mo; cSem = ms;
+    mx = d;
+  }
+  __shared__ int s_c[SB / 32][6];
+  __shared__ float s_m[SB / 32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  cI = warp_sum_i(cI); cO = warp_sum_i(cO); cT = warp_sum_i(cT);
+  cD = warp_sum_i(cD); cObj = warp_sum_i(cObj); cSem = warp_sum_i(cSem);
+  mx = warp_max(mx);
+  if (l == 0) { s_c[w][0] = cI; s_c[w][1] = cO; s_c[w][2] = cT; s_c[w][3] = cD; s_c[w][4] = cObj; s_c[w][5] = cSem; s_m[w] = mx; }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    int t = 0;
+    for (int i = 0; i < SB / 32; ++i) t += s_c[i][threadIdx.x];
+    blk_counts[((size_t)k * nb + b) * 8 + threadIdx.x] = t;
+  }
+  if (threadIdx.x == 32) {
+    float m = s_m[0];
+    for (int i = 1; i < SB / 32; ++i) m = fmaxf(m, s_m[i]);
+    blk_max[(size_t)k * nb + b] = m;
+  }
+}
+
+// (B) one block per category: exclusive scan of block counts (in place, cols 0..2), totals -> stats.
+__global__ void sample_scan_kernel(int nb, int* __restrict__ blk_counts, const float* __restrict__ blk_max,
+                                   int32_t* __restrict__ stats) {
+  const int k = blockIdx.x;
+  int* bc = blk_counts + (size_t)k * nb * 8;
+  __shared__ int s_tot[6];
+  __shared__ float s_mx;
+  if (threadIdx.x < 6) {       // serial scan per column: nb <= a few thousand, negligible
+    const int c = threadIdx.x;
+    int run = 0;
+    for (int b = 0; b < nb; ++b) {
+      const int v = bc[b * 8 + c];
+      if (c < 3) bc[b * 8 + c] = run;
+      run += v;
+    }
+    s_tot[c] = run;
+  }
+  if (threadIdx.x == 32) {
+    float m = -INFINITY;
+    for (int b = 0; b < nb; ++b) m = fmaxf(m, blk_max[(size_t)k * nb + b]);
+    s_mx = m;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t* st = stats + k * 8;
+    st[0] = s_tot[0];              // nI
+    st[1] = s_tot[1] + s_tot[2];   // nV
+    st[2] = s_tot[1];              // nO
+    st[3] = s_tot[2];              // nT
+    st[4] = s_tot[3];              // N_depth&obj
+    st[5] = s_tot[4];              // N_obj
+    st[6] = s_tot[5];              // N_sem
+    st[7] = __float_as_int(s_mx);  // max depth bits
+  }
+}
+
+// stratified z for bin k: (range*lin[k] + min) + u*(range/n)   -- scene_cateogries.py:62-77
+__device__ __forceinline__ float strat(float mn, float mxv, float lin_k, float u, float nf) {
+  const float range = __fsub_rn(mxv, mn);
+  const float lower = __fadd_rn(__fmul_rn(range, lin_k), mn);
+  const float len = __fdiv_rn(range, nf);
+  return __fadd_rn(lower, __fmul_rn(u, len));
+}
+
+// (C) emit.
+__global__ void __launch_bounds__(SB)
+sample_emit_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const float* __restrict__ depth,
+                   const float* __restrict__ origins, const float* __restrict__ dirs,
+                   const float* __restrict__ u_inv, const float* __restrict__ u_val,
+                   const float* __restrict__ n_obj, const float* __restrict__ u_oth,
+                   const float* __restrict__ lin_S, const float* __restrict__ lin_N, const float* __restrict__ lin_M,
+                   float min_bound, float eps, float stop_eps, int this_obj,
+                   const int* __restrict__ blk_counts, const int32_t* __restrict__ stats,
+                   float* __restrict__ z, float* __restrict__ pcs, uint8_t* __restrict__ valid,
+                   uint8_t* __restrict__ labels) {
+  const int k = blockIdx.y, nb = gridDim.x, b = blockIdx.x;
+  const int S = N + M;
+  const int r0 = b * SB;
+  __shared__ int s_row[SB];      // rank of the ray within its case (row of the random tensor)
+  __shared__ int s_rowv[SB];     // rank among valid rays (row of u_val)
+  __shared__ uint8_t s_case[SB];
+  __shared__ float s_depth[SB];
+  __shared__ float s_od[SB][6];
+  __shared__ int s_w[SB / 32][3];
+
+  // ---- phase 1: thread per ray: case + exclusive rank in ray order
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
+  const int r = r0 + t;
+  int c = 3;
+  float d = 0.f;
+  if (r < R) {
+    const size_t gi = (size_t)k * R + r;
+    d = depth[gi];
+    const uint8_t lab = rgbs[gi * 4 + 3];
+    c = ray_case(d, lab, min_bound, this_obj);
+    valid[gi] = (c != 0);
+    labels[gi] = lab;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { s_od[t][j] = origins[gi * 3 + j]; s_od[t][3 + j] = dirs[gi * 3 + j]; }
+  }
+  const unsigned m0 = __ballot_sync(0xffffffffu, c == 0);
+  const unsigned m1 = __ballot_sync(0xffffffffu, c == 1);
+  const unsigned m2 = __ballot_sync(0xffffffffu, c == 2);
+  const unsigned lt = (1u << l) - 1u;
+  if (l == 0) { s_w[w][0] = __popc(m0); s_w[w][1] = __popc(m1); s_w[w][2] = __popc(m2); }
+  __syncthreads();
+  int base0 = blk_counts[((size_t)k * nb + b) * 8 + 0];
+  int base1 = blk_counts[((size_t)k * nb + b) * 8 + 1];
+  int base2 = blk_counts[((size_t)k * nb + b) * 8 + 2];
+  for (int i = 0; i < w; ++i) { base0 += s_w[i][0]; base1 += s_w[i][1]; base2 += s_w[i][2]; }
+  const int rk0 = base0 + __popc(m0 & lt), rk1 = base1 + __popc(m1 & lt), rk2 = base2 + __popc(m2 & lt);
+  s_case[t] = (uint8_t)c;
+  s_depth[t] = d;
+  s_row[t] = (c == 0) ? rk0 : (c == 1 ? rk1 : rk2);
+  s_rowv[t] = rk1 + rk2;     // valid rays = case1 U case2, both counted in ray order
+  __syncthreads();
+
+  // ---- phase 2: thread per sample (coalesced z / pcs writes)
+  const float max_bound = __int_as_float(stats[k * 8 + 7]);
+  const int nrays = min(SB, R - r0);
+  const float fS = (float)S, fN = (float)N, fM = (float)M;
+  for (int e = t; e < nrays * S; e += SB) {
+    const int rr = e / S, i = e - rr * S;
+    const int cc = s_case[rr];
+    const float dd = s_depth[rr];
+    float zz;
+    if (cc == 0) {                               // :484-493 invalid depth: S bins in [min_bound, max depth]
+      const float u = u_inv[((size_t)k * R + s_row[rr]) * S + i];
+      zz = strat(min_bound, max_bound, lin_S[i], u, fS);
+    } else if (i < N) {                          // :502-504 camera -> surface - eps
+      const float u = u_val[((size_t)k * R + s_rowv[rr]) * N + i];
+      zz = strat(min_bound, __fsub_rn(dd, eps), lin_N[i], u, fN);
+    } else if (cc == 1) {                        // :519-524 sorted normals around the surface
+      const float* row = n_obj + ((size_t)k * R + s_row[rr]) * M;
+      const int j = i - N;
+      const float v = row[j];
+      int rank = 0;
+      for (int q = 0; q < M; ++q) {
+        const float o = row[q];
+        rank += (o < v) || (o == v && q < j);
+      }
+      const float cl = fminf(fmaxf(v, -eps), eps);
+      zz = __fadd_rn(dd, cl);
+      // scatter to the sorted position inside the same ray
+      const size_t zo = ((size_t)k * R + r0 + rr) * S + N + rank;
+      z[zo] = zz;
+      if (pcs) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) pcs[zo * 3 + a] = __fadd_rn(s_od[rr][a], __fmul_rn(s_od[rr][3 + a], zz));
+      }
+      continue;
+    } else {                                     // :536-539 other objects: [d-eps, d+stop_eps]
+      const float u = u_oth[((size_t)k * R + s_row[rr]) * M + (i - N)];
+      zz = strat(__fsub_rn(dd, eps), __fadd_rn(dd, stop_eps), lin_M[i - N], u, fM);
+    }
+    const size_t zo = ((size_t)k * R + r0) * S + e;
+    z[zo] = zz;
+    if (pcs) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) pcs[zo * 3 + a] = __fadd_rn(s_od[rr][a], __fmul_rn(s_od[rr][3 + a], zz));
+    }
+  }
+}
+
+__global__ void stratified_bins_kernel(int n_rays, int n_bins, const float* __restrict__ mn, int mn_s,
+                                       const float* __restrict__ mx, int mx_s, const float* __restrict__ u,
+                                       const float* __restrict__ lin, float* __restrict__ z) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)n_rays * n_bins) return;
+  const int r = (int)(e / n_bins), i = (int)(e - (size_t)r * n_bins);
+  z[e] = strat(mn[mn_s ? 0 : r], mx[mx_s ? 0 : r], lin[i], u[e], (float)n_bins);
+}
+
+}  // namespace cnf
+
+using namespace cnf;
+
+extern "C" size_t cnf_sample_workspace_bytes(int n_cat, int n_rays) {
+  const size_t nb = (size_t)(n_rays + SB - 1) / SB;
+  return align_up((size_t)n_cat * nb * 8 * sizeof(int), 256) + align_up((size_t)n_cat * nb * sizeof(float), 256);
+}
+
+extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, const float* depth,
+                              const float* origins, const float* dirs, const float* u_inv, const float* u_val,
+                              const float* n_obj, const float* u_oth, const float* lin_S, const float* lin_N,
+                              const float* lin_M, float min_bound, float eps, float stop_eps, int this_obj,
+                              float* z, float* pcs, uint8_t* valid, uint8_t* labels, int32_t* stats, void* ws,
+                              size_t ws_bytes, cnf_stream_t stream) {
+  CNF_REQUIRE(K > 0 && R > 0 && N >= 0 && M > 0, "cnf_sample_fwd: bad sizes K=%d R=%d N=%d M=%d", K, R, N, M);
+  CNF_REQUIRE(rgbs && depth && origins && dirs && z && valid && labels && stats && ws, "cnf_sample_fwd: null pointer");
+  CNF_REQUIRE(u_inv && u_val && n_obj && u_oth && lin_S && lin_M && (N == 0 || lin_N), "cnf_sample_fwd: null random/linspace input");
+  if (ws_bytes < cnf_sample_workspace_bytes(K, R)) { set_error("cnf_sample_fwd: workspace too small"); return CNF_ERR_WORKSPACE; }
+  const int nb = (R + SB - 1) / SB;
+  int* blk_counts = reinterpret_cast<int*>(ws);
+  float* blk_max = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align_up((size_t)K * nb * 8 * sizeof(int), 256));
+  cudaStream_t st = as_stream(stream);
+  sample_count_kernel<<<dim3(nb, K), SB, 0, st>>>(R, rgbs, depth, min_bound, this_obj, blk_counts, blk_max);
+  sample_scan_kernel<<<K, 64, 0, st>>>(nb, blk_counts, blk_max, stats);
+  sample_emit_kernel<<<dim3(nb, K), SB, 0, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth,
+                                                 lin_S, lin_N, lin_M, min_bound, eps, stop_eps, this_obj,
+                                                 blk_counts, stats, z, pcs, valid, labels);
+  return check_launch("cnf_sample_fwd");
+}
+
+extern "C" int cnf_stratified_bins(int n_rays, int n_bins, const float* min_d, int min_is_scalar, const float* max_d,
+                                   int max_is_scalar, const float* u, const float* lin, float* z, cnf_stream_t stream) {
+  CNF_REQUIRE(n_rays >= 0 && n_bins > 0 && min_d && max_d && u && lin && z, "cnf_stratified_bins: bad arguments");
+  if (n_rays == 0) return CNF_OK;
+  const size_t n = (size_t)n_rays * n_bins;
+  stratified_bins_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(n_rays, n_bins, min_d, min_is_scalar,
+                                                                                     max_d, max_is_scalar, u, lin, z);
+  return check_launch("cnf_stratified_bins");
+}

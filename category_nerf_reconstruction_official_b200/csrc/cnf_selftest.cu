@@ -1,0 +1,88 @@
+// tcgen05 self-test: one 128-row UMMA tile with operands staged in the blocked no-swizzle layout used by the
+// fused kernel.  Pins the shared-memory / instruction descriptor encodings on hardware for the three operand
+// views the fused step needs: forward (A,B K-major), data-gradient (B MN-major), weight-gradient (A,B MN-major).
+#include "cnf_common.cuh"
+#include "cnf_umma.cuh"
+
+namespace cnf {
+using namespace umma;
+
+__global__ void __launch_bounds__(128)
+umma_selftest_kernel(int mode, int N, int Kd, const float* __restrict__ A, const float* __restrict__ B,
+                     float* __restrict__ D) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 128 * Kd * 2;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // stage A
+  if (mode == 2) {      // A given [Kd, 128]
+    for (int i = tid; i < Kd * 128; i += 128) {
+      const int r = i / 128, c = i % 128;
+      *reinterpret_cast<__nv_bfloat16*>(sA + blk_off(r, c, 128)) = __float2bfloat16(A[i]);
+    }
+  } else {              // A given [128, Kd]
+    for (int i = tid; i < 128 * Kd; i += 128) {
+      const int r = i / Kd, c = i % Kd;
+      *reinterpret_cast<__nv_bfloat16*>(sA + blk_off(r, c, Kd)) = __float2bfloat16(A[i]);
+    }
+  }
+  if (mode == 0) {      // B given [N, Kd]
+    for (int i = tid; i < N * Kd; i += 128) {
+      const int r = i / Kd, c = i % Kd;
+      *reinterpret_cast<__nv_bfloat16*>(sB + blk_off(r, c, Kd)) = __float2bfloat16(B[i]);
+    }
+  } else {              // B given [Kd, N]
+    for (int i = tid; i < Kd * N; i += 128) {
+      const int r = i / N, c = i % N;
+      *reinterpret_cast<__nv_bfloat16*>(sB + blk_off(r, c, N)) = __float2bfloat16(B[i]);
+    }
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = idesc_bf16(128, N, mode == 2, mode >= 1);
+    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+    for (int ks = 0; ks < Kd / 16; ++ks) {
+      uint64_t ad, bd;
+      if (mode == 2) ad = smem_desc(a0 + ks * 2 * (16 * 128), /*LBO*/ 16 * 128, /*SBO*/ 128);
+      else           ad = smem_desc(a0 + ks * 2 * 128, /*LBO*/ 128, /*SBO*/ 16 * Kd);
+      if (mode == 0) bd = smem_desc(b0 + ks * 2 * 128, 128, 16 * Kd);
+      else           bd = smem_desc(b0 + ks * 2 * (16 * N), 16 * N, 128);
+      mma_ss(tmem, ad, bd, idesc, ks > 0);
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  const uint32_t tl = tmem_lane_base(tmem);
+  const int row = tid;
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tl + c0, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[row * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+}  // namespace cnf
+
+using namespace cnf;
+
+extern "C" int cnf_umma_selftest(int mode, int N, int Kdim, const float* A, const float* B, float* D, cnf_stream_t stream) {
+  CNF_REQUIRE(mode >= 0 && mode <= 2 && N >= 16 && N <= 256 && N % 16 == 0 && Kdim >= 16 && Kdim <= 256 && Kdim % 16 == 0,
+              "cnf_umma_selftest: need mode in 0..2, N%%16==0 (16..256), K%%16==0 (16..256)");
+  CNF_REQUIRE(A && B && D, "cnf_umma_selftest: null pointer");
+  const size_t smem = (size_t)128 * Kdim * 2 + (size_t)N * Kdim * 2;
+  CNF_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(mode, N, Kdim, A, B, D);
+  return check_launch("cnf_umma_selftest");
+}

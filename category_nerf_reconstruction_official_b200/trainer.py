@@ -1,0 +1,75 @@
+"""Trainer -- drop-in for the model/PE/code construction and point evaluation of the reference's
+src/trainer.py:11-60,125-151 (meshing/visualisation stays with the reference: CPU post-processing, out of scope)."""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import embedding, model, render_rays
+
+
+class Trainer:
+    def __init__(self, cfg, cls_id, inst_ids):
+        self.cls_id = cls_id
+        self.inst_id_to_index = {inst_id: inst_ids.index(inst_id) for inst_id in inst_ids}
+        self.n_obj = len(inst_ids)
+        self.device = cfg.training_device
+        self.obj_scale = cfg.obj_scale
+        self.n_unidir_funcs = cfg.n_unidir_funcs
+        self.emb_size1 = 21 * (3 + 1) + 3
+        self.emb_size2 = 21 * (5 + 1) + 3 - self.emb_size1
+        if cls_id == 0:
+            self.hidden_feature_size = cfg.hidden_feature_size
+            self.load_NeRF()
+        else:
+            self.net_hyperparams = cfg.net_hyperparams
+            self.load_codeNeRF()
+            self.load_codes()
+        self.extent_dict = None
+        self.bound_extent = 0.995 if self.cls_id == 0 else 0.9
+        self.scale_template = None
+
+    def load_codeNeRF(self):
+        self.fc_occ_map = model.CodeNeRF(self.emb_size1, self.emb_size2, **self.net_hyperparams).to(self.device)
+        self.fc_occ_map.apply(model.init_weights).to(self.device)
+        self.pe = embedding.UniDirsEmbed(max_deg=self.n_unidir_funcs, scale=self.obj_scale).to(self.device)
+
+    def load_NeRF(self):
+        self.fc_occ_map = model.OccupancyMap(self.emb_size1, self.emb_size2, hidden_size=self.hidden_feature_size)
+        self.fc_occ_map.apply(model.init_weights).to(self.device)
+        self.pe = embedding.UniDirsEmbed(max_deg=self.n_unidir_funcs, scale=self.obj_scale).to(self.device)
+
+    def load_codes(self):
+        embdim = self.net_hyperparams['latent_dim']
+        d = self.n_obj
+        self.shape_codes = nn.Embedding(d, embdim)
+        self.texture_codes = nn.Embedding(d, embdim)
+        self.shape_codes.weight = nn.Parameter(torch.randn(d, embdim) / math.sqrt(embdim / 2))
+        self.texture_codes.weight = nn.Parameter(torch.randn(d, embdim) / math.sqrt(embdim / 2))
+        self.shape_codes = self.shape_codes.to(self.device)
+        self.texture_codes = self.texture_codes.to(self.device)
+
+    def eval_points(self, points, inst_id=None, chunk_size=500000):
+        """points [P,3] -> (occupancy [P], colour [P,3]) with one instance's codes (trainer.py:125-151).
+        Outputs are written chunk by chunk into preallocated tensors (no Python list of 0-d tensors)."""
+        P = points.shape[0]
+        alpha = torch.empty(P, device=points.device)
+        color = torch.empty(P, 3, device=points.device)
+        if self.cls_id != 0:
+            obj_idx = torch.from_numpy(np.array(self.inst_id_to_index[inst_id])).to(self.device)
+            shape_code, texture_code = self.shape_codes(obj_idx), self.texture_codes(obj_idx)
+        with torch.no_grad():
+            for s in range(0, P, chunk_size):
+                emb = self.pe(points[s:s + chunk_size, ...])
+                if self.cls_id == 0:
+                    a, c = self.fc_occ_map(emb)
+                else:
+                    a, c = self.fc_occ_map(emb, shape_code, texture_code)
+                alpha[s:s + chunk_size] = a.reshape(-1)
+                color[s:s + chunk_size] = c
+        occ = render_rays.occupancy_activation(alpha).detach()
+        if occ.max() == 0:
+            print("no occ")
+            return None
+        return (occ, color)

@@ -1,0 +1,187 @@
+/* cnf.h -- C ABI of libcnf_sm100.so: B200 (sm_100a) kernels for the category-level neural-field
+ * training hot path of Taekbum/category-nerf-reconstruction-official.
+ *
+ * The reference has no FFI layer (it is pure Python/PyTorch); the boundary a
+ * maintainer binds is therefore this header, one entry point per reference function on the path.
+ * Each declaration cites the reference interface it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates everything, including
+ *    workspaces); the library allocates nothing persistent and keeps no per-device global state;
+ *  - `stream` is the cudaStream_t to launch on (torch.cuda.current_stream().cuda_stream);
+ *    all entry points are asynchronous w.r.t. the host (no synchronisation inside);
+ *  - tensors are dense row-major fp32 unless stated; a leading `n_cat` (K) dimension is the
+ *    category batch the reference obtains with functorch.vmap (train.py:154-155);
+ *  - return value: 0 = OK, <0 = argument/shape/arch error (see cnf_last_error_string),
+ *    >0 = cudaError_t.  The library never calls exit() and has NO CPU fallback.
+ */
+#ifndef CNF_H_
+#define CNF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cnf_stream_t;
+
+#define CNF_OK 0
+#define CNF_ERR_ARG (-1)
+#define CNF_ERR_ARCH (-2)
+#define CNF_ERR_WORKSPACE (-3)
+#define CNF_ERR_UNSUPPORTED (-4)
+
+#define CNF_EMB_DIM 129   /* 3 + 6*21, src/trainer.py:20-21 */
+#define CNF_EMB1 87       /* geometry branch input  */
+#define CNF_EMB2 42       /* colour branch input    */
+#define CNF_N_DIRS 21
+#define CNF_N_FREQ 6
+
+int cnf_version(void);
+const char* cnf_last_error_string(void);
+/* 0 if `device` is an sm_100 part, CNF_ERR_ARCH otherwise (no fallback exists). */
+int cnf_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Sampler -- sceneCategory.sample_3d_points, stratified_bins, normal_bins_sampling
+ *     (src/scene_cateogries.py:51-96, 453-546).  Random draws are INPUTS so results are bit-exact.
+ *     rgbs u8 [K,R,4] (last column = label 0/1/2), depth [K,R], origins/dirs [K,R,3].
+ *     u_inv [K,R,S], u_val [K,R,N], n_obj [K,R,M] (already N(0,eps/3)), u_oth [K,R,M]: per category,
+ *     row k is consumed by the k-th ray (in ray order) of the respective case, as the reference's
+ *     boolean-mask assignment does.  lin_S/lin_N/lin_M = torch.linspace(0,1,n+1) tables (not k/n).
+ *     Outputs: z [K,R,S], pcs [K,R,S,3] (may be NULL), valid u8 [K,R], labels u8 [K,R],
+ *     stats [K,8] int32 = {nI, nV, nO, nT, N_depth&obj, N_obj, N_sem, float_bits(max depth)}.
+ *     ws: >= cnf_sample_workspace_bytes(K,R) bytes.
+ * ---------------------------------------------------------------------------------------------- */
+size_t cnf_sample_workspace_bytes(int n_cat, int n_rays);
+int cnf_sample_fwd(int n_cat, int n_rays, int n_cam2surf, int n_surf,
+                   const uint8_t* rgbs, const float* depth, const float* origins, const float* dirs,
+                   const float* u_inv, const float* u_val, const float* n_obj, const float* u_oth,
+                   const float* lin_S, const float* lin_N, const float* lin_M,
+                   float min_bound, float eps, float stop_eps, int this_obj,
+                   float* z, float* pcs, uint8_t* valid, uint8_t* labels, int32_t* stats,
+                   void* ws, size_t ws_bytes, cnf_stream_t stream);
+
+/* stratified_bins(min, max, n_bins, n_rays) module-level function (src/scene_cateogries.py:51-81;
+ * also called by src/category_registration.py:146).  min_d/max_d: [n_rays] or broadcast scalar
+ * (stride 0 when *_is_scalar).  u [n_rays,n_bins], lin [n_bins+1] -> z [n_rays,n_bins]. */
+int cnf_stratified_bins(int n_rays, int n_bins, const float* min_d, int min_is_scalar,
+                        const float* max_d, int max_is_scalar, const float* u, const float* lin,
+                        float* z, cnf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Embedding -- UniDirsEmbed.forward (src/embedding.py:82-92) and its backward.
+ *     x [K,P,3], B [K,21,3], scale [K] -> emb [K,P,129] = cat(x/s, sin(pi * 2^f * (x/s) B^T)).
+ *     bwd: g_emb [K,P,129] -> g_B [K,21,3] (ACCUMULATED into), g_x [K,P,3] (may be NULL).
+ * ---------------------------------------------------------------------------------------------- */
+int cnf_embed_fwd(int n_cat, int n_pts, const float* x, const float* B, const float* scale,
+                  float* emb, cnf_stream_t stream);
+int cnf_embed_bwd(int n_cat, int n_pts, const float* x, const float* B, const float* scale,
+                  const float* g_emb, float* g_B, float* g_x, cnf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) MLPs, fp32 CUDA-core path (module-level drop-in, exact-precision reference on device).
+ *     CodeNeRF.forward (src/model.py:56-84): params = 28 tensors in named_parameters() order, each
+ *     stacked [K,...] and packed back-to-back in ONE flat buffer per category (layout from
+ *     cnf_codenerf_param_count / offsets in SURVEY appendix D order).
+ *     emb [K,P,129]; latent rows: shape_lat/tex_lat [K,NR,L] with point p using row p / pts_per_row
+ *     (the reference passes [R,1,L] per-ray rows -> NR=R, pts_per_row=S; eval_points passes one
+ *     code -> NR=1, pts_per_row=P).  Outputs sigma [K,P] (already x10), rgb [K,P,3].
+ *     ws keeps the activations needed by the backward (cnf_codenerf_workspace_floats per category).
+ * ---------------------------------------------------------------------------------------------- */
+size_t cnf_codenerf_param_count(int W, int L);
+size_t cnf_codenerf_workspace_floats(int n_pts, int n_rows, int W);
+int cnf_codenerf_fwd(int n_cat, int n_pts, int n_rows, int pts_per_row, int W, int L,
+                     const float* params, const float* emb, const float* shape_lat, const float* tex_lat,
+                     float* sigma, float* rgb, float* ws, size_t ws_floats, cnf_stream_t stream);
+/* g_params is ACCUMULATED into (caller zeroes); g_emb/g_shape_lat/g_tex_lat are overwritten (may be NULL). */
+int cnf_codenerf_bwd(int n_cat, int n_pts, int n_rows, int pts_per_row, int W, int L,
+                     const float* params, const float* emb, const float* shape_lat, const float* tex_lat,
+                     const float* rgb, const float* g_sigma, const float* g_rgb,
+                     float* ws, size_t ws_floats,
+                     float* g_params, float* g_emb, float* g_shape_lat, float* g_tex_lat,
+                     cnf_stream_t stream);
+
+/*     OccupancyMap.forward (src/model.py:124-154), hidden size H (128 for the background model). */
+size_t cnf_occmap_param_count(int H);
+size_t cnf_occmap_workspace_floats(int n_pts, int H);
+int cnf_occmap_fwd(int n_cat, int n_pts, int H, const float* params, const float* emb,
+                   float* alpha, float* rgb, float* ws, size_t ws_floats, cnf_stream_t stream);
+int cnf_occmap_bwd(int n_cat, int n_pts, int H, const float* params, const float* emb, const float* rgb,
+                   const float* g_alpha, const float* g_rgb, float* ws, size_t ws_floats,
+                   float* g_params, float* g_emb, cnf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (4) Compositing and losses -- occupancy_activation / occupancy_to_termination / render /
+ *     render_loss / reduce_batch_loss (src/render_rays.py:3-95) and step_batch_loss (src/loss.py:18-74).
+ * ---------------------------------------------------------------------------------------------- */
+/* termination weights only: occ [n_rays,S] -> w [n_rays,S] (src/render_rays.py:25-33). */
+int cnf_termination_fwd(int n_rays, int S, const float* occ, float* w, cnf_stream_t stream);
+/* mask counts for the loss denominators: labels u8 [K,R], mask_depth u8 [K,R] -> counts int32 [K,4]
+ * = {N_depth&obj, N_obj, N_sem, 0}. */
+int cnf_mask_counts(int n_cat, int n_rays, const uint8_t* labels, const uint8_t* mask_depth,
+                    int32_t* counts, cnf_stream_t stream);
+/* forward: alpha [K,R,S], color [K,R,S,3], z [K,R,S], gt_depth [K,R], gt_color [K,R,3] (0..1),
+ * labels/mask_depth u8 [K,R], counts from cnf_mask_counts.
+ * out_rays [K,R,6] = {D, var, C0, C1, C2, O};  out_loss [4 + 3K] =
+ * {loss, any_empty_depth, any_empty_obj, any_empty_sem, depth[K], color[K], opacity[K]}.
+ * ws: >= cnf_composite_workspace_bytes(K,R). */
+size_t cnf_composite_workspace_bytes(int n_cat, int n_rays);
+int cnf_composite_loss_fwd(int n_cat, int n_rays, int S, const float* alpha, const float* color,
+                           const float* z, const float* gt_depth, const float* gt_color,
+                           const uint8_t* labels, const uint8_t* mask_depth, const int32_t* counts,
+                           float color_scaling, float opacity_scaling,
+                           float* out_rays, float* out_loss, void* ws, size_t ws_bytes, cnf_stream_t stream);
+/* backward: g_loss = device pointer to the upstream scalar gradient -> g_alpha [K,R,S], g_color [K,R,S,3]. */
+int cnf_composite_loss_bwd(int n_cat, int n_rays, int S, const float* alpha, const float* color,
+                           const float* z, const float* gt_depth, const float* gt_color,
+                           const uint8_t* labels, const uint8_t* mask_depth, const int32_t* counts,
+                           float color_scaling, float opacity_scaling, const float* g_loss,
+                           float* g_alpha, float* g_color, cnf_stream_t stream);
+/* step_batch_loss_reg (src/loss.py:5-15): codes [n_obj,L] -> out[0] = sum_i ||codes_i||_2 (0 if n_obj==1);
+ * g_codes (may be NULL) += weight * codes_i/||codes_i||. */
+int cnf_code_reg(int n_obj, int L, const float* codes, float weight, float* out, float* g_codes,
+                 cnf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (5) Fused training step on tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM):
+ *     embed -> CodeNeRF(W=32) -> composite -> losses, forward AND backward in one launch, for K
+ *     categories (train.py:136-182 minus the optimizer).  Samples z come from cnf_sample_fwd.
+ *     See DESIGN.md for the tile pipeline.  Code tables are indexed in-kernel (never gathered).
+ *
+ *     params      [K, cnf_codenerf_param_count(32,L)]   fp32 master weights (appendix-D order)
+ *     pe_B [K,21,3], pe_scale [K], shape_codes/tex_codes [K,n_obj_max,L], n_obj int32 [K]
+ *     origins/dirs [K,R,3], z [K,R,S], gt_depth [K,R], gt_rgb u8 [K,R,4] (rgb + label),
+ *     mask_depth u8 [K,R], inst int32 [K,R], counts int32 [K,4] (cnf_mask_counts / sampler stats+4)
+ *     outputs (all OVERWRITTEN): g_params [K,n_param], g_B [K,21,3], g_shape/g_tex [K,n_obj_max,L],
+ *     out_loss [4+3K] as in cnf_composite_loss_fwd plus reg terms appended: [.., reg_shape[K], reg_tex[K]].
+ *     flags: bit0 = also add the code regulariser (weight reg_scaling) to loss and code grads.
+ * ---------------------------------------------------------------------------------------------- */
+size_t cnf_train_step_workspace_bytes(int n_cat, int n_rays, int S, int L, int n_obj_max);
+int cnf_train_step(int n_cat, int n_rays, int S, int L, int n_obj_max,
+                   const float* params, const float* pe_B, const float* pe_scale,
+                   const float* shape_codes, const float* tex_codes, const int32_t* n_obj,
+                   const float* origins, const float* dirs, const float* z,
+                   const float* gt_depth, const uint8_t* gt_rgb, const uint8_t* mask_depth,
+                   const int32_t* inst, const int32_t* counts,
+                   float color_scaling, float opacity_scaling, float reg_scaling, int flags,
+                   float* g_params, float* g_B, float* g_shape, float* g_tex, float* out_loss,
+                   void* ws, size_t ws_bytes, cnf_stream_t stream);
+
+/* tcgen05 self-test: D[128,N] = A[128,K] * B[N,K]^T with bf16 operands staged in shared memory in the
+ * canonical no-swizzle UMMA layout; mode 0: A,B K-major; 1: B MN-major (dgrad view); 2: A,B MN-major
+ * (wgrad view).  Used by tests to pin the descriptor encodings on hardware. */
+int cnf_umma_selftest(int mode, int N, int Kdim, const float* A, const float* B, float* D, cnf_stream_t stream);
+
+/* Fused AdamW over a flat fp32 buffer (train.py:183): decoupled weight decay as
+ * torch.optim.AdamW.  step is 1-based. */
+int cnf_adamw_step(size_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                   cnf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNF_H_ */
