@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import SAMPLER_CASES, STEP_CASES, golden, gt, step_case
+from helpers import SAMPLER_CASES, STEP_CASES, assert_grad_close, golden, gt, step_case
 from oracle import cnf_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -173,11 +173,11 @@ def test_module_api_train_step_vs_golden(name):
     torch.testing.assert_close(l.detach().cpu(), c["loss"], rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(rs.detach().cpu(), c["reg_shape"], rtol=1e-5, atol=1e-6)
     for i in range(28):
-        torch.testing.assert_close(fc_param[i].grad.cpu(), c["gfc"][i], rtol=2e-3, atol=2e-5, msg=lambda m: names[i] + m)
-    torch.testing.assert_close(pe_param[0].grad.cpu(), c["gB"], rtol=2e-3, atol=5e-4)
+        assert_grad_close(fc_param[i].grad, c["gfc"][i], name=names[i])
+    assert_grad_close(pe_param[0].grad, c["gB"], elem_atol=5e-4, name="B_layer")
     for k in range(K):
-        torch.testing.assert_close(trs[k].trainer.shape_codes.weight.grad.cpu(), c["gsc"][k], rtol=2e-3, atol=2e-6)
-        torch.testing.assert_close(trs[k].trainer.texture_codes.weight.grad.cpu(), c["gtc"][k], rtol=2e-3, atol=2e-6)
+        assert_grad_close(trs[k].trainer.shape_codes.weight.grad, c["gsc"][k], elem_atol=1e-5, name="shape_codes")
+        assert_grad_close(trs[k].trainer.texture_codes.weight.grad, c["gtc"][k], elem_atol=1e-5, name="texture_codes")
 
 
 def test_occmap_bg_step_vs_golden():
@@ -199,8 +199,8 @@ def test_occmap_bg_step_vs_golden():
     torch.testing.assert_close(c.detach().cpu(), gt("bg", p + "color"), rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(l.detach().cpu(), gt("bg", p + "loss"), rtol=1e-4, atol=1e-5)
     for i, (n, prm) in enumerate(m.named_parameters()):
-        torch.testing.assert_close(prm.grad.cpu(), gt("bg", p + "gfc%02d" % i), rtol=2e-3, atol=2e-5, msg=lambda s: n + s)
-    torch.testing.assert_close(pe.B_layer.weight.grad.cpu(), gt("bg", p + "gB"), rtol=2e-3, atol=5e-4)
+        assert_grad_close(prm.grad, gt("bg", p + "gfc%02d" % i), name=n)
+    assert_grad_close(pe.B_layer.weight.grad, gt("bg", p + "gB"), elem_atol=5e-4, name="B_layer")
 
 
 def test_eval_points_single_code():
