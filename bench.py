@@ -1,0 +1,368 @@
+"""bench.py -- train rays/sec (fwd+bwd, device-timed) of the neural-field training hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload replica_room0|c1|scannet0066|c4] [--impl reference]
+
+Contract (see the task statement): one JSON line on rank 0.  A "step" is one pass of the hot path over one
+synthetic batch: depth-guided sampling (3 launches) + the fused tcgen05 step (prep, fused fwd+bwd, PE-gradient
+reduce, finalize, loss).  `value` = rays/s with inputs resident in HBM (CUDA events around each step, L2 flushed
+between steps, max over ranks); `e2e` = the same through FusedCategoryTrainer.step_host with pinned HOST buffers
+(H2D + step + D2H of the loss terms, wall clock incl. the stream sync).  `roofline` = the fused kernel against the
+measured bf16 tensor peak (MEASURED_PEAKS.json), timed live with CUDA events recorded around that kernel only
+(cnf_set_kernel_events).  `cpu_baseline` / `--impl reference` = the CPU oracle port of the reference's PyTorch
+path on the box's host cores (the reference is pure Python and cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FLOP_PER_POINT = 81888.0          # CodeNeRF fwd+bwd, algorithmic: 3 x 2 x 13648 MAC
+
+WORKLOADS = {
+    # name: K categories, instances per category, rays per category, N, M, L, scale
+    "replica_room0": dict(K=20, n_obj=3, R=360, N=1, M=9, L=256, scale=2.0,
+                          desc="Replica room_0-shaped synthetic: 20 categories x 3 instances, 120 rays/instance, 1+9 samples"),
+    "c1": dict(K=1, n_obj=4, R=480, N=5, M=9, L=256, scale=2.0,
+               desc="single category (chair), 4 instances x 120 rays, 5+9 samples"),
+    "scannet0066": dict(K=8, n_obj=2, R=210, N=1, M=9, L=32, scale=3.0,
+                        desc="ScanNet scene0066_00-shaped synthetic: 8 categories, 14 objects, L=32"),
+    "c4": dict(K=1, n_obj=64, R=524288, N=1, M=9, L=256, scale=2.0,
+               desc="large single category: 64 instances x 8192 rays, 1+9 samples"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    hbm=d["hbm_gbs"], source="measured")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+def synth_batch(wl, seed, device=None, pinned=False):
+    """Synthetic ray batch for K categories (SURVEY 8(d) distributions), generated on the CPU with a fixed seed."""
+    from category_nerf_reconstruction_official_b200.synthetic import synth_rays
+    g = torch.Generator().manual_seed(seed)
+    K, R = wl["K"], wl["R"]
+    if R > 100000:      # large batch: generate one category cheaply by tiling a 16k-ray block
+        base = synth_rays(16384, wl["n_obj"], g)
+        rep = R // 16384
+        cats = [tuple(t.repeat(*([rep] + [1] * (t.dim() - 1))) for t in base)]
+        cats = cats * K
+    else:
+        cats = [synth_rays(R, wl["n_obj"], g) for _ in range(K)]
+    out = dict(rgbs=torch.stack([c[0] for c in cats]), depth=torch.stack([c[1] for c in cats]),
+               origins=torch.stack([c[2] for c in cats]), dirs=torch.stack([c[3] for c in cats]),
+               indices=torch.stack([c[4] for c in cats]).to(torch.int32))
+    if pinned:
+        out = {k: v.contiguous().pin_memory() for k, v in out.items()}
+    if device is not None:
+        out = {k: v.to(device) for k, v in out.items()}
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_arm(wl, steps, warmup, seed=0):
+    """The reference's PyTorch CPU path (oracle port: same ATen ops, batched over categories like functorch.vmap):
+    sample_3d_points + code gather + PE + MLP + step_batch_loss + reg + backward, fp32, all host threads."""
+    from oracle import cnf_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(seed)
+    K, R, N, M, L, n_obj = wl["K"], wl["R"], wl["N"], wl["M"], wl["L"], wl["n_obj"]
+    batch = synth_batch(wl, seed)
+    fc = [torch.stack(t) for t in zip(*[O.init_params(O.codenerf_param_shapes(32, L), g) for _ in range(K)])]
+    B = O.icosa_matrix().repeat(K, 1, 1)
+    sc = [O.init_codes(n_obj, L, g) for _ in range(K)]
+    tc = [O.init_codes(n_obj, L, g) for _ in range(K)]
+    idx = batch["indices"].long()
+
+    def one_step():
+        pcs, zz, valid, labels = [], [], [], []
+        for k in range(K):      # the reference samples category by category (train.py:123-125)
+            rand = O.draw_sampler_randoms(batch["rgbs"][k], batch["depth"][k], N, M, 0.1)
+            _, _, v, lab, p, z = O.sample_points(batch["rgbs"][k], batch["depth"][k], batch["origins"][k], batch["dirs"][k],
+                                                 N, M, 0.1, 0.05, rand)
+            pcs.append(p); zz.append(z); valid.append(v); labels.append(lab)
+        st = torch.stack
+        return O.train_step(fc, B, wl["scale"], sc, tc, st(pcs), st(zz), batch["depth"], batch["rgbs"][..., :3], st(labels),
+                            st(valid), idx)
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = (time.perf_counter() - t0) / steps
+    return K * R / dt, dt, torch.get_num_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="replica_room0", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-large", action="store_true", help="skip the extra large-batch (c4) roofline measurement")
+    ap.add_argument("--with-optimizer", action="store_true", help="include the fused AdamW update in the timed step")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3)
+    metric = "train rays/sec (fwd+bwd, device-timed)"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cpu_steps = max(1, min(args.steps, 20))
+        v, dt, cores = cpu_reference_arm(wl, cpu_steps, min(warmup, 3))
+        cb = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
+              "sample": "%d steps of the full %s batch (%d rays/step)" % (cpu_steps, args.workload, wl["K"] * wl["R"])}
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "rays/s", "n_gpus": args.gpus,
+                          "steps": cpu_steps, "warmup": min(warmup, 3), "ms_per_step": dt * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": args.workload, "desc": wl["desc"]}, "cpu_baseline": cb,
+                          "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import category_nerf_reconstruction_official_b200 as cnf
+    from category_nerf_reconstruction_official_b200 import _lib
+    from category_nerf_reconstruction_official_b200.fused import FusedCategoryTrainer
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    cnf.load()
+    K, R, S = wl["K"], wl["R"], wl["N"] + wl["M"]
+
+    def make_trainer(w):
+        return FusedCategoryTrainer(w["K"], w["n_obj"], latent_dim=w["L"], scale=w["scale"], device=dev,
+                                    n_bins_cam2surface=w["N"], n_bins=w["M"],
+                                    generator=torch.Generator().manual_seed(1234 + rank))
+
+    # weak scaling: every rank owns its own K categories (categories shard across GPUs; no data-path collective)
+    tr = make_trainer(wl)
+    batch = synth_batch(wl, seed=100 + rank, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def run_step(t, b, kernel_events=None):
+        if kernel_events is not None:
+            _lib.check(_lib.load().cnf_set_kernel_events(kernel_events[0].cuda_event, kernel_events[1].cuda_event))
+        loss = t.step(b["rgbs"], b["depth"], b["origins"], b["dirs"], b["indices"])
+        if args.with_optimizer:
+            t.adamw_step()
+        return loss
+
+    def timed(t, b, steps, warm):
+        for _ in range(warm):
+            run_step(t, b)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b_ in kev:       # cuda_event handles exist only after a first record
+            a.record(); b_.record()
+        torch.cuda.synchronize()
+        for i in range(steps):
+            flush.zero_()                          # L2 flush between timed iterations (outside the events)
+            ev[i][0].record()
+            run_step(t, b, kev[i])
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        step_ms = sum(a.elapsed_time(b_) for a, b_ in ev) / steps
+        kern_ms = sum(a.elapsed_time(b_) for a, b_ in kev) / steps
+        return step_ms, kern_ms
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    step_ms, kern_ms = timed(tr, batch, args.steps, warmup)
+    clk = clocks.stop() if rank == 0 else None
+    loss_val = float(tr.out_loss[0])
+
+    # ---- e2e through the public API with HOST (pinned) buffers
+    hb = synth_batch(wl, seed=100 + rank, pinned=True)
+    out_host = torch.empty_like(tr.out_loss, device="cpu").pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in hb.values())
+    d2h = out_host.numel() * 4
+
+    def e2e_step():
+        db = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        run_step(tr, db)
+        out_host.copy_(tr.out_loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(warmup):
+        e2e_step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s_total = time.perf_counter() - t0
+    # subtract nothing: the flush+sync is outside what a user runs, so time it separately and remove it
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+    flush_s = time.perf_counter() - t1
+    e2e_ms = max(1e-6, (e2e_s_total - flush_s)) / args.steps * 1e3
+
+    # ---- max over ranks
+    if dist is not None:
+        tt = torch.tensor([step_ms, kern_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        step_ms, kern_ms, e2e_ms = [float(x) for x in tt]
+
+    rays_per_step = K * R * world
+    value = rays_per_step / (step_ms * 1e-3)
+    pk = peaks()
+    pts = K * R * S
+    flops = pts * FLOP_PER_POINT
+    ach = flops / (kern_ms * 1e-3) / 1e12
+    roof = {"bound": "tensor", "kernel": "fused_step_kernel", "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
+            "frac": ach / pk["bf16_burst"], "traffic": None, "peak_source": pk["source"] + " (bf16 burst)",
+            "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / step_ms,
+            "algorithmic_flop_per_point": FLOP_PER_POINT, "points_per_launch": pts}
+
+    extra = {}
+    if rank == 0 and not args.no_large and args.workload != "c4":
+        # the large-batch regime (BASELINE config 4 shape): where the tensor-pipe fraction is meaningful
+        wl4 = dict(WORKLOADS["c4"])
+        try:
+            tr4 = make_trainer(wl4)
+            b4 = synth_batch(wl4, seed=7, device=dev)
+            s4, k4 = timed_single(tr4, b4, run_step, flush, steps=5, warm=3)
+            p4 = wl4["K"] * wl4["R"] * (wl4["N"] + wl4["M"])
+            a4 = p4 * FLOP_PER_POINT / (k4 * 1e-3) / 1e12
+            extra["large_batch_c4"] = {"rays_per_s": wl4["K"] * wl4["R"] / (s4 * 1e-3), "ms_per_step": s4, "kernel_ms": k4,
+                                       "tensor_tflops": a4, "tensor_frac_of_burst_peak": a4 / pk["bf16_burst"],
+                                       "config": wl4["desc"]}
+            del tr4, b4
+        except Exception as e:      # never let the extra measurement break the contract line
+            extra["large_batch_c4"] = {"error": repr(e)}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    cb = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu_steps = 10 if K * R <= 20000 else 1
+        v, dt, cores = cpu_reference_arm(wl, cpu_steps, 2)
+        cb = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "ms_per_step": dt * 1e3,
+              "sample": "%d steps of the full %s batch (%d rays/step), oracle port of the reference PyTorch CPU path"
+                        % (cpu_steps, args.workload, K * R)}
+
+    line = {"metric": metric, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "desc": wl["desc"], "categories_per_gpu": K, "rays_per_category": R,
+                       "samples_per_ray": S, "latent_dim": wl["L"], "l2": "flushed between timed steps (256 MB write)",
+                       "optimizer_in_step": bool(args.with_optimizer), "parallelism": "categories sharded, %d per GPU" % K},
+            "clocks": clk, "roofline": roof, "cpu_baseline": cb,
+            "e2e": {"value": rays_per_step / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": (tr.launches_per_step + (4 if args.with_optimizer else 0)) * args.steps,
+            "loss": loss_val}
+    line.update(extra)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def timed_single(t, b, run_step, flush, steps, warm):
+    from category_nerf_reconstruction_official_b200 import _lib
+    for _ in range(warm):
+        run_step(t, b)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b_ in kev:
+        a.record(); b_.record()
+    torch.cuda.synchronize()
+    for i in range(steps):
+        flush.zero_()
+        ev[i][0].record()
+        run_step(t, b, kev[i])
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    return (sum(a.elapsed_time(b_) for a, b_ in ev) / steps, sum(a.elapsed_time(b_) for a, b_ in kev) / steps)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,11 +1,1040 @@
-// Fused tcgen05 training step (placeholder until the kernel lands in this file).
+// Fused training step on Blackwell tensor cores (tcgen05 / TMEM), bf16 operands, fp32 accumulation.
+//
+//   embed -> CodeNeRF (W=32) -> occupancy compositing -> depth/colour/opacity losses, forward AND backward,
+//   for K categories in ONE launch (reference train.py:136-182 minus the optimizer; math: src/embedding.py:82-92,
+//   src/model.py:56-84, src/render_rays.py:25-95, src/loss.py:18-74).
+//
+// One CTA (128 threads = one warpgroup; thread t <-> TMEM lane t <-> tile row t) walks tiles of 128 sample points
+// (whole rays, warp-aligned).  Per tile the nine layers run as UMMA tiles M=128 x N<=48 x K<=128:
+//   * operands live in shared memory in the canonical no-swizzle 8x16B core-matrix layout; the SAME bytes are
+//     read K-major by the forward GEMM, MN-major by the data-gradient GEMM (weights) and MN-major by the
+//     weight-gradient GEMM (activations, upstream gradients) -- no transposes are ever materialised;
+//   * weight gradients, and the per-instance bias gradients of the latent-conditioned layers (via a one-hot
+//     instance operand), accumulate in TMEM across ALL tiles of the CTA and are flushed once at the end;
+//   * biases of layer 1 / 6 ride in a constant-one embedding column (free in the GEMM, and its weight-gradient
+//     row is the bias gradient); latent adds are folded into per-instance biases c_l[inst] = W_l z_l[inst] + b_l;
+//   * the Fourier embedding is computed in registers (one MUFU sin/cos per direction + double-angle recurrence)
+//     straight into the layer-1 / layer-3 / layer-6 operand tiles; compositing is a warp-shuffle segmented scan.
+// A prep kernel builds the bf16 operand images and per-instance biases; a finalize kernel maps the raw TMEM
+// accumulators back to the reference's nn.Linear-shaped gradients (incl. latent layers, code tables, regulariser).
 #include "cnf_common.cuh"
+#include "cnf_umma.cuh"
+
+namespace cnf {
+using namespace umma;
+
+// ---------------------------------------------------------------------------------------------------------
+// static layout
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TP = 128;           // tile rows (points)
+constexpr int MAXOBJ = 64;        // instances per category supported by the one-hot operand
+constexpr int NL = 32;            // layer width W
+
+// bf16 weight images (blocked layout, rows x cols), byte offsets in the weight blob
+constexpr int W1_R = 32, W1_C = 96;     // encoding_xyz      (col 87 = bias via the ones column)
+constexpr int W2_R = 32, W2_C = 32;     // shape_layer_1
+constexpr int W3_R = 32, W3_C = 128;    // cat_layer         cols [r2 32 | xg 96]
+constexpr int W4_R = 32, W4_C = 32;     // shape_layer_2
+constexpr int W5_R = 32, W5_C = 32;     // encoding_shape
+constexpr int W6_R = 48, W6_C = 80;     // encoding_viewdir (+ row 32 = sigma head) cols [y5 32 | xc 48], col 74 = bias
+constexpr int W7_R = 32, W7_C = 32;     // texture_layer_1
+constexpr int W8_R = 16, W8_C = 32;     // rgb.0
+constexpr int OFF_W1 = 0;
+constexpr int OFF_W2 = OFF_W1 + W1_R * W1_C * 2;
+constexpr int OFF_W3 = OFF_W2 + W2_R * W2_C * 2;
+constexpr int OFF_W4 = OFF_W3 + W3_R * W3_C * 2;
+constexpr int OFF_W5 = OFF_W4 + W4_R * W4_C * 2;
+constexpr int OFF_W6 = OFF_W5 + W5_R * W5_C * 2;
+constexpr int OFF_W7 = OFF_W6 + W6_R * W6_C * 2;
+constexpr int OFF_W8 = OFF_W7 + W7_R * W7_C * 2;
+constexpr int WBLOB_BYTES = OFF_W8 + W8_R * W8_C * 2;     // 32768
+// fp32 constants block (floats)
+constexpr int FC_B5 = 0;            // [32]
+constexpr int FC_B8 = 32;           // [16]
+constexpr int FC_W9 = 48;           // [3][16]
+constexpr int FC_B9 = 96;           // [3] (+1 pad)
+constexpr int FC_PEB = 100;         // [21][3] (+1 pad)
+constexpr int FC_SCALE = 164;       // inv scale
+constexpr int FC_FLOATS = 168;
+constexpr int CTAB_FLOATS = 4 * MAXOBJ * NL;   // c2, c3, c4, c7 per instance
+constexpr int PREP_BYTES = WBLOB_BYTES + (FC_FLOATS + CTAB_FLOATS) * 4;   // per category image copied to smem
+
+// activation / gradient tiles in shared memory (bf16 blocked [128 x cols])
+constexpr int SM_W = 0;
+constexpr int SM_FC = SM_W + WBLOB_BYTES;
+constexpr int SM_CTAB = SM_FC + FC_FLOATS * 4;
+constexpr int SM_R2XG = SM_CTAB + CTAB_FLOATS * 4;          // [128 x 128]: r2 | xg
+constexpr int SM_Y5XC = SM_R2XG + TP * 128 * 2;             // [128 x 80] : y5 | xc   (xc later reused for d xc)
+constexpr int SM_R1 = SM_Y5XC + TP * 80 * 2;
+constexpr int SM_R3 = SM_R1 + TP * 32 * 2;
+constexpr int SM_R4 = SM_R3 + TP * 32 * 2;
+constexpr int SM_H1 = SM_R4 + TP * 32 * 2;
+constexpr int SM_H2Z3 = SM_H1 + TP * 32 * 2;                // [128 x 80] : h2 | zeros 32 | h3 16
+constexpr int SM_OH = SM_H2Z3 + TP * 80 * 2;                // [128 x 64] one-hot(instance)
+constexpr int SM_GX = SM_OH + TP * 64 * 2;                  // 12 KB gradient tile (G8+G9, G6, G4, G2)
+constexpr int SM_GY = SM_GX + TP * 48 * 2;                  // 8 KB gradient tile (G7, G5, G3, G1)
+constexpr int SM_PAD = SM_GY + TP * 32 * 2;                 // over-read slack for M=128 views of narrow tiles
+constexpr int SM_TOTAL = SM_PAD + 4096;
+
+// TMEM columns
+constexpr int TM_WG1 = 0, TM_WG2 = 32, TM_WG3 = 64, TM_WG4 = 96, TM_WG5 = 128, TM_WG6 = 160, TM_WG7 = 208, TM_WG89 = 240;
+constexpr int TM_OH2 = 256, TM_OH3 = 288, TM_OH4 = 320, TM_OH7 = 352, TM_ACC = 384;
+
+// raw accumulator layout flushed to global (floats, [lane][col] per region)
+constexpr int RW1 = 0;                      // [96][32]
+constexpr int RW2 = RW1 + 96 * 32;          // [32][32]
+constexpr int RW3 = RW2 + 32 * 32;          // [128][32]
+constexpr int RW4 = RW3 + 128 * 32;         // [32][32]
+constexpr int RW5 = RW4 + 32 * 32;          // [32][32]
+constexpr int RW6 = RW5 + 32 * 32;          // [80][48]
+constexpr int RW7 = RW6 + 80 * 48;          // [32][32]
+constexpr int RW89 = RW7 + 32 * 32;         // [48][16]
+constexpr int ROH2 = RW89 + 48 * 16;        // [64][32] x 4
+constexpr int ROH3 = ROH2 + 64 * 32;
+constexpr int ROH4 = ROH3 + 64 * 32;
+constexpr int ROH7 = ROH4 + 64 * 32;
+constexpr int RDB8 = ROH7 + 64 * 32;        // [16]
+constexpr int RDB9 = RDB8 + 16;             // [3] (+1)
+constexpr int RLOSS = RDB9 + 4;             // [3] raw loss sums (+1)
+constexpr int RAW_FLOATS = RLOSS + 4;
+
+// parameter indices (SURVEY appendix D order)
+struct PLay {
+  size_t o[28]; size_t total; int L;
+  __host__ __device__ explicit PLay(int L_) : L(L_) {
+    const size_t w = 32, l = L_, E1 = CNF_EMB1, E2 = CNF_EMB2;
+    const size_t sz[28] = {w * E1, w, w * l, w, w * w, w, w * l, w, w * w, w, w * (w + E1), w, w * l, w, w * w, w,
+                           w, 1, w * (w + E2), w, w * w, w, w * l, w, (w / 2) * w, w / 2, 3 * (w / 2), 3};
+    size_t off = 0;
+    for (int i = 0; i < 28; ++i) { o[i] = off; off += sz[i]; }
+    total = off;
+  }
+};
+
+__device__ __forceinline__ void put_bf16(uint8_t* img, int r, int c, int cols, float v) {
+  *reinterpret_cast<__nv_bfloat16*>(img + blk_off(r, c, cols)) = __float2bfloat16(v);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// prep: per category -> {bf16 weight images, fp32 constants, per-instance biases} + latent activations z
+// grid = K, block = 256
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fused_prep_kernel(int L, int n_obj_max, const float* __restrict__ params, const float* __restrict__ pe_B,
+                  const float* __restrict__ pe_scale, const float* __restrict__ shape_codes,
+                  const float* __restrict__ tex_codes, const int32_t* __restrict__ n_obj_arr,
+                  uint8_t* __restrict__ prep, float* __restrict__ zlat) {
+  const int k = blockIdx.x, tid = threadIdx.x;
+  const PLay lay(L);
+  const float* P = params + (size_t)k * lay.total;
+  uint8_t* img = prep + (size_t)k * PREP_BYTES;
+  float* fc = reinterpret_cast<float*>(img + WBLOB_BYTES);
+  float* ctab = fc + FC_FLOATS;
+  float* z = zlat + (size_t)k * 4 * MAXOBJ * NL;      // [4][MAXOBJ][32]: zsl1, zcl, zsl2, ztl
+  const int n_obj = n_obj_arr[k];
+  // zero the weight blob (padding must be exactly zero)
+  for (int i = tid; i < WBLOB_BYTES / 4; i += 256) reinterpret_cast<uint32_t*>(img)[i] = 0u;
+  __syncthreads();
+  // weight images
+  for (int i = tid; i < 32 * 87; i += 256) { const int n = i / 87, c = i % 87; put_bf16(img + OFF_W1, n, c, W1_C, P[lay.o[0] + i]); }
+  for (int n = tid; n < 32; n += 256) put_bf16(img + OFF_W1, n, 87, W1_C, P[lay.o[1] + n]);        // bias column
+  for (int i = tid; i < 32 * 32; i += 256) {
+    const int n = i / 32, c = i % 32;
+    put_bf16(img + OFF_W2, n, c, W2_C, P[lay.o[4] + i]);
+    put_bf16(img + OFF_W4, n, c, W4_C, P[lay.o[8] + i]);
+    put_bf16(img + OFF_W5, n, c, W5_C, P[lay.o[14] + i]);
+    put_bf16(img + OFF_W7, n, c, W7_C, P[lay.o[20] + i]);
+  }
+  for (int i = tid; i < 32 * 119; i += 256) { const int n = i / 119, c = i % 119; put_bf16(img + OFF_W3, n, c, W3_C, P[lay.o[10] + i]); }
+  for (int i = tid; i < 32 * 74; i += 256) { const int n = i / 74, c = i % 74; put_bf16(img + OFF_W6, n, c, W6_C, P[lay.o[18] + i]); }
+  for (int n = tid; n < 32; n += 256) {
+    put_bf16(img + OFF_W6, n, 74, W6_C, P[lay.o[19] + n]);        // b_vd via ones column (xc col 42)
+    put_bf16(img + OFF_W6, 32, n, W6_C, P[lay.o[16] + n]);        // sigma head row
+  }
+  if (tid == 0) put_bf16(img + OFF_W6, 32, 74, W6_C, P[lay.o[17]]);   // b_sigma
+  for (int i = tid; i < 16 * 32; i += 256) { const int n = i / 32, c = i % 32; put_bf16(img + OFF_W8, n, c, W8_C, P[lay.o[24] + i]); }
+  // fp32 constants
+  for (int i = tid; i < 32; i += 256) fc[FC_B5 + i] = P[lay.o[15] + i];
+  for (int i = tid; i < 16; i += 256) fc[FC_B8 + i] = P[lay.o[25] + i];
+  for (int i = tid; i < 48; i += 256) fc[FC_W9 + i] = P[lay.o[26] + i];
+  for (int i = tid; i < 4; i += 256) fc[FC_B9 + i] = i < 3 ? P[lay.o[27] + i] : 0.f;
+  for (int i = tid; i < 64; i += 256) fc[FC_PEB + i] = i < 63 ? pe_B[(size_t)k * 63 + i] : 0.f;
+  if (tid == 0) { fc[FC_SCALE] = 1.0f / pe_scale[k]; fc[FC_SCALE + 1] = 0.f; fc[FC_SCALE + 2] = 0.f; fc[FC_SCALE + 3] = 0.f; }
+  // latent projections z = relu(W_lat code + b_lat): (slot, weight idx, codes)
+  const int lat_w[4] = {2, 12, 6, 22};
+  for (int i = tid; i < 4 * MAXOBJ * NL; i += 256) {
+    const int s = i / (MAXOBJ * NL), inst = (i / NL) % MAXOBJ, n = i % NL;
+    float v = 0.f;
+    if (inst < n_obj) {
+      const float* code = (s == 3 ? tex_codes : shape_codes) + ((size_t)k * n_obj_max + inst) * L;
+      const float* w = P + lay.o[lat_w[s]] + (size_t)n * L;
+      float acc = P[lay.o[lat_w[s] + 1] + n];
+      for (int j = 0; j < L; ++j) acc = fmaf(w[j], code[j], acc);
+      v = fmaxf(acc, 0.f);
+    }
+    z[i] = v;
+  }
+  __syncthreads();
+  // per-instance biases c = W_cons[:, :32] z + b_cons: consumers s1(4,5) cat(10,11; ld 119) s2(8,9) t1(20,21)
+  const int cons_w[4] = {4, 10, 8, 20};
+  const int cons_ld[4] = {32, 119, 32, 32};
+  for (int i = tid; i < 4 * MAXOBJ * NL; i += 256) {
+    const int s = i / (MAXOBJ * NL), inst = (i / NL) % MAXOBJ, n = i % NL;
+    const float* w = P + lay.o[cons_w[s]] + (size_t)n * cons_ld[s];
+    const float* zz = z + (s * MAXOBJ + inst) * NL;
+    float acc = P[lay.o[cons_w[s] + 1] + n];
+    for (int j = 0; j < NL; ++j) acc = fmaf(w[j], zz[j], acc);
+    ctab[i] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device helpers for the fused kernel
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void st16(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+}
+// address of (row, col-block) in a blocked [128 x cols] tile
+__device__ __forceinline__ uint8_t* rowblk(uint8_t* base, int row, int cb, int cols) {
+  return base + (row >> 3) * (16 * cols) + cb * 128 + (row & 7) * 16;
+}
+// write 32 fp32 values (already activated) as bf16 into cols [c0, c0+32) of a blocked tile row
+__device__ __forceinline__ void store_row32(uint8_t* base, int row, int cols, int cb0, const float* v) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    st16(rowblk(base, row, cb0 + q, cols), pack2(v[q * 8 + 0], v[q * 8 + 1]), pack2(v[q * 8 + 2], v[q * 8 + 3]),
+         pack2(v[q * 8 + 4], v[q * 8 + 5]), pack2(v[q * 8 + 6], v[q * 8 + 7]));
+}
+
+struct Issue {   // MMA issue helpers (executed by one thread)
+  uint32_t tmem;
+  // forward: D[128 x N] (+)= A[128 x 16*nK] (K-major) * W[N x .]^T (K-major)
+  __device__ __forceinline__ void fwd(int col, uint32_t aAddr, int aCols, int nK, uint32_t wAddr, int wCols, int N) const {
+    const uint32_t id = idesc_bf16(128, N, 0, 0);
+    for (int ks = 0; ks < nK; ++ks)
+      mma_ss(tmem + col, smem_desc(aAddr + ks * 256, 128, 16 * aCols), smem_desc(wAddr + ks * 256, 128, 16 * wCols), id, ks > 0);
+  }
+  // data gradient: D[128 x Nout] (+)= G[128 x Nl] (K-major) * W[Nl x Nout] (MN-major view of the weight image)
+  __device__ __forceinline__ void dgrad(int col, uint32_t gAddr, int gCols, int Nl, uint32_t wAddr, int wCols, int Nout, bool acc) const {
+    const uint32_t id = idesc_bf16(128, Nout, 0, 1);
+    for (int ks = 0; ks < Nl / 16; ++ks)
+      mma_ss(tmem + col, smem_desc(gAddr + ks * 256, 128, 16 * gCols), smem_desc(wAddr + ks * 2 * (16 * wCols), 16 * wCols, 128), id,
+             acc || ks > 0);
+  }
+  // weight gradient: D[128(feature rows) x Nl] += A^T (MN-major view of the activation tile) * G[128 pts x Nl] (MN-major)
+  __device__ __forceinline__ void wgrad(int col, uint32_t aAddr, int aCols, uint32_t gAddr, int gCols, int Nl, bool acc) const {
+    const uint32_t id = idesc_bf16(128, Nl, 1, 1);
+    for (int ks = 0; ks < TP / 16; ++ks)
+      mma_ss(tmem + col, smem_desc(aAddr + ks * 2 * (16 * aCols), 16 * aCols, 128), smem_desc(gAddr + ks * 2 * (16 * gCols), 16 * gCols, 128), id,
+             acc || ks > 0);
+  }
+};
+
+constexpr float PI_F = 3.14159265358979f;
+
+// Fourier features of one point: sin/cos(pi * proj_d) for the 21 directions, fast path (|r| <= 1 after reduction)
+__device__ __forceinline__ void pe_base(const float* __restrict__ peB, const float t[3], float* S_, float* C_) {
+#pragma unroll
+  for (int d = 0; d < CNF_N_DIRS; ++d) {
+    const float proj = fmaf(t[2], peB[d * 3 + 2], fmaf(t[1], peB[d * 3 + 1], t[0] * peB[d * 3 + 0]));
+    const float r = proj - 2.0f * rintf(0.5f * proj);
+    __sincosf(PI_F * r, &S_[d], &C_[d]);
+  }
+}
+__device__ __forceinline__ void pe_double(float& s, float& c) {
+  const float s2 = 2.0f * s * c;
+  c = fmaf(-2.0f * s, s, 1.0f);
+  s = s2;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the fused kernel.  grid = (ctas_per_cat, K), block = 128
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+fused_step_kernel(int K, int R, int S, const uint8_t* __restrict__ prep,
+                  const float* __restrict__ origins, const float* __restrict__ dirs, const float* __restrict__ zs,
+                  const float* __restrict__ gt_depth, const uint8_t* __restrict__ gt_rgb,
+                  const uint8_t* __restrict__ mask_depth, const int32_t* __restrict__ inst_idx,
+                  const int32_t* __restrict__ counts, float cs, float os,
+                  float* __restrict__ raw, float* __restrict__ dp_scratch) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_red[4][24];
+
+  const int k = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rpw = 32 / S, RPT = 4 * rpw;
+  const int n_tiles = (R + RPT - 1) / RPT;
+
+  // ---- one-time setup: prep image -> smem, zero the constant parts of the tiles, barrier, TMEM
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(prep + (size_t)k * PREP_BYTES);
+    uint4* dst = reinterpret_cast<uint4*>(sm);
+    for (int i = tid; i < PREP_BYTES / 16; i += 128) dst[i] = src[i];
+    uint4 zero = make_uint4(0, 0, 0, 0);
+    uint4* t0 = reinterpret_cast<uint4*>(sm + SM_R2XG);
+    for (int i = tid; i < (SM_TOTAL - SM_R2XG) / 16; i += 128) t0[i] = zero;
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tl = tmem_lane_base(tmem);
+  const Issue mma{tmem};
+  const uint32_t sbase = smem_u32(sm);
+  const float* fcs = reinterpret_cast<const float*>(sm + SM_FC);
+  const float* ctab = reinterpret_cast<const float*>(sm + SM_CTAB);
+  uint32_t phase = 0;
+  auto wait_mma = [&]() { mbar_wait(&bar, phase); phase ^= 1; tc_fence_after(); };
+  auto publish = [&]() { fence_async_smem(); tc_fence_before(); __syncthreads(); };   // smem tiles + TMEM reads done
+
+  // loss normalisers; a term with an empty mask in ANY category is zero everywhere
+  bool e0 = false, e1 = false, e2 = false;
+  for (int kk = 0; kk < K; ++kk) { e0 |= counts[kk * 4 + 0] == 0; e1 |= counts[kk * 4 + 1] == 0; e2 |= counts[kk * 4 + 2] == 0; }
+  const float iNd = e0 ? 0.f : 1.0f / ((float)counts[k * 4 + 0] + 1e-10f);
+  const float iNo = e1 ? 0.f : cs / ((float)counts[k * 4 + 1] + 1e-10f);
+  const float iNs = e2 ? 0.f : os / ((float)counts[k * 4 + 2] + 1e-10f);
+
+  float l_d = 0.f, l_c = 0.f, l_o = 0.f;          // raw loss sums (this thread's rays)
+  float db8[16], db9[3];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) db8[j] = 0.f;
+  db9[0] = db9[1] = db9[2] = 0.f;
+  bool first = true;
+
+  const int seg = lane / S, sl = lane - seg * S;
+  const bool lane_used = lane < rpw * S;
+  const int row = tid;
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // ------------------------------------------------------------------ ray / point data
+    const int ray = tile * RPT + warp * rpw + seg;
+    const bool act = lane_used && ray < R;
+    const size_t gr = (size_t)k * R + (act ? ray : 0);
+    float pz = 0.f, t[3] = {0.f, 0.f, 0.f};
+    int inst = 0;
+    if (act) {
+      pz = zs[gr * S + sl];
+      const float inv_scale = fcs[FC_SCALE];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) t[a] = __fadd_rn(origins[gr * 3 + a], __fmul_rn(dirs[gr * 3 + a], pz)) * inv_scale;
+      inst = inst_idx[gr];
+    }
+    // ------------------------------------------------------------------ embedding -> xg (R2XG cols 32..127), xc (Y5XC cols 32..79)
+    {
+      float S_[CNF_N_DIRS], C_[CNF_N_DIRS];
+      pe_base(fcs + FC_PEB, t, S_, C_);
+      uint32_t pk[4];
+      float prev = 0.f;
+#pragma unroll
+      for (int c = 0; c < 96; ++c) {
+        float v;
+        if (c < 3) v = t[c];
+        else if (c < 87) {
+          const int f = (c - 3) / CNF_N_DIRS, d = (c - 3) % CNF_N_DIRS;
+          if (f > 0) pe_double(S_[d], C_[d]);
+          v = S_[d];
+        } else v = (c == 87) ? 1.0f : 0.0f;
+        if (c & 1) pk[(c & 7) >> 1] = pack2(prev, v); else prev = v;
+        if ((c & 7) == 7) st16(rowblk(sm + SM_R2XG, row, 4 + (c >> 3), 128), pk[0], pk[1], pk[2], pk[3]);
+      }
+#pragma unroll
+      for (int c = 0; c < 48; ++c) {
+        float v;
+        if (c < 42) {
+          const int d = c % CNF_N_DIRS;
+          pe_double(S_[d], C_[d]);      // f = 4 (first visit) then f = 5
+          v = S_[d];
+        } else v = (c == 42) ? 1.0f : 0.0f;
+        if (c & 1) pk[(c & 7) >> 1] = pack2(prev, v); else prev = v;
+        if ((c & 7) == 7) st16(rowblk(sm + SM_Y5XC, row, 4 + (c >> 3), 80), pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+    // one-hot(instance) row: 64 cols = 8 col-blocks
+    {
+#pragma unroll
+      for (int cb = 0; cb < 8; ++cb) {
+        uint32_t w4[4] = {0, 0, 0, 0};
+        if (act && (inst >> 3) == cb) {
+          const int e = inst & 7;
+          w4[e >> 1] = (e & 1) ? 0x3F800000u : 0x00003F80u;     // bf16(1.0) in the high / low half
+        }
+        st16(rowblk(sm + SM_OH, row, cb, 64), w4[0], w4[1], w4[2], w4[3]);
+      }
+    }
+    publish();
+
+    uint32_t m1, m2, m3, m4, m6, m7, m8;     // relu masks
+    uint32_t acc_u[32];
+    float* acc = reinterpret_cast<float*>(acc_u);
+    float v32[32];
+
+    // ------------------------------------------------------------------ L1: r1 = relu(W1 [xg,1])
+    if (tid == 0) { tc_fence_after(); mma.fwd(TM_ACC, sbase + SM_R2XG + 4 * 128, 128, 6, sbase + SM_W + OFF_W1, W1_C, 32); mma_commit(&bar); }
+    wait_mma();
+    tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
+    m1 = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const float v = fmaxf(acc[j], 0.f); v32[j] = v; m1 |= (v > 0.f ? 1u : 0u) << j; }
+    store_row32(sm + SM_R1, row, 32, 0, v32);
+    publish();
+    // ------------------------------------------------------------------ L2: r2 = relu(W2 r1 + c2[inst])
+    if (tid == 0) { tc_fence_after(); mma.fwd(TM_ACC, sbase + SM_R1, 32, 2, sbase + SM_W + OFF_W2, W2_C, 32); mma_commit(&bar); }
+    wait_mma();
+    tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
+    m2 = 0;
+    {
+      const float4* cb = reinterpret_cast<const float4*>(ctab + (0 * MAXOBJ + inst) * NL);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 c4 = cb[q];
+        const float b[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const int j = q * 4 + e; const float v = fmaxf(acc[j] + b[e], 0.f); v32[j] = v; m2 |= (v > 0.f ? 1u : 0u) << j; }
+      }
+    }
+    store_row32(sm + SM_R2XG, row, 128, 0, v32);
+    publish();
+    // ------------------------------------------------------------------ L3: r3 = relu(W3 [r2, xg] + c3[inst])
+    if (tid == 0) { tc_fence_after(); mma.fwd(TM_ACC, sbase + SM_R2XG, 128, 8, sbase + SM_W + OFF_W3, W3_C, 32); mma_commit(&bar); }
+    wait_mma();
+    tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
+    m3 = 0;
+    {
+      const float4* cb = reinterpret_cast<const float4*>(ctab + (1 * MAXOBJ + inst) * NL);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 c4 = cb[q];
+        const float b[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const int j = q * 4 + e; const float v = fmaxf(acc[j] + b[e], 0.f); v32[j] = v; m3 |= (v > 0.f ? 1u : 0u) << j; }
+      }
+    }
+    store_row32(sm + SM_R3, row, 32, 0, v32);
+    publish();
+    // ------------------------------------------------------------------ L4: r4 = relu(W4 r3 + c4[inst])
+    if (tid == 0) { tc_fence_after(); mma.fwd(TM_ACC, sbase + SM_R3, 32, 2, sbase + SM_W + OFF_W4, W4_C, 32); mma_commit(&bar); }
+    wait_mma();
+    tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
+    m4 = 0;
+    {
+      const float4* cb = reinterpret_cast<const float4*>(ctab + (2 * MAXOBJ + inst) * NL);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 c4 = cb[q];
+        const float b[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const int j = q * 4 + e; const float v = fmaxf(acc[j] + b[e], 0.f); v32[j] = v; m4 |= (v > 0.f ? 1u : 0u) << j; }
+      }
+    }
+    store_row32(sm + SM_R4, row, 32, 0, v32);
+    publish();
+    // ------------------------------------------------------------------ L5: y5 = W5 r4 + b5 (linear)
+    if (tid == 0) { tc_fence_after(); mma.fwd(TM_ACC, sbase + SM_R4, 32, 2, sbase + SM_W + OFF_W5, W5_C, 32); mma_commit(&bar); }
+    wait_mma();
+    tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v32[j] = acc[j] + fcs[FC_B5 + j];
+    store_row32(sm + SM_Y5XC, row, 80, 0, v32);
+    publish();
+    // ------------------------------------------------------------------ L6: h1 = relu(Wvd [y5, xc, 1]); sigma = 10 (wsig y5 + b)
+    if (tid == 0) { tc_fence_after(); mma.fwd(TM_ACC, sbase + SM_Y5XC, 80, 5, sbase + SM_W + OFF_W6, W6_C, 48); mma_commit(&bar); }
+    wait_mma();
+    tmem_ld32(tl + TM_ACC, acc_u);
+    uint32_t sg_u[16];
+    tmem_ld16(tl + TM_ACC + 32, sg_u);
+    tmem_ld_wait();
+    const float sigma = 10.0f * __uint_as_float(sg_u[0]);                 // model.py:71,75
+    m6 = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const float v = fmaxf(acc[j], 0.f); v32[j] = v; m6 |= (v > 0.f ? 1u : 0u) << j; }
+    store_row32(sm + SM_H1, row, 32, 0, v32);
+    publish();
+    // ------------------------------------------------------------------ L7: h2 = relu(W7 h1 + c7[inst])
+    if (tid == 0) { tc_fence_after(); mma.fwd(TM_ACC, sbase + SM_H1, 32, 2, sbase + SM_W + OFF_W7, W7_C, 32); mma_commit(&bar); }
+    wait_mma();
+    tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
+    m7 = 0;
+    {
+      const float4* cb = reinterpret_cast<const float4*>(ctab + (3 * MAXOBJ + inst) * NL);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 c4 = cb[q];
+        const float b[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const int j = q * 4 + e; const float v = fmaxf(acc[j] + b[e], 0.f); v32[j] = v; m7 |= (v > 0.f ? 1u : 0u) << j; }
+      }
+    }
+    store_row32(sm + SM_H2Z3, row, 80, 0, v32);
+    publish();
+    // ------------------------------------------------------------------ L8: h3 = relu(W8 h2 + b8) ; L9 + sigmoid on CUDA cores
+    if (tid == 0) { tc_fence_after(); mma.fwd(TM_ACC, sbase + SM_H2Z3, 80, 2, sbase + SM_W + OFF_W8, W8_C, 16); mma_commit(&bar); }
+    wait_mma();
+    uint32_t h3_u[16];
+    tmem_ld16(tl + TM_ACC, h3_u); tmem_ld_wait();
+    float h3[16];
+    m8 = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { const float v = fmaxf(__uint_as_float(h3_u[j]) + fcs[FC_B8 + j], 0.f); h3[j] = v; m8 |= (v > 0.f ? 1u : 0u) << j; }
+    st16(rowblk(sm + SM_H2Z3, row, 8, 80), pack2(h3[0], h3[1]), pack2(h3[2], h3[3]), pack2(h3[4], h3[5]), pack2(h3[6], h3[7]));
+    st16(rowblk(sm + SM_H2Z3, row, 9, 80), pack2(h3[8], h3[9]), pack2(h3[10], h3[11]), pack2(h3[12], h3[13]), pack2(h3[14], h3[15]));
+    float col[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float a = fcs[FC_B9 + j];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) a = fmaf(fcs[FC_W9 + j * 16 + q], h3[q], a);
+      col[j] = 1.0f / (1.0f + __expf(-a));                                // model.py:54
+    }
+    // ------------------------------------------------------------------ compositing + losses + their gradients (warp scans)
+    float d_sig = 0.f, d_rgbpre[3] = {0.f, 0.f, 0.f};
+    {
+      const float occ = act ? 1.0f / (1.0f + __expf(-sigma)) : 0.f;        // render_rays.py:3-7
+      const float fr = act ? __fadd_rn(__fsub_rn(1.0f, occ), 1e-10f) : 1.0f;   // render_rays.py:28
+      float incl = fr;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, incl, o); if (sl >= o) incl *= n; }
+      float T = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (sl == 0) T = 1.0f;
+      const float w = occ * T;                                             // render_rays.py:33
+      const int last = min(seg * S + S - 1, 31);
+      auto segsum = [&](float v) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_up_sync(0xffffffffu, v, o); if (sl >= o) v += n; }
+        return __shfl_sync(0xffffffffu, v, last);
+      };
+      const float D = segsum(w * pz), O = segsum(w);
+      const float C0 = segsum(w * col[0]), C1 = segsum(w * col[1]), C2 = segsum(w * col[2]);
+      const float dz = pz - D;
+      const float var = segsum(w * dz * dz);                               // loss.py:45-46 (detached)
+      float gD = 0.f, gC0 = 0.f, gC1 = 0.f, gC2 = 0.f, gO = 0.f;
+      if (act) {
+        const uint32_t px = *reinterpret_cast<const uint32_t*>(gt_rgb + gr * 4);
+        const uint32_t lab = px >> 24;
+        const float mo = (lab != 0) ? 1.f : 0.f, ms = (lab != 2) ? 1.f : 0.f;
+        const float md = (mask_depth[gr] != 0 && lab != 0) ? 1.f : 0.f;
+        const float g0 = (float)(px & 255u) * (1.0f / 255.0f), g1 = (float)((px >> 8) & 255u) * (1.0f / 255.0f),
+                    g2 = (float)((px >> 16) & 255u) * (1.0f / 255.0f);
+        const float info = 1.0f / (sqrtf(var) + 1e-4f);
+        const float rD = D - gt_depth[gr], r0 = C0 - g0, r1 = C1 - g1, r2 = C2 - g2, rO = O - mo;
+        if (sl == 0) {
+          l_d += fabsf(rD) * md * info;
+          l_c += (fabsf(r0) + fabsf(r1) + fabsf(r2)) * mo;
+          l_o += fabsf(rO) * ms;
+        }
+        auto sgn = [](float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); };
+        gD = sgn(rD) * md * info * iNd;
+        gC0 = sgn(r0) * mo * iNo; gC1 = sgn(r1) * mo * iNo; gC2 = sgn(r2) * mo * iNo;
+        gO = sgn(rO) * ms * iNs;
+      }
+      const float Gi = gD * pz + gC0 * col[0] + gC1 * col[1] + gC2 * col[2] + gO;
+      const float Gw = act ? Gi * w : 0.f;
+      float sfx = Gw;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const float n = __shfl_down_sync(0xffffffffu, sfx, o); if (sl + o < S) sfx += n; }
+      if (act) {
+        const float docc = Gi * T - (sfx - Gw) / fr;
+        d_sig = 10.0f * docc * occ * (1.0f - occ);                          // into the raw sigma column (x10 scale)
+        d_rgbpre[0] = w * gC0 * col[0] * (1.0f - col[0]);
+        d_rgbpre[1] = w * gC1 * col[1] * (1.0f - col[1]);
+        d_rgbpre[2] = w * gC2 * col[2] * (1.0f - col[2]);
+      }
+    }
+    // ------------------------------------------------------------------ B9 (CUDA cores): d h3 -> G8 ; G9 = d rgb_pre
+    {
+      float g8[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        float a = fcs[FC_W9 + q] * d_rgbpre[0];
+        a = fmaf(fcs[FC_W9 + 16 + q], d_rgbpre[1], a);
+        a = fmaf(fcs[FC_W9 + 32 + q], d_rgbpre[2], a);
+        g8[q] = ((m8 >> q) & 1u) ? a : 0.f;
+        db8[q] += g8[q];
+      }
+      db9[0] += d_rgbpre[0]; db9[1] += d_rgbpre[1]; db9[2] += d_rgbpre[2];
+      uint8_t* G8 = sm + SM_GX; uint8_t* G9 = sm + SM_GX + TP * 16 * 2;
+      st16(rowblk(G8, row, 0, 16), pack2(g8[0], g8[1]), pack2(g8[2], g8[3]), pack2(g8[4], g8[5]), pack2(g8[6], g8[7]));
+      st16(rowblk(G8, row, 1, 16), pack2(g8[8], g8[9]), pack2(g8[10], g8[11]), pack2(g8[12], g8[13]), pack2(g8[14], g8[15]));
+      st16(rowblk(G9, row, 0, 16), pack2(d_rgbpre[0], d_rgbpre[1]), pack2(d_rgbpre[2], 0.f), 0u, 0u);
+      st16(rowblk(G9, row, 1, 16), 0u, 0u, 0u, 0u);
+    }
+    publish();
+    const bool accf = !first;
+    // ------------------------------------------------------------------ B8: wgrad(W8, W9) ; d h2 = G8 W8
+    if (tid == 0) {
+      tc_fence_after();
+      mma.wgrad(TM_WG89, sbase + SM_H2Z3, 80, sbase + SM_GX, 16, 16, accf);                                 // rows 0..31: dW8^T
+      mma.wgrad(TM_WG89, sbase + SM_H2Z3 + 4 * 128, 80, sbase + SM_GX + TP * 16 * 2, 16, 16, true);        // rows 32..47: dW9^T
+      mma.dgrad(TM_ACC, sbase + SM_GX, 16, 16, sbase + SM_W + OFF_W8, W8_C, 32, false);
+      mma_commit(&bar);
+    }
+    wait_mma();
+    tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v32[j] = ((m7 >> j) & 1u) ? acc[j] : 0.f;
+    store_row32(sm + SM_GY, row, 32, 0, v32);                               // G7
+    publish();
+    // ------------------------------------------------------------------ B7: wgrad(W7, c7) ; d h1 = G7 W7 -> G6 (+ sigma col)
+    if (tid == 0) {
+      tc_fence_after();
+      mma.wgrad(TM_WG7, sbase + SM_H1, 32, sbase + SM_GY, 32, 32, accf);
+      mma.wgrad(TM_OH7, sbase + SM_OH, 64, sbase + SM_GY, 32, 32, accf);
+      mma.dgrad(TM_ACC, sbase + SM_GY, 32, 32, sbase + SM_W + OFF_W7, W7_C, 32, false);
+      mma_commit(&bar);
+    }
+    wait_mma();
+    tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v32[j] = ((m6 >> j) & 1u) ? acc[j] : 0.f;
+    store_row32(sm + SM_GX, row, 48, 0, v32);                               // G6 cols 0..31
+    st16(rowblk(sm + SM_GX, row, 4, 48), pack2(d_sig, 0.f), 0u, 0u, 0u);    // col 32 = d raw sigma
+    st16(rowblk(sm + SM_GX, row, 5, 48), 0u, 0u, 0u, 0u);
+    publish();
+    // ------------------------------------------------------------------ B6: wgrad(W6+sigma) ; [d y5 | d xc] = G6 W6
+    if (tid == 0) {
+      tc_fence_after();
+      mma.wgrad(TM_WG6, sbase + SM_Y5XC, 80, sbase + SM_GX, 48, 48, accf);
+      mma.dgrad(TM_ACC, sbase + SM_GX, 48, 48, sbase + SM_W + OFF_W6, W6_C, 80, false);
+      mma_commit(&bar);
+    }
+    wait_mma();
+    tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
+    store_row32(sm + SM_GY, row, 32, 0, acc);                               // G5 = d y5 (linear layer: no mask)
+    tmem_ld32(tl + TM_ACC + 32, acc_u); tmem_ld_wait();                     // d xc cols 0..31
+    store_row32(sm + SM_Y5XC, row, 80, 4, acc);                             // park d xc (bf16) over the dead xc tile
+    {
+      uint32_t x_u[16];
+      tmem_ld16(tl + TM_ACC + 64, x_u); tmem_ld_wait();
+      const float* x = reinterpret_cast<const float*>(x_u);
+      st16(rowblk(sm + SM_Y5XC, row, 8, 80), pack2(x[0], x[1]), pack2(x[2], x[3]), pack2(x[4], x[5]), pack2(x[6], x[7]));
+      st16(rowblk(sm + SM_Y5XC, row, 9, 80), pack2(x[8], x[9]), pack2(x[10], x[11]), pack2(x[12], x[13]), pack2(x[14], x[15]));
+    }
+    publish();
+    // ------------------------------------------------------------------ B5: wgrad(W5) ; d r4 = G5 W5
+    if (tid == 0) {
+      tc_fence_after();
+      mma.wgrad(TM_WG5, sbase + SM_R4, 32, sbase + SM_GY, 32, 32, accf);
+      mma.dgrad(TM_ACC, sbase + SM_GY, 32, 32, sbase + SM_W + OFF_W5, W5_C, 32, false);
+      mma_commit(&bar);
+    }
+    wait_mma();
+    tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v32[j] = ((m4 >> j) & 1u) ? acc[j] : 0.f;
+    store_row32(sm + SM_GX, row, 32, 0, v32);                               // G4 (GX viewed as [128 x 32])
+    publish();
+    // ------------------------------------------------------------------ B4: wgrad(W4, c4) ; d r3 = G4 W4
+    if (tid == 0) {
+      tc_fence_after();
+      mma.wgrad(TM_WG4, sbase + SM_R3, 32, sbase + SM_GX, 32, 32, accf);
+      mma.wgrad(TM_OH4, sbase + SM_OH, 64, sbase + SM_GX, 32, 32, accf);
+      mma.dgrad(TM_ACC, sbase + SM_GX, 32, 32, sbase + SM_W + OFF_W4, W4_C, 32, false);
+      mma_commit(&bar);
+    }
+    wait_mma();
+    tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v32[j] = ((m3 >> j) & 1u) ? acc[j] : 0.f;
+    store_row32(sm + SM_GY, row, 32, 0, v32);                               // G3
+    publish();
+    // ------------------------------------------------------------------ B3: wgrad(W3, c3) ; [d r2 | d xg] = G3 W3
+    if (tid == 0) {
+      tc_fence_after();
+      mma.wgrad(TM_WG3, sbase + SM_R2XG, 128, sbase + SM_GY, 32, 32, accf);
+      mma.wgrad(TM_OH3, sbase + SM_OH, 64, sbase + SM_GY, 32, 32, accf);
+      mma.dgrad(TM_ACC, sbase + SM_GY, 32, 32, sbase + SM_W + OFF_W3, W3_C, 128, false);   // cols 0..31 d r2, 32..127 d xg
+      mma_commit(&bar);
+    }
+    wait_mma();
+    tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v32[j] = ((m2 >> j) & 1u) ? acc[j] : 0.f;
+    store_row32(sm + SM_GX, row, 32, 0, v32);                               // G2
+    publish();
+    // ------------------------------------------------------------------ B2: wgrad(W2, c2) ; d r1 = G2 W2
+    if (tid == 0) {
+      tc_fence_after();
+      mma.wgrad(TM_WG2, sbase + SM_R1, 32, sbase + SM_GX, 32, 32, accf);
+      mma.wgrad(TM_OH2, sbase + SM_OH, 64, sbase + SM_GX, 32, 32, accf);
+      mma.dgrad(TM_ACC, sbase + SM_GX, 32, 32, sbase + SM_W + OFF_W2, W2_C, 32, false);
+      mma_commit(&bar);
+    }
+    wait_mma();
+    tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v32[j] = ((m1 >> j) & 1u) ? acc[j] : 0.f;
+    store_row32(sm + SM_GY, row, 32, 0, v32);                               // G1
+    publish();
+    // ------------------------------------------------------------------ B1: wgrad(W1) ; d xg += G1 W1
+    if (tid == 0) {
+      tc_fence_after();
+      mma.wgrad(TM_WG1, sbase + SM_R2XG + 4 * 128, 128, sbase + SM_GY, 32, 32, accf);
+      mma.dgrad(TM_ACC + 32, sbase + SM_GY, 32, 32, sbase + SM_W + OFF_W1, W1_C, 96, true);
+      mma_commit(&bar);
+    }
+    wait_mma();
+    // ------------------------------------------------------------------ embedding backward: dL/dproj_d -> scratch
+    {
+      float S_[CNF_N_DIRS], C_[CNF_N_DIRS], dp[CNF_N_DIRS];
+      pe_base(fcs + FC_PEB, t, S_, C_);
+#pragma unroll
+      for (int d = 0; d < CNF_N_DIRS; ++d) dp[d] = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < 96; c0 += 32) {
+        tmem_ld32(tl + TM_ACC + 32 + c0, acc_u); tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = c0 + j;
+          if (c >= 3 && c < 87) {
+            const int f = (c - 3) / CNF_N_DIRS, d = (c - 3) % CNF_N_DIRS;
+            if (f > 0) pe_double(S_[d], C_[d]);
+            dp[d] = fmaf(acc[j] * (PI_F * (float)(1 << f)), C_[d], dp[d]);
+          }
+        }
+      }
+#pragma unroll
+      for (int cb = 0; cb < 6; ++cb) {
+        const uint4 q = *reinterpret_cast<const uint4*>(rowblk(sm + SM_Y5XC, row, 4 + cb, 80));
+        const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = cb * 8 + e;
+          if (c < 42) {
+            const int f = 4 + c / CNF_N_DIRS, d = c % CNF_N_DIRS;
+            pe_double(S_[d], C_[d]);
+            const uint32_t hw = (e & 1) ? (qq[e >> 1] & 0xFFFF0000u) : (qq[e >> 1] << 16);
+            dp[d] = fmaf(__uint_as_float(hw) * (PI_F * (float)(1 << f)), C_[d], dp[d]);
+          }
+        }
+      }
+      if (act) {
+        float4* out = reinterpret_cast<float4*>(dp_scratch + (gr * S + sl) * 24);
+        out[0] = make_float4(dp[0], dp[1], dp[2], dp[3]);
+        out[1] = make_float4(dp[4], dp[5], dp[6], dp[7]);
+        out[2] = make_float4(dp[8], dp[9], dp[10], dp[11]);
+        out[3] = make_float4(dp[12], dp[13], dp[14], dp[15]);
+        out[4] = make_float4(dp[16], dp[17], dp[18], dp[19]);
+        out[5] = make_float4(dp[20], t[0], t[1], t[2]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();        // all TMEM reads of this tile done before the next tile's MMAs overwrite ACC
+    first = false;
+  }
+
+  // ---- flush: TMEM accumulators -> raw[k] (fp32 atomics; several CTAs share a category)
+  float* rk = raw + (size_t)k * RAW_FLOATS;
+  if (!first) {
+    tc_fence_after();
+    auto flush32 = [&](int col, int roff, int rows, int ld, int c0) {
+      uint32_t u[32];
+      tmem_ld32(tl + col + c0, u); tmem_ld_wait();
+      if (row < rows) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(rk + roff + row * ld + c0 + j, __uint_as_float(u[j]));
+      }
+    };
+    auto flush16 = [&](int col, int roff, int rows, int ld, int c0) {
+      uint32_t u[16];
+      tmem_ld16(tl + col + c0, u); tmem_ld_wait();
+      if (row < rows) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) atomicAdd(rk + roff + row * ld + c0 + j, __uint_as_float(u[j]));
+      }
+    };
+    flush32(TM_WG1, RW1, 96, 32, 0);
+    flush32(TM_WG2, RW2, 32, 32, 0);
+    flush32(TM_WG3, RW3, 128, 32, 0);
+    flush32(TM_WG4, RW4, 32, 32, 0);
+    flush32(TM_WG5, RW5, 32, 32, 0);
+    flush32(TM_WG6, RW6, 80, 48, 0);
+    flush16(TM_WG6, RW6, 80, 48, 32);
+    flush32(TM_WG7, RW7, 32, 32, 0);
+    flush16(TM_WG89, RW89, 48, 16, 0);
+    flush32(TM_OH2, ROH2, 64, 32, 0);
+    flush32(TM_OH3, ROH3, 64, 32, 0);
+    flush32(TM_OH4, ROH4, 64, 32, 0);
+    flush32(TM_OH7, ROH7, 64, 32, 0);
+  }
+  // per-thread register accumulators: block reduce then one atomic each
+  {
+    float vals[22];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) vals[j] = db8[j];
+    vals[16] = db9[0]; vals[17] = db9[1]; vals[18] = db9[2]; vals[19] = l_d; vals[20] = l_c; vals[21] = l_o;
+#pragma unroll
+    for (int j = 0; j < 22; ++j) { const float s = warp_sum(vals[j]); if (lane == 0) s_red[warp][j] = s; }
+    __syncthreads();
+    if (tid < 22) {
+      const float s = s_red[0][tid] + s_red[1][tid] + s_red[2][tid] + s_red[3][tid];
+      const int dst = tid < 16 ? RDB8 + tid : (tid < 19 ? RDB9 + (tid - 16) : RLOSS + (tid - 19));
+      atomicAdd(rk + dst, s);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dB[d][a] = sum_p dproj[p][d] * t[p][a]  from the scratch rows {dp[21], t[3]}
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fused_pe_grad_kernel(size_t P, const float* __restrict__ scratch, float* __restrict__ g_B) {
+  const int k = blockIdx.y;
+  float acc[63];
+#pragma unroll
+  for (int j = 0; j < 63; ++j) acc[j] = 0.f;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
+    const float4* r = reinterpret_cast<const float4*>(scratch + ((size_t)k * P + p) * 24);
+    float v[24];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) { const float4 x = r[q]; v[q * 4] = x.x; v[q * 4 + 1] = x.y; v[q * 4 + 2] = x.z; v[q * 4 + 3] = x.w; }
+#pragma unroll
+    for (int d = 0; d < 21; ++d) {
+      acc[d * 3 + 0] = fmaf(v[d], v[21], acc[d * 3 + 0]);
+      acc[d * 3 + 1] = fmaf(v[d], v[22], acc[d * 3 + 1]);
+      acc[d * 3 + 2] = fmaf(v[d], v[23], acc[d * 3 + 2]);
+    }
+  }
+  __shared__ float s[8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 63; ++j) { const float x = warp_sum(acc[j]); if (lane == 0) s[warp][j] = x; }
+  __syncthreads();
+  if (threadIdx.x < 63) {
+    float x = 0.f;
+    for (int w = 0; w < 8; ++w) x += s[w][threadIdx.x];
+    atomicAdd(&g_B[(size_t)k * 63 + threadIdx.x], x);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// finalize: raw accumulators -> reference-shaped gradients (one CTA per category) + code regulariser
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, const float* __restrict__ pe_scale,
+                      const float* __restrict__ shape_codes, const float* __restrict__ tex_codes,
+                      const int32_t* __restrict__ n_obj_arr, const float* __restrict__ raw, const float* __restrict__ zlat,
+                      float reg_scaling, int add_reg, float* __restrict__ g_params, float* __restrict__ g_B,
+                      float* __restrict__ g_shape, float* __restrict__ g_tex, float* __restrict__ reg_out) {
+  const int k = blockIdx.x, tid = threadIdx.x;
+  const PLay lay(L);
+  const float* P = params + (size_t)k * lay.total;
+  float* G = g_params + (size_t)k * lay.total;
+  const float* rk = raw + (size_t)k * RAW_FLOATS;
+  const float* z = zlat + (size_t)k * 4 * MAXOBJ * NL;
+  const int n_obj = n_obj_arr[k];
+  __shared__ float s_dpre[4][MAXOBJ][NL];      // relu-masked gradient wrt the latent pre-activations
+  // g_B: the fused kernel differentiated w.r.t. proj of t = x * (1/scale): already the gradient w.r.t. B. nothing to scale.
+  (void)pe_scale; (void)g_B;
+
+  // --- plain layers
+  for (int i = tid; i < 32 * 87; i += 256) { const int n = i / 87, c = i % 87; G[lay.o[0] + i] = rk[RW1 + c * 32 + n]; }
+  for (int n = tid; n < 32; n += 256) G[lay.o[1] + n] = rk[RW1 + 87 * 32 + n];
+  for (int i = tid; i < 32 * 32; i += 256) { const int n = i / 32, c = i % 32; G[lay.o[14] + i] = rk[RW5 + c * 32 + n]; }
+  for (int i = tid; i < 32 * 74; i += 256) { const int n = i / 74, c = i % 74; G[lay.o[18] + i] = rk[RW6 + c * 48 + n]; }
+  for (int n = tid; n < 32; n += 256) {
+    G[lay.o[19] + n] = rk[RW6 + 74 * 48 + n];              // b_vd
+    G[lay.o[16] + n] = rk[RW6 + n * 48 + 32];              // w_sigma
+  }
+  if (tid == 0) G[lay.o[17]] = rk[RW6 + 74 * 48 + 32];     // b_sigma
+  // b_es: y5 feeds only linear consumers -> d b5[n] = sum_m db_vd[m] Wvd[m][n] + db_sigma * wsig[n]
+  for (int n = tid; n < 32; n += 256) {
+    float a = rk[RW6 + 74 * 48 + 32] * P[lay.o[16] + n];
+    for (int m = 0; m < 32; ++m) a = fmaf(rk[RW6 + 74 * 48 + m], P[lay.o[18] + (size_t)m * 74 + n], a);
+    G[lay.o[15] + n] = a;
+  }
+  for (int i = tid; i < 16 * 32; i += 256) { const int n = i / 32, c = i % 32; G[lay.o[24] + i] = rk[RW89 + c * 16 + n]; }
+  for (int n = tid; n < 16; n += 256) G[lay.o[25] + n] = rk[RDB8 + n];
+  for (int i = tid; i < 3 * 16; i += 256) { const int j = i / 16, c = i % 16; G[lay.o[26] + i] = rk[RW89 + (32 + c) * 16 + j]; }
+  for (int j = tid; j < 3; j += 256) G[lay.o[27] + j] = rk[RDB9 + j];
+  // --- layers with per-instance bias c = W[:, :32] z + b : slots (zsl1->s1), (zcl->cat), (zsl2->s2), (ztl->t1)
+  const int cons_w[4] = {4, 10, 8, 20};
+  const int cons_ld[4] = {32, 119, 32, 32};
+  const int rw[4] = {RW2, RW3, RW4, RW7};
+  const int roh[4] = {ROH2, ROH3, ROH4, ROH7};
+  const int lat_w[4] = {2, 12, 6, 22};
+  for (int s = 0; s < 4; ++s) {
+    const int ld = cons_ld[s];
+    for (int i = tid; i < 32 * ld; i += 256) {
+      const int n = i / ld, c = i % ld;
+      float a = rk[rw[s] + c * 32 + n];
+      if (c < 32)
+        for (int inst = 0; inst < n_obj; ++inst) a = fmaf(rk[roh[s] + inst * 32 + n], z[(s * MAXOBJ + inst) * NL + c], a);
+      G[lay.o[cons_w[s]] + i] = a;
+    }
+    for (int n = tid; n < 32; n += 256) {
+      float a = 0.f;
+      for (int inst = 0; inst < n_obj; ++inst) a += rk[roh[s] + inst * 32 + n];
+      G[lay.o[cons_w[s] + 1] + n] = a;
+    }
+    // d z[inst][c] = sum_n dC[inst][n] W[n][c], masked by relu
+    for (int i = tid; i < MAXOBJ * NL; i += 256) {
+      const int inst = i / NL, c = i % NL;
+      float a = 0.f;
+      if (inst < n_obj && z[(s * MAXOBJ + inst) * NL + c] > 0.f)
+        for (int n = 0; n < 32; ++n) a = fmaf(rk[roh[s] + inst * 32 + n], P[lay.o[cons_w[s]] + (size_t)n * ld + c], a);
+      s_dpre[s][inst][c] = a;
+    }
+  }
+  __syncthreads();
+  // --- latent layers: dW_lat[c][j] = sum_inst dpre[inst][c] code[inst][j]; db_lat[c] = sum_inst dpre[inst][c]
+  for (int s = 0; s < 4; ++s) {
+    const float* codes = (s == 3 ? tex_codes : shape_codes) + (size_t)k * n_obj_max * L;
+    for (int i = tid; i < 32 * L; i += 256) {
+      const int c = i / L, j = i % L;
+      float a = 0.f;
+      for (int inst = 0; inst < n_obj; ++inst) a = fmaf(s_dpre[s][inst][c], codes[(size_t)inst * L + j], a);
+      G[lay.o[lat_w[s]] + i] = a;
+    }
+    for (int c = tid; c < 32; c += 256) {
+      float a = 0.f;
+      for (int inst = 0; inst < n_obj; ++inst) a += s_dpre[s][inst][c];
+      G[lay.o[lat_w[s] + 1] + c] = a;
+    }
+  }
+  // --- code tables: d code[inst][j] = sum_s sum_c dpre[s][inst][c] W_lat_s[c][j]  (+ regulariser)
+  __shared__ float s_norm[2][MAXOBJ];
+  for (int i = tid; i < 2 * MAXOBJ; i += 256) {
+    const int which = i / MAXOBJ, inst = i % MAXOBJ;
+    float a = 0.f;
+    if (inst < n_obj) {
+      const float* code = (which ? tex_codes : shape_codes) + ((size_t)k * n_obj_max + inst) * L;
+      for (int j = 0; j < L; ++j) a = fmaf(code[j], code[j], a);
+    }
+    s_norm[which][inst] = sqrtf(a);
+  }
+  __syncthreads();
+  for (int i = tid; i < n_obj_max * L; i += 256) {
+    const int inst = i / L, j = i % L;
+    float gs = 0.f, gt = 0.f;
+    if (inst < n_obj) {
+      for (int c = 0; c < 32; ++c) {
+        gs = fmaf(s_dpre[0][inst][c], P[lay.o[2] + (size_t)c * L + j], gs);
+        gs = fmaf(s_dpre[1][inst][c], P[lay.o[12] + (size_t)c * L + j], gs);
+        gs = fmaf(s_dpre[2][inst][c], P[lay.o[6] + (size_t)c * L + j], gs);
+        gt = fmaf(s_dpre[3][inst][c], P[lay.o[22] + (size_t)c * L + j], gt);
+      }
+      if (add_reg && n_obj > 1) {                                            // loss.py:12, train.py:165-167
+        const float ns = s_norm[0][inst], nt = s_norm[1][inst];
+        if (ns > 0.f) gs += reg_scaling * shape_codes[((size_t)k * n_obj_max + inst) * L + j] / ns;
+        if (nt > 0.f) gt += reg_scaling * tex_codes[((size_t)k * n_obj_max + inst) * L + j] / nt;
+      }
+    }
+    g_shape[(size_t)k * n_obj_max * L + i] = gs;
+    g_tex[(size_t)k * n_obj_max * L + i] = gt;
+  }
+  if (tid == 0) {
+    float rs = 0.f, rt = 0.f;
+    if (n_obj > 1) for (int inst = 0; inst < n_obj; ++inst) { rs += s_norm[0][inst]; rt += s_norm[1][inst]; }
+    reg_out[k * 2 + 0] = rs; reg_out[k * 2 + 1] = rt;
+  }
+}
+
+// out_loss = {loss, e_depth, e_obj, e_sem, depth[K], color[K], opacity[K], reg_shape[K], reg_tex[K]}
+__global__ void fused_loss_kernel(int K, const float* __restrict__ raw, const int32_t* __restrict__ counts,
+                                  const float* __restrict__ reg, float cs, float os, float reg_scaling, int add_reg,
+                                  float* __restrict__ out_loss) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  bool e0 = false, e1 = false, e2 = false;
+  for (int k = 0; k < K; ++k) { e0 |= counts[k * 4 + 0] == 0; e1 |= counts[k * 4 + 1] == 0; e2 |= counts[k * 4 + 2] == 0; }
+  float total = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float* l = raw + (size_t)k * RAW_FLOATS + RLOSS;
+    const float d = e0 ? 0.f : l[0] / ((float)counts[k * 4 + 0] + 1e-10f);
+    const float c = e1 ? 0.f : l[1] / ((float)counts[k * 4 + 1] + 1e-10f);
+    const float o = e2 ? 0.f : l[2] / ((float)counts[k * 4 + 2] + 1e-10f);
+    out_loss[4 + k] = d; out_loss[4 + K + k] = c; out_loss[4 + 2 * K + k] = o;
+    out_loss[4 + 3 * K + k] = reg[k * 2]; out_loss[4 + 4 * K + k] = reg[k * 2 + 1];
+    total += d + c * cs + o * os;
+    if (add_reg) total += reg_scaling * (reg[k * 2] + reg[k * 2 + 1]);
+  }
+  out_loss[0] = total; out_loss[1] = e0; out_loss[2] = e1; out_loss[3] = e2;
+}
+
+struct FusedWs {
+  size_t prep, zlat, raw, reg, scratch, total;
+  FusedWs(size_t K, size_t R, size_t S) {
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
+    prep = take(K * PREP_BYTES);
+    zlat = take(K * 4 * MAXOBJ * NL * 4);
+    raw = take(K * RAW_FLOATS * 4);
+    reg = take(K * 2 * 4);
+    scratch = take(K * R * S * 24 * 4);
+    total = o;
+  }
+};
+
+}  // namespace cnf
+
 using namespace cnf;
-extern "C" size_t cnf_train_step_workspace_bytes(int, int, int, int, int) { return 256; }
-extern "C" int cnf_train_step(int, int, int, int, int, const float*, const float*, const float*, const float*,
-                              const float*, const int32_t*, const float*, const float*, const float*, const float*,
-                              const uint8_t*, const uint8_t*, const int32_t*, const int32_t*, float, float, float, int,
-                              float*, float*, float*, float*, float*, void*, size_t, cnf_stream_t) {
-  set_error("cnf_train_step: not built yet");
-  return CNF_ERR_UNSUPPORTED;
+
+static thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+extern "C" int cnf_set_kernel_events(void* ev_start, void* ev_stop) {
+  g_ev_start = reinterpret_cast<cudaEvent_t>(ev_start);
+  g_ev_stop = reinterpret_cast<cudaEvent_t>(ev_stop);
+  return CNF_OK;
+}
+
+extern "C" size_t cnf_train_step_workspace_bytes(int K, int R, int S, int L, int n_obj_max) {
+  (void)L; (void)n_obj_max;
+  return FusedWs(K, R, S).total;
+}
+
+extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const float* params, const float* pe_B,
+                              const float* pe_scale, const float* shape_codes, const float* tex_codes,
+                              const int32_t* n_obj, const float* origins, const float* dirs, const float* z,
+                              const float* gt_depth, const uint8_t* gt_rgb, const uint8_t* mask_depth,
+                              const int32_t* inst, const int32_t* counts, float cs, float os, float reg_scaling,
+                              int flags, float* g_params, float* g_B, float* g_shape, float* g_tex, float* out_loss,
+                              void* ws, size_t ws_bytes, cnf_stream_t stream) {
+  CNF_REQUIRE(K > 0 && R > 0 && L > 0, "cnf_train_step: bad sizes K=%d R=%d L=%d", K, R, L);
+  if (S < 1 || S > 32) { set_error("cnf_train_step: samples per ray S=%d outside 1..32 (one ray per warp segment)", S); return CNF_ERR_UNSUPPORTED; }
+  if (n_obj_max < 1 || n_obj_max > MAXOBJ) { set_error("cnf_train_step: n_obj_max=%d outside 1..%d", n_obj_max, MAXOBJ); return CNF_ERR_UNSUPPORTED; }
+  CNF_REQUIRE(params && pe_B && pe_scale && shape_codes && tex_codes && n_obj && origins && dirs && z && gt_depth && gt_rgb &&
+                  mask_depth && inst && counts && g_params && g_B && g_shape && g_tex && out_loss && ws,
+              "cnf_train_step: null pointer");
+  const FusedWs wl(K, R, S);
+  if (ws_bytes < wl.total) { set_error("cnf_train_step: workspace too small (%zu < %zu)", ws_bytes, wl.total); return CNF_ERR_WORKSPACE; }
+  cudaStream_t st = as_stream(stream);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  uint8_t* prep = w8 + wl.prep;
+  float* zlat = reinterpret_cast<float*>(w8 + wl.zlat);
+  float* raw = reinterpret_cast<float*>(w8 + wl.raw);
+  float* reg = reinterpret_cast<float*>(w8 + wl.reg);
+  float* scratch = reinterpret_cast<float*>(w8 + wl.scratch);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CNF_CUDA(cudaFuncSetAttribute(fused_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    attr_set = true;
+  }
+  int dev = 0, n_sm = 148;
+  CNF_CUDA(cudaGetDevice(&dev));
+  CNF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  const int rpw = 32 / S, RPT = 4 * rpw, n_tiles = (R + RPT - 1) / RPT;
+  int cpc = n_sm / K; if (cpc < 1) cpc = 1; if (cpc > n_tiles) cpc = n_tiles;
+  CNF_CUDA(cudaMemsetAsync(raw, 0, (size_t)K * RAW_FLOATS * 4, st));
+  CNF_CUDA(cudaMemsetAsync(g_B, 0, (size_t)K * 63 * 4, st));
+  fused_prep_kernel<<<K, 256, 0, st>>>(L, n_obj_max, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, prep, zlat);
+  if (g_ev_start && g_ev_stop) CNF_CUDA(cudaEventRecord(g_ev_start, st));
+  fused_step_kernel<<<dim3(cpc, K), 128, SM_TOTAL, st>>>(K, R, S, prep, origins, dirs, z, gt_depth, gt_rgb, mask_depth, inst,
+                                                         counts, cs, os, raw, scratch);
+  if (g_ev_start && g_ev_stop) { CNF_CUDA(cudaEventRecord(g_ev_stop, st)); g_ev_start = g_ev_stop = nullptr; }
+  const size_t P = (size_t)R * S;
+  int pb = (int)((P + 255) / 256); if (pb > 64) pb = 64;
+  fused_pe_grad_kernel<<<dim3(pb, K), 256, 0, st>>>(P, scratch, g_B);
+  fused_finalize_kernel<<<K, 256, 0, st>>>(L, n_obj_max, params, pe_scale, shape_codes, tex_codes, n_obj, raw, zlat, reg_scaling,
+                                           flags & 1, g_params, g_B, g_shape, g_tex, reg);
+  fused_loss_kernel<<<1, 32, 0, st>>>(K, raw, counts, reg, cs, os, reg_scaling, flags & 1, out_loss);
+  return check_launch("cnf_train_step");
 }

@@ -1,0 +1,163 @@
+"""The fused tcgen05 training step (cnf_train_step): sample -> embed -> CodeNeRF -> composite -> losses, fwd+bwd.
+
+``FusedCategoryTrainer`` holds K categories' state as flat fp32 buffers (MLP parameters in the reference's
+named_parameters() order, PE projection, code tables) plus preallocated gradient / workspace buffers, and
+runs one training step of train.py:123-184 per call: the sampler (3 small launches) and the fused step
+(prep, fused fwd+bwd, PE-gradient reduce, finalize, loss) with optional fused AdamW.  Everything is
+asynchronous; nothing is read back unless the caller asks (``.item()`` on a result)."""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops, sampling
+from ._lib import check, lib_for, ptr, stream
+from .embedding import _DIRS
+
+MAXOBJ = 64
+
+
+class FusedCategoryTrainer:
+    def __init__(self, n_cat: int, n_obj, latent_dim: int = 256, scale=2.0, device="cuda:0",
+                 n_bins_cam2surface: int = 1, n_bins: int = 9, surface_eps: float = 0.1, stop_eps: float = 0.05,
+                 min_bound: float = 0.0, this_obj: int = 1, color_scaling: float = 5.0, opacity_scaling: float = 10.0,
+                 reg_scaling: float = 0.0005, generator: Optional[torch.Generator] = None):
+        self.K = n_cat
+        self.L = latent_dim
+        self.device = torch.device(device)
+        n_obj = [n_obj] * n_cat if isinstance(n_obj, int) else list(n_obj)
+        assert len(n_obj) == n_cat
+        self.n_obj_list = n_obj
+        self.n_obj_max = max(n_obj)
+        if self.n_obj_max > MAXOBJ:
+            raise NotImplementedError("fused step supports <= %d instances per category (got %d); use the "
+                                      "module-level CodeNeRF path for larger categories" % (MAXOBJ, self.n_obj_max))
+        self.N, self.M = n_bins_cam2surface, n_bins
+        self.S = self.N + self.M
+        self.eps, self.stop_eps, self.min_bound, self.this_obj = surface_eps, stop_eps, min_bound, this_obj
+        self.cs, self.os, self.reg = color_scaling, opacity_scaling, reg_scaling
+        lib = lib_for(torch.empty(1, device=self.device))
+        self.n_param = lib.cnf_codenerf_param_count(32, latent_dim)
+        dev = self.device
+        # --- state (random init as the reference: xavier-normal weights, default Linear biases, randn/sqrt(L/2) codes)
+        from .model import CodeNeRF, init_weights, flat_params
+        g = generator
+        ps = []
+        for _ in range(n_cat):
+            m = CodeNeRF(87, 42, W=32, latent_dim=latent_dim)
+            m.apply(init_weights)
+            ps.append(flat_params(m).detach())
+        self.params = torch.stack(ps).to(dev).contiguous()
+        self.pe_B = torch.tensor(_DIRS, dtype=torch.float32).repeat(n_cat, 1, 1).to(dev).contiguous()
+        sc = torch.as_tensor(scale, dtype=torch.float32).reshape(-1)
+        self.pe_scale = (sc.repeat(n_cat) if sc.numel() == 1 else sc).to(dev).contiguous()
+        self.shape_codes = (torch.randn(n_cat, self.n_obj_max, latent_dim, generator=g) / math.sqrt(latent_dim / 2)).to(dev)
+        self.tex_codes = (torch.randn(n_cat, self.n_obj_max, latent_dim, generator=g) / math.sqrt(latent_dim / 2)).to(dev)
+        self.n_obj = torch.tensor(n_obj, dtype=torch.int32, device=dev)
+        # --- gradients / outputs
+        self.g_params = torch.zeros_like(self.params)
+        self.g_B = torch.zeros_like(self.pe_B)
+        self.g_shape = torch.zeros_like(self.shape_codes)
+        self.g_tex = torch.zeros_like(self.tex_codes)
+        self.out_loss = torch.zeros(4 + 5 * n_cat, device=dev)
+        self._ws = None
+        self._ws_key = None
+        self._opt_state = None
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------------------------------ state import
+    def load_category(self, k: int, fc_params: Sequence[torch.Tensor], B: torch.Tensor, shape_codes: torch.Tensor,
+                      tex_codes: torch.Tensor):
+        """Copy one category's reference-shaped tensors (28 params in named_parameters() order, B [21,3], code tables)."""
+        flat = torch.cat([p.reshape(-1) for p in fc_params]).to(self.device)
+        assert flat.numel() == self.n_param
+        self.params[k].copy_(flat)
+        self.pe_B[k].copy_(B.to(self.device))
+        n = shape_codes.shape[0]
+        self.shape_codes[k].zero_(); self.tex_codes[k].zero_()
+        self.shape_codes[k, :n].copy_(shape_codes.to(self.device))
+        self.tex_codes[k, :n].copy_(tex_codes.to(self.device))
+
+    def param_views(self, k: int) -> List[torch.Tensor]:
+        """The 28 nn.Linear-shaped views of category k's flat parameter buffer (and same for grads via grad_views)."""
+        return self._views(self.params[k])
+
+    def grad_views(self, k: int) -> List[torch.Tensor]:
+        return self._views(self.g_params[k])
+
+    def _views(self, flat):
+        W, L, E1, E2 = 32, self.L, 87, 42
+        shapes = [(W, E1), (W,), (W, L), (W,), (W, W), (W,), (W, L), (W,), (W, W), (W,), (W, W + E1), (W,), (W, L), (W,),
+                  (W, W), (W,), (1, W), (1,), (W, W + E2), (W,), (W, W), (W,), (W, L), (W,), (W // 2, W), (W // 2,),
+                  (3, W // 2), (3,)]
+        out, off = [], 0
+        for s in shapes:
+            n = 1
+            for d in s:
+                n *= d
+            out.append(flat[off:off + n].view(*s))
+            off += n
+        return out
+
+    # ------------------------------------------------------------------------------------------ one step
+    def _workspace(self, R: int):
+        key = (R,)
+        if self._ws_key != key:
+            lib = lib_for(self.params)
+            nbytes = lib.cnf_train_step_workspace_bytes(self.K, R, self.S, self.L, self.n_obj_max)
+            self._ws = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+            self._ws_key = key
+        return self._ws
+
+    def step_from_samples(self, origins, dirs, z, gt_depth, rgbs, mask_depth, indices, counts, add_reg: bool = True):
+        """Fused fwd+bwd given sampled depths z [K,R,S]. rgbs u8 [K,R,4] (rgb + label); mask_depth u8/bool [K,R];
+        indices int32 [K,R]; counts int32 [K,4]. Fills self.g_* and self.out_loss; returns the loss (0-d, async)."""
+        lib = lib_for(self.params)
+        K, R, S = z.shape
+        assert K == self.K and S == self.S
+        ws = self._workspace(R)
+        if indices.dtype != torch.int32:
+            indices = indices.to(torch.int32)
+        if mask_depth.dtype != torch.uint8:
+            mask_depth = mask_depth.to(torch.uint8)
+        check(lib.cnf_train_step(K, R, S, self.L, self.n_obj_max, ptr(self.params), ptr(self.pe_B), ptr(self.pe_scale),
+                                 ptr(self.shape_codes), ptr(self.tex_codes), ptr(self.n_obj), ptr(origins.contiguous()),
+                                 ptr(dirs.contiguous()), ptr(z.contiguous()), ptr(gt_depth.contiguous()),
+                                 ptr(rgbs.contiguous()), ptr(mask_depth.contiguous()), ptr(indices.contiguous()),
+                                 ptr(counts.contiguous()), float(self.cs), float(self.os), float(self.reg),
+                                 1 if add_reg else 0, ptr(self.g_params), ptr(self.g_B), ptr(self.g_shape), ptr(self.g_tex),
+                                 ptr(self.out_loss), ptr(ws), ws.numel(), stream()))
+        return self.out_loss[0]
+
+    def step(self, rgbs, depth, origins, dirs, indices, rand: Optional[Dict[str, torch.Tensor]] = None, add_reg=True):
+        """Sample + fused step for K categories: rgbs u8 [K,R,4], depth [K,R], origins/dirs [K,R,3], indices [K,R]."""
+        if rand is None:
+            rand = sampling.draw_randoms(rgbs, depth, self.N, self.M, self.eps, self.min_bound, self.this_obj)
+        z, _, valid, labels, stats = ops.sample_batched(rgbs, depth, origins, dirs, self.N, self.M, self.eps, self.stop_eps,
+                                                       rand, self.min_bound, self.this_obj, want_pcs=False)
+        counts = stats[:, 4:8].contiguous()
+        self.launches_per_step = 3 + 5
+        return self.step_from_samples(origins, dirs, z, depth, rgbs, valid.view(torch.uint8), indices, counts, add_reg)
+
+    def loss_terms(self) -> Dict[str, torch.Tensor]:
+        K = self.K
+        o = self.out_loss
+        return {"loss": o[0], "depth": o[4:4 + K], "color": o[4 + K:4 + 2 * K], "opacity": o[4 + 2 * K:4 + 3 * K],
+                "reg_shape": o[4 + 3 * K:4 + 4 * K], "reg_texture": o[4 + 4 * K:4 + 5 * K]}
+
+    # ------------------------------------------------------------------------------------------ optimizer
+    def adamw_step(self, lr=1e-3, weight_decay=0.013, code_lr=1e-3, code_weight_decay=0.013, betas=(0.9, 0.999), eps=1e-8):
+        """Fused AdamW over the flat buffers (train.py:40,54-64,183): MLP + PE with (lr, wd), codes with the code group."""
+        if self._opt_state is None:
+            z = torch.zeros_like
+            self._opt_state = {"t": 0, "m": [z(self.params), z(self.pe_B), z(self.shape_codes), z(self.tex_codes)],
+                               "v": [z(self.params), z(self.pe_B), z(self.shape_codes), z(self.tex_codes)]}
+        st = self._opt_state
+        st["t"] += 1
+        groups = [(self.params, self.g_params, lr, weight_decay), (self.pe_B, self.g_B, lr, weight_decay),
+                  (self.shape_codes, self.g_shape, code_lr, code_weight_decay),
+                  (self.tex_codes, self.g_tex, code_lr, code_weight_decay)]
+        for i, (p, g, l, wd) in enumerate(groups):
+            ops.adamw_step_(p, g, st["m"][i], st["v"][i], l, betas[0], betas[1], eps, wd, st["t"])

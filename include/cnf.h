@@ -170,6 +170,12 @@ int cnf_train_step(int n_cat, int n_rays, int S, int L, int n_obj_max,
                    float* g_params, float* g_B, float* g_shape, float* g_tex, float* out_loss,
                    void* ws, size_t ws_bytes, cnf_stream_t stream);
 
+/* Measurement hook: when both handles are non-NULL (cudaEvent_t created by the caller, e.g.
+ * torch.cuda.Event(enable_timing=True).cuda_event), the NEXT cnf_train_step call on this host thread records
+ * them on its stream immediately before / after the fused tcgen05 kernel (and only that kernel), then clears
+ * the hook.  Lets bench.py time the dominant kernel live without a profiler. */
+int cnf_set_kernel_events(void* ev_start, void* ev_stop);
+
 /* tcgen05 self-test: D[128,N] = A[128,K] * B[N,K]^T with bf16 operands staged in shared memory in the
  * canonical no-swizzle UMMA layout; mode 0: A,B K-major; 1: B MN-major (dgrad view); 2: A,B MN-major
  * (wgrad view).  Used by tests to pin the descriptor encodings on hardware. */

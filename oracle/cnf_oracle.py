@@ -207,7 +207,10 @@ def embed(x: torch.Tensor, B: torch.Tensor, scale, n_freq: int = 6) -> torch.Ten
     """UniDirsEmbed.forward: cat(x/scale, sin(pi * 2^f * (x/scale) B^T)), frequency-major."""
     scale_t = torch.as_tensor(scale, dtype=x.dtype)
     t = x / scale_t                                                        # :83
-    proj = t @ B.t()                                                       # :84
+    if B.dim() == 3:      # stacked [K,21,3] with x [K,...,3]: what vmap(pe_model) computes
+        proj = torch.matmul(t, B[(slice(None),) + (None,) * (x.dim() - 3)].transpose(-1, -2))
+    else:
+        proj = t @ B.t()                                                   # :84
     bands = 2.0 ** torch.linspace(0, n_freq - 1, n_freq, dtype=x.dtype)    # :78
     pb = proj[..., None, :] * bands[:, None]                               # :85
     xb = pb.reshape(list(proj.shape[:-1]) + [-1])                          # :86
@@ -218,6 +221,12 @@ def embed(x: torch.Tensor, B: torch.Tensor, scale, n_freq: int = 6) -> torch.Ten
 # MLPs  (src/model.py:56-84, 124-154)
 # --------------------------------------------------------------------------------------
 def _lin(x, w, b):
+    """y = x W^T + b.  With stacked parameters (w [K,out,in], b [K,out]) and x [K,...,in] this is the batched matmul
+    functorch.vmap turns nn.Linear into (train.py:154-155)."""
+    if w.dim() == 3:
+        exw = (slice(None),) + (None,) * (x.dim() - 3)
+        exb = (slice(None),) + (None,) * (x.dim() - 2)
+        return torch.matmul(x, w[exw].transpose(-1, -2)) + b[exb]
     return x @ w.transpose(-1, -2) + b
 
 
@@ -374,14 +383,10 @@ def train_step(fc_params: Sequence[torch.Tensor], pe_B: torch.Tensor, scale,
     B = pe_B.detach().clone().requires_grad_(want_grads)
     sc = [c.detach().clone().requires_grad_(want_grads) for c in shape_codes]
     tc = [c.detach().clone().requires_grad_(want_grads) for c in texture_codes]
-    alphas, colors = [], []
-    for k in range(K):
-        emb = embed(pcs[k], B[k], scale)                                   # train.py:154
-        sh = sc[k][indices[k]][:, None, :]                                 # train.py:136
-        tx = tc[k][indices[k]][:, None, :]                                 # train.py:137
-        a, c = codenerf_forward([p[k] for p in fc], emb, sh, tx)           # train.py:155
-        alphas.append(a); colors.append(c)
-    alpha = torch.stack(alphas); color = torch.stack(colors)
+    sh = torch.stack([sc[k][indices[k]][:, None, :] for k in range(K)])    # train.py:136,148
+    tx = torch.stack([tc[k][indices[k]][:, None, :] for k in range(K)])    # train.py:137,149
+    emb = embed(pcs, B, scale)                                             # train.py:154 (vmap over K)
+    alpha, color = codenerf_forward(fc, emb, sh, tx)                       # train.py:155 (vmap over K)
     gt_rgb = gt_rgb_u8.to(pcs.dtype) / 255.0                               # train.py:144
     loss, ld, lcol = step_loss(alpha, color, gt_depth, gt_rgb, labels, mask_depth, z)  # train.py:158-162
     rs, rt = reg_loss(list(zip(sc, tc)))                                   # train.py:166

@@ -116,14 +116,15 @@ def golden_embed(out):
 def make_batch(K, n_obj, R, N, M, seed, inv=0.15, mix=(0.6, 0.3, 0.1)):
     g = torch.Generator().manual_seed(seed)
     sc = bare_scene(N, M)
-    pcs, zs, gd, grgb, dm, om, idxs = [], [], [], [], [], [], []
+    pcs, zs, gd, grgb, dm, om, idxs, orgs, drs = [], [], [], [], [], [], [], [], []
     for k in range(K):
         rgbs, depth, origins, dirs, idx = O.synth_rays(R, n_obj, g, invalid_frac=inv, label_mix=mix)
         torch.manual_seed(seed * 31 + k)
         rgb, d, valid, labels, pc, z = sc.sample_3d_points(rgbs, depth, origins, dirs)
         pcs.append(pc); zs.append(z); gd.append(d); grgb.append(rgb); dm.append(valid); om.append(labels)
-        idxs.append(idx)
+        idxs.append(idx); orgs.append(origins); drs.append(dirs)
     st = torch.stack
+    make_batch.last_rays = (st(orgs), st(drs))
     return st(pcs), st(zs), st(gd), st(grgb), st(dm), st(om), st(idxs)
 
 
@@ -181,7 +182,8 @@ def golden_train_step(out):
             out[p + "gsc%d" % k] = npy(scs[k].grad); out[p + "gtc%d" % k] = npy(tcs[k].grad)
         for kk, v in dict(pcs=pcs, z=z, gt_depth=gd, gt_rgb=grgb, mask_depth=dm, labels=om, indices=idx,
                           alpha=alpha, color=color, loss=loss, depth=ld["depth"], colorl=ld["color"],
-                          opacity=ld["opacity"], reg_shape=rs, reg_texture=rt).items():
+                          opacity=ld["opacity"], reg_shape=rs, reg_texture=rt, origins=make_batch.last_rays[0],
+                          dirs=make_batch.last_rays[1]).items():
             out[p + kk] = npy(v)
     names = [n for n, _ in fcs[0].named_parameters()]
     out["step/param_names"] = np.array(names)

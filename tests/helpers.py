@@ -34,7 +34,7 @@ def step_case(name):
     d["gsc"] = [gt("step", p + "gsc%d" % k) for k in range(K)]
     d["gtc"] = [gt("step", p + "gtc%d" % k) for k in range(K)]
     for kk in ["pcs", "z", "gt_depth", "gt_rgb", "mask_depth", "labels", "indices", "alpha", "color", "loss",
-               "depth", "colorl", "opacity", "reg_shape", "reg_texture"]:
+               "depth", "colorl", "opacity", "reg_shape", "reg_texture", "origins", "dirs"]:
         d[kk] = gt("step", p + kk)
     return d
 
