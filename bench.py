@@ -165,6 +165,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-large", action="store_true", help="skip the extra large-batch (c4) roofline measurement")
     ap.add_argument("--with-optimizer", action="store_true", help="include the fused AdamW update in the timed step")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
@@ -217,9 +218,10 @@ def main():
             t.adamw_step()
         return loss
 
-    def timed(t, b, steps, warm):
+    def timed(t, b, steps, warm, graphed=False):
+        replay = t.capture(b["rgbs"], b["depth"], b["origins"], b["dirs"], b["indices"]) if graphed else None
         for _ in range(warm):
-            run_step(t, b)
+            replay() if graphed else run_step(t, b)
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
@@ -232,7 +234,10 @@ def main():
         for i in range(steps):
             flush.zero_()                          # L2 flush between timed iterations (outside the events)
             ev[i][0].record()
-            run_step(t, b, kev[i])
+            if graphed:
+                replay()
+            else:
+                run_step(t, b, kev[i])
             ev[i][1].record()
         torch.cuda.synchronize()
         if dist is not None:
@@ -245,7 +250,11 @@ def main():
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    step_ms, kern_ms = timed(tr, batch, args.steps, warmup)
+    use_graph = not args.no_graph and not args.with_optimizer
+    # pass 1 (eager launches): times the fused kernel alone via events recorded around it inside cnf_train_step
+    eager_ms, kern_ms = timed(tr, batch, args.steps, warmup)
+    # pass 2: the step as a user runs it in a training loop -- one CUDA-graph replay per step
+    step_ms = timed(tr, batch, args.steps, warmup, graphed=True)[0] if use_graph else eager_ms
     clk = clocks.stop() if rank == 0 else None
     loss_val = float(tr.out_loss[0])
 
@@ -255,10 +264,17 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in hb.values())
     d2h = out_host.numel() * 4
 
+    sb = {k: v.to(dev) for k, v in hb.items()}                             # static device staging buffers
+    e2e_replay = tr.capture(sb["rgbs"], sb["depth"], sb["origins"], sb["dirs"], sb["indices"]) if use_graph else None
+
     def e2e_step():
-        db = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
-        run_step(tr, db)
-        out_host.copy_(tr.out_loss, non_blocking=True)
+        for k_, v in hb.items():
+            sb[k_].copy_(v, non_blocking=True)                              # H2D from pinned host memory
+        if use_graph:
+            e2e_replay()
+        else:
+            run_step(tr, sb)
+        out_host.copy_(tr.out_loss, non_blocking=True)                      # D2H of the loss terms
         torch.cuda.current_stream().synchronize()
 
     for _ in range(warmup):
@@ -333,7 +349,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload, "desc": wl["desc"], "categories_per_gpu": K, "rays_per_category": R,
                        "samples_per_ray": S, "latent_dim": wl["L"], "l2": "flushed between timed steps (256 MB write)",
-                       "optimizer_in_step": bool(args.with_optimizer), "parallelism": "categories sharded, %d per GPU" % K},
+                       "optimizer_in_step": bool(args.with_optimizer), "cuda_graph": bool(use_graph),
+                       "eager_ms_per_step": eager_ms, "parallelism": "categories sharded, %d per GPU" % K},
             "clocks": clk, "roofline": roof, "cpu_baseline": cb,
             "e2e": {"value": rays_per_step / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -117,8 +117,29 @@ __device__ __forceinline__ void put_bf16(uint8_t* img, int r, int c, int cols, f
 
 // ---------------------------------------------------------------------------------------------------------
 // prep: per category -> {bf16 weight images, fp32 constants, per-instance biases} + latent activations z
-// grid = K, block = 256
+// grid = (K, 5), block = 256.  y = 0: weight images (one 16-byte core-matrix row per thread-iteration, coalesced)
+// + constants; y = 1..4: latent slot s = y-1 (zsl1, zcl, zsl2, ztl): z = relu(W_lat code + b) for the category's
+// instances (warp per output, coalesced rows), then the per-instance bias c = W_cons[:, :32] z + b_cons.
 // ---------------------------------------------------------------------------------------------------------
+struct ImgSrc { int w, b, ld, nrow, ncol, brow_col; };   // source weight idx, bias idx (or -1), source ld, valid rows/cols, bias column
+
+__device__ __forceinline__ float w_img_value(const float* __restrict__ P, const PLay& lay, int img, int r, int c) {
+  // value of element (r, c) of weight image `img` (0..7 = W1..W8), zero outside the valid region
+  switch (img) {
+    case 0: return r < 32 ? (c < 87 ? P[lay.o[0] + r * 87 + c] : (c == 87 ? P[lay.o[1] + r] : 0.f)) : 0.f;
+    case 1: return P[lay.o[4] + r * 32 + c];
+    case 2: return c < 119 ? P[lay.o[10] + r * 119 + c] : 0.f;
+    case 3: return P[lay.o[8] + r * 32 + c];
+    case 4: return P[lay.o[14] + r * 32 + c];
+    case 5:
+      if (r < 32) return c < 74 ? P[lay.o[18] + r * 74 + c] : (c == 74 ? P[lay.o[19] + r] : 0.f);
+      if (r == 32) return c < 32 ? P[lay.o[16] + c] : (c == 74 ? P[lay.o[17]] : 0.f);
+      return 0.f;
+    case 6: return P[lay.o[20] + r * 32 + c];
+    default: return P[lay.o[24] + r * 32 + c];
+  }
+}
+
 __global__ void __launch_bounds__(256)
 fused_prep_kernel(int L, int n_obj_max, const float* __restrict__ params, const float* __restrict__ pe_B,
                   const float* __restrict__ pe_scale, const float* __restrict__ shape_codes,
@@ -131,60 +152,76 @@ fused_prep_kernel(int L, int n_obj_max, const float* __restrict__ params, const 
   float* fc = reinterpret_cast<float*>(img + WBLOB_BYTES);
   float* ctab = fc + FC_FLOATS;
   float* z = zlat + (size_t)k * 4 * MAXOBJ * NL;      // [4][MAXOBJ][32]: zsl1, zcl, zsl2, ztl
-  const int n_obj = n_obj_arr[k];
-  // zero the weight blob (padding must be exactly zero)
-  for (int i = tid; i < WBLOB_BYTES / 4; i += 256) reinterpret_cast<uint32_t*>(img)[i] = 0u;
-  __syncthreads();
-  // weight images
-  for (int i = tid; i < 32 * 87; i += 256) { const int n = i / 87, c = i % 87; put_bf16(img + OFF_W1, n, c, W1_C, P[lay.o[0] + i]); }
-  for (int n = tid; n < 32; n += 256) put_bf16(img + OFF_W1, n, 87, W1_C, P[lay.o[1] + n]);        // bias column
-  for (int i = tid; i < 32 * 32; i += 256) {
-    const int n = i / 32, c = i % 32;
-    put_bf16(img + OFF_W2, n, c, W2_C, P[lay.o[4] + i]);
-    put_bf16(img + OFF_W4, n, c, W4_C, P[lay.o[8] + i]);
-    put_bf16(img + OFF_W5, n, c, W5_C, P[lay.o[14] + i]);
-    put_bf16(img + OFF_W7, n, c, W7_C, P[lay.o[20] + i]);
-  }
-  for (int i = tid; i < 32 * 119; i += 256) { const int n = i / 119, c = i % 119; put_bf16(img + OFF_W3, n, c, W3_C, P[lay.o[10] + i]); }
-  for (int i = tid; i < 32 * 74; i += 256) { const int n = i / 74, c = i % 74; put_bf16(img + OFF_W6, n, c, W6_C, P[lay.o[18] + i]); }
-  for (int n = tid; n < 32; n += 256) {
-    put_bf16(img + OFF_W6, n, 74, W6_C, P[lay.o[19] + n]);        // b_vd via ones column (xc col 42)
-    put_bf16(img + OFF_W6, 32, n, W6_C, P[lay.o[16] + n]);        // sigma head row
-  }
-  if (tid == 0) put_bf16(img + OFF_W6, 32, 74, W6_C, P[lay.o[17]]);   // b_sigma
-  for (int i = tid; i < 16 * 32; i += 256) { const int n = i / 32, c = i % 32; put_bf16(img + OFF_W8, n, c, W8_C, P[lay.o[24] + i]); }
-  // fp32 constants
-  for (int i = tid; i < 32; i += 256) fc[FC_B5 + i] = P[lay.o[15] + i];
-  for (int i = tid; i < 16; i += 256) fc[FC_B8 + i] = P[lay.o[25] + i];
-  for (int i = tid; i < 48; i += 256) fc[FC_W9 + i] = P[lay.o[26] + i];
-  for (int i = tid; i < 4; i += 256) fc[FC_B9 + i] = i < 3 ? P[lay.o[27] + i] : 0.f;
-  for (int i = tid; i < 64; i += 256) fc[FC_PEB + i] = i < 63 ? pe_B[(size_t)k * 63 + i] : 0.f;
-  if (tid == 0) { fc[FC_SCALE] = 1.0f / pe_scale[k]; fc[FC_SCALE + 1] = 0.f; fc[FC_SCALE + 2] = 0.f; fc[FC_SCALE + 3] = 0.f; }
-  // latent projections z = relu(W_lat code + b_lat): (slot, weight idx, codes)
-  const int lat_w[4] = {2, 12, 6, 22};
-  for (int i = tid; i < 4 * MAXOBJ * NL; i += 256) {
-    const int s = i / (MAXOBJ * NL), inst = (i / NL) % MAXOBJ, n = i % NL;
-    float v = 0.f;
-    if (inst < n_obj) {
-      const float* code = (s == 3 ? tex_codes : shape_codes) + ((size_t)k * n_obj_max + inst) * L;
-      const float* w = P + lay.o[lat_w[s]] + (size_t)n * L;
-      float acc = P[lay.o[lat_w[s] + 1] + n];
-      for (int j = 0; j < L; ++j) acc = fmaf(w[j], code[j], acc);
-      v = fmaxf(acc, 0.f);
+  const int n_obj = min(n_obj_arr[k], MAXOBJ);
+  if (blockIdx.y == 0) {
+    const int offs[9] = {OFF_W1, OFF_W2, OFF_W3, OFF_W4, OFF_W5, OFF_W6, OFF_W7, OFF_W8, WBLOB_BYTES};
+    const int colsv[8] = {W1_C, W2_C, W3_C, W4_C, W5_C, W6_C, W7_C, W8_C};
+    for (int q = tid; q < WBLOB_BYTES / 16; q += 256) {
+      int im = 0;
+      while (q * 16 >= offs[im + 1]) ++im;
+      const int cols = colsv[im];
+      const int ql = q - offs[im] / 16;                  // chunk inside the image: rg*cols + cb*8 + r8
+      const int rg = ql / cols, rem = ql - rg * cols, cb = rem >> 3, r8 = rem & 7;
+      const int r = rg * 8 + r8, c0 = cb * 8;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = w_img_value(P, lay, im, r, c0 + e);
+      uint4 o;
+      __nv_bfloat162 h;
+      h = __floats2bfloat162_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2bfloat162_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2bfloat162_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2bfloat162_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+      reinterpret_cast<uint4*>(img)[q] = o;
     }
-    z[i] = v;
+    for (int i = tid; i < FC_FLOATS; i += 256) {
+      float v = 0.f;
+      if (i < FC_B8) v = P[lay.o[15] + i];
+      else if (i < FC_W9) v = P[lay.o[25] + (i - FC_B8)];
+      else if (i < FC_B9) v = P[lay.o[26] + (i - FC_W9)];
+      else if (i < FC_B9 + 3) v = P[lay.o[27] + (i - FC_B9)];
+      else if (i >= FC_PEB && i < FC_PEB + 63) v = pe_B[(size_t)k * 63 + (i - FC_PEB)];
+      else if (i == FC_SCALE) v = 1.0f / pe_scale[k];
+      fc[i] = v;
+    }
+    return;
   }
-  __syncthreads();
-  // per-instance biases c = W_cons[:, :32] z + b_cons: consumers s1(4,5) cat(10,11; ld 119) s2(8,9) t1(20,21)
+  const int s = blockIdx.y - 1;
+  const int lat_w[4] = {2, 12, 6, 22};
   const int cons_w[4] = {4, 10, 8, 20};
   const int cons_ld[4] = {32, 119, 32, 32};
-  for (int i = tid; i < 4 * MAXOBJ * NL; i += 256) {
-    const int s = i / (MAXOBJ * NL), inst = (i / NL) % MAXOBJ, n = i % NL;
-    const float* w = P + lay.o[cons_w[s]] + (size_t)n * cons_ld[s];
-    const float* zz = z + (s * MAXOBJ + inst) * NL;
+  __shared__ float s_z[MAXOBJ * NL];
+  const int warp = tid >> 5, lane = tid & 31;
+  const float* codes = (s == 3 ? tex_codes : shape_codes) + (size_t)k * n_obj_max * L;
+  for (int o = warp; o < MAXOBJ * NL; o += 8) {          // warp per (inst, n): coalesced dot product over L
+    const int inst = o / NL, n = o % NL;
+    float v = 0.f;
+    if (inst < n_obj) {
+      const float* w = P + lay.o[lat_w[s]] + (size_t)n * L;
+      const float* code = codes + (size_t)inst * L;
+      float acc = 0.f;
+      for (int j = lane; j < L; j += 32) acc = fmaf(w[j], code[j], acc);
+      acc = warp_sum(acc);
+      v = fmaxf(acc + P[lay.o[lat_w[s] + 1] + n], 0.f);
+    } else if (inst > n_obj) {                            // nothing beyond: zero-fill cheaply below
+      break;
+    }
+    if (lane == 0) s_z[o] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < MAXOBJ * NL; i += 256) {
+    const int inst = i / NL, n = i % NL;
+    const float zv = inst <= n_obj && inst < MAXOBJ ? s_z[i] : 0.f;
+    z[s * MAXOBJ * NL + i] = inst < n_obj ? zv : 0.f;
+    // per-instance bias; instances beyond n_obj get the plain bias (z = 0)
     float acc = P[lay.o[cons_w[s] + 1] + n];
-    for (int j = 0; j < NL; ++j) acc = fmaf(w[j], zz[j], acc);
-    ctab[i] = acc;
+    if (inst < n_obj) {
+      const float* w = P + lay.o[cons_w[s]] + (size_t)n * cons_ld[s];
+      const float* zz = s_z + inst * NL;
+#pragma unroll 8
+      for (int j = 0; j < NL; ++j) acc = fmaf(w[j], zz[j], acc);
+    }
+    ctab[s * MAXOBJ * NL + i] = acc;
   }
 }
 
@@ -262,7 +299,7 @@ fused_step_kernel(int K, int R, int S, const uint8_t* __restrict__ prep,
                   const int32_t* __restrict__ counts, float cs, float os,
                   float* __restrict__ raw, float* __restrict__ dp_scratch) {
   extern __shared__ __align__(1024) uint8_t sm[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;      // bar: per-stage commit; bar2: end-of-tile commit covering the trailing weight-gradient MMAs
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_red[4][24];
 
@@ -280,7 +317,7 @@ fused_step_kernel(int K, int R, int S, const uint8_t* __restrict__ prep,
     uint4* t0 = reinterpret_cast<uint4*>(sm + SM_R2XG);
     for (int i = tid; i < (SM_TOTAL - SM_R2XG) / 16; i += 128) t0[i] = zero;
   }
-  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   fence_async_smem();
   tc_fence_before();
@@ -289,6 +326,7 @@ fused_step_kernel(int K, int R, int S, const uint8_t* __restrict__ prep,
   const uint32_t tmem = tmem_base_s;
   const uint32_t tl = tmem_lane_base(tmem);
   const Issue mma{tmem};
+  uint32_t phase2 = 0;
   const uint32_t sbase = smem_u32(sm);
   const float* fcs = reinterpret_cast<const float*>(sm + SM_FC);
   const float* ctab = reinterpret_cast<const float*>(sm + SM_CTAB);
@@ -315,6 +353,7 @@ fused_step_kernel(int K, int R, int S, const uint8_t* __restrict__ prep,
   const int row = tid;
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (!first) { mbar_wait(&bar2, phase2); phase2 ^= 1; tc_fence_after(); }   // previous tile's weight-gradient MMAs have read their tiles
     // ------------------------------------------------------------------ ray / point data
     const int ray = tile * RPT + warp * rpw + seg;
     const bool act = lane_used && ray < R;
@@ -326,7 +365,7 @@ fused_step_kernel(int K, int R, int S, const uint8_t* __restrict__ prep,
       const float inv_scale = fcs[FC_SCALE];
 #pragma unroll
       for (int a = 0; a < 3; ++a) t[a] = __fadd_rn(origins[gr * 3 + a], __fmul_rn(dirs[gr * 3 + a], pz)) * inv_scale;
-      inst = inst_idx[gr];
+      inst = min(max(inst_idx[gr], 0), MAXOBJ - 1);      // never index outside the per-instance tables on bad input
     }
     // ------------------------------------------------------------------ embedding -> xg (R2XG cols 32..127), xc (Y5XC cols 32..79)
     {
@@ -571,10 +610,11 @@ fused_step_kernel(int K, int R, int S, const uint8_t* __restrict__ prep,
     // ------------------------------------------------------------------ B8: wgrad(W8, W9) ; d h2 = G8 W8
     if (tid == 0) {
       tc_fence_after();
-      mma.wgrad(TM_WG89, sbase + SM_H2Z3, 80, sbase + SM_GX, 16, 16, accf);                                 // rows 0..31: dW8^T
-      mma.wgrad(TM_WG89, sbase + SM_H2Z3 + 4 * 128, 80, sbase + SM_GX + TP * 16 * 2, 16, 16, true);        // rows 32..47: dW9^T
       mma.dgrad(TM_ACC, sbase + SM_GX, 16, 16, sbase + SM_W + OFF_W8, W8_C, 32, false);
       mma_commit(&bar);
+      // weight-gradient MMAs trail the commit: they run on the tensor pipe while the warps do the epilogue below
+      mma.wgrad(TM_WG89, sbase + SM_H2Z3, 80, sbase + SM_GX, 16, 16, accf);                                 // rows 0..31: dW8^T
+      mma.wgrad(TM_WG89, sbase + SM_H2Z3 + 4 * 128, 80, sbase + SM_GX + TP * 16 * 2, 16, 16, true);        // rows 32..47: dW9^T
     }
     wait_mma();
     tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
@@ -585,10 +625,10 @@ fused_step_kernel(int K, int R, int S, const uint8_t* __restrict__ prep,
     // ------------------------------------------------------------------ B7: wgrad(W7, c7) ; d h1 = G7 W7 -> G6 (+ sigma col)
     if (tid == 0) {
       tc_fence_after();
-      mma.wgrad(TM_WG7, sbase + SM_H1, 32, sbase + SM_GY, 32, 32, accf);
-      mma.wgrad(TM_OH7, sbase + SM_OH, 64, sbase + SM_GY, 32, 32, accf);
       mma.dgrad(TM_ACC, sbase + SM_GY, 32, 32, sbase + SM_W + OFF_W7, W7_C, 32, false);
       mma_commit(&bar);
+      mma.wgrad(TM_WG7, sbase + SM_H1, 32, sbase + SM_GY, 32, 32, accf);
+      mma.wgrad(TM_OH7, sbase + SM_OH, 64, sbase + SM_GY, 32, 32, accf);
     }
     wait_mma();
     tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
@@ -601,29 +641,31 @@ fused_step_kernel(int K, int R, int S, const uint8_t* __restrict__ prep,
     // ------------------------------------------------------------------ B6: wgrad(W6+sigma) ; [d y5 | d xc] = G6 W6
     if (tid == 0) {
       tc_fence_after();
-      mma.wgrad(TM_WG6, sbase + SM_Y5XC, 80, sbase + SM_GX, 48, 48, accf);
       mma.dgrad(TM_ACC, sbase + SM_GX, 48, 48, sbase + SM_W + OFF_W6, W6_C, 80, false);
       mma_commit(&bar);
+      mma.wgrad(TM_WG6, sbase + SM_Y5XC, 80, sbase + SM_GX, 48, 48, accf);
     }
     wait_mma();
     tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
     store_row32(sm + SM_GY, row, 32, 0, acc);                               // G5 = d y5 (linear layer: no mask)
     tmem_ld32(tl + TM_ACC + 32, acc_u); tmem_ld_wait();                     // d xc cols 0..31
-    store_row32(sm + SM_Y5XC, row, 80, 4, acc);                             // park d xc (bf16) over the dead xc tile
+    // park d xc (bf16) in the dead h2/h3 tile: its readers (stage B8's MMAs) completed before stage B7's commit fired.
+    // cols 0..31 -> d xc[0..31], cols 64..79 -> d xc[32..47]; the zero block (cols 32..63) stays untouched.
+    store_row32(sm + SM_H2Z3, row, 80, 0, acc);
     {
       uint32_t x_u[16];
       tmem_ld16(tl + TM_ACC + 64, x_u); tmem_ld_wait();
       const float* x = reinterpret_cast<const float*>(x_u);
-      st16(rowblk(sm + SM_Y5XC, row, 8, 80), pack2(x[0], x[1]), pack2(x[2], x[3]), pack2(x[4], x[5]), pack2(x[6], x[7]));
-      st16(rowblk(sm + SM_Y5XC, row, 9, 80), pack2(x[8], x[9]), pack2(x[10], x[11]), pack2(x[12], x[13]), pack2(x[14], x[15]));
+      st16(rowblk(sm + SM_H2Z3, row, 8, 80), pack2(x[0], x[1]), pack2(x[2], x[3]), pack2(x[4], x[5]), pack2(x[6], x[7]));
+      st16(rowblk(sm + SM_H2Z3, row, 9, 80), pack2(x[8], x[9]), pack2(x[10], x[11]), pack2(x[12], x[13]), pack2(x[14], x[15]));
     }
     publish();
     // ------------------------------------------------------------------ B5: wgrad(W5) ; d r4 = G5 W5
     if (tid == 0) {
       tc_fence_after();
-      mma.wgrad(TM_WG5, sbase + SM_R4, 32, sbase + SM_GY, 32, 32, accf);
       mma.dgrad(TM_ACC, sbase + SM_GY, 32, 32, sbase + SM_W + OFF_W5, W5_C, 32, false);
       mma_commit(&bar);
+      mma.wgrad(TM_WG5, sbase + SM_R4, 32, sbase + SM_GY, 32, 32, accf);
     }
     wait_mma();
     tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
@@ -634,10 +676,10 @@ fused_step_kernel(int K, int R, int S, const uint8_t* __restrict__ prep,
     // ------------------------------------------------------------------ B4: wgrad(W4, c4) ; d r3 = G4 W4
     if (tid == 0) {
       tc_fence_after();
-      mma.wgrad(TM_WG4, sbase + SM_R3, 32, sbase + SM_GX, 32, 32, accf);
-      mma.wgrad(TM_OH4, sbase + SM_OH, 64, sbase + SM_GX, 32, 32, accf);
       mma.dgrad(TM_ACC, sbase + SM_GX, 32, 32, sbase + SM_W + OFF_W4, W4_C, 32, false);
       mma_commit(&bar);
+      mma.wgrad(TM_WG4, sbase + SM_R3, 32, sbase + SM_GX, 32, 32, accf);
+      mma.wgrad(TM_OH4, sbase + SM_OH, 64, sbase + SM_GX, 32, 32, accf);
     }
     wait_mma();
     tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
@@ -648,10 +690,10 @@ fused_step_kernel(int K, int R, int S, const uint8_t* __restrict__ prep,
     // ------------------------------------------------------------------ B3: wgrad(W3, c3) ; [d r2 | d xg] = G3 W3
     if (tid == 0) {
       tc_fence_after();
-      mma.wgrad(TM_WG3, sbase + SM_R2XG, 128, sbase + SM_GY, 32, 32, accf);
-      mma.wgrad(TM_OH3, sbase + SM_OH, 64, sbase + SM_GY, 32, 32, accf);
       mma.dgrad(TM_ACC, sbase + SM_GY, 32, 32, sbase + SM_W + OFF_W3, W3_C, 128, false);   // cols 0..31 d r2, 32..127 d xg
       mma_commit(&bar);
+      mma.wgrad(TM_WG3, sbase + SM_R2XG, 128, sbase + SM_GY, 32, 32, accf);
+      mma.wgrad(TM_OH3, sbase + SM_OH, 64, sbase + SM_GY, 32, 32, accf);
     }
     wait_mma();
     tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
@@ -662,10 +704,10 @@ fused_step_kernel(int K, int R, int S, const uint8_t* __restrict__ prep,
     // ------------------------------------------------------------------ B2: wgrad(W2, c2) ; d r1 = G2 W2
     if (tid == 0) {
       tc_fence_after();
-      mma.wgrad(TM_WG2, sbase + SM_R1, 32, sbase + SM_GX, 32, 32, accf);
-      mma.wgrad(TM_OH2, sbase + SM_OH, 64, sbase + SM_GX, 32, 32, accf);
       mma.dgrad(TM_ACC, sbase + SM_GX, 32, 32, sbase + SM_W + OFF_W2, W2_C, 32, false);
       mma_commit(&bar);
+      mma.wgrad(TM_WG2, sbase + SM_R1, 32, sbase + SM_GX, 32, 32, accf);
+      mma.wgrad(TM_OH2, sbase + SM_OH, 64, sbase + SM_GX, 32, 32, accf);
     }
     wait_mma();
     tmem_ld32(tl + TM_ACC, acc_u); tmem_ld_wait();
@@ -676,9 +718,10 @@ fused_step_kernel(int K, int R, int S, const uint8_t* __restrict__ prep,
     // ------------------------------------------------------------------ B1: wgrad(W1) ; d xg += G1 W1
     if (tid == 0) {
       tc_fence_after();
-      mma.wgrad(TM_WG1, sbase + SM_R2XG + 4 * 128, 128, sbase + SM_GY, 32, 32, accf);
       mma.dgrad(TM_ACC + 32, sbase + SM_GY, 32, 32, sbase + SM_W + OFF_W1, W1_C, 96, true);
       mma_commit(&bar);
+      mma.wgrad(TM_WG1, sbase + SM_R2XG + 4 * 128, 128, sbase + SM_GY, 32, 32, accf);
+      mma_commit(&bar2);                        // everything of this tile (incl. all trailing weight-gradient MMAs) done
     }
     wait_mma();
     // ------------------------------------------------------------------ embedding backward: dL/dproj_d -> scratch
@@ -702,7 +745,7 @@ fused_step_kernel(int K, int R, int S, const uint8_t* __restrict__ prep,
       }
 #pragma unroll
       for (int cb = 0; cb < 6; ++cb) {
-        const uint4 q = *reinterpret_cast<const uint4*>(rowblk(sm + SM_Y5XC, row, 4 + cb, 80));
+        const uint4 q = *reinterpret_cast<const uint4*>(rowblk(sm + SM_H2Z3, row, cb < 4 ? cb : cb + 4, 80));
         const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -733,21 +776,28 @@ fused_step_kernel(int K, int R, int S, const uint8_t* __restrict__ prep,
   // ---- flush: TMEM accumulators -> raw[k] (fp32 atomics; several CTAs share a category)
   float* rk = raw + (size_t)k * RAW_FLOATS;
   if (!first) {
+    mbar_wait(&bar2, phase2);
     tc_fence_after();
     auto flush32 = [&](int col, int roff, int rows, int ld, int c0) {
       uint32_t u[32];
       tmem_ld32(tl + col + c0, u); tmem_ld_wait();
       if (row < rows) {
+        float4* dst = reinterpret_cast<float4*>(rk + roff + row * ld + c0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(rk + roff + row * ld + c0 + j, __uint_as_float(u[j]));
+        for (int j = 0; j < 8; ++j)
+          atomicAdd(dst + j, make_float4(__uint_as_float(u[4 * j]), __uint_as_float(u[4 * j + 1]), __uint_as_float(u[4 * j + 2]),
+                                         __uint_as_float(u[4 * j + 3])));
       }
     };
     auto flush16 = [&](int col, int roff, int rows, int ld, int c0) {
       uint32_t u[16];
       tmem_ld16(tl + col + c0, u); tmem_ld_wait();
       if (row < rows) {
+        float4* dst = reinterpret_cast<float4*>(rk + roff + row * ld + c0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(rk + roff + row * ld + c0 + j, __uint_as_float(u[j]));
+        for (int j = 0; j < 4; ++j)
+          atomicAdd(dst + j, make_float4(__uint_as_float(u[4 * j]), __uint_as_float(u[4 * j + 1]), __uint_as_float(u[4 * j + 2]),
+                                         __uint_as_float(u[4 * j + 3])));
       }
     };
     flush32(TM_WG1, RW1, 96, 32, 0);
@@ -826,98 +876,103 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
                       const int32_t* __restrict__ n_obj_arr, const float* __restrict__ raw, const float* __restrict__ zlat,
                       float reg_scaling, int add_reg, float* __restrict__ g_params, float* __restrict__ g_B,
                       float* __restrict__ g_shape, float* __restrict__ g_tex, float* __restrict__ reg_out) {
+  // grid = (K, FIN_PARTS): every CTA recomputes the small per-instance terms, then takes a slice of the outputs
   const int k = blockIdx.x, tid = threadIdx.x;
+  const int gtid = blockIdx.y * 256 + tid, gstride = 256 * gridDim.y;
   const PLay lay(L);
   const float* P = params + (size_t)k * lay.total;
   float* G = g_params + (size_t)k * lay.total;
   const float* rk = raw + (size_t)k * RAW_FLOATS;
   const float* z = zlat + (size_t)k * 4 * MAXOBJ * NL;
-  const int n_obj = n_obj_arr[k];
+  const int n_obj = min(n_obj_arr[k], MAXOBJ);
   __shared__ float s_dpre[4][MAXOBJ][NL];      // relu-masked gradient wrt the latent pre-activations
-  // g_B: the fused kernel differentiated w.r.t. proj of t = x * (1/scale): already the gradient w.r.t. B. nothing to scale.
-  (void)pe_scale; (void)g_B;
-
-  // --- plain layers
-  for (int i = tid; i < 32 * 87; i += 256) { const int n = i / 87, c = i % 87; G[lay.o[0] + i] = rk[RW1 + c * 32 + n]; }
-  for (int n = tid; n < 32; n += 256) G[lay.o[1] + n] = rk[RW1 + 87 * 32 + n];
-  for (int i = tid; i < 32 * 32; i += 256) { const int n = i / 32, c = i % 32; G[lay.o[14] + i] = rk[RW5 + c * 32 + n]; }
-  for (int i = tid; i < 32 * 74; i += 256) { const int n = i / 74, c = i % 74; G[lay.o[18] + i] = rk[RW6 + c * 48 + n]; }
-  for (int n = tid; n < 32; n += 256) {
-    G[lay.o[19] + n] = rk[RW6 + 74 * 48 + n];              // b_vd
-    G[lay.o[16] + n] = rk[RW6 + n * 48 + 32];              // w_sigma
-  }
-  if (tid == 0) G[lay.o[17]] = rk[RW6 + 74 * 48 + 32];     // b_sigma
-  // b_es: y5 feeds only linear consumers -> d b5[n] = sum_m db_vd[m] Wvd[m][n] + db_sigma * wsig[n]
-  for (int n = tid; n < 32; n += 256) {
-    float a = rk[RW6 + 74 * 48 + 32] * P[lay.o[16] + n];
-    for (int m = 0; m < 32; ++m) a = fmaf(rk[RW6 + 74 * 48 + m], P[lay.o[18] + (size_t)m * 74 + n], a);
-    G[lay.o[15] + n] = a;
-  }
-  for (int i = tid; i < 16 * 32; i += 256) { const int n = i / 32, c = i % 32; G[lay.o[24] + i] = rk[RW89 + c * 16 + n]; }
-  for (int n = tid; n < 16; n += 256) G[lay.o[25] + n] = rk[RDB8 + n];
-  for (int i = tid; i < 3 * 16; i += 256) { const int j = i / 16, c = i % 16; G[lay.o[26] + i] = rk[RW89 + (32 + c) * 16 + j]; }
-  for (int j = tid; j < 3; j += 256) G[lay.o[27] + j] = rk[RDB9 + j];
-  // --- layers with per-instance bias c = W[:, :32] z + b : slots (zsl1->s1), (zcl->cat), (zsl2->s2), (ztl->t1)
+  __shared__ float s_norm[2][MAXOBJ];
+  (void)pe_scale; (void)g_B;                   // g_B is produced by fused_pe_grad_kernel (t = x/scale already applied)
   const int cons_w[4] = {4, 10, 8, 20};
   const int cons_ld[4] = {32, 119, 32, 32};
   const int rw[4] = {RW2, RW3, RW4, RW7};
   const int roh[4] = {ROH2, ROH3, ROH4, ROH7};
   const int lat_w[4] = {2, 12, 6, 22};
+  const int warp = tid >> 5, lane = tid & 31;
+
+  // --- per-instance terms: d z[inst][c] = sum_n dC[inst][n] W_cons[n][c], masked by relu(z) ; code norms
+  for (int i = tid; i < 4 * n_obj * NL; i += 256) {
+    const int s = i / (n_obj * NL), inst = (i / NL) % n_obj, c = i % NL;
+    float a = 0.f;
+    if (z[(s * MAXOBJ + inst) * NL + c] > 0.f) {
+      const int ld = cons_ld[s];
+#pragma unroll 8
+      for (int n = 0; n < 32; ++n) a = fmaf(rk[roh[s] + inst * 32 + n], P[lay.o[cons_w[s]] + (size_t)n * ld + c], a);
+    }
+    s_dpre[s][inst][c] = a;
+  }
+  for (int o = warp; o < 2 * n_obj; o += 8) {
+    const int which = o / n_obj, inst = o % n_obj;
+    const float* code = (which ? tex_codes : shape_codes) + ((size_t)k * n_obj_max + inst) * L;
+    float a = 0.f;
+    for (int j = lane; j < L; j += 32) a = fmaf(code[j], code[j], a);
+    a = warp_sum(a);
+    if (lane == 0) s_norm[which][inst] = sqrtf(a);
+  }
+  __syncthreads();
+
+  // --- plain layers (transposed copies out of the raw accumulators)
+  for (int i = gtid; i < 32 * 87; i += gstride) { const int n = i / 87, c = i % 87; G[lay.o[0] + i] = rk[RW1 + c * 32 + n]; }
+  for (int i = gtid; i < 32 * 32; i += gstride) { const int n = i / 32, c = i % 32; G[lay.o[14] + i] = rk[RW5 + c * 32 + n]; }
+  for (int i = gtid; i < 32 * 74; i += gstride) { const int n = i / 74, c = i % 74; G[lay.o[18] + i] = rk[RW6 + c * 48 + n]; }
+  for (int i = gtid; i < 16 * 32; i += gstride) { const int n = i / 32, c = i % 32; G[lay.o[24] + i] = rk[RW89 + c * 16 + n]; }
+  for (int i = gtid; i < 3 * 16; i += gstride) { const int j = i / 16, c = i % 16; G[lay.o[26] + i] = rk[RW89 + (32 + c) * 16 + j]; }
+  if (blockIdx.y == 0) {
+    for (int n = tid; n < 32; n += 256) {
+      G[lay.o[1] + n] = rk[RW1 + 87 * 32 + n];               // b_xyz (row of the ones column)
+      G[lay.o[19] + n] = rk[RW6 + 74 * 48 + n];              // b_vd
+      G[lay.o[16] + n] = rk[RW6 + n * 48 + 32];              // w_sigma
+      // b_es: y5 feeds only linear consumers -> d b5[n] = sum_m db_vd[m] Wvd[m][n] + db_sigma * wsig[n]
+      float a = rk[RW6 + 74 * 48 + 32] * P[lay.o[16] + n];
+      for (int m = 0; m < 32; ++m) a = fmaf(rk[RW6 + 74 * 48 + m], P[lay.o[18] + (size_t)m * 74 + n], a);
+      G[lay.o[15] + n] = a;
+    }
+    if (tid == 0) G[lay.o[17]] = rk[RW6 + 74 * 48 + 32];     // b_sigma
+    for (int n = tid; n < 16; n += 256) G[lay.o[25] + n] = rk[RDB8 + n];
+    for (int j = tid; j < 3; j += 256) G[lay.o[27] + j] = rk[RDB9 + j];
+  }
+  // --- layers with per-instance bias c = W[:, :32] z + b : slots (zsl1->s1), (zcl->cat), (zsl2->s2), (ztl->t1)
   for (int s = 0; s < 4; ++s) {
     const int ld = cons_ld[s];
-    for (int i = tid; i < 32 * ld; i += 256) {
+    for (int i = gtid; i < 32 * ld; i += gstride) {
       const int n = i / ld, c = i % ld;
       float a = rk[rw[s] + c * 32 + n];
       if (c < 32)
         for (int inst = 0; inst < n_obj; ++inst) a = fmaf(rk[roh[s] + inst * 32 + n], z[(s * MAXOBJ + inst) * NL + c], a);
       G[lay.o[cons_w[s]] + i] = a;
     }
-    for (int n = tid; n < 32; n += 256) {
-      float a = 0.f;
-      for (int inst = 0; inst < n_obj; ++inst) a += rk[roh[s] + inst * 32 + n];
-      G[lay.o[cons_w[s] + 1] + n] = a;
-    }
-    // d z[inst][c] = sum_n dC[inst][n] W[n][c], masked by relu
-    for (int i = tid; i < MAXOBJ * NL; i += 256) {
-      const int inst = i / NL, c = i % NL;
-      float a = 0.f;
-      if (inst < n_obj && z[(s * MAXOBJ + inst) * NL + c] > 0.f)
-        for (int n = 0; n < 32; ++n) a = fmaf(rk[roh[s] + inst * 32 + n], P[lay.o[cons_w[s]] + (size_t)n * ld + c], a);
-      s_dpre[s][inst][c] = a;
-    }
-  }
-  __syncthreads();
-  // --- latent layers: dW_lat[c][j] = sum_inst dpre[inst][c] code[inst][j]; db_lat[c] = sum_inst dpre[inst][c]
-  for (int s = 0; s < 4; ++s) {
+    if (blockIdx.y == 0)
+      for (int n = tid; n < 32; n += 256) {
+        float a = 0.f;
+        for (int inst = 0; inst < n_obj; ++inst) a += rk[roh[s] + inst * 32 + n];
+        G[lay.o[cons_w[s] + 1] + n] = a;
+      }
+    // latent layer: dW_lat[c][j] = sum_inst dpre[inst][c] code[inst][j]; db_lat[c] = sum_inst dpre[inst][c]
     const float* codes = (s == 3 ? tex_codes : shape_codes) + (size_t)k * n_obj_max * L;
-    for (int i = tid; i < 32 * L; i += 256) {
+    for (int i = gtid; i < 32 * L; i += gstride) {
       const int c = i / L, j = i % L;
       float a = 0.f;
       for (int inst = 0; inst < n_obj; ++inst) a = fmaf(s_dpre[s][inst][c], codes[(size_t)inst * L + j], a);
       G[lay.o[lat_w[s]] + i] = a;
     }
-    for (int c = tid; c < 32; c += 256) {
-      float a = 0.f;
-      for (int inst = 0; inst < n_obj; ++inst) a += s_dpre[s][inst][c];
-      G[lay.o[lat_w[s] + 1] + c] = a;
-    }
+    if (blockIdx.y == 0)
+      for (int c = tid; c < 32; c += 256) {
+        float a = 0.f;
+        for (int inst = 0; inst < n_obj; ++inst) a += s_dpre[s][inst][c];
+        G[lay.o[lat_w[s] + 1] + c] = a;
+      }
   }
   // --- code tables: d code[inst][j] = sum_s sum_c dpre[s][inst][c] W_lat_s[c][j]  (+ regulariser)
-  __shared__ float s_norm[2][MAXOBJ];
-  for (int i = tid; i < 2 * MAXOBJ; i += 256) {
-    const int which = i / MAXOBJ, inst = i % MAXOBJ;
-    float a = 0.f;
-    if (inst < n_obj) {
-      const float* code = (which ? tex_codes : shape_codes) + ((size_t)k * n_obj_max + inst) * L;
-      for (int j = 0; j < L; ++j) a = fmaf(code[j], code[j], a);
-    }
-    s_norm[which][inst] = sqrtf(a);
-  }
-  __syncthreads();
-  for (int i = tid; i < n_obj_max * L; i += 256) {
+  for (int i = gtid; i < n_obj_max * L; i += gstride) {
     const int inst = i / L, j = i % L;
     float gs = 0.f, gt = 0.f;
     if (inst < n_obj) {
+#pragma unroll 4
       for (int c = 0; c < 32; ++c) {
         gs = fmaf(s_dpre[0][inst][c], P[lay.o[2] + (size_t)c * L + j], gs);
         gs = fmaf(s_dpre[1][inst][c], P[lay.o[12] + (size_t)c * L + j], gs);
@@ -933,7 +988,7 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
     g_shape[(size_t)k * n_obj_max * L + i] = gs;
     g_tex[(size_t)k * n_obj_max * L + i] = gt;
   }
-  if (tid == 0) {
+  if (blockIdx.y == 0 && tid == 0) {
     float rs = 0.f, rt = 0.f;
     if (n_obj > 1) for (int inst = 0; inst < n_obj; ++inst) { rs += s_norm[0][inst]; rt += s_norm[1][inst]; }
     reg_out[k * 2 + 0] = rs; reg_out[k * 2 + 1] = rt;
@@ -944,11 +999,13 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
 __global__ void fused_loss_kernel(int K, const float* __restrict__ raw, const int32_t* __restrict__ counts,
                                   const float* __restrict__ reg, float cs, float os, float reg_scaling, int add_reg,
                                   float* __restrict__ out_loss) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  bool e0 = false, e1 = false, e2 = false;
-  for (int k = 0; k < K; ++k) { e0 |= counts[k * 4 + 0] == 0; e1 |= counts[k * 4 + 1] == 0; e2 |= counts[k * 4 + 2] == 0; }
+  // one warp; lane per category (strided)
+  const int lane = threadIdx.x;
+  int f0 = 0, f1 = 0, f2 = 0;
+  for (int k = lane; k < K; k += 32) { f0 |= counts[k * 4 + 0] == 0; f1 |= counts[k * 4 + 1] == 0; f2 |= counts[k * 4 + 2] == 0; }
+  const bool e0 = __any_sync(0xffffffffu, f0), e1 = __any_sync(0xffffffffu, f1), e2 = __any_sync(0xffffffffu, f2);
   float total = 0.f;
-  for (int k = 0; k < K; ++k) {
+  for (int k = lane; k < K; k += 32) {
     const float* l = raw + (size_t)k * RAW_FLOATS + RLOSS;
     const float d = e0 ? 0.f : l[0] / ((float)counts[k * 4 + 0] + 1e-10f);
     const float c = e1 ? 0.f : l[1] / ((float)counts[k * 4 + 1] + 1e-10f);
@@ -958,7 +1015,8 @@ __global__ void fused_loss_kernel(int K, const float* __restrict__ raw, const in
     total += d + c * cs + o * os;
     if (add_reg) total += reg_scaling * (reg[k * 2] + reg[k * 2 + 1]);
   }
-  out_loss[0] = total; out_loss[1] = e0; out_loss[2] = e1; out_loss[3] = e2;
+  total = warp_sum(total);
+  if (lane == 0) { out_loss[0] = total; out_loss[1] = e0; out_loss[2] = e1; out_loss[3] = e2; }
 }
 
 struct FusedWs {
@@ -1025,7 +1083,7 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
   int cpc = n_sm / K; if (cpc < 1) cpc = 1; if (cpc > n_tiles) cpc = n_tiles;
   CNF_CUDA(cudaMemsetAsync(raw, 0, (size_t)K * RAW_FLOATS * 4, st));
   CNF_CUDA(cudaMemsetAsync(g_B, 0, (size_t)K * 63 * 4, st));
-  fused_prep_kernel<<<K, 256, 0, st>>>(L, n_obj_max, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, prep, zlat);
+  fused_prep_kernel<<<dim3(K, 5), 256, 0, st>>>(L, n_obj_max, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, prep, zlat);
   if (g_ev_start && g_ev_stop) CNF_CUDA(cudaEventRecord(g_ev_start, st));
   fused_step_kernel<<<dim3(cpc, K), 128, SM_TOTAL, st>>>(K, R, S, prep, origins, dirs, z, gt_depth, gt_rgb, mask_depth, inst,
                                                          counts, cs, os, raw, scratch);
@@ -1033,7 +1091,7 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
   const size_t P = (size_t)R * S;
   int pb = (int)((P + 255) / 256); if (pb > 64) pb = 64;
   fused_pe_grad_kernel<<<dim3(pb, K), 256, 0, st>>>(P, scratch, g_B);
-  fused_finalize_kernel<<<K, 256, 0, st>>>(L, n_obj_max, params, pe_scale, shape_codes, tex_codes, n_obj, raw, zlat, reg_scaling,
+  fused_finalize_kernel<<<dim3(K, 8), 256, 0, st>>>(L, n_obj_max, params, pe_scale, shape_codes, tex_codes, n_obj, raw, zlat, reg_scaling,
                                            flags & 1, g_params, g_B, g_shape, g_tex, reg);
   fused_loss_kernel<<<1, 32, 0, st>>>(K, raw, counts, reg, cs, os, reg_scaling, flags & 1, out_loss);
   return check_launch("cnf_train_step");

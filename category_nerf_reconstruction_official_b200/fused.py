@@ -141,6 +141,23 @@ class FusedCategoryTrainer:
         self.launches_per_step = 3 + 5
         return self.step_from_samples(origins, dirs, z, depth, rgbs, valid.view(torch.uint8), indices, counts, add_reg)
 
+    def capture(self, rgbs, depth, origins, dirs, indices, add_reg=True):
+        """Capture sampler + fused step over THESE (static) input tensors into a CUDA graph and return ``replay``.
+        The step is ~15 launches of microsecond-scale work at Replica-sized batches, i.e. launch-bound from Python;
+        replaying the captured graph removes the host from the loop.  Update the input tensors in place between replays."""
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):                      # warm-up: allocations, function attributes, RNG state registration
+                self.step(rgbs, depth, origins, dirs, indices, add_reg=add_reg)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.step(rgbs, depth, origins, dirs, indices, add_reg=add_reg)
+        self._graph = graph
+        return graph.replay
+
     def loss_terms(self) -> Dict[str, torch.Tensor]:
         K = self.K
         o = self.out_loss

