@@ -78,7 +78,7 @@ SIGNATURES = {
     "cnf_device_check": (c_int, [c_int]),
     "cnf_sample_workspace_bytes": (c_size_t, [c_int, c_int]),
     "cnf_sample_fwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P,
-                               c_float, c_float, c_float, c_int, P, P, P, P, P, P, c_size_t, P]),
+                               c_float, c_float, c_float, c_int, P, P, P, P, P, P, P, c_size_t, P]),
     "cnf_stratified_bins": (c_int, [c_int, c_int, P, c_int, P, c_int, P, P, P, P]),
     "cnf_embed_fwd": (c_int, [c_int, c_int, P, P, P, P, P]),
     "cnf_embed_bwd": (c_int, [c_int, c_int, P, P, P, P, P, P, P]),

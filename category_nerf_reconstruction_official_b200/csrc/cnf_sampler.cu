@@ -57,7 +57,7 @@ __global__ void sample_count_kernel(int R, const uint8_t* __restrict__ rgbs, con
 
 // (B) one block per category: exclusive scan of block counts (in place, cols 0..2), totals -> stats.
 __global__ void sample_scan_kernel(int nb, int* __restrict__ blk_counts, const float* __restrict__ blk_max,
-                                   int32_t* __restrict__ stats) {
+                                   const float* __restrict__ max_override, int32_t* __restrict__ stats) {
   const int k = blockIdx.x;
   int* bc = blk_counts + (size_t)k * nb * 8;
   __shared__ int s_tot[6];
@@ -75,7 +75,7 @@ __global__ void sample_scan_kernel(int nb, int* __restrict__ blk_counts, const f
   if (threadIdx.x == 32) {
     float m = -INFINITY;
     for (int b = 0; b < nb; ++b) m = fmaxf(m, blk_max[(size_t)k * nb + b]);
-    s_mx = m;
+    s_mx = max_override ? max_override[k] : m;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -221,7 +221,7 @@ extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, c
                               const float* origins, const float* dirs, const float* u_inv, const float* u_val,
                               const float* n_obj, const float* u_oth, const float* lin_S, const float* lin_N,
                               const float* lin_M, float min_bound, float eps, float stop_eps, int this_obj,
-                              float* z, float* pcs, uint8_t* valid, uint8_t* labels, int32_t* stats, void* ws,
+                              const float* max_depth_override, float* z, float* pcs, uint8_t* valid, uint8_t* labels, int32_t* stats, void* ws,
                               size_t ws_bytes, cnf_stream_t stream) {
   CNF_REQUIRE(K > 0 && R > 0 && N >= 0 && M > 0, "cnf_sample_fwd: bad sizes K=%d R=%d N=%d M=%d", K, R, N, M);
   CNF_REQUIRE(rgbs && depth && origins && dirs && z && valid && labels && stats && ws, "cnf_sample_fwd: null pointer");
@@ -232,7 +232,7 @@ extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, c
   float* blk_max = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align_up((size_t)K * nb * 8 * sizeof(int), 256));
   cudaStream_t st = as_stream(stream);
   sample_count_kernel<<<dim3(nb, K), SB, 0, st>>>(R, rgbs, depth, min_bound, this_obj, blk_counts, blk_max);
-  sample_scan_kernel<<<K, 64, 0, st>>>(nb, blk_counts, blk_max, stats);
+  sample_scan_kernel<<<K, 64, 0, st>>>(nb, blk_counts, blk_max, max_depth_override, stats);
   sample_emit_kernel<<<dim3(nb, K), SB, 0, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth,
                                                  lin_S, lin_N, lin_M, min_bound, eps, stop_eps, this_obj,
                                                  blk_counts, stats, z, pcs, valid, labels);

@@ -33,7 +33,8 @@ def linspace_table(n_bins: int, device) -> torch.Tensor:
 
 
 def sample_batched(rgbs, depth, origins, dirs, n_cam2surf: int, n_surf: int, eps: float, stop_eps: float,
-                   rand: Dict[str, torch.Tensor], min_bound: float = 0.0, this_obj: int = 1, want_pcs: bool = True):
+                   rand: Dict[str, torch.Tensor], min_bound: float = 0.0, this_obj: int = 1, want_pcs: bool = True,
+                   max_depth: Optional[torch.Tensor] = None):
     """K-batched sampler. rgbs u8 [K,R,4]; depth [K,R]; origins/dirs [K,R,3];
     rand: 'u_inv' [K,R,S], 'u_val' [K,R,N], 'n_obj' [K,R,M], 'u_oth' [K,R,M] (row-compact per category).
     Returns z [K,R,S], pcs [K,R,S,3] | None, valid bool [K,R], labels u8 [K,R], stats int32 [K,8]."""
@@ -60,7 +61,7 @@ def sample_batched(rgbs, depth, origins, dirs, n_cam2surf: int, n_surf: int, eps
         u_val = u_inv
     check(lib.cnf_sample_fwd(K, R, N, M, ptr(rgbs), ptr(depth), ptr(origins), ptr(dirs), ptr(u_inv), ptr(u_val),
                              ptr(n_obj), ptr(u_oth), ptr(lin_S), ptr(lin_N), ptr(lin_M), float(min_bound), float(eps),
-                             float(stop_eps), int(this_obj), ptr(z), ptr(pcs), ptr(valid), ptr(labels), ptr(stats),
+                             float(stop_eps), int(this_obj), ptr(max_depth), ptr(z), ptr(pcs), ptr(valid), ptr(labels), ptr(stats),
                              ptr(ws), ws_bytes, stream()))
     return z, pcs, valid.view(torch.bool), labels, stats
 

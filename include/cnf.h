@@ -54,13 +54,16 @@ int cnf_device_check(int device);
  *     Outputs: z [K,R,S], pcs [K,R,S,3] (may be NULL), valid u8 [K,R], labels u8 [K,R],
  *     stats [K,8] int32 = {nI, nV, nO, nT, N_depth&obj, N_obj, N_sem, float_bits(max depth)}.
  *     ws: >= cnf_sample_workspace_bytes(K,R) bytes.
+ *     max_depth_override [K] (may be NULL): use these upper bounds for invalid-depth rays instead of the batch
+ *     maximum (scene_cateogries.py:486) -- needed when one category's batch is split across GPUs and the
+ *     maximum has been all-reduced by the caller.
  * ---------------------------------------------------------------------------------------------- */
 size_t cnf_sample_workspace_bytes(int n_cat, int n_rays);
 int cnf_sample_fwd(int n_cat, int n_rays, int n_cam2surf, int n_surf,
                    const uint8_t* rgbs, const float* depth, const float* origins, const float* dirs,
                    const float* u_inv, const float* u_val, const float* n_obj, const float* u_oth,
                    const float* lin_S, const float* lin_N, const float* lin_M,
-                   float min_bound, float eps, float stop_eps, int this_obj,
+                   float min_bound, float eps, float stop_eps, int this_obj, const float* max_depth_override,
                    float* z, float* pcs, uint8_t* valid, uint8_t* labels, int32_t* stats,
                    void* ws, size_t ws_bytes, cnf_stream_t stream);
 
