@@ -166,6 +166,8 @@ def main():
     ap.add_argument("--no-large", action="store_true", help="skip the extra large-batch (c4) roofline measurement")
     ap.add_argument("--with-optimizer", action="store_true", help="include the fused AdamW update in the timed step")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--ray-split", action="store_true",
+                    help="strong scaling: ONE copy of the workload, each rank takes R/N rays + NCCL all-reduce of counts/grads")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
@@ -206,6 +208,10 @@ def main():
                                     generator=torch.Generator().manual_seed(1234 + rank))
 
     # weak scaling: every rank owns its own K categories (categories shard across GPUs; no data-path collective)
+    if args.ray_split and world > 1:
+        ray_split_arm(args, wl, make_trainer, dev, rank, world, warmup, metric)
+        dist.destroy_process_group()
+        return
     tr = make_trainer(wl)
     batch = synth_batch(wl, seed=100 + rank, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
@@ -360,6 +366,40 @@ def main():
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def ray_split_arm(args, wl, make_trainer, dev, rank, world, warmup, metric):
+    """Strong scaling of one workload: rays split across ranks, identical model replicas, NCCL all-reduces."""
+    import torch.distributed as dist
+    from category_nerf_reconstruction_official_b200.parallel import RaySplitStep, split_rays
+    gen_seed = 1234            # same replica on every rank
+    tr = make_trainer(wl)
+    for t_ in (tr.params, tr.shape_codes, tr.tex_codes):
+        dist.broadcast(t_, src=0)
+    full = synth_batch(wl, seed=100, device=None)
+    sl = split_rays(wl["R"], world, rank)
+    b = {k: v[:, sl].contiguous().to(dev) for k, v in full.items()}
+    rs = RaySplitStep(tr)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for _ in range(warmup):
+        rs.step(b["rgbs"], b["depth"], b["origins"], b["dirs"], b["indices"])
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        rs.step(b["rgbs"], b["depth"], b["origins"], b["dirs"], b["indices"])
+        ev[i][1].record()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    ms = torch.tensor([sum(a.elapsed_time(c) for a, c in ev) / args.steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"metric": metric, "value": wl["K"] * wl["R"] / (float(ms) * 1e-3), "unit": "rays/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": warmup, "ms_per_step": float(ms), "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": args.workload, "desc": wl["desc"], "parallelism": "ray split %d-way + NCCL all-reduce" % world,
+                                     "l2": "flushed between timed steps"}, "loss": float(tr.out_loss[0]),
+                          "gpu_launches": 8 * args.steps}))
 
 
 def timed_single(t, b, run_step, flush, steps, warm):

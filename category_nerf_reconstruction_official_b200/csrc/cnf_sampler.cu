@@ -55,39 +55,61 @@ __global__ void sample_count_kernel(int R, const uint8_t* __restrict__ rgbs, con
   }
 }
 
-// (B) one block per category: exclusive scan of block counts (in place, cols 0..2), totals -> stats.
-__global__ void sample_scan_kernel(int nb, int* __restrict__ blk_counts, const float* __restrict__ blk_max,
-                                   const float* __restrict__ max_override, int32_t* __restrict__ stats) {
-  const int k = blockIdx.x;
+// (B) one block (256 threads) per category: exclusive scan of the block counts (in place, cols 0..2), totals -> stats.
+// Each thread owns a contiguous chunk of blocks; chunk sums are scanned with warp shuffles + one smem hop.
+__global__ void __launch_bounds__(256)
+sample_scan_kernel(int nb, int* __restrict__ blk_counts, const float* __restrict__ blk_max,
+                   const float* __restrict__ max_override, int32_t* __restrict__ stats) {
+  const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   int* bc = blk_counts + (size_t)k * nb * 8;
-  __shared__ int s_tot[6];
-  __shared__ float s_mx;
-  if (threadIdx.x < 6) {       // serial scan per column: nb <= a few thousand, negligible
-    const int c = threadIdx.x;
-    int run = 0;
-    for (int b = 0; b < nb; ++b) {
-      const int v = bc[b * 8 + c];
-      if (c < 3) bc[b * 8 + c] = run;
-      run += v;
-    }
-    s_tot[c] = run;
+  const int per = (nb + 255) / 256;
+  const int b0 = t * per, b1 = min(nb, b0 + per);
+  int sum[6] = {0, 0, 0, 0, 0, 0};
+  float mx = -INFINITY;
+  for (int b = b0; b < b1; ++b) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) sum[c] += bc[b * 8 + c];
+    mx = fmaxf(mx, blk_max[(size_t)k * nb + b]);
   }
-  if (threadIdx.x == 32) {
-    float m = -INFINITY;
-    for (int b = 0; b < nb; ++b) m = fmaxf(m, blk_max[(size_t)k * nb + b]);
-    s_mx = max_override ? max_override[k] : m;
+  __shared__ int s_w[8][6];
+  __shared__ float s_m[8];
+  int excl[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    int v = sum[c];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += n; }
+    excl[c] = v - sum[c];
+    if (lane == 31) s_w[warp][c] = v;
   }
+  mx = warp_max(mx);
+  if (lane == 0) s_m[warp] = mx;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  int tot[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    int before = 0, all = 0;
+    for (int w = 0; w < 8; ++w) { if (w < warp) before += s_w[w][c]; all += s_w[w][c]; }
+    excl[c] += before;
+    tot[c] = all;
+  }
+  int run[3] = {excl[0], excl[1], excl[2]};
+  for (int b = b0; b < b1; ++b) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { const int v = bc[b * 8 + c]; bc[b * 8 + c] = run[c]; run[c] += v; }
+  }
+  if (t == 0) {
+    float m = s_m[0];
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, s_m[w]);
     int32_t* st = stats + k * 8;
-    st[0] = s_tot[0];              // nI
-    st[1] = s_tot[1] + s_tot[2];   // nV
-    st[2] = s_tot[1];              // nO
-    st[3] = s_tot[2];              // nT
-    st[4] = s_tot[3];              // N_depth&obj
-    st[5] = s_tot[4];              // N_obj
-    st[6] = s_tot[5];              // N_sem
-    st[7] = __float_as_int(s_mx);  // max depth bits
+    st[0] = tot[0];              // nI
+    st[1] = tot[1] + tot[2];     // nV
+    st[2] = tot[1];              // nO
+    st[3] = tot[2];              // nT
+    st[4] = tot[3];              // N_depth&obj
+    st[5] = tot[4];              // N_obj
+    st[6] = tot[5];              // N_sem
+    st[7] = __float_as_int(max_override ? max_override[k] : m);   // max depth bits
   }
 }
 
@@ -232,7 +254,7 @@ extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, c
   float* blk_max = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align_up((size_t)K * nb * 8 * sizeof(int), 256));
   cudaStream_t st = as_stream(stream);
   sample_count_kernel<<<dim3(nb, K), SB, 0, st>>>(R, rgbs, depth, min_bound, this_obj, blk_counts, blk_max);
-  sample_scan_kernel<<<K, 64, 0, st>>>(nb, blk_counts, blk_max, max_depth_override, stats);
+  sample_scan_kernel<<<K, 256, 0, st>>>(nb, blk_counts, blk_max, max_depth_override, stats);
   sample_emit_kernel<<<dim3(nb, K), SB, 0, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth,
                                                  lin_S, lin_N, lin_M, min_bound, eps, stop_eps, this_obj,
                                                  blk_counts, stats, z, pcs, valid, labels);
