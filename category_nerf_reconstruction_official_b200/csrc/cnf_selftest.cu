@@ -73,9 +73,71 @@ umma_selftest_kernel(int mode, int N, int Kd, const float* __restrict__ A, const
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
+
+// Probe of the M=64 accumulator layout: sentinel-fill 128 lanes x N columns, run ONE K=16.. chain of M=64 MMAs with the
+// D address carrying `lane_off` in its lane field, dump all 128 lanes.  A [64,Kd], B [N,Kd] both K-major.
+__global__ void __launch_bounds__(128)
+umma_m64_probe_kernel(int N, int Kd, int lane_off, const float* __restrict__ A, const float* __restrict__ B,
+                      float* __restrict__ D) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 128 * Kd * 2;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 128 * Kd; i += 128) {
+    const int r = i / Kd, c = i % Kd;
+    *reinterpret_cast<__nv_bfloat16*>(sA + blk_off(r, c, Kd)) = __float2bfloat16(r < 64 ? A[i] : 0.f);
+  }
+  for (int i = tid; i < N * Kd; i += 128) {
+    const int r = i / Kd, c = i % Kd;
+    *reinterpret_cast<__nv_bfloat16*>(sB + blk_off(r, c, Kd)) = __float2bfloat16(B[i]);
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tl = tmem_lane_base(tmem);
+  uint32_t sent[16];
+  for (int j = 0; j < 16; ++j) sent[j] = __float_as_uint(-777.0f);
+  for (int c0 = 0; c0 < N; c0 += 16) tmem_st16(tl + c0, sent);
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc = idesc_bf16(64, N, 0, 0);
+    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+    for (int ks = 0; ks < Kd / 16; ++ks)
+      mma_ss(tmem + ((uint32_t)lane_off << 16), smem_desc(a0 + ks * 256, 128, 16 * Kd), smem_desc(b0 + ks * 256, 128, 16 * Kd), idesc, ks > 0);
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tl + c0, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[tid * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
 }  // namespace cnf
 
 using namespace cnf;
+
+extern "C" int cnf_umma_m64_probe(int N, int Kdim, int lane_off, const float* A, const float* B, float* D, cnf_stream_t stream) {
+  CNF_REQUIRE(N >= 8 && N <= 256 && N % 8 == 0 && Kdim >= 16 && Kdim <= 256 && Kdim % 16 == 0 && A && B && D, "cnf_umma_m64_probe: bad arguments");
+  const size_t smem = (size_t)128 * Kdim * 2 + (size_t)N * Kdim * 2;
+  CNF_CUDA(cudaFuncSetAttribute(umma_m64_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_m64_probe_kernel<<<1, 128, smem, as_stream(stream)>>>(N, Kdim, lane_off, A, B, D);
+  return check_launch("cnf_umma_m64_probe");
+}
 
 extern "C" int cnf_umma_selftest(int mode, int N, int Kdim, const float* A, const float* B, float* D, cnf_stream_t stream) {
   CNF_REQUIRE(mode >= 0 && mode <= 2 && N >= 16 && N <= 256 && N % 16 == 0 && Kdim >= 16 && Kdim <= 256 && Kdim % 16 == 0,

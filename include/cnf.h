@@ -184,6 +184,10 @@ int cnf_set_kernel_events(void* ev_start, void* ev_stop);
  * (wgrad view).  Used by tests to pin the descriptor encodings on hardware. */
 int cnf_umma_selftest(int mode, int N, int Kdim, const float* A, const float* B, float* D, cnf_stream_t stream);
 
+/* Hardware probe (development aid): where does an M=64 UMMA put its 64 accumulator rows in TMEM, and does the lane
+ * field of the D address offset them?  D [128,N] receives all 128 lanes (sentinel -777 where untouched). */
+int cnf_umma_m64_probe(int N, int Kdim, int lane_off, const float* A, const float* B, float* D, cnf_stream_t stream);
+
 /* Fused AdamW over a flat fp32 buffer (train.py:183): decoupled weight decay as
  * torch.optim.AdamW.  step is 1-based. */
 int cnf_adamw_step(size_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
