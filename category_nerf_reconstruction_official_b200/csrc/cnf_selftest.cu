@@ -127,6 +127,52 @@ umma_m64_probe_kernel(int N, int Kd, int lane_off, const float* __restrict__ A, 
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
+
+// Issue-rate probe: ONE thread issues `reps` back-to-back tcgen05.mma of shape M x N x 16 and the CTA measures the SM
+// cycles until the commit arrives.  mode 0: A,B from shared memory, K-major (forward view); 1: A from TMEM, B K-major;
+// 2: A,B from shared memory MN-major (weight-gradient view); 3: B MN-major (data-gradient view).
+// Operand contents are whatever the (zeroed) shared memory holds -- only the timing is of interest.
+__global__ void __launch_bounds__(128)
+umma_rate_probe_kernel(int mode, int M, int N, int reps, int ndst, long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (96 * 1024) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  long long t0 = 0, t1 = 0, t2 = 0;
+  if (tid == 0) {
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 32 * 1024);
+    const uint32_t idesc = idesc_bf16(M, N, mode == 2, mode >= 2);
+    t0 = clock64();
+    for (int i = 0; i < reps; ++i) {
+      const int ks = i & 7;
+      const uint32_t d = tmem + (uint32_t)((i % ndst) * N);          // ndst accumulators in rotation (ndst * N <= 256)
+      uint64_t ad, bd;
+      if (mode == 2) ad = smem_desc(a0 + ks * 2 * (16 * 128), 16 * 128, 128);
+      else           ad = smem_desc(a0 + ks * 256, 128, 16 * 128);
+      if (mode >= 2) bd = smem_desc(b0 + ks * 2 * (16 * N), 16 * N, 128);
+      else           bd = smem_desc(b0 + ks * 256, 128, 16 * 128);
+      if (mode == 1) mma_ts(d, tmem + 256 + ks * 8, bd, idesc, i >= ndst);
+      else           mma_ss(d, ad, bd, idesc, i >= ndst);
+    }
+    t1 = clock64();
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  t2 = clock64();
+  tc_fence_after();
+  if (tid == 0) { out[blockIdx.x * 2 + 0] = t1 - t0; out[blockIdx.x * 2 + 1] = t2 - t0; }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
 }  // namespace cnf
 
 using namespace cnf;
@@ -147,4 +193,13 @@ extern "C" int cnf_umma_selftest(int mode, int N, int Kdim, const float* A, cons
   CNF_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(mode, N, Kdim, A, B, D);
   return check_launch("cnf_umma_selftest");
+}
+
+extern "C" int cnf_umma_rate_probe(int mode, int M, int N, int reps, int ndst, int n_cta, long long* out_cycles, cnf_stream_t stream) {
+  CNF_REQUIRE(mode >= 0 && mode <= 3 && (M == 64 || M == 128) && N >= 8 && N <= 256 && N % 8 == 0 && reps > 0 && ndst >= 1 &&
+                  ndst * N <= 256 && n_cta >= 1 && out_cycles, "cnf_umma_rate_probe: bad arguments");
+  const int smem = 96 * 1024;
+  CNF_CUDA(cudaFuncSetAttribute(umma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_rate_probe_kernel<<<n_cta, 128, smem, as_stream(stream)>>>(mode, M, N, reps, ndst, out_cycles);
+  return check_launch("cnf_umma_rate_probe");
 }

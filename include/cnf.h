@@ -179,6 +179,10 @@ int cnf_train_step(int n_cat, int n_rays, int S, int L, int n_obj_max,
  * the hook.  Lets bench.py time the dominant kernel live without a profiler. */
 int cnf_set_kernel_events(void* ev_start, void* ev_stop);
 
+/* Development aid: device buffer of 128 int64 receiving SM-clock stage timestamps of one tile (threads 0 / 128 of CTA 0);
+ * NULL (default) disables it. */
+int cnf_set_debug_buffer(void* dev_ptr);
+
 /* tcgen05 self-test: D[128,N] = A[128,K] * B[N,K]^T with bf16 operands staged in shared memory in the
  * canonical no-swizzle UMMA layout; mode 0: A,B K-major; 1: B MN-major (dgrad view); 2: A,B MN-major
  * (wgrad view).  Used by tests to pin the descriptor encodings on hardware. */
@@ -187,6 +191,11 @@ int cnf_umma_selftest(int mode, int N, int Kdim, const float* A, const float* B,
 /* Hardware probe (development aid): where does an M=64 UMMA put its 64 accumulator rows in TMEM, and does the lane
  * field of the D address offset them?  D [128,N] receives all 128 lanes (sentinel -777 where untouched). */
 int cnf_umma_m64_probe(int N, int Kdim, int lane_off, const float* A, const float* B, float* D, cnf_stream_t stream);
+
+/* Development probe: one thread per CTA issues `reps` back-to-back tcgen05.mma (M x N x 16, bf16) into `ndst` rotating
+ * accumulators and the CTA reports {issue cycles, cycles until the commit arrives} per CTA in out_cycles[2 * n_cta].
+ * mode 0: A,B shared memory K-major; 1: A from TMEM; 2: A,B MN-major (weight-gradient view); 3: B MN-major. */
+int cnf_umma_rate_probe(int mode, int M, int N, int reps, int ndst, int n_cta, long long* out_cycles, cnf_stream_t stream);
 
 /* Fused AdamW over a flat fp32 buffer (train.py:183): decoupled weight decay as
  * torch.optim.AdamW.  step is 1-based. */
