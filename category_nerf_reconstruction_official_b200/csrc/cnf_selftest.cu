@@ -128,6 +128,92 @@ umma_m64_probe_kernel(int N, int Kd, int lane_off, const float* __restrict__ A, 
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// Modes 3..5 (operand views of the two-role fused kernel):
+//   3: forward with the A operand in TENSOR MEMORY (each thread packs its row's bf16 pairs, one 32-bit column per two K
+//      elements, tcgen05.st) and B [N,Kd] K-major in shared memory; D [128,N].
+//   4/5: weight-gradient view with M = 64: A given [Kd, 64] and B given [Kd, N], both MN-major in shared memory; the D
+//      address carries lane offset 0 (mode 4) / 16 (mode 5).  ALL 128 lanes are dumped (sentinel -777 where untouched):
+//      accumulator row r must land in lane 32*(r/16) + r%16 (+16 in mode 5).
+__global__ void __launch_bounds__(128)
+umma_selftest2_kernel(int mode, int N, int Kd, const float* __restrict__ A, const float* __restrict__ B,
+                      float* __restrict__ D) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 128 * 128 * 2;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 * 128 * 2 + 256 * 128 * 2) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (mode >= 4) {
+    for (int i = tid; i < Kd * 64; i += 128) {
+      const int r = i / 64, c = i % 64;
+      *reinterpret_cast<__nv_bfloat16*>(sA + blk_off(r, c, 64)) = __float2bfloat16(A[i]);
+    }
+    for (int i = tid; i < Kd * N; i += 128) {
+      const int r = i / N, c = i % N;
+      *reinterpret_cast<__nv_bfloat16*>(sB + blk_off(r, c, N)) = __float2bfloat16(B[i]);
+    }
+  } else {
+    for (int i = tid; i < N * Kd; i += 128) {
+      const int r = i / Kd, c = i % Kd;
+      *reinterpret_cast<__nv_bfloat16*>(sB + blk_off(r, c, Kd)) = __float2bfloat16(B[i]);
+    }
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tl = tmem_lane_base(tmem);
+  if (mode == 3) {
+    for (int c0 = 0; c0 < Kd; c0 += 16) {     // 16 K elements -> 8 columns
+      uint32_t w[8];
+      for (int j = 0; j < 8; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(A[tid * Kd + c0 + 2 * j], A[tid * Kd + c0 + 2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      tmem_st8(tl + 256 + c0 / 2, w);
+    }
+  } else {
+    uint32_t sent[16];
+    for (int j = 0; j < 16; ++j) sent[j] = __float_as_uint(-777.0f);
+    for (int c0 = 0; c0 < N; c0 += 16) tmem_st16(tl + c0, sent);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0 && elect_one()) {
+    tc_fence_after();
+    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+    if (mode == 3) {
+      const uint32_t idesc = idesc_bf16(128, N, 0, 0);
+      for (int ks = 0; ks < Kd / 16; ++ks)
+        mma_ts(tmem, tmem + 256 + ks * 8, smem_desc(b0 + ks * 256, 128, 16 * Kd), idesc, ks > 0);
+    } else {
+      const uint32_t idesc = idesc_bf16(64, N, 1, 1);
+      const uint32_t d = tmem + (mode == 5 ? (16u << 16) : 0u);
+      for (int ks = 0; ks < Kd / 16; ++ks)
+        mma_ss(d, smem_desc(a0 + ks * 2 * (16 * 64), 16 * 64, 128), smem_desc(b0 + ks * 2 * (16 * N), 16 * N, 128), idesc, ks > 0);
+    }
+    mma_commit(&bar);
+  }
+  __syncwarp();
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tl + c0, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[tid * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // Issue-rate probe: ONE thread issues `reps` back-to-back tcgen05.mma of shape M x N x 16 and the CTA measures the SM
 // cycles until the commit arrives.  mode 0: A,B from shared memory, K-major (forward view); 1: A from TMEM, B K-major;
 // 2: A,B from shared memory MN-major (weight-gradient view); 3: B MN-major (data-gradient view).
@@ -147,20 +233,29 @@ umma_rate_probe_kernel(int mode, int M, int N, int reps, int ndst, long long* __
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   long long t0 = 0, t1 = 0, t2 = 0;
-  if (tid == 0) {
+  const bool issuer = warp == 0 && elect_one();
+  if (issuer) {
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 32 * 1024);
     const uint32_t idesc = idesc_bf16(M, N, mode == 2, mode >= 2);
+    uint64_t ad[8], bd[8];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      if (mode == 2) ad[ks] = smem_desc(a0 + ks * 2 * (16 * 128), 16 * 128, 128);
+      else           ad[ks] = smem_desc(a0 + ks * 256, 128, 16 * 128);
+      if (mode >= 2) bd[ks] = smem_desc(b0 + ks * 2 * (16 * N), 16 * N, 128);
+      else           bd[ks] = smem_desc(b0 + ks * 256, 128, 16 * 128);
+    }
+    const uint32_t d0 = tmem, d1 = tmem + (ndst > 1 ? N : 0);
     t0 = clock64();
-    for (int i = 0; i < reps; ++i) {
-      const int ks = i & 7;
-      const uint32_t d = tmem + (uint32_t)((i % ndst) * N);          // ndst accumulators in rotation (ndst * N <= 256)
-      uint64_t ad, bd;
-      if (mode == 2) ad = smem_desc(a0 + ks * 2 * (16 * 128), 16 * 128, 128);
-      else           ad = smem_desc(a0 + ks * 256, 128, 16 * 128);
-      if (mode >= 2) bd = smem_desc(b0 + ks * 2 * (16 * N), 16 * N, 128);
-      else           bd = smem_desc(b0 + ks * 256, 128, 16 * 128);
-      if (mode == 1) mma_ts(d, tmem + 256 + ks * 8, bd, idesc, i >= ndst);
-      else           mma_ss(d, ad, bd, idesc, i >= ndst);
+    for (int i = 0; i < reps; i += 8) {
+      const uint32_t acc = i > 0;
+      if (mode == 1) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) mma_ts((ks & 1) ? d1 : d0, tmem + 256 + ks * 8, bd[ks], idesc, acc | (ks > 1));
+      } else {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) mma_ss((ks & 1) ? d1 : d0, ad[ks], bd[ks], idesc, acc | (ks > 1));
+      }
     }
     t1 = clock64();
     mma_commit(&bar);
@@ -168,7 +263,7 @@ umma_rate_probe_kernel(int mode, int M, int N, int reps, int ndst, long long* __
   mbar_wait(&bar, 0);
   t2 = clock64();
   tc_fence_after();
-  if (tid == 0) { out[blockIdx.x * 2 + 0] = t1 - t0; out[blockIdx.x * 2 + 1] = t2 - t0; }
+  if (issuer) { out[blockIdx.x * 2 + 0] = t1 - t0; out[blockIdx.x * 2 + 1] = t2 - t0; }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
@@ -186,9 +281,16 @@ extern "C" int cnf_umma_m64_probe(int N, int Kdim, int lane_off, const float* A,
 }
 
 extern "C" int cnf_umma_selftest(int mode, int N, int Kdim, const float* A, const float* B, float* D, cnf_stream_t stream) {
-  CNF_REQUIRE(mode >= 0 && mode <= 2 && N >= 16 && N <= 256 && N % 16 == 0 && Kdim >= 16 && Kdim <= 256 && Kdim % 16 == 0,
-              "cnf_umma_selftest: need mode in 0..2, N%%16==0 (16..256), K%%16==0 (16..256)");
+  CNF_REQUIRE(mode >= 0 && mode <= 5 && N >= 16 && N <= 256 && N % 16 == 0 && Kdim >= 16 && Kdim <= 256 && Kdim % 16 == 0,
+              "cnf_umma_selftest: need mode in 0..5, N%%16==0 (16..256), K%%16==0 (16..256)");
   CNF_REQUIRE(A && B && D, "cnf_umma_selftest: null pointer");
+  if (mode >= 3) {
+    CNF_REQUIRE(Kdim <= 128, "cnf_umma_selftest: modes 3..5 need K <= 128");
+    const int smem2 = 128 * 128 * 2 + 256 * 128 * 2;
+    CNF_CUDA(cudaFuncSetAttribute(umma_selftest2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    umma_selftest2_kernel<<<1, 128, smem2, as_stream(stream)>>>(mode, N, Kdim, A, B, D);
+    return check_launch("cnf_umma_selftest");
+  }
   const size_t smem = (size_t)128 * Kdim * 2 + (size_t)N * Kdim * 2;
   CNF_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(mode, N, Kdim, A, B, D);

@@ -185,7 +185,10 @@ int cnf_set_debug_buffer(void* dev_ptr);
 
 /* tcgen05 self-test: D[128,N] = A[128,K] * B[N,K]^T with bf16 operands staged in shared memory in the
  * canonical no-swizzle UMMA layout; mode 0: A,B K-major; 1: B MN-major (dgrad view); 2: A,B MN-major
- * (wgrad view).  Used by tests to pin the descriptor encodings on hardware. */
+ * (wgrad view).  Used by tests to pin the descriptor encodings on hardware.
+ * mode 3: A [128,K] staged in TENSOR MEMORY (packed bf16 pairs), B [N,K] K-major in shared memory.
+ * mode 4/5: M = 64 weight-gradient view: A given [K,64], B given [K,N], both MN-major; D address lane offset 0 / 16;
+ *           D receives ALL 128 lanes x N (sentinel -777 where untouched): row r lands in lane 32*(r/16) + r%16 (+16). */
 int cnf_umma_selftest(int mode, int N, int Kdim, const float* A, const float* B, float* D, cnf_stream_t stream);
 
 /* Hardware probe (development aid): where does an M=64 UMMA put its 64 accumulator rows in TMEM, and does the lane

@@ -238,3 +238,32 @@ def test_umma_descriptor_selftest(mode, N, Kd):
         A = bf(torch.randn(Kd, 128, generator=g)); B = bf(torch.randn(Kd, N, generator=g)); ref = A.t() @ B
     D = ops.umma_selftest(mode, A.to(DEV), B.to(DEV), N, Kd)
     torch.testing.assert_close(D.cpu(), ref, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("N,Kd", [(32, 96), (48, 80), (32, 32), (96, 32), (16, 32), (32, 128)])
+def test_umma_tmem_operand_selftest(N, Kd):
+    """A operand staged in tensor memory (packed bf16 pairs per 32-bit column), as the fused forward / data-gradient GEMMs use it."""
+    *_, ops, _, _ = _pkg()
+    g = torch.Generator().manual_seed(300 + N + Kd)
+    bf = lambda t: t.bfloat16().float()
+    A = bf(torch.randn(128, Kd, generator=g)); B = bf(torch.randn(N, Kd, generator=g))
+    D = ops.umma_selftest(3, A.to(DEV), B.to(DEV), N, Kd)
+    torch.testing.assert_close(D.cpu(), A @ B.t(), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("mode", [4, 5])
+@pytest.mark.parametrize("N", [32, 48, 16])
+def test_umma_m64_wgrad_lane_mapping(mode, N):
+    """M = 64 weight-gradient tiles: accumulator row r lands in lane 32*(r/16) + r%16 (+16 with the lane offset); other lanes untouched."""
+    *_, ops, _, _ = _pkg()
+    g = torch.Generator().manual_seed(400 + mode + N)
+    bf = lambda t: t.bfloat16().float()
+    Kd = 128
+    A = bf(torch.randn(Kd, 64, generator=g)); B = bf(torch.randn(Kd, N, generator=g))
+    ref = A.t() @ B                                   # [64, N]
+    D = ops.umma_selftest(mode, A.to(DEV), B.to(DEV), N, Kd).cpu()
+    off = 16 if mode == 5 else 0
+    lanes = torch.tensor([32 * (r // 16) + r % 16 + off for r in range(64)])
+    torch.testing.assert_close(D[lanes], ref, rtol=1e-4, atol=2e-3)
+    other = torch.ones(128, dtype=torch.bool); other[lanes] = False
+    assert torch.all(D[other] == -777.0)
