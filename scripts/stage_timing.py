@@ -1,3 +1,5 @@
+"""Stage timestamps of one tile of the fused kernel (development aid): SM clock deltas of forward-role thread 0 and
+backward-role thread 0 of CTA (0,0), third tile of the CTA."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -17,16 +19,18 @@ tr.step(b["rgbs"], b["depth"], b["origins"], b["dirs"], b["indices"])
 torch.cuda.synchronize()
 _lib.check(lib.cnf_set_debug_buffer(None))
 d = dbg.cpu()
-names = ["start", "pe+oh done(publish)"]
-for st in ["L1","L2","L3","L4","L6","L7","L8","B8","B7","B6","B4","B3","B2"]:
-    names += [st+" wait-begin", st+" mma-done"]
-    if st == "L8":
-        names += ["  L8 h3 stored", "  L9 colours done", "  compositing done"]
-    names += [st+" epi-done(publish)"]
-names += ["B1 wait-begin", "B1 mma-done", "pe-bwd done"]
-for h in range(1):
-    t = d[h*64:(h+1)*64].tolist()
-    n = max(i for i,v in enumerate(t) if v) + 1
-    print("half", h, "stamps", n, "tile cycles", t[n-1]-t[0])
+fn = ["start", "PE done (publish)"]
+for st in ["L1", "L2", "L3", "L4", "L6", "L7"]:
+    fn += [st + " wait-begin", st + " mma-done", st + " epi-done (publish)"]
+fn += ["L8 wait-begin", "L8 mma-done", "  h3 stored", "  colours", "  compositing", "tile done (arrive full)"]
+bn = ["start (rays loaded)", "PE recompute done"]
+for st in ["B8", "B7", "B6", "B4", "B3", "B2"]:
+    bn += [st + " wait-begin", st + " mma-done", st + " epi-done (publish)"]
+bn += ["B1 wait-begin", "B1 mma-done", "PE bwd done (publish)"]
+for role, names, off in (("forward", fn, 0), ("backward", bn, 64)):
+    t = d[off:off + 64].tolist()
+    n = max([i for i, v in enumerate(t) if v] + [0]) + 1
+    print(role, "stamps", n, "tile cycles", t[n - 1] - t[0])
     for i in range(1, n):
-        print("   %-28s +%6d" % (names[i] if i < len(names) else str(i), t[i]-t[i-1]))
+        print("   %-28s +%6d" % (names[i] if i < len(names) else str(i), t[i] - t[i - 1]))
+print("forward start -> backward start of the same iteration: %d cycles" % (d[64] - d[0]))
