@@ -116,12 +116,13 @@ def load(auto_build: bool = True):
     with _lock:
         if _lib is not None:
             return _lib
-        if auto_build and _stale():
+        path = os.environ.get("CNF_LIB_PATH", LIB_PATH)      # development aid: load a variant build of the same library
+        if path == LIB_PATH and auto_build and _stale():
             build()
-        if not os.path.exists(LIB_PATH):
+        if not os.path.exists(path):
             raise CnfError("libcnf_sm100.so is missing (%s): run __graft_entry__.build(); there is no fallback path"
-                           % LIB_PATH)
-        lib = ctypes.CDLL(LIB_PATH)
+                           % path)
+        lib = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)       # AttributeError if a declared symbol is not exported
             fn.restype = res

@@ -286,7 +286,8 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
   int32_t* perm = reinterpret_cast<int32_t*>(w8 + wl.perm);
   static bool attr_set = false;
   if (!attr_set) {
-    CNF_CUDA(cudaFuncSetAttribute(fused_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    CNF_CUDA(cudaFuncSetAttribute(fused_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    CNF_CUDA(cudaFuncSetAttribute(fused_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     attr_set = true;
   }
   int dev = 0, n_sm = 148;
@@ -307,7 +308,8 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
   fa.perm = perm; fa.seg_ray0 = seg_ray0; fa.seg_tile0 = seg_tile0; fa.n_obj = n_obj; fa.counts = counts;
   fa.cs = cs; fa.os = os; fa.raw = raw; fa.rawi = rawi; fa.dbg = g_dbg;
   if (g_ev_start && g_ev_stop) CNF_CUDA(cudaEventRecord(g_ev_start, st));
-  fused_step_kernel<<<dim3(cpc, K), NT, SM_TOTAL, st>>>(fa);
+  if (g_dbg) fused_step_kernel<true><<<dim3(cpc, K), NT, SM_TOTAL, st>>>(fa);
+  else fused_step_kernel<false><<<dim3(cpc, K), NT, SM_TOTAL, st>>>(fa);
   if (g_ev_start && g_ev_stop) { CNF_CUDA(cudaEventRecord(g_ev_stop, st)); g_ev_start = g_ev_stop = nullptr; }
   fused_finalize_kernel<<<dim3(K, 8), 256, 0, st>>>(L, nom, params, pe_scale, shape_codes, tex_codes, n_obj, raw, rawi, zlat, reg_scaling,
                                                     flags & 1, g_params, g_B, g_shape, g_tex, reg);
