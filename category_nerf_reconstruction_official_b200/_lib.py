@@ -19,7 +19,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libcnf_sm100.so")
 SOURCES = ["cnf_api.cu", "cnf_sampler.cu", "cnf_embed.cu", "cnf_composite.cu", "cnf_mlp_simt.cu",
            "cnf_selftest.cu", "cnf_fused.cu"]
-HEADERS = ["cnf_common.cuh", "cnf_umma.cuh", os.path.join("..", "..", "include", "cnf.h")]
+HEADERS = ["cnf_common.cuh", "cnf_umma.cuh", "cnf_fused_a.inc", "cnf_fused_b.inc", os.path.join("..", "..", "include", "cnf.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

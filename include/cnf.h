@@ -179,8 +179,9 @@ int cnf_train_step(int n_cat, int n_rays, int S, int L, int n_obj_max,
  * the hook.  Lets bench.py time the dominant kernel live without a profiler. */
 int cnf_set_kernel_events(void* ev_start, void* ev_stop);
 
-/* Development aid: device buffer of 128 int64 receiving SM-clock stage timestamps of one tile (threads 0 / 128 of CTA 0);
- * NULL (default) disables it. */
+/* Development aid: device buffer of 256 int64 receiving SM-clock timestamps of CTA (0,0): [0..59] / [64..127] stage stamps of
+ * the third tile (forward / backward role), [60..63] loop ends / flush end / kernel start, [128..191] / [192..255] tile-start
+ * clocks of the first 64 tiles of each role.  NULL (default) selects the production kernel without any of it. */
 int cnf_set_debug_buffer(void* dev_ptr);
 
 /* tcgen05 self-test: D[128,N] = A[128,K] * B[N,K]^T with bf16 operands staged in shared memory in the

@@ -6,11 +6,11 @@ import torch
 from bench import WORKLOADS, synth_batch
 from category_nerf_reconstruction_official_b200 import _lib
 from category_nerf_reconstruction_official_b200.fused import FusedCategoryTrainer
-wl = dict(WORKLOADS["c4"]); wl["R"] = 65536
+wl = dict(WORKLOADS["c4"]); wl["R"] = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
 dev = torch.device("cuda:0")
 tr = FusedCategoryTrainer(wl["K"], wl["n_obj"], latent_dim=wl["L"], scale=wl["scale"], device=dev, n_bins_cam2surface=wl["N"], n_bins=wl["M"])
 b = synth_batch(wl, seed=3, device=dev)
-dbg = torch.zeros(128, dtype=torch.int64, device=dev)
+dbg = torch.zeros(256, dtype=torch.int64, device=dev)
 lib = _lib.load()
 for i in range(3):
     tr.step(b["rgbs"], b["depth"], b["origins"], b["dirs"], b["indices"])
@@ -34,3 +34,11 @@ for role, names, off in (("forward", fn, 0), ("backward", bn, 64)):
     for i in range(1, n):
         print("   %-28s +%6d" % (names[i] if i < len(names) else str(i), t[i] - t[i - 1]))
 print("forward start -> backward start of the same iteration: %d cycles" % (d[64] - d[0]))
+
+f = d[128:192].tolist(); bk = d[192:256].tolist()
+per = lambda x: [x[i + 1] - x[i] for i in range(len(x) - 1) if x[i + 1] and x[i]]
+pf, pb = per(f), per(bk)
+print("forward tile period (cycles), tiles 0..62:", pf[:6], "... median", sorted(pf)[len(pf) // 2] if pf else None)
+print("backward tile period (cycles):", pb[:6], "... median", sorted(pb)[len(pb) // 2] if pb else None)
+print("kernel start -> forward loop end %d, -> backward loop end %d, -> after flush %d (first forward tile at +%d)" %
+      (d[60] - d[63], d[61] - d[63], d[62] - d[63], f[0] - d[63]))
