@@ -101,6 +101,7 @@ SIGNATURES = {
     "cnf_train_step_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "cnf_train_step": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P, P,
                                c_float, c_float, c_float, c_int, P, P, P, P, P, P, c_size_t, P]),
+    "cnf_train_step_prepare": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_size_t, P]),
     "cnf_set_debug_buffer": (c_int, [P]),
     "cnf_set_kernel_events": (c_int, [P, P]),
     "cnf_umma_m64_probe": (c_int, [c_int, c_int, c_int, P, P, P, P]),

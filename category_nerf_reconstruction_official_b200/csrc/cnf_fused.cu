@@ -37,16 +37,46 @@ using namespace umma;
 // ---------------------------------------------------------------------------------------------------------
 // finalize: raw accumulators -> reference-shaped gradients (one CTA per category) + code regulariser
 // ---------------------------------------------------------------------------------------------------------
+// out_loss = {loss, e_depth, e_obj, e_sem, depth[K], color[K], opacity[K], reg_shape[K], reg_tex[K]}; executed by one warp
+__device__ __forceinline__ void loss_outputs(int K, const float* __restrict__ raw, const int32_t* __restrict__ counts, int cstride,
+                                             const float* reg, float cs, float os, float reg_scaling, int add_reg,
+                                             float* __restrict__ out_loss) {
+  const int lane = threadIdx.x & 31;
+  int f0 = 0, f1 = 0, f2 = 0;
+  for (int k = lane; k < K; k += 32) { f0 |= counts[k * cstride + 0] == 0; f1 |= counts[k * cstride + 1] == 0; f2 |= counts[k * cstride + 2] == 0; }
+  const bool e0 = __any_sync(0xffffffffu, f0), e1 = __any_sync(0xffffffffu, f1), e2 = __any_sync(0xffffffffu, f2);
+  float total = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float* l = raw + (size_t)k * RAW_FLOATS + RLOSS;
+    const float r0 = __ldcg(reg + k * 2), r1 = __ldcg(reg + k * 2 + 1);     // written by other CTAs of this launch: bypass L1
+    const float d = e0 ? 0.f : l[0] / ((float)counts[k * cstride + 0] + 1e-10f);
+    const float c = e1 ? 0.f : l[1] / ((float)counts[k * cstride + 1] + 1e-10f);
+    const float o = e2 ? 0.f : l[2] / ((float)counts[k * cstride + 2] + 1e-10f);
+    out_loss[4 + k] = d; out_loss[4 + K + k] = c; out_loss[4 + 2 * K + k] = o;
+    out_loss[4 + 3 * K + k] = r0; out_loss[4 + 4 * K + k] = r1;
+    total += d + c * cs + o * os;
+    if (add_reg) total += reg_scaling * (r0 + r1);
+  }
+  total = warp_sum(total);
+  if (lane == 0) { out_loss[0] = total; out_loss[1] = e0; out_loss[2] = e1; out_loss[3] = e2; }
+}
+
+// grid = (K, FIN_JOBS): one CTA per (category, job); a job is ONE family of outputs, so a CTA's dependent global-load chain is
+// short (the kernel is latency-bound: ~6 M instructions in total).
+//   0: encoding_xyz, rgb layers, PE matrix      1: encoding_viewdir (+ b_vd, b_sigma)     2: encoding_shape, its bias, sigma weights
+//   3..6: conditioned layer s (weights + bias)  7..10: latent layer s (needs d z of slot s)
+//   11..14: a quarter of the code tables (needs d z of all slots + code norms)            15: regulariser values
+constexpr int FIN_JOBS = 16;
 __global__ void __launch_bounds__(256)
 fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, const float* __restrict__ pe_scale,
                       const float* __restrict__ shape_codes, const float* __restrict__ tex_codes,
                       const int32_t* __restrict__ n_obj_arr, const float* __restrict__ raw, const float* __restrict__ rawi,
                       const float* __restrict__ zlat,
                       float reg_scaling, int add_reg, float* __restrict__ g_params, float* __restrict__ g_B,
-                      float* __restrict__ g_shape, float* __restrict__ g_tex, float* __restrict__ reg_out) {
-  // grid = (K, FIN_PARTS): every CTA recomputes the small per-instance terms, then takes a slice of the outputs
-  const int k = blockIdx.x, tid = threadIdx.x;
-  const int gtid = blockIdx.y * 256 + tid, gstride = 256 * gridDim.y;
+                      float* __restrict__ g_shape, float* __restrict__ g_tex, float* __restrict__ reg_out,
+                      const int32_t* __restrict__ counts, int cstride, float cs, float os, int* __restrict__ done_counter,
+                      float* __restrict__ out_loss) {
+  const int k = blockIdx.x, job = blockIdx.y, tid = threadIdx.x;
   const PLay lay(L);
   const float* P = params + (size_t)k * lay.total;
   float* G = g_params + (size_t)k * lay.total;
@@ -57,167 +87,172 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
   __shared__ float s_dpre[4][MAXOBJ][NL];      // relu-masked gradient wrt the latent pre-activations
   __shared__ float s_norm[2][MAXOBJ];
   (void)pe_scale;                              // t = x/scale is already applied in the accumulated operand
-  const int cons_w[4] = {4, 10, 8, 20};
-  const int cons_ld[4] = {32, 119, 32, 32};
-  const int rw[4] = {RW2, RW3, RW4, RW7};
-  const int lat_w[4] = {2, 12, 6, 22};
   const int warp = tid >> 5, lane = tid & 31;
+  // conditioned layers: parameter index of the consumer weights, their row length, raw region; latent layer parameter index
+  auto cons_w = [](int s) { return s == 0 ? 4 : (s == 1 ? 10 : (s == 2 ? 8 : 20)); };
+  auto cons_ld = [](int s) { return s == 1 ? 119 : 32; };
+  auto rw = [](int s) { return s == 0 ? RW2 : (s == 1 ? RW3 : (s == 2 ? RW4 : RW7)); };
+  auto lat_w = [](int s) { return s == 0 ? 2 : (s == 1 ? 12 : (s == 2 ? 6 : 22)); };
 
-  // --- per-instance terms: d z[inst][c] = sum_n dC[inst][n] W_cons[n][c], masked by relu(z) ; code norms
-  for (int i = tid; i < 4 * n_obj * NL; i += 256) {
-    const int s = i / (n_obj * NL), inst = (i / NL) % n_obj, c = i % NL;
-    float a = 0.f;
-    if (z[((size_t)s * n_obj_max + inst) * NL + c] > 0.f) {
-      const int ld = cons_ld[s];
-#pragma unroll 8
-      for (int n = 0; n < 32; ++n) a = fmaf(ri[(inst * 4 + s) * 32 + n], P[lay.o[cons_w[s]] + (size_t)n * ld + c], a);
+  // d z[inst][c] = sum_n dC[inst][n] W_cons[n][c], masked by relu(z), for slots [s0, s1)
+  auto compute_dpre = [&](int s0, int s1) {
+    for (int i = tid; i < (s1 - s0) * n_obj * NL; i += 256) {
+      const int s = s0 + i / (n_obj * NL), inst = (i / NL) % n_obj, c = i % NL;
+      float a = 0.f;
+      if (z[((size_t)s * n_obj_max + inst) * NL + c] > 0.f) {
+        const int ld = cons_ld(s);
+        const float* w = P + lay.o[cons_w(s)] + c;
+        const float* r = ri + (inst * 4 + s) * 32;
+#pragma unroll
+        for (int n = 0; n < 32; ++n) a = fmaf(r[n], w[(size_t)n * ld], a);
+      }
+      s_dpre[s][inst][c] = a;
     }
-    s_dpre[s][inst][c] = a;
-  }
-  for (int o = warp; o < 2 * n_obj; o += 8) {
-    const int which = o / n_obj, inst = o % n_obj;
-    const float* code = (which ? tex_codes : shape_codes) + ((size_t)k * n_obj_max + inst) * L;
-    float a = 0.f;
-    for (int j = lane; j < L; j += 32) a = fmaf(code[j], code[j], a);
-    a = warp_sum(a);
-    if (lane == 0) s_norm[which][inst] = sqrtf(a);
-  }
-  __syncthreads();
+  };
+  auto compute_norms = [&]() {
+    for (int o = warp; o < 2 * n_obj; o += 8) {
+      const int which = o / n_obj, inst = o % n_obj;
+      const float* code = (which ? tex_codes : shape_codes) + ((size_t)k * n_obj_max + inst) * L;
+      float a = 0.f;
+      for (int j = lane; j < L; j += 32) a = fmaf(code[j], code[j], a);
+      a = warp_sum(a);
+      if (lane == 0) s_norm[which][inst] = sqrtf(a);
+    }
+  };
 
-  // --- PE projection matrix: dB[d][a] = sum_p d(proj)[p][d] * t[p][a]  (accumulated as [t0 t1 t2 ONE]^T d(proj))
-  if (blockIdx.y == 0)
+  if (job == 0) {
+    // PE projection matrix: dB[d][a] = sum_p d(proj)[p][d] * t[p][a]  (accumulated as [t0 t1 t2 ONE]^T d(proj))
     for (int i = tid; i < 63; i += 256) { const int d = i / 3, ax = i % 3; g_B[(size_t)k * 63 + i] = rk[RPE + ax * 32 + pe_col(d)]; }
-  // --- plain layers (transposed copies out of the raw accumulators; xg / xc lanes follow the tile column order)
-  for (int i = gtid; i < 32 * 87; i += gstride) { const int n = i / 87, e = i % 87; G[lay.o[0] + i] = rk[RW1 + xg_col(e) * 32 + n]; }
-  for (int i = gtid; i < 16 * 32; i += gstride) { const int n = i / 32, c = i % 32; G[lay.o[24] + i] = rk[RW89 + c * 16 + n]; }
-  for (int i = gtid; i < 3 * 16; i += gstride) { const int j = i / 16, c = i % 16; G[lay.o[26] + i] = rk[RW89 + (32 + c) * 16 + j]; }
-  // encoding_viewdir / encoding_shape / sigma: the kernel trained the folded weights
-  //   W6a' = Wvd[:, :32] W5, b6' = Wvd[:, :32] b5 + b_vd, wsig' = wsig W5, bsig' = wsig b5 + bsig.
-  // With Ga'[n][k] = dL/dW6a'[n][k], gb6'[n], gws'[k], gbs':
-  //   dWvd[n][j<32] = sum_k Ga'[n][k] W5[j][k] + gb6'[n] b5[j]         dWvd[n][32+e] direct
-  //   dW5[j][k]     = sum_n Wvd[n][j] Ga'[n][k] + wsig[j] gws'[k]      db5[j] = sum_n Wvd[n][j] gb6'[n] + wsig[j] gbs'
-  //   dwsig[j]      = sum_k gws'[k] W5[j][k] + gbs' b5[j]              db_vd = gb6', dbsig = gbs'
-  {
+    // plain layers (transposed copies out of the raw accumulators; xg / xc lanes follow the tile column order)
+    for (int i = tid; i < 32 * 87; i += 256) { const int n = i / 87, e = i % 87; G[lay.o[0] + i] = rk[RW1 + xg_col(e) * 32 + n]; }
+    for (int i = tid; i < 16 * 32; i += 256) { const int n = i / 32, c = i % 32; G[lay.o[24] + i] = rk[RW89 + c * 16 + n]; }
+    for (int i = tid; i < 3 * 16; i += 256) { const int j = i / 16, c = i % 16; G[lay.o[26] + i] = rk[RW89 + (32 + c) * 16 + j]; }
+    for (int j = tid; j < 32; j += 256) G[lay.o[1] + j] = rk[RW1 + XG_BIAS_COL * 32 + j];              // b_xyz (row of the ones column)
+    for (int n = tid; n < 16; n += 256) G[lay.o[25] + n] = rk[RDB8 + n];
+    for (int j = tid; j < 3; j += 256) G[lay.o[27] + j] = rk[RDB9 + j];
+  } else if (job == 1 || job == 2) {
+    // encoding_viewdir / encoding_shape / sigma: the kernel trained the folded weights
+    //   W6a' = Wvd[:, :32] W5, b6' = Wvd[:, :32] b5 + b_vd, wsig' = wsig W5, bsig' = wsig b5 + bsig.
+    // With Ga'[n][k] = dL/dW6a'[n][k], gb6'[n], gws'[k], gbs':
+    //   dWvd[n][j<32] = sum_k Ga'[n][k] W5[j][k] + gb6'[n] b5[j]         dWvd[n][32+e] direct
+    //   dW5[j][k]     = sum_n Wvd[n][j] Ga'[n][k] + wsig[j] gws'[k]      db5[j] = sum_n Wvd[n][j] gb6'[n] + wsig[j] gbs'
+    //   dwsig[j]      = sum_k gws'[k] W5[j][k] + gbs' b5[j]              db_vd = gb6', dbsig = gbs'
     const int BL = 32 + XC_BIAS_COL;                                   // lane of the ones column in the [r4 | xc] tile
     const float gbs = rk[RW6 + BL * 48 + 32];
-    for (int i = gtid; i < 32 * 74; i += gstride) {
-      const int n = i / 74, j = i % 74;
-      float a;
-      if (j < 32) {
-        a = rk[RW6 + BL * 48 + n] * P[lay.o[15] + j];
-        for (int kk = 0; kk < 32; ++kk) a = fmaf(rk[RW6 + kk * 48 + n], P[lay.o[14] + j * 32 + kk], a);
-      } else {
-        a = rk[RW6 + (32 + xc_col(87 + (j - 32))) * 48 + n];
+    if (job == 1) {
+      for (int i = tid; i < 32 * 74; i += 256) {
+        const int n = i / 74, j = i % 74;
+        float a;
+        if (j < 32) {
+          a = rk[RW6 + BL * 48 + n] * P[lay.o[15] + j];
+#pragma unroll
+          for (int kk = 0; kk < 32; ++kk) a = fmaf(rk[RW6 + kk * 48 + n], P[lay.o[14] + j * 32 + kk], a);
+        } else {
+          a = rk[RW6 + (32 + xc_col(87 + (j - 32))) * 48 + n];
+        }
+        G[lay.o[18] + i] = a;
       }
-      G[lay.o[18] + i] = a;
-    }
-    for (int i = gtid; i < 32 * 32; i += gstride) {                    // dW5[j][k]
-      const int j = i / 32, kk = i % 32;
-      float a = P[lay.o[16] + j] * rk[RW6 + kk * 48 + 32];
-      for (int n = 0; n < 32; ++n) a = fmaf(P[lay.o[18] + (size_t)n * 74 + j], rk[RW6 + kk * 48 + n], a);
-      G[lay.o[14] + i] = a;
-    }
-    if (blockIdx.y == 0) {
+      for (int j = tid; j < 32; j += 256) G[lay.o[19] + j] = rk[RW6 + BL * 48 + j];                      // b_vd
+      if (tid == 0) G[lay.o[17]] = gbs;                                                                   // b_sigma
+    } else {
+      for (int i = tid; i < 32 * 32; i += 256) {                      // dW5[j][k]
+        const int j = i / 32, kk = i % 32;
+        float a = P[lay.o[16] + j] * rk[RW6 + kk * 48 + 32];
+#pragma unroll
+        for (int n = 0; n < 32; ++n) a = fmaf(P[lay.o[18] + (size_t)n * 74 + j], rk[RW6 + kk * 48 + n], a);
+        G[lay.o[14] + i] = a;
+      }
       for (int j = tid; j < 32; j += 256) {
         float b5 = P[lay.o[16] + j] * gbs;                             // db5[j]
+#pragma unroll
         for (int n = 0; n < 32; ++n) b5 = fmaf(P[lay.o[18] + (size_t)n * 74 + j], rk[RW6 + BL * 48 + n], b5);
         G[lay.o[15] + j] = b5;
         float ws = gbs * P[lay.o[15] + j];                             // dwsig[j]
+#pragma unroll
         for (int kk = 0; kk < 32; ++kk) ws = fmaf(rk[RW6 + kk * 48 + 32], P[lay.o[14] + j * 32 + kk], ws);
         G[lay.o[16] + j] = ws;
-        G[lay.o[19] + j] = rk[RW6 + BL * 48 + j];                      // b_vd
-        G[lay.o[1] + j] = rk[RW1 + XG_BIAS_COL * 32 + j];              // b_xyz (row of the ones column)
       }
-      if (tid == 0) G[lay.o[17]] = gbs;                                // b_sigma
-      for (int n = tid; n < 16; n += 256) G[lay.o[25] + n] = rk[RDB8 + n];
-      for (int j = tid; j < 3; j += 256) G[lay.o[27] + j] = rk[RDB9 + j];
     }
-  }
-  // --- layers with per-instance bias c = W[:, :32] z + b : slots (zsl1->s1), (zcl->cat), (zsl2->s2), (ztl->t1)
-  for (int s = 0; s < 4; ++s) {
-    const int ld = cons_ld[s];
-    for (int i = gtid; i < 32 * ld; i += gstride) {
+  } else if (job < 7) {
+    // layer with per-instance bias c = W[:, :32] z + b : slots (zsl1->s1), (zcl->cat), (zsl2->s2), (ztl->t1)
+    const int s = job - 3, ld = cons_ld(s);
+    for (int i = tid; i < 32 * ld; i += 256) {
       const int n = i / ld, c = i % ld;
-      float a = rk[rw[s] + (c < 32 ? c : 32 + xg_col(c - 32)) * 32 + n];     // only the cat layer (s = 1) has c >= 32
+      float a = rk[rw(s) + (c < 32 ? c : 32 + xg_col(c - 32)) * 32 + n];     // only the cat layer (s = 1) has c >= 32
       if (c < 32)
         for (int inst = 0; inst < n_obj; ++inst) a = fmaf(ri[(inst * 4 + s) * 32 + n], z[((size_t)s * n_obj_max + inst) * NL + c], a);
-      G[lay.o[cons_w[s]] + i] = a;
+      G[lay.o[cons_w(s)] + i] = a;
     }
-    if (blockIdx.y == 0)
-      for (int n = tid; n < 32; n += 256) {
-        float a = 0.f;
-        for (int inst = 0; inst < n_obj; ++inst) a += ri[(inst * 4 + s) * 32 + n];
-        G[lay.o[cons_w[s] + 1] + n] = a;
-      }
+    for (int n = tid; n < 32; n += 256) {
+      float a = 0.f;
+      for (int inst = 0; inst < n_obj; ++inst) a += ri[(inst * 4 + s) * 32 + n];
+      G[lay.o[cons_w(s) + 1] + n] = a;
+    }
+  } else if (job < 11) {
     // latent layer: dW_lat[c][j] = sum_inst dpre[inst][c] code[inst][j]; db_lat[c] = sum_inst dpre[inst][c]
+    const int s = job - 7;
+    compute_dpre(s, s + 1);
+    __syncthreads();
     const float* codes = (s == 3 ? tex_codes : shape_codes) + (size_t)k * n_obj_max * L;
-    for (int i = gtid; i < 32 * L; i += gstride) {
+    for (int i = tid; i < 32 * L; i += 256) {
       const int c = i / L, j = i % L;
       float a = 0.f;
       for (int inst = 0; inst < n_obj; ++inst) a = fmaf(s_dpre[s][inst][c], codes[(size_t)inst * L + j], a);
-      G[lay.o[lat_w[s]] + i] = a;
+      G[lay.o[lat_w(s)] + i] = a;
     }
-    if (blockIdx.y == 0)
-      for (int c = tid; c < 32; c += 256) {
-        float a = 0.f;
-        for (int inst = 0; inst < n_obj; ++inst) a += s_dpre[s][inst][c];
-        G[lay.o[lat_w[s] + 1] + c] = a;
-      }
-  }
-  // --- code tables: d code[inst][j] = sum_s sum_c dpre[s][inst][c] W_lat_s[c][j]  (+ regulariser)
-  for (int i = gtid; i < n_obj_max * L; i += gstride) {
-    const int inst = i / L, j = i % L;
-    float gs = 0.f, gt = 0.f;
-    if (inst < n_obj) {
-#pragma unroll 4
-      for (int c = 0; c < 32; ++c) {
-        gs = fmaf(s_dpre[0][inst][c], P[lay.o[2] + (size_t)c * L + j], gs);
-        gs = fmaf(s_dpre[1][inst][c], P[lay.o[12] + (size_t)c * L + j], gs);
-        gs = fmaf(s_dpre[2][inst][c], P[lay.o[6] + (size_t)c * L + j], gs);
-        gt = fmaf(s_dpre[3][inst][c], P[lay.o[22] + (size_t)c * L + j], gt);
-      }
-      if (add_reg && n_obj > 1) {                                            // loss.py:12, train.py:165-167
-        const float ns = s_norm[0][inst], nt = s_norm[1][inst];
-        if (ns > 0.f) gs += reg_scaling * shape_codes[((size_t)k * n_obj_max + inst) * L + j] / ns;
-        if (nt > 0.f) gt += reg_scaling * tex_codes[((size_t)k * n_obj_max + inst) * L + j] / nt;
-      }
+    for (int c = tid; c < 32; c += 256) {
+      float a = 0.f;
+      for (int inst = 0; inst < n_obj; ++inst) a += s_dpre[s][inst][c];
+      G[lay.o[lat_w(s) + 1] + c] = a;
     }
-    g_shape[(size_t)k * n_obj_max * L + i] = gs;
-    g_tex[(size_t)k * n_obj_max * L + i] = gt;
+  } else if (job < 15) {
+    // code tables: d code[inst][j] = sum_s sum_c dpre[s][inst][c] W_lat_s[c][j]  (+ regulariser)
+    compute_dpre(0, 4);
+    compute_norms();
+    __syncthreads();
+    const int total = n_obj_max * L, q = job - 11;
+    const int lo = (int)((long long)total * q / 4), hi = (int)((long long)total * (q + 1) / 4);
+    for (int i = lo + tid; i < hi; i += 256) {
+      const int inst = i / L, j = i % L;
+      float gs = 0.f, gt = 0.f;
+      if (inst < n_obj) {
+#pragma unroll 16
+        for (int c = 0; c < 32; ++c) {
+          gs = fmaf(s_dpre[0][inst][c], P[lay.o[2] + (size_t)c * L + j], gs);
+          gs = fmaf(s_dpre[1][inst][c], P[lay.o[12] + (size_t)c * L + j], gs);
+          gs = fmaf(s_dpre[2][inst][c], P[lay.o[6] + (size_t)c * L + j], gs);
+          gt = fmaf(s_dpre[3][inst][c], P[lay.o[22] + (size_t)c * L + j], gt);
+        }
+        if (add_reg && n_obj > 1) {                                            // loss.py:12, train.py:165-167
+          const float ns = s_norm[0][inst], nt = s_norm[1][inst];
+          if (ns > 0.f) gs += reg_scaling * shape_codes[((size_t)k * n_obj_max + inst) * L + j] / ns;
+          if (nt > 0.f) gt += reg_scaling * tex_codes[((size_t)k * n_obj_max + inst) * L + j] / nt;
+        }
+      }
+      g_shape[(size_t)k * n_obj_max * L + i] = gs;
+      g_tex[(size_t)k * n_obj_max * L + i] = gt;
+    }
+  } else {
+    compute_norms();
+    __syncthreads();
+    __shared__ int s_last;
+    if (tid == 0) {
+      float rs = 0.f, rt = 0.f;
+      if (n_obj > 1) for (int inst = 0; inst < n_obj; ++inst) { rs += s_norm[0][inst]; rt += s_norm[1][inst]; }
+      reg_out[k * 2 + 0] = rs; reg_out[k * 2 + 1] = rt;
+      __threadfence();
+      s_last = atomicAdd(done_counter, 1) == (int)gridDim.x - 1;     // the last category to finish writes the loss outputs
+    }
+    __syncthreads();
+    if (s_last && tid < 32) {
+      __threadfence();
+      loss_outputs(gridDim.x, raw, counts, cstride, reg_out, cs, os, reg_scaling, add_reg, out_loss);
+    }
   }
-  if (blockIdx.y == 0 && tid == 0) {
-    float rs = 0.f, rt = 0.f;
-    if (n_obj > 1) for (int inst = 0; inst < n_obj; ++inst) { rs += s_norm[0][inst]; rt += s_norm[1][inst]; }
-    reg_out[k * 2 + 0] = rs; reg_out[k * 2 + 1] = rt;
-  }
-}
-
-// out_loss = {loss, e_depth, e_obj, e_sem, depth[K], color[K], opacity[K], reg_shape[K], reg_tex[K]}
-__global__ void fused_loss_kernel(int K, const float* __restrict__ raw, const int32_t* __restrict__ counts,
-                                  const float* __restrict__ reg, float cs, float os, float reg_scaling, int add_reg,
-                                  float* __restrict__ out_loss) {
-  // one warp; lane per category (strided)
-  const int lane = threadIdx.x;
-  int f0 = 0, f1 = 0, f2 = 0;
-  for (int k = lane; k < K; k += 32) { f0 |= counts[k * 4 + 0] == 0; f1 |= counts[k * 4 + 1] == 0; f2 |= counts[k * 4 + 2] == 0; }
-  const bool e0 = __any_sync(0xffffffffu, f0), e1 = __any_sync(0xffffffffu, f1), e2 = __any_sync(0xffffffffu, f2);
-  float total = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    const float* l = raw + (size_t)k * RAW_FLOATS + RLOSS;
-    const float d = e0 ? 0.f : l[0] / ((float)counts[k * 4 + 0] + 1e-10f);
-    const float c = e1 ? 0.f : l[1] / ((float)counts[k * 4 + 1] + 1e-10f);
-    const float o = e2 ? 0.f : l[2] / ((float)counts[k * 4 + 2] + 1e-10f);
-    out_loss[4 + k] = d; out_loss[4 + K + k] = c; out_loss[4 + 2 * K + k] = o;
-    out_loss[4 + 3 * K + k] = reg[k * 2]; out_loss[4 + 4 * K + k] = reg[k * 2 + 1];
-    total += d + c * cs + o * os;
-    if (add_reg) total += reg_scaling * (reg[k * 2] + reg[k * 2 + 1]);
-  }
-  total = warp_sum(total);
-  if (lane == 0) { out_loss[0] = total; out_loss[1] = e0; out_loss[2] = e1; out_loss[3] = e2; }
 }
 
 struct FusedWs {
-  size_t prep, ctab, zlat, raw, rawi, reg, hist, base, seg_ray0, seg_tile0, perm, total;
+  size_t prep, ctab, zlat, raw, rawi, done, reg, hist, base, seg_ray0, seg_tile0, perm, total;
   int nblk;
   FusedWs(size_t K, size_t R, size_t nom) {
     size_t o = 0;
@@ -228,6 +263,7 @@ struct FusedWs {
     zlat = take(K * 4 * nom * NL * 4);
     raw = take(K * RAW_FLOATS * 4);          // raw and rawi are adjacent: one memset
     rawi = take(K * nom * 4 * 32 * 4);
+    done = take(256);                          // finalize completion counter (zeroed with raw / rawi)
     reg = take(K * 2 * 4);
     hist = take(K * nom * nblk * 4);
     base = take(K * nom * nblk * 4);
@@ -256,6 +292,50 @@ extern "C" size_t cnf_train_step_workspace_bytes(int K, int R, int S, int L, int
   return FusedWs(K, R, n_obj_max).total;
 }
 
+// prep + instance sort + accumulator clear: everything of a step that does not depend on the sampled depths
+static int train_step_prepare(int K, int R, int S, int L, int nom, const float* params, const float* pe_B, const float* pe_scale,
+                              const float* shape_codes, const float* tex_codes, const int32_t* n_obj, const int32_t* inst,
+                              uint8_t* w8, const FusedWs& wl, cudaStream_t st) {
+  uint8_t* prep = w8 + wl.prep;
+  float* ctab = reinterpret_cast<float*>(w8 + wl.ctab);
+  float* zlat = reinterpret_cast<float*>(w8 + wl.zlat);
+  float* raw = reinterpret_cast<float*>(w8 + wl.raw);
+  int32_t* hist = reinterpret_cast<int32_t*>(w8 + wl.hist);
+  int32_t* base = reinterpret_cast<int32_t*>(w8 + wl.base);
+  int32_t* seg_ray0 = reinterpret_cast<int32_t*>(w8 + wl.seg_ray0);
+  int32_t* seg_tile0 = reinterpret_cast<int32_t*>(w8 + wl.seg_tile0);
+  int32_t* perm = reinterpret_cast<int32_t*>(w8 + wl.perm);
+  const int rpw = 32 / S, RPT = 4 * rpw, nblk = wl.nblk;
+  CNF_CUDA(cudaMemsetAsync(raw, 0, wl.reg - wl.raw, st));            // raw, rawi and the finalize completion counter
+  fused_prep_kernel<<<dim3(K, PREP_IMG_PARTS + 4), 256, 0, st>>>(L, nom, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, prep, zlat, ctab);
+  if (nblk <= SORT_SMALL_BLOCKS) {
+    sort_small_kernel<<<K, 256, nom * sizeof(int), st>>>(R, nom, RPT, inst, n_obj, seg_ray0, seg_tile0, perm);
+  } else {
+    sort_count_kernel<<<dim3(nblk, K), 256, nom * sizeof(int), st>>>(R, nom, nblk, inst, n_obj, hist);
+    sort_scan_kernel<<<K, 256, nom * sizeof(int), st>>>(nom, nblk, RPT, hist, base, seg_ray0, seg_tile0);
+    sort_scatter_kernel<<<dim3(nblk, K), 256, 0, st>>>(R, nom, nblk, inst, n_obj, base, seg_ray0, perm);
+  }
+  return check_launch("cnf_train_step_prepare");
+}
+
+static int check_step_sizes(const char* who, int K, int R, int S, int L, int n_obj_max) {
+  if (!(K > 0 && R > 0 && L > 0)) { set_error("%s: bad sizes K=%d R=%d L=%d", who, K, R, L); return CNF_ERR_ARG; }
+  if (S < 1 || S > 32) { set_error("%s: samples per ray S=%d outside 1..32 (one ray per warp segment)", who, S); return CNF_ERR_UNSUPPORTED; }
+  if (n_obj_max < 1 || n_obj_max > MAXOBJ) { set_error("%s: n_obj_max=%d outside 1..%d", who, n_obj_max, MAXOBJ); return CNF_ERR_UNSUPPORTED; }
+  return CNF_OK;
+}
+
+extern "C" int cnf_train_step_prepare(int K, int R, int S, int L, int n_obj_max, const float* params, const float* pe_B,
+                                      const float* pe_scale, const float* shape_codes, const float* tex_codes,
+                                      const int32_t* n_obj, const int32_t* inst, void* ws, size_t ws_bytes, cnf_stream_t stream) {
+  if (int e = check_step_sizes("cnf_train_step_prepare", K, R, S, L, n_obj_max)) return e;
+  CNF_REQUIRE(params && pe_B && pe_scale && shape_codes && tex_codes && n_obj && inst && ws, "cnf_train_step_prepare: null pointer");
+  const FusedWs wl(K, R, n_obj_max);
+  if (ws_bytes < wl.total) { set_error("cnf_train_step_prepare: workspace too small (%zu < %zu)", ws_bytes, wl.total); return CNF_ERR_WORKSPACE; }
+  return train_step_prepare(K, R, S, L, n_obj_max, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, inst,
+                            reinterpret_cast<uint8_t*>(ws), wl, as_stream(stream));
+}
+
 extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const float* params, const float* pe_B,
                               const float* pe_scale, const float* shape_codes, const float* tex_codes,
                               const int32_t* n_obj, const float* origins, const float* dirs, const float* z,
@@ -263,9 +343,7 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
                               const int32_t* inst, const int32_t* counts, float cs, float os, float reg_scaling,
                               int flags, float* g_params, float* g_B, float* g_shape, float* g_tex, float* out_loss,
                               void* ws, size_t ws_bytes, cnf_stream_t stream) {
-  CNF_REQUIRE(K > 0 && R > 0 && L > 0, "cnf_train_step: bad sizes K=%d R=%d L=%d", K, R, L);
-  if (S < 1 || S > 32) { set_error("cnf_train_step: samples per ray S=%d outside 1..32 (one ray per warp segment)", S); return CNF_ERR_UNSUPPORTED; }
-  if (n_obj_max < 1 || n_obj_max > MAXOBJ) { set_error("cnf_train_step: n_obj_max=%d outside 1..%d", n_obj_max, MAXOBJ); return CNF_ERR_UNSUPPORTED; }
+  if (int e = check_step_sizes("cnf_train_step", K, R, S, L, n_obj_max)) return e;
   CNF_REQUIRE(params && pe_B && pe_scale && shape_codes && tex_codes && n_obj && origins && dirs && z && gt_depth && gt_rgb &&
                   mask_depth && inst && counts && g_params && g_B && g_shape && g_tex && out_loss && ws,
               "cnf_train_step: null pointer");
@@ -273,17 +351,13 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
   if (ws_bytes < wl.total) { set_error("cnf_train_step: workspace too small (%zu < %zu)", ws_bytes, wl.total); return CNF_ERR_WORKSPACE; }
   cudaStream_t st = as_stream(stream);
   uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
-  uint8_t* prep = w8 + wl.prep;
-  float* ctab = reinterpret_cast<float*>(w8 + wl.ctab);
-  float* zlat = reinterpret_cast<float*>(w8 + wl.zlat);
+  const int nom = n_obj_max;
+  if (!(flags & 2)) {          // not prepared by cnf_train_step_prepare (e.g. on a side stream, overlapping the sampler)
+    if (int e = train_step_prepare(K, R, S, L, nom, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, inst, w8, wl, st)) return e;
+  }
   float* raw = reinterpret_cast<float*>(w8 + wl.raw);
   float* rawi = reinterpret_cast<float*>(w8 + wl.rawi);
   float* reg = reinterpret_cast<float*>(w8 + wl.reg);
-  int32_t* hist = reinterpret_cast<int32_t*>(w8 + wl.hist);
-  int32_t* base = reinterpret_cast<int32_t*>(w8 + wl.base);
-  int32_t* seg_ray0 = reinterpret_cast<int32_t*>(w8 + wl.seg_ray0);
-  int32_t* seg_tile0 = reinterpret_cast<int32_t*>(w8 + wl.seg_tile0);
-  int32_t* perm = reinterpret_cast<int32_t*>(w8 + wl.perm);
   static bool attr_set = false;
   if (!attr_set) {
     CNF_CUDA(cudaFuncSetAttribute(fused_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
@@ -295,24 +369,21 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
   CNF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   const int rpw = 32 / S, RPT = 4 * rpw, n_tiles_ub = (R + RPT - 1) / RPT + n_obj_max;
   int cpc = n_sm / K; if (cpc < 1) cpc = 1; if (cpc > n_tiles_ub) cpc = n_tiles_ub;
-  const int nblk = wl.nblk, nom = n_obj_max;
-  CNF_CUDA(cudaMemsetAsync(raw, 0, (wl.rawi - wl.raw) + (size_t)K * nom * 4 * 32 * 4, st));
-  fused_prep_kernel<<<dim3(K, 5), 256, 0, st>>>(L, nom, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, prep, zlat, ctab);
-  sort_count_kernel<<<dim3(nblk, K), 256, nom * sizeof(int), st>>>(R, nom, nblk, inst, n_obj, hist);
-  sort_scan_kernel<<<K, 256, nom * sizeof(int), st>>>(nom, nblk, RPT, hist, base, seg_ray0, seg_tile0);
-  sort_scatter_kernel<<<dim3(nblk, K), 256, 0, st>>>(R, nom, nblk, inst, n_obj, base, seg_ray0, perm);
   FusedArgs fa;
   fa.K = K; fa.R = R; fa.S = S; fa.nom = nom;
-  fa.prep = prep; fa.ctab = ctab;
+  fa.prep = w8 + wl.prep; fa.ctab = reinterpret_cast<float*>(w8 + wl.ctab);
   fa.origins = origins; fa.dirs = dirs; fa.zs = z; fa.gt_depth = gt_depth; fa.gt_rgb = gt_rgb; fa.mask_depth = mask_depth;
-  fa.perm = perm; fa.seg_ray0 = seg_ray0; fa.seg_tile0 = seg_tile0; fa.n_obj = n_obj; fa.counts = counts;
+  fa.perm = reinterpret_cast<int32_t*>(w8 + wl.perm); fa.seg_ray0 = reinterpret_cast<int32_t*>(w8 + wl.seg_ray0);
+  fa.seg_tile0 = reinterpret_cast<int32_t*>(w8 + wl.seg_tile0); fa.n_obj = n_obj; fa.counts = counts;
+  const int cstride = ((flags >> 8) & 0xFF) ? ((flags >> 8) & 0xFF) : 4;
+  fa.cstride = cstride;
   fa.cs = cs; fa.os = os; fa.raw = raw; fa.rawi = rawi; fa.dbg = g_dbg;
   if (g_ev_start && g_ev_stop) CNF_CUDA(cudaEventRecord(g_ev_start, st));
   if (g_dbg) fused_step_kernel<true><<<dim3(cpc, K), NT, SM_TOTAL, st>>>(fa);
   else fused_step_kernel<false><<<dim3(cpc, K), NT, SM_TOTAL, st>>>(fa);
   if (g_ev_start && g_ev_stop) { CNF_CUDA(cudaEventRecord(g_ev_stop, st)); g_ev_start = g_ev_stop = nullptr; }
-  fused_finalize_kernel<<<dim3(K, 8), 256, 0, st>>>(L, nom, params, pe_scale, shape_codes, tex_codes, n_obj, raw, rawi, zlat, reg_scaling,
-                                                    flags & 1, g_params, g_B, g_shape, g_tex, reg);
-  fused_loss_kernel<<<1, 32, 0, st>>>(K, raw, counts, reg, cs, os, reg_scaling, flags & 1, out_loss);
+  fused_finalize_kernel<<<dim3(K, FIN_JOBS), 256, 0, st>>>(L, nom, params, pe_scale, shape_codes, tex_codes, n_obj, raw, rawi,
+                                                            reinterpret_cast<float*>(w8 + wl.zlat), reg_scaling, flags & 1, g_params, g_B,
+                                                            g_shape, g_tex, reg, counts, cstride, cs, os, reinterpret_cast<int*>(w8 + wl.done), out_loss);
   return check_launch("cnf_train_step");
 }

@@ -8,6 +8,7 @@ asynchronous; nothing is read back unless the caller asks (``.item()`` on a resu
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -65,6 +66,7 @@ class FusedCategoryTrainer:
         self._ws = None
         self._ws_key = None
         self._opt_state = None
+        self._side = None
         self.launches_per_step = 0
 
     # ------------------------------------------------------------------------------------------ state import
@@ -111,9 +113,20 @@ class FusedCategoryTrainer:
             self._ws_key = key
         return self._ws
 
-    def step_from_samples(self, origins, dirs, z, gt_depth, rgbs, mask_depth, indices, counts, add_reg: bool = True):
+    def prepare(self, indices, R: int):
+        """First half of a step (cnf_train_step_prepare): operand images, per-instance biases, instance sort, accumulator clear.
+        Independent of the sampled depths, so ``step`` runs it on a side stream next to the sampler."""
+        lib = lib_for(self.params)
+        ws = self._workspace(R)
+        check(lib.cnf_train_step_prepare(self.K, R, self.S, self.L, self.n_obj_max, ptr(self.params), ptr(self.pe_B),
+                                         ptr(self.pe_scale), ptr(self.shape_codes), ptr(self.tex_codes), ptr(self.n_obj),
+                                         ptr(indices), ptr(ws), ws.numel(), stream()))
+
+    def step_from_samples(self, origins, dirs, z, gt_depth, rgbs, mask_depth, indices, counts, add_reg: bool = True,
+                          prepared: bool = False):
         """Fused fwd+bwd given sampled depths z [K,R,S]. rgbs u8 [K,R,4] (rgb + label); mask_depth u8/bool [K,R];
-        indices int32 [K,R]; counts int32 [K,4]. Fills self.g_* and self.out_loss; returns the loss (0-d, async)."""
+        indices int32 [K,R]; counts int32 [K,4] (or a [K,>=4]-strided view, e.g. the sampler's stats[:, 4:8]).
+        Fills self.g_* and self.out_loss; returns the loss (0-d, async)."""
         lib = lib_for(self.params)
         K, R, S = z.shape
         assert K == self.K and S == self.S
@@ -122,24 +135,44 @@ class FusedCategoryTrainer:
             indices = indices.to(torch.int32)
         if mask_depth.dtype != torch.uint8:
             mask_depth = mask_depth.to(torch.uint8)
+        assert counts.dtype == torch.int32 and counts.stride(1) == 1 and 4 <= counts.stride(0) < 256
+        flags = (1 if add_reg else 0) | (2 if prepared else 0) | (counts.stride(0) << 8)
         check(lib.cnf_train_step(K, R, S, self.L, self.n_obj_max, ptr(self.params), ptr(self.pe_B), ptr(self.pe_scale),
                                  ptr(self.shape_codes), ptr(self.tex_codes), ptr(self.n_obj), ptr(origins.contiguous()),
                                  ptr(dirs.contiguous()), ptr(z.contiguous()), ptr(gt_depth.contiguous()),
                                  ptr(rgbs.contiguous()), ptr(mask_depth.contiguous()), ptr(indices.contiguous()),
-                                 ptr(counts.contiguous()), float(self.cs), float(self.os), float(self.reg),
-                                 1 if add_reg else 0, ptr(self.g_params), ptr(self.g_B), ptr(self.g_shape), ptr(self.g_tex),
+                                 counts.data_ptr(), float(self.cs), float(self.os), float(self.reg),     # row-strided view allowed
+                                 flags, ptr(self.g_params), ptr(self.g_B), ptr(self.g_shape), ptr(self.g_tex),
                                  ptr(self.out_loss), ptr(ws), ws.numel(), stream()))
         return self.out_loss[0]
 
     def step(self, rgbs, depth, origins, dirs, indices, rand: Optional[Dict[str, torch.Tensor]] = None, add_reg=True):
-        """Sample + fused step for K categories: rgbs u8 [K,R,4], depth [K,R], origins/dirs [K,R,3], indices [K,R]."""
+        """Sample + fused step for K categories: rgbs u8 [K,R,4], depth [K,R], origins/dirs [K,R,3], indices [K,R].
+        The step's sampler-independent half (prep + instance sort) runs on a side stream next to the random draws and the
+        sampler; both join before the fused kernel (the fork/join is captured as graph dependencies by ``capture``)."""
+        if indices.dtype != torch.int32:
+            indices = indices.to(torch.int32)
+        indices = indices.contiguous()
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        self._workspace(rgbs.shape[1])                       # allocate on the main stream
+        overlap = os.environ.get("CNF_NO_SIDE_STREAM") is None      # debugging aid: run the prepare half inline
+        if overlap:
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self.prepare(indices, rgbs.shape[1])
+        else:
+            self.prepare(indices, rgbs.shape[1])
         if rand is None:
             rand = sampling.draw_randoms(rgbs, depth, self.N, self.M, self.eps, self.min_bound, self.this_obj)
         z, _, valid, labels, stats = ops.sample_batched(rgbs, depth, origins, dirs, self.N, self.M, self.eps, self.stop_eps,
                                                        rand, self.min_bound, self.this_obj, want_pcs=False)
-        counts = stats[:, 4:8].contiguous()
-        self.launches_per_step = 3 + 5
-        return self.step_from_samples(origins, dirs, z, depth, rgbs, valid.view(torch.uint8), indices, counts, add_reg)
+        if overlap:
+            main.wait_stream(self._side)
+        self.launches_per_step = 3 + 4
+        return self.step_from_samples(origins, dirs, z, depth, rgbs, valid.view(torch.uint8), indices, stats[:, 4:8], add_reg,
+                                      prepared=True)
 
     def capture(self, rgbs, depth, origins, dirs, indices, add_reg=True):
         """Capture sampler + fused step over THESE (static) input tensors into a CUDA graph and return ``replay``.

@@ -160,9 +160,18 @@ int cnf_code_reg(int n_obj, int L, const float* codes, float weight, float* out,
  *     mask_depth u8 [K,R], inst int32 [K,R], counts int32 [K,4] (cnf_mask_counts / sampler stats+4)
  *     outputs (all OVERWRITTEN): g_params [K,n_param], g_B [K,21,3], g_shape/g_tex [K,n_obj_max,L],
  *     out_loss [4+3K] as in cnf_composite_loss_fwd plus reg terms appended: [.., reg_shape[K], reg_tex[K]].
- *     flags: bit0 = also add the code regulariser (weight reg_scaling) to loss and code grads.
+ *     flags: bit0 = also add the code regulariser (weight reg_scaling) to loss and code grads;
+ *            bit1 = the workspace was prepared by cnf_train_step_prepare (same arguments) -- skip that half;
+ *            bits 8-15 = row stride of `counts` in int32 elements (0 means 4), so cnf_sample_fwd's stats[K,8] + 4 can be passed as is.
  * ---------------------------------------------------------------------------------------------- */
 size_t cnf_train_step_workspace_bytes(int n_cat, int n_rays, int S, int L, int n_obj_max);
+/* Optional first half of a step: everything that does not depend on the sampled depths (bf16 operand images, per-instance
+ * biases, instance sort of the rays, accumulator clear).  Call it on ANY stream (e.g. a side stream overlapping the sampler),
+ * make the stream of cnf_train_step wait for it, then pass flags | 2 to cnf_train_step with the same arguments / workspace. */
+int cnf_train_step_prepare(int n_cat, int n_rays, int S, int L, int n_obj_max,
+                           const float* params, const float* pe_B, const float* pe_scale,
+                           const float* shape_codes, const float* tex_codes, const int32_t* n_obj,
+                           const int32_t* inst, void* ws, size_t ws_bytes, cnf_stream_t stream);
 int cnf_train_step(int n_cat, int n_rays, int S, int L, int n_obj_max,
                    const float* params, const float* pe_B, const float* pe_scale,
                    const float* shape_codes, const float* tex_codes, const int32_t* n_obj,

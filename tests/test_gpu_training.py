@@ -127,3 +127,25 @@ def test_loss_curves_overlap_1k_steps():
     # fused step itself repeats to 1e-7).  Measured over repeated runs on B200: median 0.03-0.10, q90 0.13-0.35, max 0.18-0.40.
     assert float(rel.median()) < 0.2 and float(rel.quantile(0.9)) < 0.6, \
         ("smoothed loss curves diverge", rel.tolist(), sa.tolist(), sb.tolist())
+
+
+def test_fused_step_repeats_to_atomic_noise():
+    """Race detector: the same step repeated many times must agree to fp32 atomic-order noise (1e-7 measured).  A data race in
+    the two-role kernel (e.g. an MMA operand overwritten while a trailing MMA still reads it) shows up as 1e-5..1e-3 deviations."""
+    from category_nerf_reconstruction_official_b200 import sampling
+    from category_nerf_reconstruction_official_b200.fused import FusedCategoryTrainer
+    for K, R, n_obj, L, N in ((6, 360, 3, 32, 1), (1, 4096, 8, 64, 5)):
+        tr = FusedCategoryTrainer(K, n_obj, latent_dim=L, device=DEV, n_bins_cam2surface=N, n_bins=9,
+                                  generator=torch.Generator().manual_seed(5))
+        rgbs, depth, org, dirs, idx = _batch(K, R, n_obj, 7)
+        rand = sampling.draw_randoms(rgbs, depth, N, 9, 0.1)
+        ref, worst = None, 0.0
+        for _ in range(60):
+            tr.step(rgbs, depth, org, dirs, idx, rand=rand)
+            g = torch.cat([tr.g_params.flatten(), tr.g_B.flatten(), tr.g_shape.flatten(), tr.g_tex.flatten(), tr.out_loss.flatten()]).clone()
+            if ref is None:
+                ref = g
+                continue
+            worst = max(worst, float((g - ref).abs().max() / ref.abs().max()))
+        assert torch.isfinite(ref).all()
+        assert worst < 5e-6, "fused step is not repeatable: worst deviation %.3e" % worst
