@@ -7,7 +7,7 @@ for r in rows[1:]:
     v = float(r[vi].replace(",", ""))
     if r[ui] in ("ns", "nsecond"): v /= 1000.0
     seq.append((r[ki].split("(")[0][-48:], v))
-ends = [i for i, (n, _) in enumerate(seq) if "loss_kernel" in n]
+ends = [i for i, (n, _) in enumerate(seq) if "finalize_kernel" in n]      # last kernel of a step
 a, b = (ends[0] + 1, ends[1] + 1) if len(ends) >= 2 else (0, len(seq))
 tot = sum(v for _, v in seq[a:b])
 for n, v in seq[a:b]:
