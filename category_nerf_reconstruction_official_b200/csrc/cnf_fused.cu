@@ -61,12 +61,25 @@ __device__ __forceinline__ void loss_outputs(int K, const float* __restrict__ ra
   if (lane == 0) { out_loss[0] = total; out_loss[1] = e0; out_loss[2] = e1; out_loss[3] = e2; }
 }
 
-// grid = (K, FIN_JOBS): one CTA per (category, job); a job is ONE family of outputs, so a CTA's dependent global-load chain is
-// short (the kernel is latency-bound: ~6 M instructions in total).
-//   0: encoding_xyz, rgb layers, PE matrix      1: encoding_viewdir (+ b_vd, b_sigma)     2: encoding_shape, its bias, sigma weights
-//   3..6: conditioned layer s (weights + bias)  7..10: latent layer s (needs d z of slot s)
-//   11..14: a quarter of the code tables (needs d z of all slots + code norms)            15: regulariser values
-constexpr int FIN_JOBS = 16;
+// grid = (K, FIN_JOBS): one CTA per (category, job); a job is a SLICE of ONE family of outputs, so a CTA's chain of dependent
+// global-load rounds is short (the kernel is latency-bound: ~6 M instructions in total).  kind / slot / part of a job:
+//   0 encoding_xyz, rgb layers, PE matrix   1 encoding_viewdir (4 parts)   2 encoding_shape, its bias, sigma weights
+//   3 conditioned layer s (cat_layer in 4 parts)   4 latent layer s (4 parts each; needs d z of slot s)
+//   5 code tables (4 parts; need d z of all slots + code norms)   6 regulariser values + loss outputs
+struct FinJob { int kind, s, part, nparts; };
+constexpr int FIN_JOBS = 34;
+__device__ __forceinline__ FinJob fin_job(int j) {
+  if (j == 0) return {0, 0, 0, 1};
+  if (j < 5) return {1, 0, j - 1, 4};
+  if (j == 5) return {2, 0, 0, 1};
+  if (j == 6) return {3, 0, 0, 1};
+  if (j < 11) return {3, 1, j - 7, 4};
+  if (j == 11) return {3, 2, 0, 1};
+  if (j == 12) return {3, 3, 0, 1};
+  if (j < 29) return {4, (j - 13) >> 2, (j - 13) & 3, 4};
+  if (j < 33) return {5, 0, j - 29, 4};
+  return {6, 0, 0, 1};
+}
 __global__ void __launch_bounds__(256)
 fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, const float* __restrict__ pe_scale,
                       const float* __restrict__ shape_codes, const float* __restrict__ tex_codes,
@@ -76,7 +89,10 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
                       float* __restrict__ g_shape, float* __restrict__ g_tex, float* __restrict__ reg_out,
                       const int32_t* __restrict__ counts, int cstride, float cs, float os, int* __restrict__ done_counter,
                       float* __restrict__ out_loss) {
-  const int k = blockIdx.x, job = blockIdx.y, tid = threadIdx.x;
+  const int k = blockIdx.x, tid = threadIdx.x;
+  const FinJob jb = fin_job(blockIdx.y);
+  auto part_lo = [&](int n) { return (int)((long long)n * jb.part / jb.nparts); };
+  auto part_hi = [&](int n) { return (int)((long long)n * (jb.part + 1) / jb.nparts); };
   const PLay lay(L);
   const float* P = params + (size_t)k * lay.total;
   float* G = g_params + (size_t)k * lay.total;
@@ -120,7 +136,7 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
     }
   };
 
-  if (job == 0) {
+  if (jb.kind == 0) {
     // PE projection matrix: dB[d][a] = sum_p d(proj)[p][d] * t[p][a]  (accumulated as [t0 t1 t2 ONE]^T d(proj))
     for (int i = tid; i < 63; i += 256) { const int d = i / 3, ax = i % 3; g_B[(size_t)k * 63 + i] = rk[RPE + ax * 32 + pe_col(d)]; }
     // plain layers (transposed copies out of the raw accumulators; xg / xc lanes follow the tile column order)
@@ -130,7 +146,7 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
     for (int j = tid; j < 32; j += 256) G[lay.o[1] + j] = rk[RW1 + XG_BIAS_COL * 32 + j];              // b_xyz (row of the ones column)
     for (int n = tid; n < 16; n += 256) G[lay.o[25] + n] = rk[RDB8 + n];
     for (int j = tid; j < 3; j += 256) G[lay.o[27] + j] = rk[RDB9 + j];
-  } else if (job == 1 || job == 2) {
+  } else if (jb.kind == 1 || jb.kind == 2) {
     // encoding_viewdir / encoding_shape / sigma: the kernel trained the folded weights
     //   W6a' = Wvd[:, :32] W5, b6' = Wvd[:, :32] b5 + b_vd, wsig' = wsig W5, bsig' = wsig b5 + bsig.
     // With Ga'[n][k] = dL/dW6a'[n][k], gb6'[n], gws'[k], gbs':
@@ -139,8 +155,8 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
     //   dwsig[j]      = sum_k gws'[k] W5[j][k] + gbs' b5[j]              db_vd = gb6', dbsig = gbs'
     const int BL = 32 + XC_BIAS_COL;                                   // lane of the ones column in the [r4 | xc] tile
     const float gbs = rk[RW6 + BL * 48 + 32];
-    if (job == 1) {
-      for (int i = tid; i < 32 * 74; i += 256) {
+    if (jb.kind == 1) {
+      for (int i = part_lo(32 * 74) + tid; i < part_hi(32 * 74); i += 256) {
         const int n = i / 74, j = i % 74;
         float a;
         if (j < 32) {
@@ -152,8 +168,10 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
         }
         G[lay.o[18] + i] = a;
       }
-      for (int j = tid; j < 32; j += 256) G[lay.o[19] + j] = rk[RW6 + BL * 48 + j];                      // b_vd
-      if (tid == 0) G[lay.o[17]] = gbs;                                                                   // b_sigma
+      if (jb.part == 0) {
+        for (int j = tid; j < 32; j += 256) G[lay.o[19] + j] = rk[RW6 + BL * 48 + j];                    // b_vd
+        if (tid == 0) G[lay.o[17]] = gbs;                                                                 // b_sigma
+      }
     } else {
       for (int i = tid; i < 32 * 32; i += 256) {                      // dW5[j][k]
         const int j = i / 32, kk = i % 32;
@@ -173,45 +191,47 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
         G[lay.o[16] + j] = ws;
       }
     }
-  } else if (job < 7) {
+  } else if (jb.kind == 3) {
     // layer with per-instance bias c = W[:, :32] z + b : slots (zsl1->s1), (zcl->cat), (zsl2->s2), (ztl->t1)
-    const int s = job - 3, ld = cons_ld(s);
-    for (int i = tid; i < 32 * ld; i += 256) {
+    const int s = jb.s, ld = cons_ld(s);
+    for (int i = part_lo(32 * ld) + tid; i < part_hi(32 * ld); i += 256) {
       const int n = i / ld, c = i % ld;
       float a = rk[rw(s) + (c < 32 ? c : 32 + xg_col(c - 32)) * 32 + n];     // only the cat layer (s = 1) has c >= 32
       if (c < 32)
         for (int inst = 0; inst < n_obj; ++inst) a = fmaf(ri[(inst * 4 + s) * 32 + n], z[((size_t)s * n_obj_max + inst) * NL + c], a);
       G[lay.o[cons_w(s)] + i] = a;
     }
-    for (int n = tid; n < 32; n += 256) {
-      float a = 0.f;
-      for (int inst = 0; inst < n_obj; ++inst) a += ri[(inst * 4 + s) * 32 + n];
-      G[lay.o[cons_w(s) + 1] + n] = a;
-    }
-  } else if (job < 11) {
+    if (jb.part == 0)
+      for (int n = tid; n < 32; n += 256) {
+        float a = 0.f;
+        for (int inst = 0; inst < n_obj; ++inst) a += ri[(inst * 4 + s) * 32 + n];
+        G[lay.o[cons_w(s) + 1] + n] = a;
+      }
+  } else if (jb.kind == 4) {
     // latent layer: dW_lat[c][j] = sum_inst dpre[inst][c] code[inst][j]; db_lat[c] = sum_inst dpre[inst][c]
-    const int s = job - 7;
+    const int s = jb.s;
     compute_dpre(s, s + 1);
     __syncthreads();
     const float* codes = (s == 3 ? tex_codes : shape_codes) + (size_t)k * n_obj_max * L;
-    for (int i = tid; i < 32 * L; i += 256) {
+    for (int i = part_lo(32 * L) + tid; i < part_hi(32 * L); i += 256) {
       const int c = i / L, j = i % L;
       float a = 0.f;
       for (int inst = 0; inst < n_obj; ++inst) a = fmaf(s_dpre[s][inst][c], codes[(size_t)inst * L + j], a);
       G[lay.o[lat_w(s)] + i] = a;
     }
+    if (jb.part == 0)
     for (int c = tid; c < 32; c += 256) {
       float a = 0.f;
       for (int inst = 0; inst < n_obj; ++inst) a += s_dpre[s][inst][c];
       G[lay.o[lat_w(s) + 1] + c] = a;
     }
-  } else if (job < 15) {
+  } else if (jb.kind == 5) {
     // code tables: d code[inst][j] = sum_s sum_c dpre[s][inst][c] W_lat_s[c][j]  (+ regulariser)
     compute_dpre(0, 4);
     compute_norms();
     __syncthreads();
-    const int total = n_obj_max * L, q = job - 11;
-    const int lo = (int)((long long)total * q / 4), hi = (int)((long long)total * (q + 1) / 4);
+    const int total = n_obj_max * L;
+    const int lo = part_lo(total), hi = part_hi(total);
     for (int i = lo + tid; i < hi; i += 256) {
       const int inst = i / L, j = i % L;
       float gs = 0.f, gt = 0.f;

@@ -122,7 +122,8 @@ __device__ __forceinline__ float strat(float mn, float mxv, float lin_k, float u
 }
 
 // (C) emit.
-__global__ void __launch_bounds__(SB)
+constexpr int EMIT_T = 1024;  // threads of the emit kernel: the first SB rank the rays, all of them write samples
+__global__ void __launch_bounds__(EMIT_T)
 sample_emit_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const float* __restrict__ depth,
                    const float* __restrict__ origins, const float* __restrict__ dirs,
                    const float* __restrict__ u_inv, const float* __restrict__ u_val,
@@ -142,43 +143,49 @@ sample_emit_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const 
   __shared__ float s_od[SB][6];
   __shared__ int s_w[SB / 32][3];
 
-  // ---- phase 1: thread per ray: case + exclusive rank in ray order
+  // ---- phase 1: thread per ray (threads 0..SB-1): case + exclusive rank in ray order
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
-  const int r = r0 + t;
-  int c = 3;
-  float d = 0.f;
-  if (r < R) {
-    const size_t gi = (size_t)k * R + r;
-    d = depth[gi];
-    const uint8_t lab = rgbs[gi * 4 + 3];
-    c = ray_case(d, lab, min_bound, this_obj);
-    valid[gi] = (c != 0);
-    labels[gi] = lab;
+  if (t < SB) {           // warp-uniform (SB is a multiple of 32)
+    const int r = r0 + t;
+    int c = 3;
+    float d = 0.f;
+    if (r < R) {
+      const size_t gi = (size_t)k * R + r;
+      d = depth[gi];
+      const uint8_t lab = rgbs[gi * 4 + 3];
+      c = ray_case(d, lab, min_bound, this_obj);
+      valid[gi] = (c != 0);
+      labels[gi] = lab;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { s_od[t][j] = origins[gi * 3 + j]; s_od[t][3 + j] = dirs[gi * 3 + j]; }
+      for (int j = 0; j < 3; ++j) { s_od[t][j] = origins[gi * 3 + j]; s_od[t][3 + j] = dirs[gi * 3 + j]; }
+    }
+    const unsigned m0 = __ballot_sync(0xffffffffu, c == 0);
+    const unsigned m1 = __ballot_sync(0xffffffffu, c == 1);
+    const unsigned m2 = __ballot_sync(0xffffffffu, c == 2);
+    const unsigned lt = (1u << l) - 1u;
+    if (l == 0) { s_w[w][0] = __popc(m0); s_w[w][1] = __popc(m1); s_w[w][2] = __popc(m2); }
+    s_case[t] = (uint8_t)c;
+    s_depth[t] = d;
+    s_row[t] = (c == 0) ? __popc(m0 & lt) : (c == 1 ? __popc(m1 & lt) : __popc(m2 & lt));     // rank inside the warp
+    s_rowv[t] = __popc(m1 & lt) + __popc(m2 & lt);
   }
-  const unsigned m0 = __ballot_sync(0xffffffffu, c == 0);
-  const unsigned m1 = __ballot_sync(0xffffffffu, c == 1);
-  const unsigned m2 = __ballot_sync(0xffffffffu, c == 2);
-  const unsigned lt = (1u << l) - 1u;
-  if (l == 0) { s_w[w][0] = __popc(m0); s_w[w][1] = __popc(m1); s_w[w][2] = __popc(m2); }
   __syncthreads();
-  int base0 = blk_counts[((size_t)k * nb + b) * 8 + 0];
-  int base1 = blk_counts[((size_t)k * nb + b) * 8 + 1];
-  int base2 = blk_counts[((size_t)k * nb + b) * 8 + 2];
-  for (int i = 0; i < w; ++i) { base0 += s_w[i][0]; base1 += s_w[i][1]; base2 += s_w[i][2]; }
-  const int rk0 = base0 + __popc(m0 & lt), rk1 = base1 + __popc(m1 & lt), rk2 = base2 + __popc(m2 & lt);
-  s_case[t] = (uint8_t)c;
-  s_depth[t] = d;
-  s_row[t] = (c == 0) ? rk0 : (c == 1 ? rk1 : rk2);
-  s_rowv[t] = rk1 + rk2;     // valid rays = case1 U case2, both counted in ray order
+  if (t < SB) {           // add the block base and the counts of the preceding warps
+    int base0 = blk_counts[((size_t)k * nb + b) * 8 + 0];
+    int base1 = blk_counts[((size_t)k * nb + b) * 8 + 1];
+    int base2 = blk_counts[((size_t)k * nb + b) * 8 + 2];
+    for (int i = 0; i < w; ++i) { base0 += s_w[i][0]; base1 += s_w[i][1]; base2 += s_w[i][2]; }
+    const int c = s_case[t];
+    s_row[t] += (c == 0) ? base0 : (c == 1 ? base1 : base2);
+    s_rowv[t] += base1 + base2;     // valid rays = case1 U case2, both counted in ray order
+  }
   __syncthreads();
 
   // ---- phase 2: thread per sample (coalesced z / pcs writes)
   const float max_bound = __int_as_float(stats[k * 8 + 7]);
   const int nrays = min(SB, R - r0);
   const float fS = (float)S, fN = (float)N, fM = (float)M;
-  for (int e = t; e < nrays * S; e += SB) {
+  for (int e = t; e < nrays * S; e += EMIT_T) {
     const int rr = e / S, i = e - rr * S;
     const int cc = s_case[rr];
     const float dd = s_depth[rr];
@@ -255,7 +262,7 @@ extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, c
   cudaStream_t st = as_stream(stream);
   sample_count_kernel<<<dim3(nb, K), SB, 0, st>>>(R, rgbs, depth, min_bound, this_obj, blk_counts, blk_max);
   sample_scan_kernel<<<K, 256, 0, st>>>(nb, blk_counts, blk_max, max_depth_override, stats);
-  sample_emit_kernel<<<dim3(nb, K), SB, 0, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth,
+  sample_emit_kernel<<<dim3(nb, K), EMIT_T, 0, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth,
                                                  lin_S, lin_N, lin_M, min_bound, eps, stop_eps, this_obj,
                                                  blk_counts, stats, z, pcs, valid, labels);
   return check_launch("cnf_sample_fwd");

@@ -41,9 +41,12 @@ def draw_randoms(rgbs, depth, n_cam2surf, n_surf, eps, min_bound=0.0, this_obj=1
     N, M = n_cam2surf, n_surf
     dev = depth.device
     if not exact_rng:
-        return {"u_inv": torch.rand(K, R, N + M, device=dev), "u_val": torch.rand(K, R, N, device=dev),
+        # all uniforms in ONE launch (contiguous slices of a flat draw), the normals in a second one
+        n1, n2, n3 = K * R * (N + M), K * R * N, K * R * M
+        u = torch.rand(n1 + n2 + n3, device=dev)
+        return {"u_inv": u[:n1].view(K, R, N + M), "u_val": u[n1:n1 + n2].view(K, R, N),
                 "n_obj": torch.empty(K, R, M, device=dev).normal_(mean=0., std=eps / 3.),
-                "u_oth": torch.rand(K, R, M, device=dev)}
+                "u_oth": u[n1 + n2:].view(K, R, M)}
     out = {"u_inv": torch.zeros(K, R, N + M, device=dev), "u_val": torch.zeros(K, R, N, device=dev),
            "n_obj": torch.zeros(K, R, M, device=dev), "u_oth": torch.zeros(K, R, M, device=dev)}
     for k in range(K):          # reference order per category: rand[nI,S], rand[nV,N], normal_[nO,M], rand[nT,M]
