@@ -3,8 +3,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload replica_room0|c1|scannet0066|c4] [--impl reference]
 
 Contract (see the task statement): one JSON line on rank 0.  A "step" is one pass of the hot path over one
-synthetic batch: depth-guided sampling (3 launches) + the fused tcgen05 step (prep, fused fwd+bwd, PE-gradient
-reduce, finalize, loss).  `value` = rays/s with inputs resident in HBM (CUDA events around each step, L2 flushed
+synthetic batch: the sampler's random draws (2 torch launches), depth-guided sampling (3 launches) and the fused tcgen05 step
+(prep + instance sort on a side stream, fused fwd+bwd, finalize incl. the loss outputs).  `value` = rays/s with inputs resident in HBM (CUDA events around each step, L2 flushed
 between steps, max over ranks); `e2e` = the same through FusedCategoryTrainer.step_host with pinned HOST buffers
 (H2D + step + D2H of the loss terms, wall clock incl. the stream sync).  `roofline` = the fused kernel against the
 measured bf16 tensor peak (MEASURED_PEAKS.json), timed live with CUDA events recorded around that kernel only
@@ -315,8 +315,12 @@ def main():
     pts = K * R * S
     flops = pts * FLOP_PER_POINT
     ach = flops / (kern_ms * 1e-3) / 1e12
+    traffic = None                       # DRAM bytes of the fused kernel per launch, from the committed ncu capture of this workload
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {}).get("bytes_per_launch")
     roof = {"bound": "tensor", "kernel": "fused_step_kernel", "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
-            "frac": ach / pk["bf16_burst"], "traffic": None, "peak_source": pk["source"] + " (bf16 burst)",
+            "frac": ach / pk["bf16_burst"], "traffic": traffic, "peak_source": pk["source"] + " (bf16 burst)",
             "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / step_ms,
             "algorithmic_flop_per_point": FLOP_PER_POINT, "points_per_launch": pts}
 
