@@ -190,7 +190,8 @@ int cnf_set_kernel_events(void* ev_start, void* ev_stop);
 
 /* Development aid: device buffer of 256 int64 receiving SM-clock timestamps of CTA (0,0): [0..59] / [64..127] stage stamps of
  * the third tile (forward / backward role), [60..63] loop ends / flush end / kernel start, [128..191] / [192..255] tile-start
- * clocks of the first 64 tiles of each role.  NULL (default) selects the production kernel without any of it. */
+ * clocks of the first 64 tiles of each role, [256 + 8*cta ..] per-CTA %globaltimer stamps {entry, setup done, forward end,
+ * backward end, flush done, tiles} (buffer of 256 + 8 * #CTAs int64).  NULL (default) selects the production kernel without any of it. */
 int cnf_set_debug_buffer(void* dev_ptr);
 
 /* tcgen05 self-test: D[128,N] = A[128,K] * B[N,K]^T with bf16 operands staged in shared memory in the

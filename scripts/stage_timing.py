@@ -6,11 +6,13 @@ import torch
 from bench import WORKLOADS, synth_batch
 from category_nerf_reconstruction_official_b200 import _lib
 from category_nerf_reconstruction_official_b200.fused import FusedCategoryTrainer
-wl = dict(WORKLOADS["c4"]); wl["R"] = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
+name = sys.argv[2] if len(sys.argv) > 2 else "c4"
+wl = dict(WORKLOADS[name])
+if name == "c4": wl["R"] = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
 dev = torch.device("cuda:0")
 tr = FusedCategoryTrainer(wl["K"], wl["n_obj"], latent_dim=wl["L"], scale=wl["scale"], device=dev, n_bins_cam2surface=wl["N"], n_bins=wl["M"])
 b = synth_batch(wl, seed=3, device=dev)
-dbg = torch.zeros(256, dtype=torch.int64, device=dev)
+dbg = torch.zeros(256 + 8 * 1024, dtype=torch.int64, device=dev)
 lib = _lib.load()
 for i in range(3):
     tr.step(b["rgbs"], b["depth"], b["origins"], b["dirs"], b["indices"])
@@ -42,3 +44,13 @@ print("forward tile period (cycles), tiles 0..62:", pf[:6], "... median", sorted
 print("backward tile period (cycles):", pb[:6], "... median", sorted(pb)[len(pb) // 2] if pb else None)
 print("kernel start -> forward loop end %d, -> backward loop end %d, -> after flush %d (first forward tile at +%d)" %
       (d[60] - d[63], d[61] - d[63], d[62] - d[63], f[0] - d[63]))
+
+c = d[256:].view(-1, 8)
+c = c[c[:, 0] > 0]
+if len(c):
+    t0 = int(c[:, 0].min())
+    import statistics as st
+    f = lambda col: [(int(x) - t0) / 1e3 for x in c[:, col].tolist()]
+    print("per-CTA wall clock (us after the first CTA started), %d CTAs: entry max %.1f | setup done median %.1f max %.1f | forward loop end median %.1f max %.1f | backward loop end median %.1f max %.1f | flush done median %.1f max %.1f" %
+          (len(c), max(f(0)), st.median(f(1)), max(f(1)), st.median(f(2)), max(f(2)), st.median(f(3)), max(f(3)), st.median(f(4)), max(f(4))))
+    print("tiles per CTA: min %d max %d" % (int(c[:, 5].min()), int(c[:, 5].max())))

@@ -103,3 +103,57 @@ def test_fused_step_multi_tile_vs_oracle():
         _grad_ok(tr.g_B[k], out["g_B"][k], "B")
         _grad_ok(tr.g_shape[k], out["g_shape"][k], "sc")
         _grad_ok(tr.g_tex[k], out["g_texture"][k], "tc")
+
+
+def test_fused_gradients_well_conditioned_vs_oracle(capsys):
+    """bf16 tensor-core path against the fp32 oracle on a WELL-CONDITIONED loss: every ray has an invalid depth, so the depth term
+    (whose 1/(sqrt(var)+1e-4) weighting amplifies rounding noise without bound) is switched off by the reference's empty-mask rule
+    and the loss is 5*colour + 10*opacity.  Tolerances: loss 2e-3 relative; every gradient tensor relative L2 <= 0.15 and
+    cosine >= 0.99 (measured values are printed: 1-9 %).  The residual is not only bf16 rounding (2^-9 per operand over a 7-layer chain): the
+    losses are L1, so a ray whose rendered colour / opacity is within the forward error of its target flips the SIGN of its gradient."""
+    from category_nerf_reconstruction_official_b200.fused import FusedCategoryTrainer
+    g = torch.Generator().manual_seed(11)
+    K, n_obj, R, N, M, L = 2, 4, 1536, 1, 9, 32
+    tr = FusedCategoryTrainer(K, n_obj, latent_dim=L, scale=2.0, device=DEV, n_bins_cam2surface=N, n_bins=M, generator=g)
+    cats = [O.synth_rays(R, n_obj, g) for _ in range(K)]
+    rgbs = torch.stack([c[0] for c in cats]); depth = torch.zeros(K, R)
+    org = torch.stack([c[2] for c in cats]); dirs = torch.stack([c[3] for c in cats]); idx = torch.stack([c[4] for c in cats])
+    rand = {"u_inv": torch.rand(K, R, N + M, generator=g), "u_val": torch.rand(K, R, N, generator=g),
+            "n_obj": torch.randn(K, R, M, generator=g) * (0.1 / 3), "u_oth": torch.rand(K, R, M, generator=g)}
+    max_d = torch.full((K,), 3.0)
+    from category_nerf_reconstruction_official_b200 import ops
+    dv = lambda t: t.to(DEV)
+    z, _, valid, labels, stats = ops.sample_batched(dv(rgbs), dv(depth), dv(org), dv(dirs), N, M, 0.1, 0.05, {k: dv(v) for k, v in rand.items()},
+                                                     max_depth=dv(max_d), want_pcs=False)
+    loss = tr.step_from_samples(dv(org), dv(dirs), z, dv(depth), dv(rgbs), valid.view(torch.uint8), dv(idx).to(torch.int32), stats[:, 4:8])
+    torch.cuda.synchronize()
+    zc = z.cpu()
+    pcs = org[:, :, None, :] + dirs[:, :, None, :] * zc[..., None]
+    fc = [torch.stack([tr.param_views(k)[i].cpu() for k in range(K)]) for i in range(28)]
+    out = O.train_step(fc, tr.pe_B.cpu(), 2.0, [tr.shape_codes[k].cpu() for k in range(K)], [tr.tex_codes[k].cpu() for k in range(K)],
+                       pcs, zc, depth, rgbs[..., :3], labels.cpu(), valid.cpu().bool(), idx)
+    assert float(out["loss"]) > 1.0
+    torch.testing.assert_close(loss.cpu(), out["loss"], rtol=2e-3, atol=1e-4)
+    worst_rel, worst_cos = 0.0, 1.0
+    errs = []
+    def chk(a, e, name):
+        nonlocal worst_rel, worst_cos
+        a = a.detach().double().cpu().flatten(); e = e.detach().double().cpu().flatten()
+        if float(e.norm()) < 1e-12:
+            return
+        rel = float((a - e).norm() / e.norm()); cos = float(torch.nn.functional.cosine_similarity(a, e, dim=0))
+        worst_rel, worst_cos = max(worst_rel, rel), min(worst_cos, cos)
+        errs.append("%s %.4f" % (name.split(".")[0], rel))
+        assert rel <= 0.15 and cos >= 0.99, "%s: rel L2 %.4f cos %.5f" % (name, rel, cos)
+    names = [n for n, _ in O.codenerf_param_shapes(32, L)]
+    for k in range(K):
+        gv = tr.grad_views(k)
+        for i in range(28):
+            chk(gv[i], out["g_fc"][i][k], names[i])
+        chk(tr.g_B[k], out["g_B"][k], "B_layer")
+        chk(tr.g_shape[k], out["g_shape"][k], "shape_codes")
+        chk(tr.g_tex[k], out["g_texture"][k], "texture_codes")
+    with capsys.disabled():
+        print("\n[well-conditioned parity] loss rel err %.2e, worst gradient rel L2 %.4f, worst cosine %.6f"
+              % (abs(float(loss) - float(out["loss"])) / float(out["loss"]), worst_rel, worst_cos))
+        print("  per-tensor rel L2 (category 1):", " ".join(errs[len(errs) // 2:]))
