@@ -63,21 +63,28 @@ __device__ __forceinline__ void loss_outputs(int K, const float* __restrict__ ra
 
 // grid = (K, FIN_JOBS): one CTA per (category, job); a job is a SLICE of ONE family of outputs, so a CTA's chain of dependent
 // global-load rounds is short (the kernel is latency-bound: ~6 M instructions in total).  kind / slot / part of a job:
-//   0 encoding_xyz, rgb layers, PE matrix   1 encoding_viewdir (4 parts)   2 encoding_shape, its bias, sigma weights
-//   3 conditioned layer s (cat_layer in 4 parts)   4 latent layer s (4 parts each; needs d z of slot s)
+//   0 encoding_xyz, rgb layers, PE matrix   1 encoding_viewdir (sliced)   2 encoding_shape, its bias, sigma weights
+//   3 conditioned layer s (cat_layer sliced)   4 latent layer s (sliced; needs d z of slot s)
 //   5 code tables (4 parts; need d z of all slots + code norms)   6 regulariser values + loss outputs
 struct FinJob { int kind, s, part, nparts; };
-constexpr int FIN_JOBS = 34;
+constexpr int FIN_P_VD = 3, FIN_P_CAT = 3, FIN_P_LAT = 3, FIN_P_CODE = 4;     // parts of the sliced jobs
+constexpr int FIN_JOBS = 1 + FIN_P_VD + 1 + (3 + FIN_P_CAT) + 4 * FIN_P_LAT + FIN_P_CODE + 1;     // 28: K = 20 categories fit one wave
 __device__ __forceinline__ FinJob fin_job(int j) {
   if (j == 0) return {0, 0, 0, 1};
-  if (j < 5) return {1, 0, j - 1, 4};
-  if (j == 5) return {2, 0, 0, 1};
-  if (j == 6) return {3, 0, 0, 1};
-  if (j < 11) return {3, 1, j - 7, 4};
-  if (j == 11) return {3, 2, 0, 1};
-  if (j == 12) return {3, 3, 0, 1};
-  if (j < 29) return {4, (j - 13) >> 2, (j - 13) & 3, 4};
-  if (j < 33) return {5, 0, j - 29, 4};
+  j -= 1;
+  if (j < FIN_P_VD) return {1, 0, j, FIN_P_VD};
+  j -= FIN_P_VD;
+  if (j == 0) return {2, 0, 0, 1};
+  j -= 1;
+  if (j == 0) return {3, 0, 0, 1};
+  j -= 1;
+  if (j < FIN_P_CAT) return {3, 1, j, FIN_P_CAT};
+  j -= FIN_P_CAT;
+  if (j < 2) return {3, 2 + j, 0, 1};
+  j -= 2;
+  if (j < 4 * FIN_P_LAT) return {4, j / FIN_P_LAT, j % FIN_P_LAT, FIN_P_LAT};
+  j -= 4 * FIN_P_LAT;
+  if (j < FIN_P_CODE) return {5, 0, j, FIN_P_CODE};
   return {6, 0, 0, 1};
 }
 __global__ void __launch_bounds__(256)

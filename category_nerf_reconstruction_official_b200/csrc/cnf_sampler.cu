@@ -121,27 +121,28 @@ __device__ __forceinline__ float strat(float mn, float mxv, float lin_k, float u
   return __fadd_rn(lower, __fmul_rn(u, len));
 }
 
-// (C) emit.
+// (C) emit: one block of SB rays; `base` = number of earlier rays of the category in case 0 / 1 / 2 (ray order)
 constexpr int EMIT_T = 1024;  // threads of the emit kernel: the first SB rank the rays, all of them write samples
-__global__ void __launch_bounds__(EMIT_T)
-sample_emit_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const float* __restrict__ depth,
-                   const float* __restrict__ origins, const float* __restrict__ dirs,
-                   const float* __restrict__ u_inv, const float* __restrict__ u_val,
-                   const float* __restrict__ n_obj, const float* __restrict__ u_oth,
-                   const float* __restrict__ lin_S, const float* __restrict__ lin_N, const float* __restrict__ lin_M,
-                   float min_bound, float eps, float stop_eps, int this_obj,
-                   const int* __restrict__ blk_counts, const int32_t* __restrict__ stats,
-                   float* __restrict__ z, float* __restrict__ pcs, uint8_t* __restrict__ valid,
-                   uint8_t* __restrict__ labels) {
-  const int k = blockIdx.y, nb = gridDim.x, b = blockIdx.x;
+struct EmitSmem {
+  int row[SB];        // rank of the ray within its case (row of the random tensor)
+  int rowv[SB];       // rank among valid rays (row of u_val)
+  uint8_t cs[SB];
+  float depth[SB];
+  float od[SB][6];
+  int w[SB / 32][3];
+};
+__device__ __forceinline__ void
+emit_block(EmitSmem& sh, int k, int b, int R, int N, int M, const uint8_t* __restrict__ rgbs, const float* __restrict__ depth,
+           const float* __restrict__ origins, const float* __restrict__ dirs,
+           const float* __restrict__ u_inv, const float* __restrict__ u_val,
+           const float* __restrict__ n_obj, const float* __restrict__ u_oth,
+           const float* __restrict__ lin_S, const float* __restrict__ lin_N, const float* __restrict__ lin_M,
+           float min_bound, float eps, float stop_eps, int this_obj, int base0_in, int base1_in, int base2_in, float max_bound,
+           float* __restrict__ z, float* __restrict__ pcs, uint8_t* __restrict__ valid, uint8_t* __restrict__ labels) {
   const int S = N + M;
   const int r0 = b * SB;
-  __shared__ int s_row[SB];      // rank of the ray within its case (row of the random tensor)
-  __shared__ int s_rowv[SB];     // rank among valid rays (row of u_val)
-  __shared__ uint8_t s_case[SB];
-  __shared__ float s_depth[SB];
-  __shared__ float s_od[SB][6];
-  __shared__ int s_w[SB / 32][3];
+  int (&s_row)[SB] = sh.row; int (&s_rowv)[SB] = sh.rowv; uint8_t (&s_case)[SB] = sh.cs; float (&s_depth)[SB] = sh.depth;
+  float (&s_od)[SB][6] = sh.od; int (&s_w)[SB / 32][3] = sh.w;
 
   // ---- phase 1: thread per ray (threads 0..SB-1): case + exclusive rank in ray order
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
@@ -171,9 +172,7 @@ sample_emit_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const 
   }
   __syncthreads();
   if (t < SB) {           // add the block base and the counts of the preceding warps
-    int base0 = blk_counts[((size_t)k * nb + b) * 8 + 0];
-    int base1 = blk_counts[((size_t)k * nb + b) * 8 + 1];
-    int base2 = blk_counts[((size_t)k * nb + b) * 8 + 2];
+    int base0 = base0_in, base1 = base1_in, base2 = base2_in;
     for (int i = 0; i < w; ++i) { base0 += s_w[i][0]; base1 += s_w[i][1]; base2 += s_w[i][2]; }
     const int c = s_case[t];
     s_row[t] += (c == 0) ? base0 : (c == 1 ? base1 : base2);
@@ -182,7 +181,6 @@ sample_emit_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const 
   __syncthreads();
 
   // ---- phase 2: thread per sample (coalesced z / pcs writes)
-  const float max_bound = __int_as_float(stats[k * 8 + 7]);
   const int nrays = min(SB, R - r0);
   const float fS = (float)S, fN = (float)N, fM = (float)M;
   for (int e = t; e < nrays * S; e += EMIT_T) {
@@ -228,6 +226,97 @@ sample_emit_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const 
   }
 }
 
+__global__ void __launch_bounds__(EMIT_T)
+sample_emit_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const float* __restrict__ depth,
+                   const float* __restrict__ origins, const float* __restrict__ dirs,
+                   const float* __restrict__ u_inv, const float* __restrict__ u_val,
+                   const float* __restrict__ n_obj, const float* __restrict__ u_oth,
+                   const float* __restrict__ lin_S, const float* __restrict__ lin_N, const float* __restrict__ lin_M,
+                   float min_bound, float eps, float stop_eps, int this_obj,
+                   const int* __restrict__ blk_counts, const int32_t* __restrict__ stats,
+                   float* __restrict__ z, float* __restrict__ pcs, uint8_t* __restrict__ valid,
+                   uint8_t* __restrict__ labels) {
+  __shared__ EmitSmem sh;
+  const int k = blockIdx.y, nb = gridDim.x, b = blockIdx.x;
+  const int* bc = blk_counts + ((size_t)k * nb + b) * 8;
+  emit_block(sh, k, b, R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth, lin_S, lin_N, lin_M, min_bound, eps, stop_eps,
+             this_obj, bc[0], bc[1], bc[2], __int_as_float(stats[k * 8 + 7]), z, pcs, valid, labels);
+}
+
+// Single-launch sampler for small ray batches (R <= SAMPLE_SMALL_RAYS): one CTA per category counts the cases / loss masks and
+// the maximum depth, writes the stats row, then emits the category's ray blocks in order with running case offsets.
+constexpr int SAMPLE_SMALL_RAYS = 4096;
+__global__ void __launch_bounds__(EMIT_T)
+sample_small_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const float* __restrict__ depth,
+                    const float* __restrict__ origins, const float* __restrict__ dirs,
+                    const float* __restrict__ u_inv, const float* __restrict__ u_val,
+                    const float* __restrict__ n_obj, const float* __restrict__ u_oth,
+                    const float* __restrict__ lin_S, const float* __restrict__ lin_N, const float* __restrict__ lin_M,
+                    float min_bound, float eps, float stop_eps, int this_obj, const float* __restrict__ max_override,
+                    int32_t* __restrict__ stats, float* __restrict__ z, float* __restrict__ pcs, uint8_t* __restrict__ valid,
+                    uint8_t* __restrict__ labels) {
+  __shared__ EmitSmem sh;
+  __shared__ int s_c[EMIT_T / 32][6];
+  __shared__ float s_m[EMIT_T / 32];
+  __shared__ int s_tot[6];
+  __shared__ float s_max;
+  __shared__ int s_blk[SAMPLE_SMALL_RAYS / SB][3];     // per ray block: number of rays in case 0 / 1 / 2
+  const int k = blockIdx.x, t = threadIdx.x, w = t >> 5, l = t & 31;
+  const int nb = (R + SB - 1) / SB;
+  if (t < 3 * (SAMPLE_SMALL_RAYS / SB)) (&s_blk[0][0])[t] = 0;
+  __syncthreads();
+  // ---- counts: thread per ray (R <= 4 * EMIT_T)
+  int cD = 0, cObj = 0, cSem = 0;
+  float mx = -INFINITY;
+  for (int r = t; r < nb * SB; r += EMIT_T) {
+    int cI = 0, cO = 0, cT = 0;
+    if (r < R) {
+      const float d = depth[(size_t)k * R + r];
+      const uint8_t lab = rgbs[((size_t)k * R + r) * 4 + 3];
+      const int c = ray_case(d, lab, min_bound, this_obj);
+      cI = (c == 0); cO = (c == 1); cT = (c == 2);
+      const bool mo = lab != 0;
+      cD += (c != 0) && mo; cObj += mo; cSem += lab != 2;
+      mx = fmaxf(mx, d);
+    }
+    // a warp covers 32 consecutive rays of ONE block (SB is a multiple of 32): per-block case counts by ballot
+    const unsigned m0 = __ballot_sync(0xffffffffu, cI), m1 = __ballot_sync(0xffffffffu, cO), m2 = __ballot_sync(0xffffffffu, cT);
+    if (l == 0 && r - l < nb * SB) { const int b = (r - l) / SB; atomicAdd(&s_blk[b][0], __popc(m0)); atomicAdd(&s_blk[b][1], __popc(m1)); atomicAdd(&s_blk[b][2], __popc(m2)); }
+  }
+  cD = warp_sum_i(cD); cObj = warp_sum_i(cObj); cSem = warp_sum_i(cSem); mx = warp_max(mx);
+  if (l == 0) { s_c[w][3] = cD; s_c[w][4] = cObj; s_c[w][5] = cSem; s_m[w] = mx; }
+  __syncthreads();
+  if (t < 3) {
+    int v = 0;
+    for (int i = 0; i < EMIT_T / 32; ++i) v += s_c[i][3 + t];
+    s_tot[3 + t] = v;
+  }
+  if (t == 32) {
+    float m = s_m[0];
+    for (int i = 1; i < EMIT_T / 32; ++i) m = fmaxf(m, s_m[i]);
+    s_max = max_override ? max_override[k] : m;
+    int a0 = 0, a1 = 0, a2 = 0;                      // exclusive scan of the per-block case counts (in place)
+    for (int b = 0; b < nb; ++b) {
+      const int v0 = s_blk[b][0], v1 = s_blk[b][1], v2 = s_blk[b][2];
+      s_blk[b][0] = a0; s_blk[b][1] = a1; s_blk[b][2] = a2;
+      a0 += v0; a1 += v1; a2 += v2;
+    }
+    s_tot[0] = a0; s_tot[1] = a1; s_tot[2] = a2;
+  }
+  __syncthreads();
+  if (t == 0) {
+    int32_t* st = stats + k * 8;
+    st[0] = s_tot[0]; st[1] = s_tot[1] + s_tot[2]; st[2] = s_tot[1]; st[3] = s_tot[2];
+    st[4] = s_tot[3]; st[5] = s_tot[4]; st[6] = s_tot[5]; st[7] = __float_as_int(s_max);
+  }
+  // ---- emit, block by block
+  for (int b = 0; b < nb; ++b) {
+    emit_block(sh, k, b, R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth, lin_S, lin_N, lin_M, min_bound, eps, stop_eps,
+               this_obj, s_blk[b][0], s_blk[b][1], s_blk[b][2], s_max, z, pcs, valid, labels);
+    __syncthreads();
+  }
+}
+
 __global__ void stratified_bins_kernel(int n_rays, int n_bins, const float* __restrict__ mn, int mn_s,
                                        const float* __restrict__ mx, int mx_s, const float* __restrict__ u,
                                        const float* __restrict__ lin, float* __restrict__ z) {
@@ -260,6 +349,11 @@ extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, c
   int* blk_counts = reinterpret_cast<int*>(ws);
   float* blk_max = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align_up((size_t)K * nb * 8 * sizeof(int), 256));
   cudaStream_t st = as_stream(stream);
+  if (R <= SAMPLE_SMALL_RAYS) {
+    sample_small_kernel<<<K, EMIT_T, 0, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth, lin_S, lin_N, lin_M, min_bound,
+                                              eps, stop_eps, this_obj, max_depth_override, stats, z, pcs, valid, labels);
+    return check_launch("cnf_sample_fwd");
+  }
   sample_count_kernel<<<dim3(nb, K), SB, 0, st>>>(R, rgbs, depth, min_bound, this_obj, blk_counts, blk_max);
   sample_scan_kernel<<<K, 256, 0, st>>>(nb, blk_counts, blk_max, max_depth_override, stats);
   sample_emit_kernel<<<dim3(nb, K), EMIT_T, 0, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth,
