@@ -2,9 +2,10 @@
 // Reference: src/render_rays.py:3-95 (occupancy_activation, occupancy_to_termination, render, render_loss,
 // reduce_batch_loss) and src/loss.py:5-74 (step_batch_loss, step_batch_loss_reg); math in SURVEY appendix A.
 //
-// One ray occupies a power-of-two segment of a warp (G = 16 lanes for S = 10/14); the exclusive cumprod of
-// the free-space factors and the reverse (suffix) sum of the backward are warp-shuffle scans.  S > 32 runs
-// the segment over 32-sample chunks with a carry.  HBM-bound: 20 B/sample in, 24 B/ray out (fwd).
+// S <= 32 (training): tile kernels -- coalesced staging of 128 rays in shared memory, one thread per ray (see below).
+// S > 32 (e.g. the 96-sample uncertainty renders): one ray occupies a power-of-two segment of a warp; the exclusive
+// cumprod of the free-space factors and the reverse (suffix) sum of the backward are warp-shuffle scans over 32-sample
+// chunks with a carry.  HBM-bound: 20 B/sample in, 24 B/ray out (fwd).
 #include "cnf_common.cuh"
 
 namespace cnf {
@@ -148,23 +149,25 @@ composite_fwd_kernel(int K, int R, int S, const float* __restrict__ alpha, const
 __global__ void composite_finalize_kernel(int K, int nblk, const float* __restrict__ partial,
                                           const int32_t* __restrict__ counts, float cs, float os,
                                           float* __restrict__ out_loss) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // one warp; fixed summation order (lane-strided partial sums, then a shuffle tree) -> deterministic
+  const int lane = threadIdx.x;
   bool e0, e1, e2;
   empty_flags(K, counts, e0, e1, e2);
   float total = 0.f;
   for (int k = 0; k < K; ++k) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int b = 0; b < nblk; ++b) {
+    for (int b = lane; b < nblk; b += 32) {
       const float* p = partial + ((size_t)k * nblk + b) * 3;
       s0 += p[0]; s1 += p[1]; s2 += p[2];
     }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
     const float d = e0 ? 0.f : s0 / ((float)counts[k * 4 + 0] + 1e-10f);      // render_rays.py:86
     const float c = e1 ? 0.f : s1 / ((float)counts[k * 4 + 1] + 1e-10f);
     const float o = e2 ? 0.f : s2 / ((float)counts[k * 4 + 2] + 1e-10f);
-    out_loss[4 + k] = d; out_loss[4 + K + k] = c; out_loss[4 + 2 * K + k] = o;
+    if (lane == 0) { out_loss[4 + k] = d; out_loss[4 + K + k] = c; out_loss[4 + 2 * K + k] = o; }
     total += d + c * cs + o * os;                                             // loss.py:69-70
   }
-  out_loss[0] = total; out_loss[1] = e0; out_loss[2] = e1; out_loss[3] = e2;
+  if (lane == 0) { out_loss[0] = total; out_loss[1] = e0; out_loss[2] = e1; out_loss[3] = e2; }
 }
 
 __global__ void __launch_bounds__(CT)
@@ -238,6 +241,133 @@ composite_bwd_kernel(int K, int R, int S, const float* __restrict__ alpha, const
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Tile kernels for S <= 32 (the training configurations): a block of TR threads stages TR consecutive rays (alpha, z, colour:
+// 20 B per sample) in shared memory with fully coalesced loads, then ONE THREAD PER RAY runs the compositing in registers
+// (sequential exclusive cumprod / suffix sum, no shuffles); the backward writes its per-sample gradients back into the
+// staged tile and the block copies them out coalesced.  Row strides are odd (bank-conflict free).  HBM-bound.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TR = 128;
+__host__ __device__ inline int tile_smem_floats(int S, bool bwd) { return TR * ((S | 1) * (bwd ? 3 : 2) + (3 * S | 1)); }
+
+// asynchronous global -> shared copies (cp.async, 4 B each): no register round trip, so ALL of a thread's loads are in flight
+// at once (a plain load/store loop keeps only the unrolled few in flight and reaches a fraction of the HBM bandwidth)
+__device__ __forceinline__ void tile_load(float* __restrict__ dst, int stride, const float* __restrict__ src, int n_rows, int cols) {
+  const unsigned inv = 0xFFFFFFFFu / (unsigned)cols + 1u;            // exact e / cols for e < 2^16
+  const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
+  for (int e = threadIdx.x; e < n_rows * cols; e += TR) {
+    const int r = (int)__umulhi((unsigned)e, inv), c = e - r * cols;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + 4u * (uint32_t)(r * stride + c)), "l"(src + e) : "memory");
+  }
+}
+__device__ __forceinline__ void tile_load_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tile_store(float* __restrict__ dst, const float* __restrict__ src, int stride, int n_rows, int cols) {
+  const unsigned inv = 0xFFFFFFFFu / (unsigned)cols + 1u;
+  for (int e = threadIdx.x; e < n_rows * cols; e += TR) {
+    const int r = (int)__umulhi((unsigned)e, inv), c = e - r * cols;
+    dst[e] = src[r * stride + c];
+  }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(TR)
+composite_tile_kernel(int K, int R, int S, const float* __restrict__ alpha, const float* __restrict__ color,
+                      const float* __restrict__ z, const float* __restrict__ gt_depth, const float* __restrict__ gt_color,
+                      const uint8_t* __restrict__ labels, const uint8_t* __restrict__ mask_depth,
+                      const int32_t* __restrict__ counts, float cs, float os, const float* __restrict__ g_loss,
+                      float* __restrict__ out_rays, float* __restrict__ partial, float* __restrict__ g_alpha, float* __restrict__ g_color) {
+  extern __shared__ float sm_t[];
+  const int k = blockIdx.y, t = threadIdx.x;
+  const int SP = S | 1, CP = (3 * S) | 1;
+  float* sA = sm_t;                    // alpha -> (fwd) weights w_i / (bwd) occupancy -> d alpha
+  float* sZ = sA + TR * SP;
+  float* sC = sZ + TR * SP;            // colour -> (bwd) d colour
+  float* sT = sC + TR * CP;            // (bwd) transmittance T_i
+  float iNd = 0.f, iNo = 0.f, iNs = 0.f;
+  if (BWD) {
+    bool e0, e1, e2;
+    empty_flags(K, counts, e0, e1, e2);
+    const float gl = g_loss ? g_loss[0] : 1.0f;
+    iNd = e0 ? 0.f : gl / ((float)counts[k * 4 + 0] + 1e-10f);
+    iNo = e1 ? 0.f : gl * cs / ((float)counts[k * 4 + 1] + 1e-10f);
+    iNs = e2 ? 0.f : gl * os / ((float)counts[k * 4 + 2] + 1e-10f);
+  }
+  float ld = 0.f, lc = 0.f, lo = 0.f;
+  for (int r0 = blockIdx.x * TR; r0 < R; r0 += gridDim.x * TR) {
+    const int n = min(TR, R - r0);
+    const size_t g0 = (size_t)k * R + r0;
+    tile_load(sA, SP, alpha + g0 * S, n, S);
+    tile_load(sZ, SP, z + g0 * S, n, S);
+    tile_load(sC, CP, color + g0 * S * 3, n, 3 * S);
+    tile_load_wait();
+    __syncthreads();
+    if (t < n) {
+      const size_t g = g0 + t;
+      float* a = sA + t * SP; const float* zz = sZ + t * SP; float* c = sC + t * CP; float* tt = sT + t * SP;
+      float T = 1.0f, D = 0.f, O = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+      for (int i = 0; i < S; ++i) {
+        const float occ = sigmoid_acc(a[i]);
+        const float w = occ * T;                                               // render_rays.py:33
+        D += w * zz[i]; O += w; C0 += w * c[3 * i]; C1 += w * c[3 * i + 1]; C2 += w * c[3 * i + 2];
+        if (BWD) { tt[i] = T; a[i] = occ; } else a[i] = w;
+        T *= __fadd_rn(__fsub_rn(1.0f, occ), 1e-10f);                          // render_rays.py:28
+      }
+      float var = 0.f;
+      for (int i = 0; i < S; ++i) {
+        const float w = BWD ? a[i] * tt[i] : a[i];
+        const float dz = zz[i] - D;
+        var += w * dz * dz;                                                    // loss.py:45-46 (detached)
+      }
+      const uint8_t lab = labels[g];
+      const float mo = (lab != 0) ? 1.f : 0.f, ms = (lab != 2) ? 1.f : 0.f;
+      const float md = (mask_depth[g] != 0 && lab != 0) ? 1.f : 0.f;
+      const float info = 1.0f / (sqrtf(var) + 1e-4f);                          // render_rays.py:73-80
+      const float gd = gt_depth[g], q0 = gt_color[g * 3], q1 = gt_color[g * 3 + 1], q2 = gt_color[g * 3 + 2];
+      if (!BWD) {
+        float* orow = out_rays + g * 6;
+        orow[0] = D; orow[1] = var; orow[2] = C0; orow[3] = C1; orow[4] = C2; orow[5] = O;
+        ld += fabsf(D - gd) * md * info;                                       // loss.py:52-54
+        lc += (fabsf(C0 - q0) + fabsf(C1 - q1) + fabsf(C2 - q2)) * mo;
+        lo += fabsf(O - mo) * ms;                                              // loss.py:64-66
+      } else {
+        auto sgn = [](float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); };
+        const float gD = sgn(D - gd) * md * info * iNd;
+        const float gC0 = sgn(C0 - q0) * mo * iNo, gC1 = sgn(C1 - q1) * mo * iNo, gC2 = sgn(C2 - q2) * mo * iNo;
+        const float gO = sgn(O - mo) * ms * iNs;
+        float suffix = 0.f;                                                    // sum_{i>j} G_i w_i
+        for (int j = S - 1; j >= 0; --j) {
+          const float occ = a[j], Tj = tt[j], w = occ * Tj;
+          const float Gi = gD * zz[j] + gC0 * c[3 * j] + gC1 * c[3 * j + 1] + gC2 * c[3 * j + 2] + gO;
+          const float f = __fadd_rn(__fsub_rn(1.0f, occ), 1e-10f);
+          const float docc = Gi * Tj - suffix / f;
+          a[j] = docc * occ * (1.0f - occ);
+          c[3 * j] = w * gC0; c[3 * j + 1] = w * gC1; c[3 * j + 2] = w * gC2;
+          suffix += Gi * w;
+        }
+      }
+    }
+    __syncthreads();
+    if (BWD) {
+      tile_store(g_alpha + g0 * S, sA, SP, n, S);
+      tile_store(g_color + g0 * S * 3, sC, CP, n, 3 * S);
+      __syncthreads();
+    }
+  }
+  if (!BWD) {
+    __shared__ float s_p[TR / 32][3];
+    const int lane = t & 31, warp = t >> 5;
+    ld = warp_sum(ld); lc = warp_sum(lc); lo = warp_sum(lo);
+    if (lane == 0) { s_p[warp][0] = ld; s_p[warp][1] = lc; s_p[warp][2] = lo; }
+    __syncthreads();
+    if (t < 3) {
+      float v = 0.f;
+      for (int i = 0; i < TR / 32; ++i) v += s_p[i][t];
+      partial[((size_t)k * gridDim.x + blockIdx.x) * 3 + t] = v;               // deterministic 2-stage reduce
+    }
+  }
+}
+
 __global__ void termination_kernel(int n_rays, int S, const float* __restrict__ occ_in, float* __restrict__ w_out) {
   const int G = seg_width(S), rpw = 32 / G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -299,6 +429,12 @@ static int comp_blocks(int R, int S) {
   return nb < 1 ? 1 : nb;
 }
 
+static int tile_blocks(int R) {
+  int nb = (R + TR - 1) / TR;
+  if (nb > 1184) nb = 1184;      // partial-sum workspace is sized for 8 x 148 blocks; grid-stride beyond
+  return nb < 1 ? 1 : nb;
+}
+
 extern "C" int cnf_termination_fwd(int n_rays, int S, const float* occ, float* w, cnf_stream_t stream) {
   CNF_REQUIRE(n_rays >= 0 && S > 0 && occ && w, "cnf_termination_fwd: bad arguments");
   if (n_rays == 0) return CNF_OK;
@@ -325,9 +461,19 @@ extern "C" int cnf_composite_loss_fwd(int K, int R, int S, const float* alpha, c
   CNF_REQUIRE(alpha && color && z && gt_depth && gt_color && labels && mask_depth && counts && out_rays && out_loss && ws,
               "cnf_composite_loss_fwd: null pointer");
   if (ws_bytes < cnf_composite_workspace_bytes(K, R)) { set_error("cnf_composite_loss_fwd: workspace too small"); return CNF_ERR_WORKSPACE; }
-  const int nb = comp_blocks(R, S);
-  composite_fwd_kernel<<<dim3(nb, K), CT, 0, as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels,
-                                                                  mask_depth, out_rays, (float*)ws);
+  int nb;
+  if (S <= 32) {
+    nb = tile_blocks(R);
+    const int smem = tile_smem_floats(S, false) * 4;
+    static bool attr = false;
+    if (!attr) { CNF_CUDA(cudaFuncSetAttribute(composite_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_floats(32, false) * 4)); attr = true; }
+    composite_tile_kernel<false><<<dim3(nb, K), TR, smem, as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth,
+                                                                              counts, cs, os, nullptr, out_rays, (float*)ws, nullptr, nullptr);
+  } else {
+    nb = comp_blocks(R, S);
+    composite_fwd_kernel<<<dim3(nb, K), CT, 0, as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels,
+                                                                    mask_depth, out_rays, (float*)ws);
+  }
   composite_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(K, nb, (const float*)ws, counts, cs, os, out_loss);
   return check_launch("cnf_composite_loss_fwd");
 }
@@ -339,6 +485,14 @@ extern "C" int cnf_composite_loss_bwd(int K, int R, int S, const float* alpha, c
   CNF_REQUIRE(K > 0 && R > 0 && S > 0, "cnf_composite_loss_bwd: bad sizes");
   CNF_REQUIRE(alpha && color && z && gt_depth && gt_color && labels && mask_depth && counts && g_alpha && g_color,
               "cnf_composite_loss_bwd: null pointer");
+  if (S <= 32) {
+    const int smem = tile_smem_floats(S, true) * 4;
+    static bool attr = false;
+    if (!attr) { CNF_CUDA(cudaFuncSetAttribute(composite_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_floats(32, true) * 4)); attr = true; }
+    composite_tile_kernel<true><<<dim3(tile_blocks(R), K), TR, smem, as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels,
+                                                                                        mask_depth, counts, cs, os, g_loss, nullptr, nullptr, g_alpha, g_color);
+    return check_launch("cnf_composite_loss_bwd");
+  }
   composite_bwd_kernel<<<dim3(comp_blocks(R, S), K), CT, 0, as_stream(stream)>>>(
       K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth, counts, cs, os, g_loss, g_alpha, g_color);
   return check_launch("cnf_composite_loss_bwd");

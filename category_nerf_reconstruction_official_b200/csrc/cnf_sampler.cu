@@ -122,7 +122,8 @@ __device__ __forceinline__ float strat(float mn, float mxv, float lin_k, float u
 }
 
 // (C) emit: one block of SB rays; `base` = number of earlier rays of the category in case 0 / 1 / 2 (ray order)
-constexpr int EMIT_T = 1024;  // threads of the emit kernel: the first SB rank the rays, all of them write samples
+constexpr int EMIT_T = 1024;      // threads of the single-launch small-batch kernel: the first SB rank the rays, all of them write samples
+constexpr int EMIT_BIG_T = 512;   // threads per 256-ray block of the large-batch emit kernel (4 blocks per SM hide each other's phases)
 struct EmitSmem {
   int row[SB];        // rank of the ray within its case (row of the random tensor)
   int rowv[SB];       // rank among valid rays (row of u_val)
@@ -130,6 +131,7 @@ struct EmitSmem {
   float depth[SB];
   float od[SB][6];
   int w[SB / 32][3];
+  float nrm[SB * 16];   // the block's rows of the normal draws (case-1 rays, rows are consecutive in ray order), n_bins <= 16
 };
 __device__ __forceinline__ void
 emit_block(EmitSmem& sh, int k, int b, int R, int N, int M, const uint8_t* __restrict__ rgbs, const float* __restrict__ depth,
@@ -178,12 +180,21 @@ emit_block(EmitSmem& sh, int k, int b, int R, int N, int M, const uint8_t* __res
     s_row[t] += (c == 0) ? base0 : (c == 1 ? base1 : base2);
     s_rowv[t] += base1 + base2;     // valid rays = case1 U case2, both counted in ray order
   }
+  // stage the normal draws of the block's this-object rays (every sample ranks itself against the ray's M draws)
+  const bool stage = M <= 16;
+  if (stage) {
+    int cnt1 = 0;
+#pragma unroll
+    for (int i = 0; i < SB / 32; ++i) cnt1 += s_w[i][1];
+    const float* src = n_obj + ((size_t)k * R + base1_in) * M;
+    for (int e = t; e < cnt1 * M; e += blockDim.x) sh.nrm[e] = src[e];
+  }
   __syncthreads();
 
   // ---- phase 2: thread per sample (coalesced z / pcs writes)
   const int nrays = min(SB, R - r0);
   const float fS = (float)S, fN = (float)N, fM = (float)M;
-  for (int e = t; e < nrays * S; e += EMIT_T) {
+  for (int e = t; e < nrays * S; e += blockDim.x) {
     const int rr = e / S, i = e - rr * S;
     const int cc = s_case[rr];
     const float dd = s_depth[rr];
@@ -195,7 +206,7 @@ emit_block(EmitSmem& sh, int k, int b, int R, int N, int M, const uint8_t* __res
       const float u = u_val[((size_t)k * R + s_rowv[rr]) * N + i];
       zz = strat(min_bound, __fsub_rn(dd, eps), lin_N[i], u, fN);
     } else if (cc == 1) {                        // :519-524 sorted normals around the surface
-      const float* row = n_obj + ((size_t)k * R + s_row[rr]) * M;
+      const float* row = stage ? sh.nrm + (s_row[rr] - base1_in) * M : n_obj + ((size_t)k * R + s_row[rr]) * M;
       const int j = i - N;
       const float v = row[j];
       int rank = 0;
@@ -356,7 +367,7 @@ extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, c
   }
   sample_count_kernel<<<dim3(nb, K), SB, 0, st>>>(R, rgbs, depth, min_bound, this_obj, blk_counts, blk_max);
   sample_scan_kernel<<<K, 256, 0, st>>>(nb, blk_counts, blk_max, max_depth_override, stats);
-  sample_emit_kernel<<<dim3(nb, K), EMIT_T, 0, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth,
+  sample_emit_kernel<<<dim3(nb, K), EMIT_BIG_T, 0, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth,
                                                  lin_S, lin_N, lin_M, min_bound, eps, stop_eps, this_obj,
                                                  blk_counts, stats, z, pcs, valid, labels);
   return check_launch("cnf_sample_fwd");
