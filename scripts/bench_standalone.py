@@ -21,14 +21,25 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
 def timeit(fn, iters=5 if not quick else 2):
-    for _ in range(2):
+    """Device time of one call, as a CUDA-graph replay (the ops are a few launches of ~100 us: eager launches from Python
+    would measure the host, not the kernels); L2 flushed before every timed replay."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
         fn()
+    g.replay()
     torch.cuda.synchronize()
     tot = 0.0
     for _ in range(iters):
         flush.zero_()
         a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record()
+        a.record(); g.replay(); b.record()
         torch.cuda.synchronize()
         tot += a.elapsed_time(b)
     return tot / iters * 1e-3
