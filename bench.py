@@ -341,6 +341,30 @@ def main():
         except Exception as e:      # never let the extra measurement break the contract line
             extra["large_batch_c4"] = {"error": repr(e)}
 
+    if rank == 0 and not args.no_large:
+        # inference sweep (BASELINE config 5 / Trainer.eval_points): forward-only tensor-core kernel on a 256^3 grid
+        try:
+            from category_nerf_reconstruction_official_b200 import ops as _ops
+            P = 256 ** 3
+            pts = (torch.rand(P, 3, device=dev) - 0.5) * 3.0
+            fl = tr.params[0]; sc0 = tr.shape_codes[0, 0]; tc0 = tr.tex_codes[0, 0]
+            for _ in range(2):
+                _ops.eval_points_fused(pts, fl, tr.pe_B[0], tr.pe_scale[0], sc0, tc0)
+            torch.cuda.synchronize()
+            tms = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); _ops.eval_points_fused(pts, fl, tr.pe_B[0], tr.pe_scale[0], sc0, tc0); e1.record()
+                torch.cuda.synchronize(); tms.append(e0.elapsed_time(e1))
+            ms5 = sorted(tms)[2]
+            extra["eval_points_256cube"] = {"points": P, "ms": ms5, "points_per_s": P / (ms5 * 1e-3),
+                                            "tensor_tflops": P * 27296.0 / (ms5 * 1e-3) / 1e12,
+                                            "tensor_frac_of_burst_peak": P * 27296.0 / (ms5 * 1e-3) / 1e12 / pk["bf16_burst"],
+                                            "note": "forward-only CodeNeRF (27296 FLOP/point) incl. the operand-image prep launch; inputs larger than L2"}
+            del pts
+        except Exception as e:
+            extra["eval_points_256cube"] = {"error": repr(e)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -19,7 +19,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libcnf_sm100.so")
 SOURCES = ["cnf_api.cu", "cnf_sampler.cu", "cnf_embed.cu", "cnf_composite.cu", "cnf_mlp_simt.cu",
            "cnf_selftest.cu", "cnf_fused.cu"]
-HEADERS = ["cnf_common.cuh", "cnf_umma.cuh", "cnf_fused_a.inc", "cnf_fused_b.inc", os.path.join("..", "..", "include", "cnf.h")]
+HEADERS = ["cnf_common.cuh", "cnf_umma.cuh", "cnf_fused_a.inc", "cnf_fused_b.inc", "cnf_fused_c.inc", os.path.join("..", "..", "include", "cnf.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -102,6 +102,8 @@ SIGNATURES = {
     "cnf_train_step": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P, P,
                                c_float, c_float, c_float, c_int, P, P, P, P, P, P, c_size_t, P]),
     "cnf_train_step_prepare": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_size_t, P]),
+    "cnf_eval_points_workspace_bytes": (c_size_t, []),
+    "cnf_eval_points": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     "cnf_set_debug_buffer": (c_int, [P]),
     "cnf_set_kernel_events": (c_int, [P, P]),
     "cnf_umma_m64_probe": (c_int, [c_int, c_int, c_int, P, P, P, P]),

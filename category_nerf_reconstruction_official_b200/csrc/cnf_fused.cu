@@ -33,6 +33,7 @@ using namespace umma;
 
 #include "cnf_fused_a.inc"
 #include "cnf_fused_b.inc"
+#include "cnf_fused_c.inc"
 
 // ---------------------------------------------------------------------------------------------------------
 // finalize: raw accumulators -> reference-shaped gradients (one CTA per category) + code regulariser
@@ -413,4 +414,33 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
                                                             reinterpret_cast<float*>(w8 + wl.zlat), reg_scaling, flags & 1, g_params, g_B,
                                                             g_shape, g_tex, reg, counts, cstride, cs, os, reinterpret_cast<int*>(w8 + wl.done), out_loss);
   return check_launch("cnf_train_step");
+}
+
+// ---- forward-only evaluation at arbitrary points with one instance's codes (trainer.py:125-151)
+static size_t eval_ws_prep() { return 0; }
+static size_t eval_ws_ctab() { return align_up(PREP_BYTES, 256); }
+static size_t eval_ws_zlat() { return eval_ws_ctab() + 512; }
+static size_t eval_ws_nobj() { return eval_ws_zlat() + 512; }
+extern "C" size_t cnf_eval_points_workspace_bytes(void) { return eval_ws_nobj() + 256; }
+
+extern "C" int cnf_eval_points(int P, int L, const float* params, const float* pe_B, const float* pe_scale, const float* shape_code,
+                               const float* tex_code, const float* points, float* occ, float* rgb, void* ws, size_t ws_bytes,
+                               cnf_stream_t stream) {
+  CNF_REQUIRE(P >= 0 && L > 0, "cnf_eval_points: bad sizes P=%d L=%d", P, L);
+  CNF_REQUIRE(params && pe_B && pe_scale && shape_code && tex_code && ws && (P == 0 || (points && occ && rgb)), "cnf_eval_points: null pointer");
+  if (ws_bytes < cnf_eval_points_workspace_bytes()) { set_error("cnf_eval_points: workspace too small"); return CNF_ERR_WORKSPACE; }
+  if (P == 0) return CNF_OK;
+  cudaStream_t st = as_stream(stream);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  int32_t* n_obj = reinterpret_cast<int32_t*>(w8 + eval_ws_nobj());
+  CNF_CUDA(cudaMemsetAsync(n_obj, 1, 4, st));                      // any value >= 1: one instance (clamped to n_obj_max = 1)
+  fused_prep_kernel<<<dim3(1, PREP_IMG_PARTS + 4), 256, 0, st>>>(L, 1, params, pe_B, pe_scale, shape_code, tex_code, n_obj, w8 + eval_ws_prep(),
+                                                                  reinterpret_cast<float*>(w8 + eval_ws_zlat()), reinterpret_cast<float*>(w8 + eval_ws_ctab()));
+  int dev = 0, n_sm = 148;
+  CNF_CUDA(cudaGetDevice(&dev));
+  CNF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  const int n_tiles = (P + TP - 1) / TP;
+  int grid = (n_tiles + EV_CHAINS - 1) / EV_CHAINS; if (grid > n_sm) grid = n_sm;
+  eval_points_kernel<<<grid, EV_NT, EV_SMEM, st>>>(P, w8 + eval_ws_prep(), reinterpret_cast<const float*>(w8 + eval_ws_ctab()), points, occ, rgb);
+  return check_launch("cnf_eval_points");
 }

@@ -283,6 +283,22 @@ def adamw_step_(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_
                              float(beta2), float(eps), float(weight_decay), int(step), stream()))
 
 
+def eval_points_fused(points: torch.Tensor, flat_params: torch.Tensor, pe_B: torch.Tensor, pe_scale: torch.Tensor,
+                      shape_code: torch.Tensor, tex_code: torch.Tensor):
+    """Forward-only tensor-core evaluation (cnf_eval_points): points [P,3], one category's flat CodeNeRF(W=32) parameters,
+    B [21,3], scale (0-d / [1]), one instance's codes [L] -> (occupancy [P] = sigmoid(10*sigma), rgb [P,3])."""
+    lib = lib_for(points)
+    P, L = points.shape[0], shape_code.numel()
+    dev = points.device
+    occ = torch.empty(P, device=dev, dtype=torch.float32)
+    rgb = torch.empty(P, 3, device=dev, dtype=torch.float32)
+    ws = torch.empty(lib.cnf_eval_points_workspace_bytes(), device=dev, dtype=torch.uint8)
+    check(lib.cnf_eval_points(P, L, ptr(_f32c(flat_params.detach())), ptr(_f32c(pe_B.detach())), ptr(_f32c(pe_scale.detach().reshape(1))),
+                              ptr(_f32c(shape_code.detach().reshape(-1))), ptr(_f32c(tex_code.detach().reshape(-1))), ptr(_f32c(points)),
+                              ptr(occ), ptr(rgb), ptr(ws), ws.numel(), stream()))
+    return occ, rgb
+
+
 def umma_selftest(mode: int, A: torch.Tensor, B: torch.Tensor, N: int, Kd: int) -> torch.Tensor:
     lib = lib_for(A)
     D = torch.empty(128, N, device=A.device, dtype=torch.float32)

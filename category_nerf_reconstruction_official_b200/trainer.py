@@ -29,6 +29,7 @@ class Trainer:
         self.extent_dict = None
         self.bound_extent = 0.995 if self.cls_id == 0 else 0.9
         self.scale_template = None
+        self.use_tensor_cores = True      # eval_points of CodeNeRF categories through cnf_eval_points (False: fp32 CUDA-core modules)
 
     def load_codeNeRF(self):
         self.fc_occ_map = model.CodeNeRF(self.emb_size1, self.emb_size2, **self.net_hyperparams).to(self.device)
@@ -59,6 +60,16 @@ class Trainer:
         if self.cls_id != 0:
             obj_idx = torch.from_numpy(np.array(self.inst_id_to_index[inst_id])).to(self.device)
             shape_code, texture_code = self.shape_codes(obj_idx), self.texture_codes(obj_idx)
+        if self.cls_id != 0 and points.is_cuda and getattr(self.fc_occ_map, "W", 32) == 32 and self.use_tensor_cores:
+            # tensor-core forward (bf16 operands, fp32 accumulation): one launch for all points, no chunking needed
+            from . import model as _model, ops
+            with torch.no_grad():
+                occ, color = ops.eval_points_fused(points, _model.flat_params(self.fc_occ_map), self.pe.B_layer.weight, self.pe.scale,
+                                                   shape_code, texture_code)
+            if occ.max() == 0:
+                print("no occ")
+                return None
+            return (occ, color)
         with torch.no_grad():
             for s in range(0, P, chunk_size):
                 emb = self.pe(points[s:s + chunk_size, ...])

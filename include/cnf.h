@@ -182,6 +182,17 @@ int cnf_train_step(int n_cat, int n_rays, int S, int L, int n_obj_max,
                    float* g_params, float* g_B, float* g_shape, float* g_tex, float* out_loss,
                    void* ws, size_t ws_bytes, cnf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (5b) Forward-only tensor-core evaluation of CodeNeRF (W=32) at arbitrary points with ONE instance's codes:
+ *      Trainer.eval_points (src/trainer.py:125-151) -- meshing grids, mesh-vertex colours, dense render sweeps.
+ *      params [cnf_codenerf_param_count(32,L)], pe_B [21,3], pe_scale [1], shape_code / tex_code [L], points [P,3] ->
+ *      occ [P] = sigmoid(10 * sigma) (occupancy_activation), rgb [P,3].  bf16 operands, fp32 accumulation.
+ * ---------------------------------------------------------------------------------------------- */
+size_t cnf_eval_points_workspace_bytes(void);
+int cnf_eval_points(int n_points, int L, const float* params, const float* pe_B, const float* pe_scale,
+                    const float* shape_code, const float* tex_code, const float* points, float* occ, float* rgb,
+                    void* ws, size_t ws_bytes, cnf_stream_t stream);
+
 /* Measurement hook: when both handles are non-NULL (cudaEvent_t created by the caller, e.g.
  * torch.cuda.Event(enable_timing=True).cuda_event), the NEXT cnf_train_step call on this host thread records
  * them on its stream immediately before / after the fused tcgen05 kernel (and only that kernel), then clears

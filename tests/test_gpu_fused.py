@@ -157,3 +157,26 @@ def test_fused_gradients_well_conditioned_vs_oracle(capsys):
         print("\n[well-conditioned parity] loss rel err %.2e, worst gradient rel L2 %.4f, worst cosine %.6f"
               % (abs(float(loss) - float(out["loss"])) / float(out["loss"]), worst_rel, worst_cos))
         print("  per-tensor rel L2 (category 1):", " ".join(errs[len(errs) // 2:]))
+
+
+def test_eval_points_tensor_core_vs_oracle():
+    """cnf_eval_points (forward-only tcgen05 path behind Trainer.eval_points) against the fp32 oracle: ragged point count
+    (3 chains x several tiles + a partial tile).  Tolerance: occupancy / colour 2e-2 absolute (bf16 operands; measured ~3e-3)."""
+    from category_nerf_reconstruction_official_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    L, P = 32, 128 * 7 + 37
+    shapes = O.codenerf_param_shapes(32, L)
+    params = O.init_params(shapes, g)
+    B = O.icosa_matrix() + 0.01 * torch.randn(21, 3, generator=g)
+    sc = O.init_codes(1, L, g)[0]; tc = O.init_codes(1, L, g)[0]
+    pts = (torch.rand(P, 3, generator=g) - 0.5) * 3.0
+    flat = torch.cat([p.reshape(-1) for p in params])
+    occ, rgb = ops.eval_points_fused(pts.to(DEV), flat.to(DEV), B.to(DEV), torch.tensor(2.0, device=DEV), sc.to(DEV), tc.to(DEV))
+    torch.cuda.synchronize()
+    emb = O.embed(pts[:, None, :], B, 2.0)
+    a_o, c_o = O.codenerf_forward(params, emb, sc.reshape(1, 1, L).expand(P, 1, L), tc.reshape(1, 1, L).expand(P, 1, L))
+    occ_o = torch.sigmoid(a_o.reshape(P)); c_o = c_o.reshape(P, 3)
+    err_o = float((occ.cpu() - occ_o).abs().max()); err_c = float((rgb.cpu() - c_o).abs().max())
+    print("eval_points: max abs err occupancy %.2e colour %.2e (occupancy range %.3f..%.3f)" % (err_o, err_c, float(occ_o.min()), float(occ_o.max())))
+    assert float(occ_o.max() - occ_o.min()) > 0.05
+    assert err_o < 2e-2 and err_c < 2e-2
