@@ -180,3 +180,46 @@ def test_eval_points_tensor_core_vs_oracle():
     print("eval_points: max abs err occupancy %.2e colour %.2e (occupancy range %.3f..%.3f)" % (err_o, err_c, float(occ_o.min()), float(occ_o.max())))
     assert float(occ_o.max() - occ_o.min()) > 0.05
     assert err_o < 2e-2 and err_c < 2e-2
+
+
+@pytest.mark.parametrize("K,n_obj,R,N,M,L,empty_inst", [
+    (1, 4, 480, 5, 9, 256, None),      # BASELINE config 1: S = 14, L = 256
+    (3, 6, 200, 1, 9, 32, 2),          # instance 2 has NO rays in the batch (empty segment), ragged tiles
+    (2, 1, 97, 1, 9, 32, None),        # single-instance categories (regulariser skipped), fewer rays than one warp group
+    (1, 64, 1024, 3, 5, 64, None),     # the maximum instance count of the fused path, S = 8
+    (5, 2, 64, 1, 15, 32, None),       # S = 16: two rays per warp
+])
+def test_fused_step_shapes_vs_oracle(K, n_obj, R, N, M, L, empty_inst):
+    """Shape / edge-case sweep of the fused step against the oracle (same tolerances as the golden-vector test)."""
+    from category_nerf_reconstruction_official_b200.fused import FusedCategoryTrainer
+    g = torch.Generator().manual_seed(1000 + K * 7 + n_obj)
+    tr = FusedCategoryTrainer(K, n_obj, latent_dim=L, scale=2.0, device=DEV, n_bins_cam2surface=N, n_bins=M, generator=g)
+    cats = [O.synth_rays(R, n_obj, g) for _ in range(K)]
+    rgbs = torch.stack([c[0] for c in cats]); depth = torch.stack([c[1] for c in cats])
+    org = torch.stack([c[2] for c in cats]); dirs = torch.stack([c[3] for c in cats]); idx = torch.stack([c[4] for c in cats])
+    if empty_inst is not None:
+        idx = torch.where(idx == empty_inst, torch.zeros_like(idx), idx)
+    rand = {"u_inv": torch.rand(K, R, N + M, generator=g), "u_val": torch.rand(K, R, N, generator=g),
+            "n_obj": torch.randn(K, R, M, generator=g) * (0.1 / 3), "u_oth": torch.rand(K, R, M, generator=g)}
+    loss = tr.step(rgbs.to(DEV), depth.to(DEV), org.to(DEV), dirs.to(DEV), idx.to(DEV), rand={k: v.to(DEV) for k, v in rand.items()})
+    torch.cuda.synchronize()
+    pcs, zz, valid, labels = [], [], [], []
+    for k in range(K):
+        _, _, v, lab, p, z = O.sample_points(rgbs[k], depth[k], org[k], dirs[k], N, M, 0.1, 0.05, {kk: vv[k] for kk, vv in rand.items()})
+        pcs.append(p); zz.append(z); valid.append(v); labels.append(lab)
+    st = torch.stack
+    fc = [torch.stack([tr.param_views(k)[i].cpu() for k in range(K)]) for i in range(28)]
+    out = O.train_step(fc, tr.pe_B.cpu(), 2.0, [tr.shape_codes[k].cpu() for k in range(K)], [tr.tex_codes[k].cpu() for k in range(K)],
+                       st(pcs), st(zz), depth, rgbs[..., :3], st(labels), st(valid), idx)
+    assert torch.isfinite(tr.g_params).all() and torch.isfinite(tr.g_shape).all() and torch.isfinite(tr.g_B).all()
+    torch.testing.assert_close(loss.cpu(), out["loss"], rtol=LOSS_RTOL, atol=1e-2)
+    for k in range(K):
+        gv = tr.grad_views(k)
+        for i in range(28):
+            _grad_ok(gv[i], out["g_fc"][i][k], "p%d" % i)
+        _grad_ok(tr.g_B[k], out["g_B"][k], "B")
+        _grad_ok(tr.g_shape[k], out["g_shape"][k], "sc")
+        _grad_ok(tr.g_tex[k], out["g_texture"][k], "tc")
+    if empty_inst is not None:      # an instance without rays only gets the regulariser gradient
+        reg_only = 0.0005 * tr.shape_codes[:, empty_inst] / tr.shape_codes[:, empty_inst].norm(dim=-1, keepdim=True)
+        torch.testing.assert_close(tr.g_shape[:, empty_inst], reg_only, rtol=1e-4, atol=1e-8)
