@@ -1,7 +1,7 @@
 // Standalone positional/Fourier embedding: UniDirsEmbed.forward (reference src/embedding.py:82-92) + backward.
 // emb[p] = cat(t, sin(pi * 2^f * (t . B_d)))  with t = x/scale, f-major / direction-minor (3 + f*21 + d).
 // HBM-bound (12 B in, 516 B out per point): the tile is built in shared memory and written back as
-// one contiguous, fully coalesced run of 129*PTS floats.
+// one contiguous, fully coalesced run of 129*PTS floats; one libm sincos per direction + double-angle recurrence.
 #include "cnf_common.cuh"
 
 namespace cnf {
@@ -33,12 +33,17 @@ embed_fwd_kernel(int P, const float* __restrict__ x, const float* __restrict__ B
     float proj = __fmul_rn(s_t[p][0], s_B[d * 3 + 0]);
     proj = __fmaf_rn(s_t[p][1], s_B[d * 3 + 1], proj);
     proj = __fmaf_rn(s_t[p][2], s_B[d * 3 + 2], proj);
-    float band = 1.0f;
+    // embedding.py:85-88: sin(pi * 2^f * proj), f = 0..5.  ONE accurate sincos (f = 0) + the double-angle recurrence: 126
+    // libm sinf per point made this kernel compute-bound (1.3 G sinf per 10 M points); the recurrence doubles the absolute
+    // error per octave (<= 32 x 1.2e-7 ~ 4e-6, inside the 3e-5 parity bound) and leaves the kernel HBM-bound.
+    float sn, cs;
+    sincosf(__fmul_rn(proj, pi_f), &sn, &cs);
 #pragma unroll
     for (int f = 0; f < CNF_N_FREQ; ++f) {
-      const float xb = __fmul_rn(proj, band);                         // embedding.py:85 (exact: power of two)
-      s_e[p * CNF_EMB_DIM + 3 + f * CNF_N_DIRS + d] = sinf(__fmul_rn(xb, pi_f));   // embedding.py:88
-      band *= 2.0f;
+      s_e[p * CNF_EMB_DIM + 3 + f * CNF_N_DIRS + d] = sn;
+      const float s2 = 2.0f * sn * cs;
+      cs = fmaf(-2.0f * sn, sn, 1.0f);
+      sn = s2;
     }
   }
   __syncthreads();
@@ -71,11 +76,14 @@ embed_bwd_kernel(int P, const float* __restrict__ x, const float* __restrict__ B
       float proj = __fmul_rn(s_t[p][0], s_B[d * 3 + 0]);
       proj = __fmaf_rn(s_t[p][1], s_B[d * 3 + 1], proj);
       proj = __fmaf_rn(s_t[p][2], s_B[d * 3 + 2], proj);
-      float band = 1.0f;
+      float band = 1.0f, sn, cs;
+      sincosf(__fmul_rn(proj, pi_f), &sn, &cs);                         // one accurate sincos + double-angle recurrence (see forward)
 #pragma unroll
       for (int f = 0; f < CNF_N_FREQ; ++f) {
-        const float a = __fmul_rn(__fmul_rn(proj, band), pi_f);
-        gp += s_g[p * CNF_EMB_DIM + 3 + f * CNF_N_DIRS + d] * (pi_f * band) * cosf(a);
+        gp += s_g[p * CNF_EMB_DIM + 3 + f * CNF_N_DIRS + d] * (pi_f * band) * cs;
+        const float s2 = 2.0f * sn * cs;
+        cs = fmaf(-2.0f * sn, sn, 1.0f);
+        sn = s2;
         band *= 2.0f;
       }
     }
