@@ -107,8 +107,8 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
   const float* rk = raw + (size_t)k * RAW_FLOATS;
   const float* z = zlat + (size_t)k * 4 * n_obj_max * NL;            // [4][n_obj_max][32]
   const float* ri = rawi + (size_t)k * n_obj_max * 4 * 32;            // [n_obj_max][4][32] per-instance bias gradients
-  const int n_obj = min(min(n_obj_arr[k], n_obj_max), MAXOBJ);
-  __shared__ float s_dpre[4][MAXOBJ][NL];      // relu-masked gradient wrt the latent pre-activations
+  const int n_obj = min(n_obj_arr[k], n_obj_max);
+  __shared__ float s_dpre[4][MAXOBJ][NL];      // relu-masked gradient wrt the latent pre-activations, one chunk of MAXOBJ instances
   __shared__ float s_norm[2][MAXOBJ];
   (void)pe_scale;                              // t = x/scale is already applied in the accumulated operand
   const int warp = tid >> 5, lane = tid & 31;
@@ -118,10 +118,10 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
   auto rw = [](int s) { return s == 0 ? RW2 : (s == 1 ? RW3 : (s == 2 ? RW4 : RW7)); };
   auto lat_w = [](int s) { return s == 0 ? 2 : (s == 1 ? 12 : (s == 2 ? 6 : 22)); };
 
-  // d z[inst][c] = sum_n dC[inst][n] W_cons[n][c], masked by relu(z), for slots [s0, s1)
-  auto compute_dpre = [&](int s0, int s1) {
-    for (int i = tid; i < (s1 - s0) * n_obj * NL; i += 256) {
-      const int s = s0 + i / (n_obj * NL), inst = (i / NL) % n_obj, c = i % NL;
+  // d z[inst][c] = sum_n dC[inst][n] W_cons[n][c], masked by relu(z), for slots [s0, s1) and instances [i0, i0 + nc)
+  auto compute_dpre = [&](int s0, int s1, int i0, int nc) {
+    for (int i = tid; i < (s1 - s0) * nc * NL; i += 256) {
+      const int s = s0 + i / (nc * NL), li = (i / NL) % nc, inst = i0 + li, c = i % NL;
       float a = 0.f;
       if (z[((size_t)s * n_obj_max + inst) * NL + c] > 0.f) {
         const int ld = cons_ld(s);
@@ -130,17 +130,19 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
 #pragma unroll
         for (int n = 0; n < 32; ++n) a = fmaf(r[n], w[(size_t)n * ld], a);
       }
-      s_dpre[s][inst][c] = a;
+      s_dpre[s][li][c] = a;
     }
   };
-  auto compute_norms = [&]() {
-    for (int o = warp; o < 2 * n_obj; o += 8) {
-      const int which = o / n_obj, inst = o % n_obj;
-      const float* code = (which ? tex_codes : shape_codes) + ((size_t)k * n_obj_max + inst) * L;
-      float a = 0.f;
-      for (int j = lane; j < L; j += 32) a = fmaf(code[j], code[j], a);
-      a = warp_sum(a);
-      if (lane == 0) s_norm[which][inst] = sqrtf(a);
+  auto code_norm = [&](int which, int inst) {           // whole warp; every lane gets |code|
+    const float* code = (which ? tex_codes : shape_codes) + ((size_t)k * n_obj_max + inst) * L;
+    float a = 0.f;
+    for (int j = lane; j < L; j += 32) a = fmaf(code[j], code[j], a);
+    return sqrtf(warp_sum(a));
+  };
+  auto compute_norms = [&](int i0, int nc) {
+    for (int o = warp; o < 2 * nc; o += 8) {
+      const float a = code_norm(o / nc, i0 + o % nc);
+      if (lane == 0) s_norm[o / nc][o % nc] = a;
     }
   };
 
@@ -218,55 +220,68 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
   } else if (jb.kind == 4) {
     // latent layer: dW_lat[c][j] = sum_inst dpre[inst][c] code[inst][j]; db_lat[c] = sum_inst dpre[inst][c]
     const int s = jb.s;
-    compute_dpre(s, s + 1);
-    __syncthreads();
     const float* codes = (s == 3 ? tex_codes : shape_codes) + (size_t)k * n_obj_max * L;
-    for (int i = part_lo(32 * L) + tid; i < part_hi(32 * L); i += 256) {
-      const int c = i / L, j = i % L;
-      float a = 0.f;
-      for (int inst = 0; inst < n_obj; ++inst) a = fmaf(s_dpre[s][inst][c], codes[(size_t)inst * L + j], a);
-      G[lay.o[lat_w(s)] + i] = a;
-    }
-    if (jb.part == 0)
-    for (int c = tid; c < 32; c += 256) {
-      float a = 0.f;
-      for (int inst = 0; inst < n_obj; ++inst) a += s_dpre[s][inst][c];
-      G[lay.o[lat_w(s) + 1] + c] = a;
+    for (int i0 = 0; i0 == 0 || i0 < n_obj; i0 += MAXOBJ) {         // chunks of MAXOBJ instances; later chunks add to the first
+      const int nc = max(0, min(MAXOBJ, n_obj - i0));
+      if (i0) __syncthreads();
+      compute_dpre(s, s + 1, i0, nc);
+      __syncthreads();
+      for (int i = part_lo(32 * L) + tid; i < part_hi(32 * L); i += 256) {
+        const int c = i / L, j = i % L;
+        float a = i0 ? G[lay.o[lat_w(s)] + i] : 0.f;
+        for (int li = 0; li < nc; ++li) a = fmaf(s_dpre[s][li][c], codes[(size_t)(i0 + li) * L + j], a);
+        G[lay.o[lat_w(s)] + i] = a;
+      }
+      if (jb.part == 0)
+      for (int c = tid; c < 32; c += 256) {
+        float a = i0 ? G[lay.o[lat_w(s) + 1] + c] : 0.f;
+        for (int li = 0; li < nc; ++li) a += s_dpre[s][li][c];
+        G[lay.o[lat_w(s) + 1] + c] = a;
+      }
     }
   } else if (jb.kind == 5) {
     // code tables: d code[inst][j] = sum_s sum_c dpre[s][inst][c] W_lat_s[c][j]  (+ regulariser)
-    compute_dpre(0, 4);
-    compute_norms();
-    __syncthreads();
+    // this part's slice [lo, hi) of the [n_obj_max][L] tables, walked in chunks of MAXOBJ instances (d z only for those)
     const int total = n_obj_max * L;
     const int lo = part_lo(total), hi = part_hi(total);
-    for (int i = lo + tid; i < hi; i += 256) {
-      const int inst = i / L, j = i % L;
-      float gs = 0.f, gt = 0.f;
-      if (inst < n_obj) {
+    for (int i0 = lo / L; i0 * L < hi; i0 += MAXOBJ) {
+      const int nc = max(0, min(min(MAXOBJ, n_obj - i0), (hi - 1) / L + 1 - i0));     // live instances of the chunk
+      if (i0 != lo / L) __syncthreads();
+      compute_dpre(0, 4, i0, nc);
+      if (add_reg && n_obj > 1) compute_norms(i0, nc);
+      __syncthreads();
+      const int c_lo = max(lo, i0 * L), c_hi = min(hi, (i0 + MAXOBJ) * L);
+      for (int i = c_lo + tid; i < c_hi; i += 256) {
+        const int inst = i / L, li = inst - i0, j = i % L;
+        float gs = 0.f, gt = 0.f;
+        if (inst < n_obj) {
 #pragma unroll 16
-        for (int c = 0; c < 32; ++c) {
-          gs = fmaf(s_dpre[0][inst][c], P[lay.o[2] + (size_t)c * L + j], gs);
-          gs = fmaf(s_dpre[1][inst][c], P[lay.o[12] + (size_t)c * L + j], gs);
-          gs = fmaf(s_dpre[2][inst][c], P[lay.o[6] + (size_t)c * L + j], gs);
-          gt = fmaf(s_dpre[3][inst][c], P[lay.o[22] + (size_t)c * L + j], gt);
+          for (int c = 0; c < 32; ++c) {
+            gs = fmaf(s_dpre[0][li][c], P[lay.o[2] + (size_t)c * L + j], gs);
+            gs = fmaf(s_dpre[1][li][c], P[lay.o[12] + (size_t)c * L + j], gs);
+            gs = fmaf(s_dpre[2][li][c], P[lay.o[6] + (size_t)c * L + j], gs);
+            gt = fmaf(s_dpre[3][li][c], P[lay.o[22] + (size_t)c * L + j], gt);
+          }
+          if (add_reg && n_obj > 1) {                                            // loss.py:12, train.py:165-167
+            const float ns = s_norm[0][li], nt = s_norm[1][li];
+            if (ns > 0.f) gs += reg_scaling * shape_codes[((size_t)k * n_obj_max + inst) * L + j] / ns;
+            if (nt > 0.f) gt += reg_scaling * tex_codes[((size_t)k * n_obj_max + inst) * L + j] / nt;
+          }
         }
-        if (add_reg && n_obj > 1) {                                            // loss.py:12, train.py:165-167
-          const float ns = s_norm[0][inst], nt = s_norm[1][inst];
-          if (ns > 0.f) gs += reg_scaling * shape_codes[((size_t)k * n_obj_max + inst) * L + j] / ns;
-          if (nt > 0.f) gt += reg_scaling * tex_codes[((size_t)k * n_obj_max + inst) * L + j] / nt;
-        }
+        g_shape[(size_t)k * n_obj_max * L + i] = gs;
+        g_tex[(size_t)k * n_obj_max * L + i] = gt;
       }
-      g_shape[(size_t)k * n_obj_max * L + i] = gs;
-      g_tex[(size_t)k * n_obj_max * L + i] = gt;
     }
   } else {
-    compute_norms();
+    float part[2] = {0.f, 0.f};                                    // this warp's share of sum |shape code|, sum |texture code|
+    if (n_obj > 1)
+      for (int o = warp; o < 2 * n_obj; o += 8) { const float a = code_norm(o / n_obj, o % n_obj); part[o / n_obj] += a; }
+    if (lane == 0) { s_norm[0][warp] = part[0]; s_norm[1][warp] = part[1]; }
     __syncthreads();
     __shared__ int s_last;
     if (tid == 0) {
       float rs = 0.f, rt = 0.f;
-      if (n_obj > 1) for (int inst = 0; inst < n_obj; ++inst) { rs += s_norm[0][inst]; rt += s_norm[1][inst]; }
+      for (int w = 0; w < 8; ++w) { rs += s_norm[0][w]; rt += s_norm[1][w]; }
       reg_out[k * 2 + 0] = rs; reg_out[k * 2 + 1] = rt;
       __threadfence();
       s_last = atomicAdd(done_counter, 1) == (int)gridDim.x - 1;     // the last category to finish writes the loss outputs
@@ -349,7 +364,7 @@ static int train_step_prepare(int K, int R, int S, int L, int nom, const float* 
 static int check_step_sizes(const char* who, int K, int R, int S, int L, int n_obj_max) {
   if (!(K > 0 && R > 0 && L > 0)) { set_error("%s: bad sizes K=%d R=%d L=%d", who, K, R, L); return CNF_ERR_ARG; }
   if (S < 1 || S > 32) { set_error("%s: samples per ray S=%d outside 1..32 (one ray per warp segment)", who, S); return CNF_ERR_UNSUPPORTED; }
-  if (n_obj_max < 1 || n_obj_max > MAXOBJ) { set_error("%s: n_obj_max=%d outside 1..%d", who, n_obj_max, MAXOBJ); return CNF_ERR_UNSUPPORTED; }
+  if (n_obj_max < 1 || n_obj_max > MAX_INSTANCES) { set_error("%s: n_obj_max=%d outside 1..%d", who, n_obj_max, MAX_INSTANCES); return CNF_ERR_UNSUPPORTED; }
   return CNF_OK;
 }
 

@@ -17,7 +17,7 @@ from . import ops, sampling
 from ._lib import check, lib_for, ptr, stream
 from .embedding import _DIRS
 
-MAXOBJ = 64
+MAXOBJ = 4096        # cnf_fused_a.inc MAX_INSTANCES
 
 
 class FusedCategoryTrainer:

@@ -160,6 +160,7 @@ int cnf_code_reg(int n_obj, int L, const float* codes, float weight, float* out,
  *     mask_depth u8 [K,R], inst int32 [K,R], counts int32 [K,4] (cnf_mask_counts / sampler stats+4)
  *     outputs (all OVERWRITTEN): g_params [K,n_param], g_B [K,21,3], g_shape/g_tex [K,n_obj_max,L],
  *     out_loss [4+3K] as in cnf_composite_loss_fwd plus reg terms appended: [.., reg_shape[K], reg_tex[K]].
+ *     limits: S <= 32, 1 <= n_obj_max <= 4096 (CNF_ERR_UNSUPPORTED otherwise).
  *     flags: bit0 = also add the code regulariser (weight reg_scaling) to loss and code grads;
  *            bit1 = the workspace was prepared by cnf_train_step_prepare (same arguments) -- skip that half;
  *            bits 8-15 = row stride of `counts` in int32 elements (0 means 4), so cnf_sample_fwd's stats[K,8] + 4 can be passed as is.
