@@ -376,6 +376,35 @@ def main():
         except Exception as e:
             extra["eval_points_256cube"] = {"error": repr(e)}
 
+    if rank == 0 and not args.no_large:
+        # dense view rendering (BASELINE config 5): 512x512 rays of one instance, forward only, S = 14 and S = 96
+        try:
+            from category_nerf_reconstruction_official_b200 import ops as _ops
+            Rv = 512 * 512
+            fl = tr.params[0]; sc0 = tr.shape_codes[0, 0]; tc0 = tr.tex_codes[0, 0]
+            org = (torch.rand(Rv, 3, device=dev) - 0.5) * 2.0
+            dr = torch.nn.functional.normalize(torch.randn(Rv, 3, device=dev), dim=-1)
+            for Sv in (14, 96):
+                zv = torch.sort(torch.rand(Rv, Sv, device=dev) * 2.5, dim=-1).values
+                for _ in range(2):
+                    _ops.render_rays_fused(org, dr, zv, fl, tr.pe_B[0], tr.pe_scale[0], sc0, tc0)
+                torch.cuda.synchronize()
+                tms = []
+                for _ in range(5):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); _ops.render_rays_fused(org, dr, zv, fl, tr.pe_B[0], tr.pe_scale[0], sc0, tc0); e1.record()
+                    torch.cuda.synchronize(); tms.append(e0.elapsed_time(e1))
+                msv = sorted(tms)[2]
+                tf = Rv * Sv * 27296.0 / (msv * 1e-3) / 1e12
+                extra["render_512x512_S%d" % Sv] = {"rays": Rv, "samples_per_ray": Sv, "ms": msv, "rays_per_s": Rv / (msv * 1e-3),
+                                                    "points_per_s": Rv * Sv / (msv * 1e-3), "tensor_tflops": tf,
+                                                    "tensor_frac_of_burst_peak": tf / pk["bf16_burst"]}
+                del zv
+            del org, dr
+        except Exception as e:
+            extra["render_512x512"] = {"error": repr(e)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

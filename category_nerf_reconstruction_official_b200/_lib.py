@@ -104,6 +104,8 @@ SIGNATURES = {
     "cnf_train_step_prepare": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_size_t, P]),
     "cnf_eval_points_workspace_bytes": (c_size_t, []),
     "cnf_eval_points": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, c_size_t, P]),
+    "cnf_render_rays_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "cnf_render_rays": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     "cnf_set_debug_buffer": (c_int, [P]),
     "cnf_set_kernel_events": (c_int, [P, P]),
     "cnf_umma_m64_probe": (c_int, [c_int, c_int, c_int, P, P, P, P]),

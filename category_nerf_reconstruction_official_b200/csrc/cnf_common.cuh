@@ -57,6 +57,10 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// cnf_composite.cu: per-ray compositing of already-activated points pt[n_rays*S] = {occ, r, g, b} -> out_rays [n_rays,6]
+// = {D, var, C0, C1, C2, O}, optional termination weights out_w [n_rays,S] (used by cnf_render_rays in cnf_fused.cu)
+int render_composite_launch(int n_rays, int S, const float* pt, const float* z, float* out_rays, float* out_w, cudaStream_t st);
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 }  // namespace cnf

@@ -391,6 +391,69 @@ __global__ void termination_kernel(int n_rays, int S, const float* __restrict__ 
   }
 }
 
+// Inference compositing of points whose occupancy is already activated: pt[r*S+i] = {occ, r, g, b}; one ray per G-lane warp
+// segment, exclusive cumprod by shuffle scans over chunks of G samples with a carry (render_rays.py:25-50, loss.py:44-48).
+__global__ void __launch_bounds__(CT)
+render_composite_kernel(int n_rays, int S, const float4* __restrict__ pt, const float* __restrict__ z,
+                        float* __restrict__ out_rays, float* __restrict__ out_w) {
+  const int G = seg_width(S), rpw = 32 / G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = lane / G, sl = lane - seg * G;
+  const int rays_per_block = (CT / 32) * rpw;
+  for (int rb = blockIdx.x * rays_per_block; rb < n_rays; rb += gridDim.x * rays_per_block) {
+    const int r = rb + warp * rpw + seg;
+    const int rr = min(r, n_rays - 1);
+    const float4* p = pt + (size_t)rr * S;
+    const float* zr = z + (size_t)rr * S;
+    float carry = 1.0f, D = 0.f, O = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    for (int c0 = 0; c0 < S; c0 += G) {
+      const int i = c0 + sl;
+      const bool act = i < S;
+      const float4 v = act ? p[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float f = act ? __fadd_rn(__fsub_rn(1.0f, v.x), 1e-10f) : 1.0f;     // render_rays.py:28
+      const float incl = seg_scan_mul(f, G, sl);
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (sl == 0) excl = 1.0f;
+      const float w = v.x * (carry * excl);                                     // render_rays.py:33
+      carry *= __shfl_sync(0xffffffffu, incl, G - 1, G);
+      if (act) {
+        D += w * zr[i]; O += w; C0 += w * v.y; C1 += w * v.z; C2 += w * v.w;
+        if (out_w != nullptr && r < n_rays) out_w[(size_t)rr * S + i] = w;
+      }
+    }
+    D = seg_sum(D, G); O = seg_sum(O, G); C0 = seg_sum(C0, G); C1 = seg_sum(C1, G); C2 = seg_sum(C2, G);
+    float var = 0.f;                                                            // second pass: needs D (loss.py:45)
+    carry = 1.0f;
+    for (int c0 = 0; c0 < S; c0 += G) {
+      const int i = c0 + sl;
+      const bool act = i < S;
+      const float occ = act ? p[i].x : 0.f;
+      const float f = act ? __fadd_rn(__fsub_rn(1.0f, occ), 1e-10f) : 1.0f;
+      const float incl = seg_scan_mul(f, G, sl);
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (sl == 0) excl = 1.0f;
+      const float w = occ * (carry * excl);
+      carry *= __shfl_sync(0xffffffffu, incl, G - 1, G);
+      if (act) { const float dz = zr[i] - D; var += w * dz * dz; }
+    }
+    var = seg_sum(var, G);
+    if (sl == 0 && r < n_rays) {
+      float* o = out_rays + (size_t)r * 6;
+      o[0] = D; o[1] = var; o[2] = C0; o[3] = C1; o[4] = C2; o[5] = O;
+    }
+  }
+}
+
+int render_composite_launch(int n_rays, int S, const float* pt, const float* z, float* out_rays, float* out_w, cudaStream_t st) {
+  if (n_rays <= 0) return CNF_OK;
+  const int G = S >= 32 ? 32 : (S > 16 ? 32 : (S > 8 ? 16 : (S > 4 ? 8 : (S > 2 ? 4 : (S > 1 ? 2 : 1)))));
+  const int rays_per_block = (CT / 32) * (32 / G);
+  long long blocks = ((long long)n_rays + rays_per_block - 1) / rays_per_block;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  render_composite_kernel<<<(int)blocks, CT, 0, st>>>(n_rays, S, reinterpret_cast<const float4*>(pt), z, out_rays, out_w);
+  return check_launch("render_composite");
+}
+
 // one block; warp per code row
 __global__ void code_reg_kernel(int n_obj, int L, const float* __restrict__ codes, float weight,
                                 float* __restrict__ out, float* __restrict__ g_codes) {

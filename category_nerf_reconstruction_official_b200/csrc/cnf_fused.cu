@@ -456,6 +456,49 @@ extern "C" int cnf_eval_points(int P, int L, const float* params, const float* p
   CNF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   const int n_tiles = (P + TP - 1) / TP;
   int grid = (n_tiles + EV_CHAINS - 1) / EV_CHAINS; if (grid > n_sm) grid = n_sm;
-  eval_points_kernel<<<grid, EV_NT, EV_SMEM, st>>>(P, w8 + eval_ws_prep(), reinterpret_cast<const float*>(w8 + eval_ws_ctab()), points, occ, rgb);
+  eval_points_kernel<false><<<grid, EV_NT, EV_SMEM, st>>>(P, w8 + eval_ws_prep(), reinterpret_cast<const float*>(w8 + eval_ws_ctab()), points, occ, rgb,
+                                                           1, nullptr, nullptr);
   return check_launch("cnf_eval_points");
+}
+
+// ---- forward-only rendering of rays with one instance's codes (BASELINE config 5: dense views; category_registration.py:146-152
+// uncertainty fields): tensor-core point evaluation in chunks whose per-point results stay in L2, then per-ray compositing.
+constexpr int RENDER_CHUNK_POINTS = 4 << 20;                      // 4 Mi points x 16 B = 64 MiB of {occ, rgb} per chunk (L2: 126 MB)
+static size_t render_chunk_rays(int R, int S) { size_t rc = (size_t)RENDER_CHUNK_POINTS / S; if (rc < 1) rc = 1; return rc < (size_t)R ? rc : (size_t)R; }
+static size_t render_ws_pts() { return align_up(cnf_eval_points_workspace_bytes(), 256); }
+extern "C" size_t cnf_render_rays_workspace_bytes(int R, int S) {
+  if (R < 1 || S < 1) return render_ws_pts();
+  return render_ws_pts() + render_chunk_rays(R, S) * (size_t)S * 16;
+}
+
+extern "C" int cnf_render_rays(int R, int S, int L, const float* params, const float* pe_B, const float* pe_scale,
+                               const float* shape_code, const float* tex_code, const float* origins, const float* dirs,
+                               const float* z, float* out_rays, float* out_w, void* ws, size_t ws_bytes, cnf_stream_t stream) {
+  CNF_REQUIRE(R >= 0 && S >= 1 && L > 0, "cnf_render_rays: bad sizes R=%d S=%d L=%d", R, S, L);
+  CNF_REQUIRE(params && pe_B && pe_scale && shape_code && tex_code && ws && (R == 0 || (origins && dirs && z && out_rays)),
+              "cnf_render_rays: null pointer");
+  if (ws_bytes < cnf_render_rays_workspace_bytes(R, S)) { set_error("cnf_render_rays: workspace too small"); return CNF_ERR_WORKSPACE; }
+  if (R == 0) return CNF_OK;
+  cudaStream_t st = as_stream(stream);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  int32_t* n_obj = reinterpret_cast<int32_t*>(w8 + eval_ws_nobj());
+  CNF_CUDA(cudaMemsetAsync(n_obj, 1, 4, st));
+  fused_prep_kernel<<<dim3(1, PREP_IMG_PARTS + 4), 256, 0, st>>>(L, 1, params, pe_B, pe_scale, shape_code, tex_code, n_obj, w8 + eval_ws_prep(),
+                                                                  reinterpret_cast<float*>(w8 + eval_ws_zlat()), reinterpret_cast<float*>(w8 + eval_ws_ctab()));
+  int dev = 0, n_sm = 148;
+  CNF_CUDA(cudaGetDevice(&dev));
+  CNF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  float* pts = reinterpret_cast<float*>(w8 + render_ws_pts());
+  const size_t rc = render_chunk_rays(R, S);
+  for (size_t r0 = 0; r0 < (size_t)R; r0 += rc) {
+    const int nr = (int)((size_t)R - r0 < rc ? (size_t)R - r0 : rc);
+    const long long P = (long long)nr * S;
+    CNF_REQUIRE(P < (1ll << 31), "cnf_render_rays: chunk too large");
+    const int n_tiles = (int)((P + TP - 1) / TP);
+    int grid = (n_tiles + EV_CHAINS - 1) / EV_CHAINS; if (grid > n_sm) grid = n_sm;
+    eval_points_kernel<true><<<grid, EV_NT, EV_SMEM, st>>>((int)P, w8 + eval_ws_prep(), reinterpret_cast<const float*>(w8 + eval_ws_ctab()),
+                                                            origins + r0 * 3, pts, nullptr, S, dirs + r0 * 3, z + r0 * S);
+    if (int e = render_composite_launch(nr, S, pts, z + r0 * S, out_rays + r0 * 6, out_w ? out_w + r0 * S : nullptr, st)) return e;
+  }
+  return check_launch("cnf_render_rays");
 }

@@ -46,10 +46,14 @@ class FusedCategoryTrainer:
         from .model import CodeNeRF, init_weights, flat_params
         g = generator
         ps = []
-        for _ in range(n_cat):
-            m = CodeNeRF(87, 42, W=32, latent_dim=latent_dim)
-            m.apply(init_weights)
-            ps.append(flat_params(m).detach())
+        import contextlib
+        with (torch.random.fork_rng(devices=[]) if g is not None else contextlib.nullcontext()):
+            if g is not None:               # nn.Linear / xavier_normal_ draw from the global CPU RNG: seed it from the generator
+                torch.manual_seed(int(torch.randint(0, 2 ** 31 - 1, (1,), generator=g)))
+            for _ in range(n_cat):
+                m = CodeNeRF(87, 42, W=32, latent_dim=latent_dim)
+                m.apply(init_weights)
+                ps.append(flat_params(m).detach())
         self.params = torch.stack(ps).to(dev).contiguous()
         self.pe_B = torch.tensor(_DIRS, dtype=torch.float32).repeat(n_cat, 1, 1).to(dev).contiguous()
         sc = torch.as_tensor(scale, dtype=torch.float32).reshape(-1)

@@ -299,6 +299,27 @@ def eval_points_fused(points: torch.Tensor, flat_params: torch.Tensor, pe_B: tor
     return occ, rgb
 
 
+def render_rays_fused(origins: torch.Tensor, dirs: torch.Tensor, z: torch.Tensor, flat_params: torch.Tensor, pe_B: torch.Tensor,
+                      pe_scale: torch.Tensor, shape_code: torch.Tensor, tex_code: torch.Tensor, want_weights: bool = False):
+    """Forward-only rendering (cnf_render_rays): origins/dirs [R,3], z [R,S], one category's flat CodeNeRF(W=32) parameters and one
+    instance's codes -> dict(depth [R], var [R], rgb [R,3], opacity [R][, weights [R,S] = termination probabilities])."""
+    lib = lib_for(origins)
+    R, S = z.shape
+    L = shape_code.numel()
+    dev = origins.device
+    out = torch.empty(R, 6, device=dev, dtype=torch.float32)
+    w = torch.empty(R, S, device=dev, dtype=torch.float32) if want_weights else None
+    ws = torch.empty(lib.cnf_render_rays_workspace_bytes(R, S), device=dev, dtype=torch.uint8)
+    check(lib.cnf_render_rays(R, S, L, ptr(_f32c(flat_params.detach())), ptr(_f32c(pe_B.detach())), ptr(_f32c(pe_scale.detach().reshape(1))),
+                              ptr(_f32c(shape_code.detach().reshape(-1))), ptr(_f32c(tex_code.detach().reshape(-1))),
+                              ptr(_f32c(origins)), ptr(_f32c(dirs)), ptr(_f32c(z)), ptr(out), ptr(w) if want_weights else None,
+                              ptr(ws), ws.numel(), stream()))
+    res = {"depth": out[:, 0], "var": out[:, 1], "rgb": out[:, 2:5], "opacity": out[:, 5]}
+    if want_weights:
+        res["weights"] = w
+    return res
+
+
 def umma_selftest(mode: int, A: torch.Tensor, B: torch.Tensor, N: int, Kd: int) -> torch.Tensor:
     lib = lib_for(A)
     D = torch.empty(128, N, device=A.device, dtype=torch.float32)

@@ -84,3 +84,16 @@ class Trainer:
             print("no occ")
             return None
         return (occ, color)
+
+    def render_rays(self, origins, dirs, z_vals, inst_id, want_weights=False):
+        """Forward-only rendering of rays through one instance's field (extension; the reference renders views with un-shipped
+        scripts and builds its uncertainty fields inline, category_registration.py:146-152): origins/dirs [R,3], z_vals [R,S] ->
+        dict(depth, var, rgb, opacity[, weights = termination probabilities]).  CodeNeRF categories on a CUDA device only
+        (tensor-core kernel cnf_render_rays; there is no CPU path)."""
+        if self.cls_id == 0:
+            raise NotImplementedError("render_rays: background OccupancyMap is rendered through the module-level fp32 path")
+        from . import model as _model, ops
+        obj_idx = torch.from_numpy(np.array(self.inst_id_to_index[inst_id])).to(self.device)
+        with torch.no_grad():
+            return ops.render_rays_fused(origins, dirs, z_vals, _model.flat_params(self.fc_occ_map), self.pe.B_layer.weight,
+                                         self.pe.scale, self.shape_codes(obj_idx), self.texture_codes(obj_idx), want_weights)

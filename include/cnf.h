@@ -194,6 +194,21 @@ int cnf_eval_points(int n_points, int L, const float* params, const float* pe_B,
                     const float* shape_code, const float* tex_code, const float* points, float* occ, float* rgb,
                     void* ws, size_t ws_bytes, cnf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (5c) Forward-only rendering of rays with ONE instance's codes (BASELINE config 5: dense 512x512 views per instance;
+ *      the 96-sample uncertainty-field renders of src/category_registration.py:146-152): points origin + dir * z
+ *      (src/scene_cateogries.py:543-544) -> UniDirsEmbed -> CodeNeRF -> occupancy_activation -> occupancy_to_termination
+ *      -> render (src/render_rays.py:3-50, src/loss.py:44-48).  Any S >= 1.
+ *      origins/dirs [R,3], z [R,S] -> out_rays [R,6] = {depth, variance, r, g, b, opacity};
+ *      out_w [R,S] = termination probabilities (may be NULL).
+ *      The tensor-core point kernel runs in chunks of 4 Mi points whose {occ, rgb} stay L2-resident for the per-ray
+ *      compositing kernel; ws >= cnf_render_rays_workspace_bytes(R, S) (<= 64 MiB + 32 KiB).
+ * ---------------------------------------------------------------------------------------------- */
+size_t cnf_render_rays_workspace_bytes(int n_rays, int S);
+int cnf_render_rays(int n_rays, int S, int L, const float* params, const float* pe_B, const float* pe_scale,
+                    const float* shape_code, const float* tex_code, const float* origins, const float* dirs,
+                    const float* z, float* out_rays, float* out_w, void* ws, size_t ws_bytes, cnf_stream_t stream);
+
 /* Measurement hook: when both handles are non-NULL (cudaEvent_t created by the caller, e.g.
  * torch.cuda.Event(enable_timing=True).cuda_event), the NEXT cnf_train_step call on this host thread records
  * them on its stream immediately before / after the fused tcgen05 kernel (and only that kernel), then clears

@@ -24,3 +24,12 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _seed_global_rng():
+    """Module constructors (nn.Linear, xavier_normal_) draw from torch's global RNG: fix it per test so that every run of the
+    suite sees the same weights (results then repeat to fp32 atomic-order noise)."""
+    import torch
+    torch.manual_seed(1234)
+    yield
