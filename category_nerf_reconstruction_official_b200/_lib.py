@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libcnf_sm100.so")
 SOURCES = ["cnf_api.cu", "cnf_sampler.cu", "cnf_embed.cu", "cnf_composite.cu", "cnf_mlp_simt.cu",
-           "cnf_selftest.cu", "cnf_fused.cu"]
+           "cnf_selftest.cu", "cnf_fused.cu", "cnf_occmap_tc.cu"]
 HEADERS = ["cnf_common.cuh", "cnf_umma.cuh", "cnf_fused_a.inc", "cnf_fused_b.inc", "cnf_fused_c.inc", os.path.join("..", "..", "include", "cnf.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -106,6 +106,9 @@ SIGNATURES = {
     "cnf_eval_points": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     "cnf_render_rays_workspace_bytes": (c_size_t, [c_int, c_int]),
     "cnf_render_rays": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
+    "cnf_occmap_tc_workspace_bytes": (c_size_t, [c_int]),
+    "cnf_occmap_tc_fwd": (c_int, [c_int, P, P, P, P, P, c_size_t, P]),
+    "cnf_occmap_tc_bwd": (c_int, [c_int, P, P, P, P, P, c_size_t, P, P, P]),
     "cnf_set_debug_buffer": (c_int, [P]),
     "cnf_set_kernel_events": (c_int, [P, P]),
     "cnf_umma_m64_probe": (c_int, [c_int, c_int, c_int, P, P, P, P]),

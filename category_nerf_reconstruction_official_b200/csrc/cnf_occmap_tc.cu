@@ -1,0 +1,680 @@
+// OccupancyMap (hidden size 128: the background model of the reference) on Blackwell tensor cores, forward and backward.
+// Reference: src/model.py:86-154 (fc_block :8-12); called from train.py:174 on 1200 rays x (5+9) samples per step.
+//
+//   fc1 = relu(W_in xg + b)        fc2 = relu(W_mid1 fc1 + b)      fc3 = relu(W_cat [fc2 | xg] + b)     fc4 = relu(W_mid2 fc3 + b)
+//   alpha = 10 (w_a . fc4 + b_a)   h = relu(W_col [fc4 | xc] + b)  rgb = sigmoid(W_oc h + b_oc)         (xg = emb[:87], xc = emb[87:])
+//
+// One CTA works on tiles of 128 points.  All GEMM operands are bf16 "core-matrix" images in shared memory (cnf_umma.cuh blk_off):
+// the SAME bytes serve as the K-major operand of the forward GEMM, the MN-major operand of the data-gradient GEMM (weights) and
+// the MN-major operands of the weight-gradient GEMM (activations / deltas, contraction over the tile's 128 points).  fp32
+// accumulators live in tensor memory.  Weight images (192.5 KB, built by a prep kernel) do not fit next to the activations, so
+// they stream through a 3-slot ring by 1-D bulk copies (TMA engine, mbarrier complete_tx) issued two layers ahead.
+// Biases of in_layer / cat_layer / color_linear ride in a constant-one column of xg / xc (their weight-gradient column is the
+// bias gradient).  The forward spills every activation image to a workspace (bulk shared->global copies; 1.5 KB/point, L2
+// resident at the reference's batch size); the backward streams them back while the previous layer's GEMMs run.
+// Weight gradients: each CTA owns a private fp32 partial (plain stores, no atomics); a reduce kernel sums the partials and
+// scatters them into nn.Linear order.
+#include <cuda_bf16.h>
+
+#include "cnf_common.cuh"
+#include "cnf_umma.cuh"
+
+namespace cnf {
+using namespace umma;
+namespace otc {
+
+constexpr int H = 128, TPT = 128;
+constexpr int E1 = 87, E2 = 42, EMB = 129;
+constexpr int XG_C = 96, XC_C = 48, XG_ONE = 87, XC_ONE = 42;
+constexpr int NT = 160;                         // 4 epilogue warps (thread = tile row = TMEM lane) + 1 control warp
+
+// weight blocks (bf16 images [128 x cols]): in | mid1 | cat(fc2 part) | cat(xg part) | mid2 | color(fc4 part) | color(xc part)
+constexpr int NBLK = 7;
+__host__ __device__ constexpr int blk_cols(int b) { return (b == 0 || b == 3) ? 96 : (b == 6 ? 48 : 128); }
+__host__ __device__ constexpr int blk_byte(int b) {
+  int o = 0;
+  for (int i = 0; i < b; ++i) o += blk_cols(i) * 256;
+  return o;
+}
+constexpr int WIMG_BYTES = 752 * 256;           // 192512
+// fp32 constants behind the images
+constexpr int C_BMID1 = 0, C_BMID2 = 128, C_WA = 256, C_WOC = 384, C_BA = 768, C_BOC = 769, C_FLOATS = 776;
+constexpr int PREP_BYTES = WIMG_BYTES + C_FLOATS * 4;
+// flat parameter offsets (named_parameters() order, H = 128)
+constexpr int P_INW = 0, P_INB = 11136, P_M1W = 11264, P_M1B = 27648, P_CATW = 27776, P_CATB = 55296, P_M2W = 55424,
+              P_M2B = 71808, P_AW = 71936, P_AB = 72064, P_COLW = 72065, P_COLB = 93825, P_OCW = 93953, P_OCB = 94337,
+              P_TOTAL = 94340;
+// activation images of one tile in the workspace
+constexpr int IMG_XG = 0, IMG_XC = 24576, IMG_FC1 = 36864, IMG_FC2 = 69632, IMG_FC3 = 102400, IMG_FC4 = 135168, IMG_H = 167936,
+              TILE_IMG_BYTES = 200704;
+constexpr int ACT_BYTES = 32768;
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint8_t* rowblk(uint8_t* base, int row, int cb, int cols) {
+  return base + (row >> 3) * (16 * cols) + cb * 128 + (row & 7) * 16;
+}
+
+__device__ __forceinline__ float wval(const float* __restrict__ P, int b, int n, int k) {
+  switch (b) {
+    case 0: return k < E1 ? P[P_INW + n * E1 + k] : (k == XG_ONE ? P[P_INB + n] : 0.f);
+    case 1: return P[P_M1W + n * H + k];
+    case 2: return P[P_CATW + n * (H + E1) + k];
+    case 3: return k < E1 ? P[P_CATW + n * (H + E1) + H + k] : (k == XG_ONE ? P[P_CATB + n] : 0.f);
+    case 4: return P[P_M2W + n * H + k];
+    case 5: return P[P_COLW + n * (H + E2) + k];
+    default: return k < E2 ? P[P_COLW + n * (H + E2) + H + k] : (k == XC_ONE ? P[P_COLB + n] : 0.f);
+  }
+}
+
+// fp32 nn.Linear parameters -> bf16 operand images + fp32 constants.  One thread per 16-byte chunk.
+__global__ void prep_kernel(const float* __restrict__ P, uint8_t* __restrict__ prep) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < WIMG_BYTES / 16) {
+    const int byte = i * 16;
+    int b = 0;
+    while (b + 1 < NBLK && byte >= blk_byte(b + 1)) ++b;
+    const int cols = blk_cols(b), local = byte - blk_byte(b);
+    const int rg = local / (16 * cols), rem = local - rg * (16 * cols), cb = rem >> 7, r8 = (rem & 127) >> 4;
+    const int n = rg * 8 + r8, k0 = cb * 8;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = pack2(wval(P, b, n, k0 + 2 * j), wval(P, b, n, k0 + 2 * j + 1));
+    *reinterpret_cast<uint4*>(prep + byte) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  if (i < C_FLOATS) {
+    float v = 0.f;
+    if (i < C_BMID2) v = P[P_M1B + i];
+    else if (i < C_WA) v = P[P_M2B + i - C_BMID2];
+    else if (i < C_WOC) v = P[P_AW + i - C_WA];
+    else if (i < C_BA) v = P[P_OCW + i - C_WOC];
+    else if (i == C_BA) v = P[P_AB];
+    else if (i < C_BOC + 3) v = P[P_OCB + i - C_BOC];
+    reinterpret_cast<float*>(prep + WIMG_BYTES)[i] = v;
+  }
+}
+
+// forward issue: D[128 x 128] (+)= A[128 x aCols] (K-major image) * W[128 x aCols]^T (K-major image)
+__device__ __forceinline__ void issue_fwd(uint32_t d, uint32_t aAddr, int aCols, uint32_t wAddr, bool acc) {
+  const uint32_t id = idesc_bf16(128, 128, 0, 0);
+  for (int ks = 0; ks < aCols / 16; ++ks)
+    mma_ss(d, smem_desc(aAddr + ks * 256, 128, 16 * aCols), smem_desc(wAddr + ks * 256, 128, 16 * aCols), id, (acc || ks > 0) ? 1u : 0u);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------
+constexpr int F_XG = 0, F_XC = 24576, F_A0 = 36864, F_A1 = 69632, F_W = 102400, F_C = 200704, F_SMEM = F_C + C_FLOATS * 4;
+
+__global__ void __launch_bounds__(NT, 1)
+fwd_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ emb, uint8_t* __restrict__ imgs,
+           float* __restrict__ alpha_out, float* __restrict__ rgb_out) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  __shared__ uint64_t full[3];
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < C_FLOATS; i += NT) reinterpret_cast<float*>(sm + F_C)[i] = reinterpret_cast<const float*>(prep + WIMG_BYTES)[i];
+  if (tid == 0) {
+    for (int s = 0; s < 3; ++s) mbar_init(&full[s], 1);
+    mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int n_tiles = (P + TPT - 1) / TPT;
+  const int nt = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const uint32_t sbase = smem_u32(sm);
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ control warp: weight ring, spills, MMA issue
+    int loaded = 0, consumed = 0, stage = 0;
+    uint32_t mph = 0;
+    const int total_blocks = nt * NBLK;
+    auto load_more = [&]() {
+      while (loaded < consumed + 3 && loaded < total_blocks) {
+        const int b = loaded % NBLK, slot = loaded % 3;
+        if (lane == 0) {
+          const uint32_t bytes = blk_cols(b) * 256;
+          mbar_expect_tx(&full[slot], bytes);
+          bulk_g2s(sm + F_W + slot * ACT_BYTES, prep + blk_byte(b), bytes, &full[slot]);
+        }
+        ++loaded;
+      }
+      __syncwarp();
+    };
+    load_more();
+    for (int it = 0; it < nt; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      uint8_t* img = imgs + (size_t)tile * TILE_IMG_BYTES;
+      for (int l = 0; l < 5; ++l) {
+        const int a1 = (l == 0) ? F_XG : ((l & 1) ? F_A0 : F_A1);                 // input activation of layer l
+        const int a1c = (l == 0) ? XG_C : H;
+        const int a2 = (l == 2) ? F_XG : F_XC, a2c = (l == 2) ? XG_C : XC_C;     // second operand of the concatenating layers
+        const int nb = (l == 2 || l == 4) ? 2 : 1;
+        const int sp_src = (l == 0) ? F_XG : a1, sp_bytes = (l == 0) ? (XG_C + XC_C) * 256 : ACT_BYTES;
+        const int sp_dst = (l == 0) ? IMG_XG : IMG_FC1 + (l - 1) * ACT_BYTES;
+        nbar_sync(1 + (stage & 1), NT); ++stage;                                  // the layer's input image is complete
+        for (int q = 0; q < nb; ++q) mbar_wait(&full[(consumed + q) % 3], ((consumed + q) / 3) & 1);
+        if (lane == 0) {
+          bulk_s2g(img + sp_dst, sm + sp_src, sp_bytes);                         // spill for the backward
+          bulk_commit();
+          bulk_wait_read<1>();                                                   // the image spilled one layer ago is free again
+        }
+        __syncwarp();
+        if (elect_one()) {
+          tc_fence_after();
+          issue_fwd(tmem, sbase + a1, a1c, sbase + F_W + (consumed % 3) * ACT_BYTES, false);
+          if (nb == 2) issue_fwd(tmem, sbase + a2, a2c, sbase + F_W + ((consumed + 1) % 3) * ACT_BYTES, true);
+          mma_commit(&bar_mma);
+        }
+        __syncwarp();
+        mbar_wait(&bar_mma, mph); mph ^= 1;
+        consumed += nb;
+        load_more();
+      }
+      nbar_sync(1 + (stage & 1), NT); ++stage;                                    // h is complete
+      if (lane == 0) { bulk_s2g(img + IMG_H, sm + F_A0, ACT_BYTES); bulk_commit(); }
+      __syncwarp();
+    }
+    if (lane == 0) bulk_wait<0>();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps: thread = tile row
+    const int row = tid;
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    const float* cs = reinterpret_cast<const float*>(sm + F_C);
+    uint32_t mph = 0;
+    int stage = 0;
+    auto publish = [&]() { fence_async_smem(); tc_fence_before(); nbar_arrive(1 + (stage & 1), NT); ++stage; };
+    // one layer's epilogue: D (+ bias) -> relu -> bf16 image; optional head dot products on the fp32 activations
+    auto layer = [&](uint8_t* dst, const float* bias, const float* hw, int nh, float* hacc) {
+      mbar_wait(&bar_mma, mph); mph ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t u[32];
+        tmem_ld32(tl + ch * 32, u);
+        tmem_ld_wait();
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a = __uint_as_float(u[2 * j]), b = __uint_as_float(u[2 * j + 1]);
+          if (bias != nullptr) { a += bias[ch * 32 + 2 * j]; b += bias[ch * 32 + 2 * j + 1]; }
+          a = fmaxf(a, 0.f); b = fmaxf(b, 0.f);
+          for (int q = 0; q < nh; ++q) hacc[q] = fmaf(hw[q * H + ch * 32 + 2 * j + 1], b, fmaf(hw[q * H + ch * 32 + 2 * j], a, hacc[q]));
+          w[j] = pack2(a, b);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(rowblk(dst, row, ch * 4 + q, H)) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+      }
+    };
+    for (int it = 0; it < nt; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int p0 = tile * TPT, p = p0 + row;
+      // embedding tile -> xg | xc images (coalesced read of the tile's contiguous [128 x 129] block)
+      const float* e = emb + (size_t)p0 * EMB;
+      const int nvalid = min(TPT, P - p0) * EMB;
+      for (int i = tid; i < TPT * EMB; i += 128) {
+        const int r = i / EMB, c = i - r * EMB;
+        const __nv_bfloat16 hv = __float2bfloat16_rn(i < nvalid ? e[i] : 0.f);
+        if (c < E1) *reinterpret_cast<__nv_bfloat16*>(sm + F_XG + blk_off(r, c, XG_C)) = hv;
+        else *reinterpret_cast<__nv_bfloat16*>(sm + F_XC + blk_off(r, c - E1, XC_C)) = hv;
+      }
+      {
+        const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
+        *reinterpret_cast<__nv_bfloat16*>(sm + F_XG + blk_off(row, XG_ONE, XG_C)) = one;
+        *reinterpret_cast<uint4*>(rowblk(sm + F_XG, row, 11, XG_C)) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<__nv_bfloat16*>(sm + F_XC + blk_off(row, XC_ONE, XC_C)) = one;
+        for (int c = XC_ONE + 1; c < XC_C; ++c) *reinterpret_cast<__nv_bfloat16*>(sm + F_XC + blk_off(row, c, XC_C)) = zero;
+      }
+      publish();
+      layer(sm + F_A0, nullptr, nullptr, 0, nullptr); publish();                  // fc1
+      layer(sm + F_A1, cs + C_BMID1, nullptr, 0, nullptr); publish();             // fc2
+      layer(sm + F_A0, nullptr, nullptr, 0, nullptr); publish();                  // fc3
+      float ha[1] = {0.f};
+      layer(sm + F_A1, cs + C_BMID2, cs + C_WA, 1, ha); publish();                // fc4 + alpha head
+      float hc[3] = {0.f, 0.f, 0.f};
+      layer(sm + F_A0, nullptr, cs + C_WOC, 3, hc); publish();                    // h + colour head
+      if (p < P) {
+        alpha_out[p] = 10.0f * (ha[0] + cs[C_BA]);                                // model.py:142-146
+#pragma unroll
+        for (int q = 0; q < 3; ++q) rgb_out[(size_t)p * 3 + q] = 1.0f / (1.0f + __expf(-(hc[q] + cs[C_BOC + q])));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------------
+// data gradient: D[128 x Nout] (+)= G[128 x 128] (K-major image) * W[128 x Nout] (MN-major view of the weight image)
+__device__ __forceinline__ void issue_dgrad(uint32_t d, uint32_t gAddr, uint32_t wAddr, int Nout, bool acc) {
+  const uint32_t id = idesc_bf16(128, Nout, 0, 1);
+  for (int ks = 0; ks < H / 16; ++ks)
+    mma_ss(d, smem_desc(gAddr + ks * 256, 128, 16 * H), smem_desc(wAddr + ks * 2 * (16 * Nout), 16 * Nout, 128), id, (acc || ks > 0) ? 1u : 0u);
+}
+// weight gradient: D[aCols (rows) x bCols] = A^T * B, both MN-major views of [128 points x cols] images (contraction over the points)
+__device__ __forceinline__ void issue_wgrad(uint32_t d, uint32_t aAddr, int aCols, uint32_t bAddr, int bCols) {
+  const uint32_t id = idesc_bf16(128, bCols, 1, 1);
+  for (int ks = 0; ks < TPT / 16; ++ks)
+    mma_ss(d, smem_desc(aAddr + ks * 2 * (16 * aCols), 16 * aCols, 128), smem_desc(bAddr + ks * 2 * (16 * bCols), 16 * bCols, 128), id,
+           ks > 0 ? 1u : 0u);
+}
+
+constexpr int B_A0 = 0, B_A1 = 32768, B_AX = 65536, B_G0 = 90112, B_G1 = 122880, B_W0 = 155648, B_W1 = 188416, B_ONES = 221184,
+              B_HD = 225280, B_C = 229376, B_SMEM = B_C + (128 + 384) * 4;
+constexpr int T_DA = 0, T_DB = 128, T_DW = 224, T_DO = 448, T_DH = 464;
+// per-CTA partial weight gradients (fp32): rows = output feature (TMEM lane), row lengths 96 / 128 / 224 / 128 / 176 / 1 / 1 / 32
+constexpr int PR_IN = 0, PR_MID1 = 12288, PR_CAT = 28672, PR_MID2 = 57344, PR_COL = 73728, PR_DB1 = 96256, PR_DB2 = 96384,
+              PR_HEAD = 96512, PR_HB = 100608, PART_FLOATS = 100616;
+
+__global__ void __launch_bounds__(NT, 1)
+bwd_kernel(int P, const uint8_t* __restrict__ prep, const uint8_t* __restrict__ imgs, const float* __restrict__ rgb,
+           const float* __restrict__ g_alpha, const float* __restrict__ g_rgb, float* __restrict__ partials,
+           float* __restrict__ g_emb) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  __shared__ uint64_t fullA0, fullA1, fullAX, fullH, fullW0, fullW1, bar_d, bar_w;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_hb[4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {
+    float* c = reinterpret_cast<float*>(sm + B_C);
+    const float* src = reinterpret_cast<const float*>(prep + WIMG_BYTES);
+    for (int i = tid; i < 128 + 384; i += NT) c[i] = src[C_WA + i];             // w_alpha | W_oc
+    // constant-one image [128 points x 16]: column 0 = 1
+    for (int i = tid; i < 4096 / 16; i += NT) {
+      // chunk i: row-group i / 2, column block i % 2 ... rows x 16 B; column 0 lives in column block 0
+      *reinterpret_cast<uint4*>(sm + B_ONES + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid < 4) s_hb[tid] = 0.f;
+  }
+  __syncthreads();
+  if (tid < TPT) *reinterpret_cast<__nv_bfloat16*>(sm + B_ONES + blk_off(tid, 0, 16)) = __float2bfloat16_rn(1.0f);
+  if (tid == 0) {
+    mbar_init(&fullA0, 1); mbar_init(&fullA1, 1); mbar_init(&fullAX, 1); mbar_init(&fullH, 1); mbar_init(&fullW0, 1); mbar_init(&fullW1, 1);
+    mbar_init(&bar_d, 1); mbar_init(&bar_w, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int n_tiles = (P + TPT - 1) / TPT;
+  const int nt = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const uint32_t sb = smem_u32(sm);
+  float* part = partials + (size_t)blockIdx.x * PART_FLOATS;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ control warp
+    uint32_t pA0 = 0, pA1 = 0, pAX = 0, pH = 0, pW0 = 0, pW1 = 0, pD = 0;
+    int sg = 0, sd = 0;                                      // named-barrier stage counters: G-ready (ids 1,2), drained (ids 3,4)
+    auto load = [&](int dst, const uint8_t* src, uint32_t bytes, uint64_t* bar) {
+      if (lane == 0) { mbar_expect_tx(bar, bytes); bulk_g2s(sm + dst, src, bytes, bar); }
+    };
+    auto g_ready = [&]() { nbar_sync(1 + (sg & 1), NT); ++sg; };
+    auto drained = [&]() { nbar_sync(3 + (sd & 1), NT); ++sd; };
+    auto wait = [&](uint64_t* bar, uint32_t& ph) { mbar_wait(bar, ph); ph ^= 1; };
+    for (int it = 0; it < nt; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const uint8_t* img = imgs + (size_t)tile * TILE_IMG_BYTES;
+      if (it > 0) drained();                                 // previous tile's last accumulators are read out
+      load(B_G1, img + IMG_H, ACT_BYTES, &fullH);
+      load(B_A1, img + IMG_FC4, ACT_BYTES, &fullA1);
+      load(B_AX, img + IMG_XC, XC_C * 256, &fullAX);
+      load(B_A0, img + IMG_FC3, ACT_BYTES, &fullA0);
+      load(B_W0, prep + blk_byte(5), 32768, &fullW0);
+      load(B_W1, prep + blk_byte(6), XC_C * 256, &fullW1);
+      __syncwarp();
+      // ---- S1: color_linear (delta = d h in G0; h in G1)
+      g_ready();
+      wait(&fullH, pH); wait(&fullW0, pW0); wait(&fullW1, pW1);
+      if (elect_one()) {
+        tc_fence_after();
+        issue_wgrad(tmem + T_DH, sb + B_G1, H, sb + B_HD, 16);                   // out_color weights: h^T x [d rgb_pre | d raw]
+        issue_dgrad(tmem + T_DA, sb + B_G0, sb + B_W0, H, false);                // d fc4 (colour branch)
+        issue_dgrad(tmem + T_DB, sb + B_G0, sb + B_W1, XC_C, false);             // d xc
+        mma_commit(&bar_d);
+      }
+      __syncwarp();
+      wait(&fullA1, pA1); wait(&fullAX, pAX);
+      if (elect_one()) {
+        issue_wgrad(tmem + T_DW, sb + B_G0, H, sb + B_A1, H);                    // color_linear weights: fc4 part
+        issue_wgrad(tmem + T_DW + H, sb + B_G0, H, sb + B_AX, XC_C);             //                       xc part (+ bias column)
+        issue_wgrad(tmem + T_DH + 16, sb + B_A1, H, sb + B_HD, 16);              // out_alpha weights: fc4^T x [.. | d raw]
+        mma_commit(&bar_w);
+      }
+      __syncwarp();
+      wait(&bar_d, pD);
+      load(B_W0, prep + blk_byte(4), 32768, &fullW0);
+      load(B_W1, prep + blk_byte(2), 32768, &fullW1);
+      __syncwarp();
+      // ---- S2: mid2 (delta = d fc4 in G1)
+      g_ready();
+      wait(&fullW0, pW0);
+      if (elect_one()) { tc_fence_after(); issue_dgrad(tmem + T_DA, sb + B_G1, sb + B_W0, H, false); mma_commit(&bar_d); }
+      __syncwarp();
+      drained();                                             // S1's weight-gradient GEMMs are complete and read out: A1, AX free
+      load(B_A1, img + IMG_FC2, ACT_BYTES, &fullA1);
+      load(B_AX, img + IMG_XG, XG_C * 256, &fullAX);
+      __syncwarp();
+      wait(&fullA0, pA0);
+      if (elect_one()) {
+        tc_fence_after();
+        issue_wgrad(tmem + T_DW, sb + B_G1, H, sb + B_A0, H);                    // mid2 weights
+        issue_wgrad(tmem + T_DO, sb + B_G1, H, sb + B_ONES, 16);                 // mid2 bias
+        mma_commit(&bar_w);
+      }
+      __syncwarp();
+      wait(&bar_d, pD);
+      load(B_W0, prep + blk_byte(3), XG_C * 256, &fullW0);
+      __syncwarp();
+      // ---- S3: cat_layer (delta = d fc3 in G0)
+      g_ready();
+      wait(&fullW1, pW1); wait(&fullW0, pW0);
+      if (elect_one()) {
+        tc_fence_after();
+        issue_dgrad(tmem + T_DA, sb + B_G0, sb + B_W1, H, false);                // d fc2
+        issue_dgrad(tmem + T_DB, sb + B_G0, sb + B_W0, XG_C, false);             // d xg (cat part)
+        mma_commit(&bar_d);
+      }
+      __syncwarp();
+      drained();
+      load(B_A0, img + IMG_FC1, ACT_BYTES, &fullA0);
+      __syncwarp();
+      wait(&fullA1, pA1); wait(&fullAX, pAX);
+      if (elect_one()) {
+        tc_fence_after();
+        issue_wgrad(tmem + T_DW, sb + B_G0, H, sb + B_A1, H);                    // cat weights: fc2 part
+        issue_wgrad(tmem + T_DW + H, sb + B_G0, H, sb + B_AX, XG_C);             //              xg part (+ bias column)
+        mma_commit(&bar_w);
+      }
+      __syncwarp();
+      wait(&bar_d, pD);
+      load(B_W1, prep + blk_byte(1), 32768, &fullW1);
+      load(B_W0, prep + blk_byte(0), XG_C * 256, &fullW0);
+      __syncwarp();
+      // ---- S4: mid1 (delta = d fc2 in G1)
+      g_ready();
+      wait(&fullW1, pW1);
+      if (elect_one()) { tc_fence_after(); issue_dgrad(tmem + T_DA, sb + B_G1, sb + B_W1, H, false); mma_commit(&bar_d); }
+      __syncwarp();
+      drained();
+      wait(&fullA0, pA0);
+      if (elect_one()) {
+        tc_fence_after();
+        issue_wgrad(tmem + T_DW, sb + B_G1, H, sb + B_A0, H);                    // mid1 weights
+        issue_wgrad(tmem + T_DO, sb + B_G1, H, sb + B_ONES, 16);                 // mid1 bias
+        mma_commit(&bar_w);
+      }
+      __syncwarp();
+      wait(&bar_d, pD);
+      // ---- S5: in_layer (delta = d fc1 in G0)
+      g_ready();
+      wait(&fullW0, pW0);
+      if (elect_one()) { tc_fence_after(); issue_dgrad(tmem + T_DB, sb + B_G0, sb + B_W0, XG_C, true); mma_commit(&bar_d); }   // += onto cat's d xg
+      __syncwarp();
+      drained();
+      if (elect_one()) { tc_fence_after(); issue_wgrad(tmem + T_DW, sb + B_G0, H, sb + B_AX, XG_C); mma_commit(&bar_w); }       // in_layer weights (+ bias column)
+      __syncwarp();
+      wait(&bar_d, pD);
+    }
+    if (nt > 0) drained();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps: thread = tile row / accumulator lane
+    const int row = tid;
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    const float* wa = reinterpret_cast<const float*>(sm + B_C);
+    const float* woc = wa + 128;
+    uint32_t pA0 = 0, pA1 = 0, pH = 0, pD = 0, pW = 0;
+    int sg = 0, sd = 0;
+    auto wait = [&](uint64_t* bar, uint32_t& ph) { mbar_wait(bar, ph); ph ^= 1; };
+    auto publish = [&]() { fence_async_smem(); tc_fence_before(); nbar_arrive(1 + (sg & 1), NT); ++sg; };
+    auto mark_drained = [&]() { tc_fence_before(); nbar_arrive(3 + (sd & 1), NT); ++sd; };
+    for (int it = 0; it < nt; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int p = tile * TPT + row;
+      const bool act = p < P, first = it == 0;
+      // read one accumulator row segment out of tensor memory into this CTA's partial (plain stores; += after the first tile)
+      auto drain = [&](int tcol, int ncols, float* dst) {
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t u[32];
+          const int n = min(32, ncols - c0);
+          if (n == 32) tmem_ld32(tl + tcol + c0, u); else tmem_ld16(tl + tcol + c0, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (q * 4 < n) {
+              float4 v = make_float4(__uint_as_float(u[4 * q]), __uint_as_float(u[4 * q + 1]), __uint_as_float(u[4 * q + 2]), __uint_as_float(u[4 * q + 3]));
+              float4* d4 = reinterpret_cast<float4*>(dst + c0 + 4 * q);
+              if (!first) { const float4 o = *d4; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+              *d4 = v;
+            }
+          }
+        }
+      };
+      // delta epilogue: D (+ extra * xw) masked by the layer's own activation (> 0) -> bf16 image
+      auto delta = [&](const uint8_t* actImg, uint8_t* dst, float extra, const float* xw) {
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t u[32];
+          tmem_ld32(tl + T_DA + ch * 32, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 a = *reinterpret_cast<const uint4*>(actImg + (row >> 3) * (16 * H) + (ch * 4 + q) * 128 + (row & 7) * 16);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = ch * 32 + q * 8 + e * 2;
+              float v0 = __uint_as_float(u[q * 8 + e * 2]), v1 = __uint_as_float(u[q * 8 + e * 2 + 1]);
+              if (xw != nullptr) { v0 = fmaf(extra, xw[c], v0); v1 = fmaf(extra, xw[c + 1], v1); }
+              // bf16 activations are >= 0 after relu: positive <=> non-zero bits (no negative zero is ever produced by fmaxf(x, 0))
+              if ((aw[e] & 0xffffu) == 0u) v0 = 0.f;
+              if ((aw[e] >> 16) == 0u) v1 = 0.f;
+              w[e] = pack2(v0, v1);
+            }
+            *reinterpret_cast<uint4*>(rowblk(dst, row, ch * 4 + q, H)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      };
+      // ---- S0: loss gradients of the heads -> d h (G0) and the head-delta image
+      float dp[3] = {0.f, 0.f, 0.f}, draw = 0.f;
+      if (act) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { const float c = rgb[(size_t)p * 3 + q]; dp[q] = g_rgb[(size_t)p * 3 + q] * c * (1.0f - c); }   // sigmoid head
+        draw = 10.0f * g_alpha[p];                                                                                                     // alpha = 10 raw
+      }
+      *reinterpret_cast<uint4*>(rowblk(sm + B_HD, row, 0, 16)) = make_uint4(pack2(dp[0], dp[1]), pack2(dp[2], draw), 0u, 0u);
+      *reinterpret_cast<uint4*>(rowblk(sm + B_HD, row, 1, 16)) = make_uint4(0u, 0u, 0u, 0u);
+      {
+        float s0 = warp_sum(dp[0]), s1 = warp_sum(dp[1]), s2 = warp_sum(dp[2]), s3 = warp_sum(draw);
+        if (lane == 0) { atomicAdd(&s_hb[0], s0); atomicAdd(&s_hb[1], s1); atomicAdd(&s_hb[2], s2); atomicAdd(&s_hb[3], s3); }
+      }
+      wait(&fullH, pH);
+#pragma unroll 1
+      for (int cb = 0; cb < 16; ++cb) {
+        const uint4 a = *reinterpret_cast<const uint4*>(sm + B_G1 + (row >> 3) * (16 * H) + cb * 128 + (row & 7) * 16);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = cb * 8 + e * 2;
+          float v0 = fmaf(woc[2 * H + c], dp[2], fmaf(woc[H + c], dp[1], woc[c] * dp[0]));
+          float v1 = fmaf(woc[2 * H + c + 1], dp[2], fmaf(woc[H + c + 1], dp[1], woc[c + 1] * dp[0]));
+          if ((aw[e] & 0xffffu) == 0u) v0 = 0.f;
+          if ((aw[e] >> 16) == 0u) v1 = 0.f;
+          w[e] = pack2(v0, v1);
+        }
+        *reinterpret_cast<uint4*>(rowblk(sm + B_G0, row, cb, H)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      publish();
+      // ---- S1: color_linear
+      wait(&bar_d, pD); tc_fence_after();
+      wait(&fullA1, pA1);
+      delta(sm + B_A1, sm + B_G1, draw, wa);                                     // d fc4 = mask(fc4) (colour branch + alpha head)
+      if (g_emb != nullptr) {                                                    // d xc -> g_emb[:, 87:]
+        uint32_t u[32], v[16];
+        tmem_ld32(tl + T_DB, u); tmem_ld16(tl + T_DB + 32, v); tmem_ld_wait();
+        if (act) {
+          float* ge = g_emb + (size_t)p * EMB + E1;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) ge[c] = __uint_as_float(u[c]);
+#pragma unroll
+          for (int c = 0; c < E2 - 32; ++c) ge[32 + c] = __uint_as_float(v[c]);
+        }
+      }
+      publish();
+      wait(&bar_w, pW); tc_fence_after();
+      drain(T_DW, H + XC_C, part + PR_COL + row * (H + XC_C));
+      drain(T_DH, 32, part + PR_HEAD + row * 32);
+      mark_drained();
+      // ---- S2: mid2
+      wait(&bar_d, pD); tc_fence_after();
+      wait(&fullA0, pA0);
+      delta(sm + B_A0, sm + B_G0, 0.f, nullptr);                                 // d fc3
+      publish();
+      wait(&bar_w, pW); tc_fence_after();
+      drain(T_DW, H, part + PR_MID2 + row * H);
+      { uint32_t u[4]; tmem_ld4(tl + T_DO, u); tmem_ld_wait(); float v = __uint_as_float(u[0]); if (!first) v += part[PR_DB2 + row]; part[PR_DB2 + row] = v; }
+      mark_drained();
+      // ---- S3: cat_layer
+      wait(&bar_d, pD); tc_fence_after();
+      wait(&fullA1, pA1);
+      delta(sm + B_A1, sm + B_G1, 0.f, nullptr);                                 // d fc2
+      publish();
+      wait(&bar_w, pW); tc_fence_after();
+      drain(T_DW, H + XG_C, part + PR_CAT + row * (H + XG_C));
+      mark_drained();
+      // ---- S4: mid1
+      wait(&bar_d, pD); tc_fence_after();
+      wait(&fullA0, pA0);
+      delta(sm + B_A0, sm + B_G0, 0.f, nullptr);                                 // d fc1
+      publish();
+      wait(&bar_w, pW); tc_fence_after();
+      drain(T_DW, H, part + PR_MID1 + row * H);
+      { uint32_t u[4]; tmem_ld4(tl + T_DO, u); tmem_ld_wait(); float v = __uint_as_float(u[0]); if (!first) v += part[PR_DB1 + row]; part[PR_DB1 + row] = v; }
+      mark_drained();
+      // ---- S5: in_layer
+      wait(&bar_d, pD); tc_fence_after();
+      if (g_emb != nullptr) {                                                    // d xg (cat part + in part) -> g_emb[:, :87]
+#pragma unroll 1
+        for (int ch = 0; ch < 3; ++ch) {
+          uint32_t u[32];
+          tmem_ld32(tl + T_DB + ch * 32, u); tmem_ld_wait();
+          if (act) {
+            float* ge = g_emb + (size_t)p * EMB + ch * 32;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) if (ch * 32 + c < E1) ge[c] = __uint_as_float(u[c]);
+          }
+        }
+      }
+      wait(&bar_w, pW); tc_fence_after();
+      drain(T_DW, XG_C, part + PR_IN + row * XG_C);
+      mark_drained();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 4) part[PR_HB + tid] = s_hb[tid];
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// sum of the per-CTA partials, scattered into the flat nn.Linear-ordered gradient (OVERWRITES g_params)
+__global__ void reduce_kernel(int n_part, const float* __restrict__ partials, float* __restrict__ g_params) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= P_TOTAL) return;
+  int src;
+  if (i < P_INB) { const int n = i / E1, k = i - n * E1; src = PR_IN + n * XG_C + k; }
+  else if (i < P_M1W) src = PR_IN + (i - P_INB) * XG_C + XG_ONE;
+  else if (i < P_M1B) src = PR_MID1 + (i - P_M1W);
+  else if (i < P_CATW) src = PR_DB1 + (i - P_M1B);
+  else if (i < P_CATB) { const int j = i - P_CATW, n = j / (H + E1), k = j - n * (H + E1); src = PR_CAT + n * (H + XG_C) + k; }
+  else if (i < P_M2W) src = PR_CAT + (i - P_CATB) * (H + XG_C) + H + XG_ONE;
+  else if (i < P_M2B) src = PR_MID2 + (i - P_M2W);
+  else if (i < P_AW) src = PR_DB2 + (i - P_M2B);
+  else if (i < P_AB) src = PR_HEAD + (i - P_AW) * 32 + 16 + 3;
+  else if (i < P_COLW) src = PR_HB + 3;
+  else if (i < P_COLB) { const int j = i - P_COLW, n = j / (H + E2), k = j - n * (H + E2); src = PR_COL + n * (H + XC_C) + k; }
+  else if (i < P_OCW) src = PR_COL + (i - P_COLB) * (H + XC_C) + H + XC_ONE;
+  else if (i < P_OCB) { const int j = i - P_OCW, q = j / H, c = j - q * H; src = PR_HEAD + c * 32 + q; }
+  else src = PR_HB + (i - P_OCB);
+  float a = 0.f;
+  for (int c = 0; c < n_part; ++c) a += partials[(size_t)c * PART_FLOATS + src];
+  g_params[i] = a;
+}
+
+}  // namespace otc
+}  // namespace cnf
+
+using namespace cnf;
+using namespace cnf::otc;
+
+static size_t ws_prep() { return 0; }
+static size_t ws_imgs() { return align_up(PREP_BYTES, 1024); }
+static size_t ws_imgs_bytes(int P) { return (size_t)((P + TPT - 1) / TPT) * TILE_IMG_BYTES; }
+
+static size_t ws_parts(int P) { return ws_imgs() + align_up(ws_imgs_bytes(P), 1024); }
+constexpr int MAX_PARTS = 148;
+
+extern "C" size_t cnf_occmap_tc_workspace_bytes(int n_pts) {
+  if (n_pts < 0) n_pts = 0;
+  return ws_parts(n_pts) + (size_t)MAX_PARTS * PART_FLOATS * sizeof(float);
+}
+
+extern "C" int cnf_occmap_tc_fwd(int P, const float* params, const float* emb, float* alpha, float* rgb, void* ws, size_t ws_bytes,
+                                 cnf_stream_t stream) {
+  CNF_REQUIRE(P >= 0, "cnf_occmap_tc_fwd: bad size P=%d", P);
+  CNF_REQUIRE(params && ws && (P == 0 || (emb && alpha && rgb)), "cnf_occmap_tc_fwd: null pointer");
+  if (ws_bytes < cnf_occmap_tc_workspace_bytes(P)) { set_error("cnf_occmap_tc_fwd: workspace too small"); return CNF_ERR_WORKSPACE; }
+  if (P == 0) return CNF_OK;
+  cudaStream_t st = as_stream(stream);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CNF_CUDA(cudaFuncSetAttribute(fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+    attr_set = true;
+  }
+  int dev = 0, n_sm = 148;
+  CNF_CUDA(cudaGetDevice(&dev));
+  CNF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  prep_kernel<<<(WIMG_BYTES / 16 + 255) / 256, 256, 0, st>>>(params, w8 + ws_prep());
+  const int n_tiles = (P + TPT - 1) / TPT;
+  fwd_kernel<<<n_tiles < n_sm ? n_tiles : n_sm, NT, F_SMEM, st>>>(P, w8 + ws_prep(), emb, w8 + ws_imgs(), alpha, rgb);
+  return check_launch("cnf_occmap_tc_fwd");
+}
+
+extern "C" int cnf_occmap_tc_bwd(int P, const float* params, const float* rgb, const float* g_alpha, const float* g_rgb, void* ws,
+                                 size_t ws_bytes, float* g_params, float* g_emb, cnf_stream_t stream) {
+  CNF_REQUIRE(P > 0, "cnf_occmap_tc_bwd: bad size P=%d", P);
+  CNF_REQUIRE(params && rgb && g_alpha && g_rgb && ws && g_params, "cnf_occmap_tc_bwd: null pointer");
+  if (ws_bytes < cnf_occmap_tc_workspace_bytes(P)) { set_error("cnf_occmap_tc_bwd: workspace too small"); return CNF_ERR_WORKSPACE; }
+  cudaStream_t st = as_stream(stream);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CNF_CUDA(cudaFuncSetAttribute(bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    attr_set = true;
+  }
+  int dev = 0, n_sm = 148;
+  CNF_CUDA(cudaGetDevice(&dev));
+  CNF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  const int n_tiles = (P + TPT - 1) / TPT;
+  int grid = n_tiles < n_sm ? n_tiles : n_sm;
+  if (grid > MAX_PARTS) grid = MAX_PARTS;
+  float* parts = reinterpret_cast<float*>(w8 + ws_parts(P));
+  bwd_kernel<<<grid, NT, B_SMEM, st>>>(P, w8 + ws_prep(), w8 + ws_imgs(), rgb, g_alpha, g_rgb, parts, g_emb);
+  reduce_kernel<<<(P_TOTAL + 255) / 256, 256, 0, st>>>(grid, parts, g_params);
+  return check_launch("cnf_occmap_tc_bwd");
+}

@@ -1,2 +1,2 @@
-timeout 1500 python -m pytest tests -m gpu -q 2>&1 | grep -E "passed|failed|^E  |well-cond" | head -20 > gpurun_out/t.log
+timeout 120 python scripts/check_otc.py > gpurun_out/t.log 2>&1
 cat gpurun_out/t.log

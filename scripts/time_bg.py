@@ -1,0 +1,35 @@
+"""Background OccupancyMap (W=128) training step through the fp32 module path: 1200 rays x (5+9) samples (SURVEY C2 background)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from category_nerf_reconstruction_official_b200 import model, embedding, loss, ops
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+R, S = 1200, 14
+m = model.OccupancyMap(87, 42, hidden_size=128).to(dev)
+pe = embedding.UniDirsEmbed(max_deg=5, scale=5.0).to(dev) if hasattr(embedding, "UniDirsEmbed") else None
+pcs = (torch.rand(R, S, 3, device=dev) - 0.5) * 6
+z = torch.sort(torch.rand(R, S, device=dev) * 5, dim=-1).values
+gt_d = torch.rand(R, device=dev) * 4 + 0.5; gt_c = torch.rand(R, 3, device=dev)
+labels = torch.ones(R, dtype=torch.uint8, device=dev); md = torch.ones(R, dtype=torch.bool, device=dev)
+params = list(m.parameters()) + list(pe.parameters())
+def step():
+    for p in params: p.grad = None
+    emb = pe(pcs)
+    a, c = m(emb)
+    l, _, _ = loss.step_batch_loss(a[None], c[None], gt_d[None], gt_c[None], labels[None], md[None], z[None])
+    l.backward()
+    return l
+for _ in range(5): step()
+torch.cuda.synchronize()
+ts = []
+for _ in range(20):
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); step(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+print("bg step eager (module path, fp32): median %.3f ms  min %.3f ms" % (sorted(ts)[10], min(ts)))
+# kernel-only: time the two MLP launches
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(5): step()
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=12, max_name_column_width=60))
