@@ -84,6 +84,10 @@ def codenerf_apply(x, shape_latent, texture_latent, params, W, batched):
 
 
 class OccupancyMap(torch.nn.Module):
+    # True: hidden_size == 128 models (the reference's background model) run on tcgen05 tensor cores (bf16 operands, fp32
+    # accumulation; gradients match a bf16-rounding emulation to 1e-3, the fp32 path to ~6 %).  False (default): fp32 CUDA cores.
+    use_tensor_cores = False
+
     def __init__(self, emb_size1, emb_size2, hidden_size=256, do_color=True, hidden_layers_block=1):
         super().__init__()
         if (emb_size1, emb_size2) != (ops.EMB1, ops.EMB2) or hidden_layers_block != 1 or not do_color:
@@ -105,7 +109,10 @@ class OccupancyMap(torch.nn.Module):
         if not do_cat:
             raise NotImplementedError("do_cat=False is never used by the reference's callers")
         lead = x.shape[:-1]
-        alpha, rgb = ops.OccMapFn.apply(x.reshape(1, -1, ops.EMB_DIM), flat_params(self)[None], self.hidden_size)
+        if self.use_tensor_cores and self.hidden_size == 128 and x.numel() > 0:
+            alpha, rgb = ops.OccMapTCFn.apply(x.reshape(-1, ops.EMB_DIM), flat_params(self))     # bf16 tcgen05 path
+        else:
+            alpha, rgb = ops.OccMapFn.apply(x.reshape(1, -1, ops.EMB_DIM), flat_params(self)[None], self.hidden_size)
         alpha = alpha.reshape(*lead, 1)
         if noise_std is not None:
             alpha = alpha + torch.randn(alpha.shape, device=x.device) * noise_std * 10.

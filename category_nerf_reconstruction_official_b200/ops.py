@@ -194,6 +194,38 @@ class OccMapFn(torch.autograd.Function):
         return g_emb, g_params, None
 
 
+class OccMapTCFn(torch.autograd.Function):
+    """alpha, rgb = OccupancyMap(emb), hidden size 128, on tensor cores (cnf_occmap_tc_fwd / _bwd; bf16 operands).
+    emb [P,129]; params [n_param] flat (one model)."""
+
+    @staticmethod
+    def forward(ctx, emb, params):
+        lib = lib_for(emb)
+        emb = _f32c(emb); params = _f32c(params)
+        P = emb.shape[0]
+        assert emb.shape[1] == EMB_DIM and params.numel() == lib.cnf_occmap_param_count(128)
+        ws = torch.empty(lib.cnf_occmap_tc_workspace_bytes(P), device=emb.device, dtype=torch.uint8)
+        alpha = torch.empty(P, device=emb.device, dtype=torch.float32)
+        rgb = torch.empty(P, 3, device=emb.device, dtype=torch.float32)
+        check(lib.cnf_occmap_tc_fwd(P, ptr(params), ptr(emb), ptr(alpha), ptr(rgb), ptr(ws), ws.numel(), stream()))
+        ctx.save_for_backward(params, rgb, ws)
+        ctx.P = P
+        return alpha, rgb
+
+    @staticmethod
+    def backward(ctx, g_alpha, g_rgb):
+        params, rgb, ws = ctx.saved_tensors
+        P = ctx.P
+        lib = lib_for(params)
+        g_alpha = _f32c(g_alpha) if g_alpha is not None else torch.zeros(P, device=params.device)
+        g_rgb = _f32c(g_rgb) if g_rgb is not None else torch.zeros(P, 3, device=params.device)
+        g_params = torch.empty_like(params)
+        g_emb = torch.empty(P, EMB_DIM, device=params.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        check(lib.cnf_occmap_tc_bwd(P, ptr(params), ptr(rgb), ptr(g_alpha), ptr(g_rgb), ptr(ws), ws.numel(), ptr(g_params),
+                                    ptr(g_emb), stream()))
+        return g_emb, g_params
+
+
 # ------------------------------------------------------------------------------------------------
 # compositing + losses
 # ------------------------------------------------------------------------------------------------

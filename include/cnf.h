@@ -116,6 +116,18 @@ int cnf_occmap_bwd(int n_cat, int n_pts, int H, const float* params, const float
                    const float* g_alpha, const float* g_rgb, float* ws, size_t ws_floats,
                    float* g_params, float* g_emb, cnf_stream_t stream);
 
+/*     OccupancyMap.forward with hidden size 128 (the reference's background model, train.py:172-180) on tcgen05 tensor cores:
+ *     bf16 operands, fp32 accumulation; same flat parameter layout as cnf_occmap_* with H = 128; ONE model (n_cat = 1).
+ *     fwd: emb [P,129] -> alpha [P] (already x10), rgb [P,3]; keeps bf16 activation images in ws for the backward.
+ *     bwd (after fwd on the same ws, same params): rgb (fwd output), g_alpha [P], g_rgb [P,3] ->
+ *          g_params [cnf_occmap_param_count(128)] OVERWRITTEN (not accumulated), g_emb [P,129] (may be NULL).
+ *     ws >= cnf_occmap_tc_workspace_bytes(P) (1568 B/point of activation images + 58 MiB of per-CTA partial gradients). */
+size_t cnf_occmap_tc_workspace_bytes(int n_pts);
+int cnf_occmap_tc_fwd(int n_pts, const float* params, const float* emb, float* alpha, float* rgb,
+                      void* ws, size_t ws_bytes, cnf_stream_t stream);
+int cnf_occmap_tc_bwd(int n_pts, const float* params, const float* rgb, const float* g_alpha, const float* g_rgb,
+                      void* ws, size_t ws_bytes, float* g_params, float* g_emb, cnf_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (4) Compositing and losses -- occupancy_activation / occupancy_to_termination / render /
  *     render_loss / reduce_batch_loss (src/render_rays.py:3-95) and step_batch_loss (src/loss.py:18-74).

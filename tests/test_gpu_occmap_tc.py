@@ -1,0 +1,124 @@
+"""Tensor-core OccupancyMap (hidden size 128, the reference's background model; src/model.py:86-154, train.py:172-180).
+
+Two references:
+  * a torch fp32 restatement with the kernel's bf16 roundings made explicit (operands of every GEMM bf16, accumulation fp32):
+    the kernel must agree with it to accumulation-order noise (gradients 5e-3 relative L2; measured ~1e-3);
+  * the fp32 oracle (oracle/cnf_oracle.py): what the reference computes.  ReLU masks flip for pre-activations within the bf16
+    forward error of zero, which bounds the agreement of the gradients at a few percent (measured 5-7 %; bound 15 %).
+"""
+import pytest
+import torch
+
+from oracle import cnf_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def occmap_bf16_emulation(params, emb, g_alpha, g_rgb):
+    Wi, bi, W1, b1, Wc, bc, W2, b2, wa, ba, Wl, bl, Wo, bo = [p.detach().float() for p in params]
+    xg = bf(emb[:, :87]); xc = bf(emb[:, 87:])
+    fc1 = bf(torch.relu(xg @ bf(Wi).T + bf(bi)))
+    fc2 = bf(torch.relu(fc1 @ bf(W1).T + b1))
+    fc3 = bf(torch.relu(fc2 @ bf(Wc[:, :128]).T + xg @ bf(Wc[:, 128:]).T + bf(bc)))
+    pre4 = torch.relu(fc3 @ bf(W2).T + b2); fc4 = bf(pre4)
+    alpha = 10.0 * (pre4 @ wa.T + ba).reshape(-1)
+    preh = torch.relu(fc4 @ bf(Wl[:, :128]).T + xc @ bf(Wl[:, 128:]).T + bf(bl)); h = bf(preh)
+    rgb = torch.sigmoid(preh @ Wo.T + bo)
+    dp = g_rgb * rgb * (1 - rgb); draw = 10.0 * g_alpha
+    hd = bf(torch.cat([dp, draw[:, None]], 1))
+    dh = bf((dp @ Wo) * (h > 0))
+    g_Wo = hd[:, :3].T @ h; g_bo = dp.sum(0)
+    g_wa = hd[:, 3:4].T @ fc4; g_ba = draw.sum().reshape(1)
+    g_Wl = torch.cat([dh.T @ fc4, dh.T @ xc], 1); g_bl = dh.sum(0)
+    d4 = bf((dh @ bf(Wl[:, :128]) + draw[:, None] * wa) * (fc4 > 0)); g_xc = dh @ bf(Wl[:, 128:])
+    g_W2 = d4.T @ fc3; g_b2 = d4.sum(0)
+    d3 = bf((d4 @ bf(W2)) * (fc3 > 0))
+    g_Wc = torch.cat([d3.T @ fc2, d3.T @ xg], 1); g_bc = d3.sum(0)
+    d2 = bf((d3 @ bf(Wc[:, :128])) * (fc2 > 0)); g_xg = d3 @ bf(Wc[:, 128:])
+    g_W1 = d2.T @ fc1; g_b1 = d2.sum(0)
+    d1 = bf((d2 @ bf(W1)) * (fc1 > 0))
+    g_Wi = d1.T @ xg; g_bi = d1.sum(0)
+    g_xg = g_xg + d1 @ bf(Wi)
+    gp = torch.cat([t.reshape(-1) for t in (g_Wi, g_bi, g_W1, g_b1, g_Wc, g_bc, g_W2, g_b2, g_wa, g_ba, g_Wl, g_bl, g_Wo, g_bo)])
+    return alpha, rgb, gp, torch.cat([g_xg, g_xc], 1)
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("P", [1, 127, 128, 129, 1200 * 14, 148 * 128 + 5, 3 * 148 * 128 + 77])
+def test_occmap_tc_fwd_bwd(P):
+    """Ragged point counts: one partial tile, exactly one tile, the reference's 1200 x 14 background batch (one wave), more tiles
+    than SMs (per-CTA partials accumulate over several tiles)."""
+    from category_nerf_reconstruction_official_b200 import ops
+    g = torch.Generator().manual_seed(400 + P % 97)
+    params = O.init_params(O.occmap_param_shapes(128), g)
+    B = O.icosa_matrix() + 0.01 * torch.randn(21, 3, generator=g)
+    pts = (torch.rand(P, 3, generator=g) - 0.5) * 6.0
+    emb = O.embed(pts[:, None, :], B, 5.0).reshape(P, 129)
+    ga = torch.randn(P, generator=g) * 0.1; gc = torch.randn(P, 3, generator=g)
+    flat = torch.cat([p.reshape(-1) for p in params]).to(DEV).requires_grad_(True)
+    emb_d = emb.to(DEV).requires_grad_(True)
+    alpha, rgb = ops.OccMapTCFn.apply(emb_d, flat)
+    ((alpha * ga.to(DEV)).sum() + (rgb * gc.to(DEV)).sum()).backward()
+    torch.cuda.synchronize()
+    # (1) bf16 emulation
+    a_e, c_e, gp_e, ge_e = occmap_bf16_emulation(params, emb, ga, gc)
+    assert float((alpha.detach().cpu() - a_e).abs().max()) < 5e-2 and float((rgb.detach().cpu() - c_e).abs().max()) < 2e-3
+    r_p, r_e = rel(flat.grad.cpu(), gp_e), rel(emb_d.grad.cpu(), ge_e)
+    # (2) fp32 oracle
+    fc = [p.clone().requires_grad_(True) for p in params]
+    emb_o = emb.clone().requires_grad_(True)
+    a_o, c_o = O.occmap_forward(fc, emb_o)
+    ((a_o.reshape(-1) * ga).sum() + (c_o.reshape(-1, 3) * gc).sum()).backward()
+    gp_o = torch.cat([p.grad.reshape(-1) for p in fc])
+    err_a = float((alpha.detach().cpu() - a_o.detach().reshape(-1)).abs().max())
+    err_c = float((rgb.detach().cpu() - c_o.detach().reshape(-1, 3)).abs().max())
+    r_po, r_eo = rel(flat.grad.cpu(), gp_o), rel(emb_d.grad.cpu(), emb_o.grad)
+    print("P=%d: vs bf16 emulation grads %.2e g_emb %.2e | vs fp32 oracle alpha %.2e rgb %.2e grads %.3f g_emb %.3f"
+          % (P, r_p, r_e, err_a, err_c, r_po, r_eo))
+    assert torch.isfinite(flat.grad).all() and torch.isfinite(emb_d.grad).all()
+    assert r_p < 5e-3 and r_e < 5e-3
+    assert err_a < 0.25 and err_c < 1e-2          # alpha = 10 x raw, |alpha| up to ~15
+    if P >= 1000:                                 # few-point gradients are dominated by single ReLU flips
+        assert r_po < 0.15 and r_eo < 0.15
+
+
+def test_occmap_module_tensor_core_background_step():
+    """OccupancyMap module with use_tensor_cores: the reference's background step (train.py:172-180: embed -> OccupancyMap ->
+    step_batch_loss -> backward) against the fp32 oracle step on a well-conditioned loss (all depths invalid -> depth term off)."""
+    from category_nerf_reconstruction_official_b200 import model, embedding, loss
+    g = torch.Generator().manual_seed(5)
+    R, S = 1200, 14
+    params = O.init_params(O.occmap_param_shapes(128), g)
+    m = model.OccupancyMap(87, 42, hidden_size=128).to(DEV)
+    with torch.no_grad():
+        for prm, src in zip(m.parameters(), params):
+            prm.copy_(src)
+    m.use_tensor_cores = True
+    pe = embedding.UniDirsEmbed(max_deg=5, scale=5.0).to(DEV)
+    B = pe.B_layer.weight.detach().cpu().clone()
+    org = (torch.rand(R, 3, generator=g) - 0.5) * 2; dirs = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    z = torch.sort(torch.rand(R, S, generator=g) * 4.0, dim=-1).values
+    pcs = org[:, None, :] + dirs[:, None, :] * z[..., None]
+    gt_d = torch.zeros(R); gt_rgb = torch.randint(0, 256, (R, 3), generator=g, dtype=torch.uint8)
+    labels = torch.randint(0, 3, (R,), generator=g, dtype=torch.uint8); md = torch.zeros(R, dtype=torch.bool)
+    emb = pe(pcs.to(DEV))
+    a, c = m(emb)
+    l, ld, _ = loss.step_batch_loss(a[None], c[None], gt_d.to(DEV)[None], (gt_rgb.to(DEV) / 255.)[None], labels.to(DEV)[None],
+                                    md.to(DEV)[None], z.to(DEV)[None])
+    l.backward()
+    torch.cuda.synchronize()
+    out = O.bg_train_step(params, B, 5.0, pcs, z, gt_d, gt_rgb, labels, md)
+    torch.testing.assert_close(l.detach().cpu(), out["loss"], rtol=5e-3, atol=1e-4)
+    gp = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).cpu()
+    gp_o = torch.cat([t.reshape(-1) for t in out["g_fc"]])
+    r_p, r_B = rel(gp, gp_o), rel(pe.B_layer.weight.grad.cpu(), out["g_B"])
+    print("background step: loss %.5f vs %.5f, whole MLP gradient rel L2 %.3f, B_layer gradient rel L2 %.3f" % (float(l), float(out["loss"]), r_p, r_B))
+    assert r_p < 0.15 and r_B < 0.2
