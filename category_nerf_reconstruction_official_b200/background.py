@@ -1,0 +1,163 @@
+"""The background model's training step (reference train.py:172-180) without autograd, on tensor cores.
+
+``FusedBackgroundTrainer`` holds the background ``OccupancyMap`` (hidden size 128, src/model.py:86-154) and its positional
+embedding as flat fp32 buffers and runs one step per call through the C ABI only:
+
+    sampler (cnf_sample_fwd) -> embedding (cnf_embed_fwd) -> OccupancyMap forward (cnf_occmap_tc_fwd, tcgen05, bf16 operands)
+    -> compositing + losses forward / backward (cnf_composite_loss_fwd / _bwd) -> OccupancyMap backward (cnf_occmap_tc_bwd)
+    -> embedding backward (cnf_embed_bwd)
+
+Every buffer is preallocated, nothing is read back, so the step can be captured into a CUDA graph (``capture``).  Parameter
+order and shapes are the module's (``model.OccupancyMap(87, 42, 128)``), so state interchanges with the drop-in module path."""
+from __future__ import annotations
+
+import contextlib
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import ops, sampling
+from ._lib import check, lib_for, ptr, stream
+from .embedding import _DIRS
+
+
+class FusedBackgroundTrainer:
+    def __init__(self, scale: float = 5.0, device="cuda:0", n_bins_cam2surface: int = 5, n_bins: int = 9,
+                 surface_eps: float = 0.1, stop_eps: float = 0.05, min_bound: float = 0.0, this_obj: int = 1,
+                 color_scaling: float = 5.0, opacity_scaling: float = 10.0, generator: Optional[torch.Generator] = None):
+        self.device = torch.device(device)
+        self.N, self.M = n_bins_cam2surface, n_bins
+        self.S = self.N + self.M
+        self.eps, self.stop_eps, self.min_bound, self.this_obj = surface_eps, stop_eps, min_bound, this_obj
+        self.cs, self.os = color_scaling, opacity_scaling
+        from .model import OccupancyMap, flat_params, init_weights
+        g = generator
+        with (torch.random.fork_rng(devices=[]) if g is not None else contextlib.nullcontext()):
+            if g is not None:
+                torch.manual_seed(int(torch.randint(0, 2 ** 31 - 1, (1,), generator=g)))
+            m = OccupancyMap(87, 42, hidden_size=128)
+            m.apply(init_weights)
+        self._shapes = [tuple(p.shape) for p in m.parameters()]
+        dev = self.device
+        self.params = flat_params(m).detach().to(dev).contiguous()
+        self.pe_B = torch.tensor(_DIRS, dtype=torch.float32, device=dev).contiguous()
+        self.pe_scale = torch.tensor([float(scale)], dtype=torch.float32, device=dev)
+        self.g_params = torch.zeros_like(self.params)
+        self.g_B = torch.zeros_like(self.pe_B)
+        self.out_loss = torch.zeros(7, device=dev)          # {loss, e_depth, e_obj, e_sem, depth, color, opacity}
+        self._one = torch.ones(1, device=dev)
+        self._buf_key = None
+        self._opt_state = None
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------------------------------ views / state import
+    def param_views(self):
+        out, off = [], 0
+        for s in self._shapes:
+            n = 1
+            for d in s:
+                n *= d
+            out.append(self.params[off:off + n].view(*s))
+            off += n
+        return out
+
+    def grad_views(self):
+        out, off = [], 0
+        for s in self._shapes:
+            n = 1
+            for d in s:
+                n *= d
+            out.append(self.g_params[off:off + n].view(*s))
+            off += n
+        return out
+
+    def load(self, fc_params: Sequence[torch.Tensor], B: torch.Tensor):
+        """Copy reference-shaped tensors (14 parameters in named_parameters() order, B [21,3])."""
+        self.params.copy_(torch.cat([p.detach().reshape(-1).float() for p in fc_params]).to(self.device))
+        self.pe_B.copy_(B.detach().to(self.device))
+
+    # ------------------------------------------------------------------------------------------ one step
+    def _buffers(self, R: int):
+        if self._buf_key != R:
+            lib = lib_for(self.params)
+            dev, S = self.device, self.S
+            P = R * S
+            f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+            self._emb, self._alpha, self._rgb = f(P, 129), f(P), f(P, 3)
+            self._g_alpha, self._g_rgb, self._g_emb = f(P), f(P, 3), f(P, 129)
+            self._rays = f(R, 6)
+            self._counts = torch.empty(1, 4, device=dev, dtype=torch.int32)
+            self._gt_color = f(R, 3)
+            self._ws = torch.empty(lib.cnf_occmap_tc_workspace_bytes(P), device=dev, dtype=torch.uint8)
+            self._cws = torch.empty(lib.cnf_composite_workspace_bytes(1, R), device=dev, dtype=torch.uint8)
+            self._buf_key = R
+        return self._buf_key
+
+    def step_from_samples(self, pcs, z, gt_depth, gt_rgb_u8, labels, mask_depth):
+        """Forward + backward given sampled points: pcs [R,S,3], z [R,S], gt_depth [R], gt_rgb_u8 u8 [R,3+] (first three channels),
+        labels u8 [R], mask_depth u8/bool [R].  Fills self.g_params / self.g_B / self.out_loss; returns the loss (0-d, async)."""
+        lib = lib_for(self.params)
+        R, S = z.shape
+        assert S == self.S
+        P = R * S
+        self._buffers(R)
+        st = stream()
+        pcs = pcs.contiguous(); z = z.contiguous(); gt_depth = gt_depth.contiguous()
+        labels = labels.contiguous()
+        mask_depth = mask_depth.view(torch.uint8) if mask_depth.dtype == torch.bool else mask_depth
+        mask_depth = mask_depth.contiguous()
+        torch.div(gt_rgb_u8[:, :3], 255.0, out=self._gt_color)                                   # train.py:128 (gt_rgb / 255)
+        check(lib.cnf_embed_fwd(1, P, ptr(pcs), ptr(self.pe_B), ptr(self.pe_scale), ptr(self._emb), st))
+        check(lib.cnf_occmap_tc_fwd(P, ptr(self.params), ptr(self._emb), ptr(self._alpha), ptr(self._rgb), ptr(self._ws),
+                                    self._ws.numel(), st))
+        check(lib.cnf_mask_counts(1, R, ptr(labels), ptr(mask_depth), ptr(self._counts), st))
+        args = (1, R, S, ptr(self._alpha), ptr(self._rgb), ptr(z), ptr(gt_depth), ptr(self._gt_color), ptr(labels), ptr(mask_depth),
+                ptr(self._counts), float(self.cs), float(self.os))
+        check(lib.cnf_composite_loss_fwd(*args, ptr(self._rays), ptr(self.out_loss), ptr(self._cws), self._cws.numel(), st))
+        check(lib.cnf_composite_loss_bwd(*args, ptr(self._one), ptr(self._g_alpha), ptr(self._g_rgb), st))
+        check(lib.cnf_occmap_tc_bwd(P, ptr(self.params), ptr(self._rgb), ptr(self._g_alpha), ptr(self._g_rgb), ptr(self._ws),
+                                    self._ws.numel(), ptr(self.g_params), ptr(self._g_emb), st))
+        self.g_B.zero_()
+        check(lib.cnf_embed_bwd(1, P, ptr(pcs), ptr(self.pe_B), ptr(self.pe_scale), ptr(self._g_emb), ptr(self.g_B), None, st))
+        return self.out_loss[0]
+
+    def step(self, rgbs, depth, origins, dirs, rand: Optional[Dict[str, torch.Tensor]] = None):
+        """Sample + step: rgbs u8 [R,4] (rgb + label), depth [R], origins / dirs [R,3] (scene_cateogries.py:453-546 sampler)."""
+        if rand is None:
+            rand = sampling.draw_randoms(rgbs[None], depth[None], self.N, self.M, self.eps, self.min_bound, self.this_obj)
+        elif rand["u_inv"].dim() == 2:
+            rand = {k: v[None] for k, v in rand.items()}
+        z, pcs, valid, labels, _ = ops.sample_batched(rgbs[None], depth[None], origins[None], dirs[None], self.N, self.M, self.eps,
+                                                       self.stop_eps, rand, self.min_bound, self.this_obj, want_pcs=True)
+        self.launches_per_step = 3 + 10
+        return self.step_from_samples(pcs[0], z[0], depth, rgbs, labels[0], valid[0])
+
+    def capture(self, rgbs, depth, origins, dirs):
+        """Capture sampler + step over THESE (static) input tensors into a CUDA graph; returns ``replay``."""
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.step(rgbs, depth, origins, dirs)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.step(rgbs, depth, origins, dirs)
+        self._graph = graph
+        return graph.replay
+
+    def loss_terms(self) -> Dict[str, torch.Tensor]:
+        o = self.out_loss
+        return {"loss": o[0], "depth": o[4:5], "color": o[5:6], "opacity": o[6:7]}
+
+    # ------------------------------------------------------------------------------------------ optimizer
+    def adamw_step(self, lr=1e-3, weight_decay=0.013, betas=(0.9, 0.999), eps=1e-8):
+        """Fused AdamW over the flat buffers (train.py:40,54-64,183-184)."""
+        if self._opt_state is None:
+            z = torch.zeros_like
+            self._opt_state = {"t": 0, "m": [z(self.params), z(self.pe_B)], "v": [z(self.params), z(self.pe_B)]}
+        st = self._opt_state
+        st["t"] += 1
+        for i, (p, g) in enumerate(((self.params, self.g_params), (self.pe_B, self.g_B))):
+            ops.adamw_step_(p, g, st["m"][i], st["v"][i], lr, betas[0], betas[1], eps, weight_decay, st["t"])

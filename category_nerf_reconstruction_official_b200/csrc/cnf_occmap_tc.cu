@@ -12,8 +12,9 @@
 // Biases of in_layer / cat_layer / color_linear ride in a constant-one column of xg / xc (their weight-gradient column is the
 // bias gradient).  The forward spills every activation image to a workspace (bulk shared->global copies; 1.5 KB/point, L2
 // resident at the reference's batch size); the backward streams them back while the previous layer's GEMMs run.
-// Weight gradients: each CTA owns a private fp32 partial (plain stores, no atomics); a reduce kernel sums the partials and
-// scatters them into nn.Linear order.
+// Weight gradients: every layer's accumulator is read out of tensor memory once per tile and added (coalesced RED.ADD.F32, stored
+// transposed so that a warp's 32 lanes hit 128 contiguous bytes) into ONE pre-zeroed fp32 buffer; a small kernel scatters it
+// into nn.Linear order.  (Per-CTA partial buffers + a reduce pass measured 26 % slower: 53 MB of extra L2 traffic.)
 #include <cuda_bf16.h>
 
 #include "cnf_common.cuh"
@@ -48,6 +49,12 @@ constexpr int P_INW = 0, P_INB = 11136, P_M1W = 11264, P_M1B = 27648, P_CATW = 2
 constexpr int IMG_XG = 0, IMG_XC = 24576, IMG_FC1 = 36864, IMG_FC2 = 69632, IMG_FC3 = 102400, IMG_FC4 = 135168, IMG_H = 167936,
               TILE_IMG_BYTES = 200704;
 constexpr int ACT_BYTES = 32768;
+
+// development aid: SM-clock stamps of CTA 0 (epilogue thread 0: slots 0..31, control lane 0: slots 32..63); NULL = off
+__device__ long long* g_stamp = nullptr;
+__device__ __forceinline__ void stamp(int slot) {
+  if (g_stamp != nullptr && blockIdx.x == 0) g_stamp[slot] = clock64();
+}
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -106,20 +113,24 @@ __device__ __forceinline__ void issue_fwd(uint32_t d, uint32_t aAddr, int aCols,
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
-constexpr int F_XG = 0, F_XC = 24576, F_A0 = 36864, F_A1 = 69632, F_W = 102400, F_C = 200704, F_SMEM = F_C + C_FLOATS * 4;
+// The fp32 embedding tile (128 x 129 floats = 66048 B, contiguous in global memory) is staged over A0 | A1 (+ 512 B of slack)
+constexpr int EMB_TILE_BYTES = TPT * EMB * 4;
+constexpr int F_XG = 0, F_XC = 24576, F_A0 = 36864, F_A1 = 69632, F_W = 103424, F_C = F_W + 3 * 32768, F_SMEM = F_C + C_FLOATS * 4;
+static_assert(F_A0 + EMB_TILE_BYTES <= F_W, "embedding staging overlaps the weight ring");
 
 __global__ void __launch_bounds__(NT, 1)
 fwd_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ emb, uint8_t* __restrict__ imgs,
            float* __restrict__ alpha_out, float* __restrict__ rgb_out) {
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint64_t full[3];
-  __shared__ uint64_t bar_mma;
+  __shared__ uint64_t bar_mma, full_emb;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < C_FLOATS; i += NT) reinterpret_cast<float*>(sm + F_C)[i] = reinterpret_cast<const float*>(prep + WIMG_BYTES)[i];
   if (tid == 0) {
     for (int s = 0; s < 3; ++s) mbar_init(&full[s], 1);
     mbar_init(&bar_mma, 1);
+    mbar_init(&full_emb, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 128);
@@ -152,6 +163,14 @@ fwd_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ em
     for (int it = 0; it < nt; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       uint8_t* img = imgs + (size_t)tile * TILE_IMG_BYTES;
+      if ((tile + 1) * TPT <= P) {                       // full tile: one bulk copy of its contiguous fp32 embedding block
+        if (lane == 0) {
+          bulk_wait_read<0>();                           // the previous tile's spills out of A0 / A1 have been read
+          mbar_expect_tx(&full_emb, EMB_TILE_BYTES);
+          bulk_g2s(sm + F_A0, emb + (size_t)tile * TPT * EMB, EMB_TILE_BYTES, &full_emb);
+        }
+        __syncwarp();
+      }
       for (int l = 0; l < 5; ++l) {
         const int a1 = (l == 0) ? F_XG : ((l & 1) ? F_A0 : F_A1);                 // input activation of layer l
         const int a1c = (l == 0) ? XG_C : H;
@@ -188,18 +207,22 @@ fwd_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ em
     const int row = tid;
     const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
     const float* cs = reinterpret_cast<const float*>(sm + F_C);
-    uint32_t mph = 0;
-    int stage = 0;
-    auto publish = [&]() { fence_async_smem(); tc_fence_before(); nbar_arrive(1 + (stage & 1), NT); ++stage; };
+    uint32_t mph = 0, eph = 0;
+    int stage = 0, si = 0;
+    auto mark = [&]() { if (tid == 0) stamp(si); ++si; };
+    auto publish = [&]() { fence_async_smem(); tc_fence_before(); nbar_arrive(1 + (stage & 1), NT); ++stage; mark(); };
     // one layer's epilogue: D (+ bias) -> relu -> bf16 image; optional head dot products on the fp32 activations
     auto layer = [&](uint8_t* dst, const float* bias, const float* hw, int nh, float* hacc) {
       mbar_wait(&bar_mma, mph); mph ^= 1;
       tc_fence_after();
-#pragma unroll 1
+      mark();
+      uint32_t uu[4][32];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) tmem_ld32(tl + ch * 32, uu[ch]);
+      tmem_ld_wait();
+#pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
-        uint32_t u[32];
-        tmem_ld32(tl + ch * 32, u);
-        tmem_ld_wait();
+        const uint32_t* u = uu[ch];
         uint32_t w[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -217,16 +240,37 @@ fwd_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ em
     for (int it = 0; it < nt; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int p0 = tile * TPT, p = p0 + row;
+      mark();
       // embedding tile -> xg | xc images (coalesced read of the tile's contiguous [128 x 129] block)
-      const float* e = emb + (size_t)p0 * EMB;
-      const int nvalid = min(TPT, P - p0) * EMB;
-      for (int i = tid; i < TPT * EMB; i += 128) {
-        const int r = i / EMB, c = i - r * EMB;
-        const __nv_bfloat16 hv = __float2bfloat16_rn(i < nvalid ? e[i] : 0.f);
-        if (c < E1) *reinterpret_cast<__nv_bfloat16*>(sm + F_XG + blk_off(r, c, XG_C)) = hv;
-        else *reinterpret_cast<__nv_bfloat16*>(sm + F_XC + blk_off(r, c - E1, XC_C)) = hv;
-      }
-      {
+      if (p0 + TPT <= P) {
+        // staged tile: thread = row converts its 129 floats (row stride 129 words: conflict-free) into the two images
+        mbar_wait(&full_emb, eph); eph ^= 1;
+        const float* src = reinterpret_cast<const float*>(sm + F_A0) + row * EMB;
+#pragma unroll
+        for (int cb = 0; cb < 11; ++cb) {
+          const float last = (cb == 10) ? 1.0f : 0.f;    // column 87 = constant one
+          *reinterpret_cast<uint4*>(rowblk(sm + F_XG, row, cb, XG_C)) =
+              make_uint4(pack2(src[8 * cb], src[8 * cb + 1]), pack2(src[8 * cb + 2], src[8 * cb + 3]), pack2(src[8 * cb + 4], src[8 * cb + 5]),
+                         pack2(src[8 * cb + 6], cb == 10 ? last : src[8 * cb + 7]));
+        }
+        *reinterpret_cast<uint4*>(rowblk(sm + F_XG, row, 11, XG_C)) = make_uint4(0u, 0u, 0u, 0u);
+        const float* sc = src + E1;
+#pragma unroll
+        for (int cb = 0; cb < 5; ++cb)
+          *reinterpret_cast<uint4*>(rowblk(sm + F_XC, row, cb, XC_C)) =
+              make_uint4(pack2(sc[8 * cb], sc[8 * cb + 1]), pack2(sc[8 * cb + 2], sc[8 * cb + 3]), pack2(sc[8 * cb + 4], sc[8 * cb + 5]),
+                         pack2(sc[8 * cb + 6], sc[8 * cb + 7]));
+        *reinterpret_cast<uint4*>(rowblk(sm + F_XC, row, 5, XC_C)) = make_uint4(pack2(sc[40], sc[41]), pack2(1.0f, 0.f), 0u, 0u);
+      } else {
+        // ragged last tile: cooperative coalesced read of the valid rows
+        const float* e = emb + (size_t)p0 * EMB;
+        const int nvalid = min(TPT, P - p0) * EMB;
+        for (int i = tid; i < TPT * EMB; i += 128) {
+          const int r = i / EMB, c = i - r * EMB;
+          const __nv_bfloat16 hv = __float2bfloat16_rn(i < nvalid ? e[i] : 0.f);
+          if (c < E1) *reinterpret_cast<__nv_bfloat16*>(sm + F_XG + blk_off(r, c, XG_C)) = hv;
+          else *reinterpret_cast<__nv_bfloat16*>(sm + F_XC + blk_off(r, c - E1, XC_C)) = hv;
+        }
         const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
         *reinterpret_cast<__nv_bfloat16*>(sm + F_XG + blk_off(row, XG_ONE, XG_C)) = one;
         *reinterpret_cast<uint4*>(rowblk(sm + F_XG, row, 11, XG_C)) = make_uint4(0u, 0u, 0u, 0u);
@@ -279,7 +323,7 @@ constexpr int PR_IN = 0, PR_MID1 = 12288, PR_CAT = 28672, PR_MID2 = 57344, PR_CO
 
 __global__ void __launch_bounds__(NT, 1)
 bwd_kernel(int P, const uint8_t* __restrict__ prep, const uint8_t* __restrict__ imgs, const float* __restrict__ rgb,
-           const float* __restrict__ g_alpha, const float* __restrict__ g_rgb, float* __restrict__ partials,
+           const float* __restrict__ g_alpha, const float* __restrict__ g_rgb, float* __restrict__ part /* [PART_FLOATS], zeroed */,
            float* __restrict__ g_emb) {
   extern __shared__ __align__(1024) uint8_t sm[];
   __shared__ uint64_t fullA0, fullA1, fullAX, fullH, fullW0, fullW1, bar_d, bar_w;
@@ -313,7 +357,6 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, const uint8_t* __restrict__ 
   const int n_tiles = (P + TPT - 1) / TPT;
   const int nt = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const uint32_t sb = smem_u32(sm);
-  float* part = partials + (size_t)blockIdx.x * PART_FLOATS;
 
   if (warp == 4) {
     // ------------------------------------------------------------------ control warp
@@ -437,15 +480,18 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, const uint8_t* __restrict__ 
     const float* wa = reinterpret_cast<const float*>(sm + B_C);
     const float* woc = wa + 128;
     uint32_t pA0 = 0, pA1 = 0, pH = 0, pD = 0, pW = 0;
-    int sg = 0, sd = 0;
-    auto wait = [&](uint64_t* bar, uint32_t& ph) { mbar_wait(bar, ph); ph ^= 1; };
-    auto publish = [&]() { fence_async_smem(); tc_fence_before(); nbar_arrive(1 + (sg & 1), NT); ++sg; };
-    auto mark_drained = [&]() { tc_fence_before(); nbar_arrive(3 + (sd & 1), NT); ++sd; };
+    int sg = 0, sd = 0, si = 0;
+    auto mark = [&]() { if (tid == 0) stamp(si); ++si; };
+    auto wait = [&](uint64_t* bar, uint32_t& ph) { mbar_wait(bar, ph); ph ^= 1; mark(); };
+    auto publish = [&]() { fence_async_smem(); tc_fence_before(); nbar_arrive(1 + (sg & 1), NT); ++sg; mark(); };
+    auto mark_drained = [&]() { tc_fence_before(); nbar_arrive(3 + (sd & 1), NT); ++sd; mark(); };
     for (int it = 0; it < nt; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int p = tile * TPT + row;
-      const bool act = p < P, first = it == 0;
-      // read one accumulator row segment out of tensor memory into this CTA's partial (plain stores; += after the first tile)
+      const bool act = p < P;
+      mark();
+      // add one accumulator row segment (this thread = accumulator lane) into the shared gradient buffer
+      // (stored TRANSPOSED, [column][row], so that the 32 lanes of a warp write 128 contiguous bytes per column)
       auto drain = [&](int tcol, int ncols, float* dst) {
         for (int c0 = 0; c0 < ncols; c0 += 32) {
           uint32_t u[32];
@@ -453,23 +499,27 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, const uint8_t* __restrict__ 
           if (n == 32) tmem_ld32(tl + tcol + c0, u); else tmem_ld16(tl + tcol + c0, u);
           tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (q * 4 < n) {
-              float4 v = make_float4(__uint_as_float(u[4 * q]), __uint_as_float(u[4 * q + 1]), __uint_as_float(u[4 * q + 2]), __uint_as_float(u[4 * q + 3]));
-              float4* d4 = reinterpret_cast<float4*>(dst + c0 + 4 * q);
-              if (!first) { const float4 o = *d4; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-              *d4 = v;
+          for (int j = 0; j < 32; ++j) {
+            if (j < n) {
+              float* d = dst + (size_t)(c0 + j) * 128;
+              float v = __uint_as_float(u[j]);
+              atomicAdd(d, v);                           // one shared, pre-zeroed accumulator: coalesced RED.ADD at the L2
             }
           }
         }
       };
+      auto drain1 = [&](float* d, float v) {
+        atomicAdd(d, v);
+      };
       // delta epilogue: D (+ extra * xw) masked by the layer's own activation (> 0) -> bf16 image
       auto delta = [&](const uint8_t* actImg, uint8_t* dst, float extra, const float* xw) {
-#pragma unroll 1
+        uint32_t uu[4][32];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) tmem_ld32(tl + T_DA + ch * 32, uu[ch]);
+        tmem_ld_wait();
+#pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          uint32_t u[32];
-          tmem_ld32(tl + T_DA + ch * 32, u);
-          tmem_ld_wait();
+          const uint32_t* u = uu[ch];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint4 a = *reinterpret_cast<const uint4*>(actImg + (row >> 3) * (16 * H) + (ch * 4 + q) * 128 + (row & 7) * 16);
@@ -537,8 +587,8 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, const uint8_t* __restrict__ 
       }
       publish();
       wait(&bar_w, pW); tc_fence_after();
-      drain(T_DW, H + XC_C, part + PR_COL + row * (H + XC_C));
-      drain(T_DH, 32, part + PR_HEAD + row * 32);
+      drain(T_DW, H + XC_C, part + PR_COL + row);
+      drain(T_DH, 32, part + PR_HEAD + row);
       mark_drained();
       // ---- S2: mid2
       wait(&bar_d, pD); tc_fence_after();
@@ -546,8 +596,8 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, const uint8_t* __restrict__ 
       delta(sm + B_A0, sm + B_G0, 0.f, nullptr);                                 // d fc3
       publish();
       wait(&bar_w, pW); tc_fence_after();
-      drain(T_DW, H, part + PR_MID2 + row * H);
-      { uint32_t u[4]; tmem_ld4(tl + T_DO, u); tmem_ld_wait(); float v = __uint_as_float(u[0]); if (!first) v += part[PR_DB2 + row]; part[PR_DB2 + row] = v; }
+      drain(T_DW, H, part + PR_MID2 + row);
+      { uint32_t u[4]; tmem_ld4(tl + T_DO, u); tmem_ld_wait(); drain1(part + PR_DB2 + row, __uint_as_float(u[0])); }
       mark_drained();
       // ---- S3: cat_layer
       wait(&bar_d, pD); tc_fence_after();
@@ -555,7 +605,7 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, const uint8_t* __restrict__ 
       delta(sm + B_A1, sm + B_G1, 0.f, nullptr);                                 // d fc2
       publish();
       wait(&bar_w, pW); tc_fence_after();
-      drain(T_DW, H + XG_C, part + PR_CAT + row * (H + XG_C));
+      drain(T_DW, H + XG_C, part + PR_CAT + row);
       mark_drained();
       // ---- S4: mid1
       wait(&bar_d, pD); tc_fence_after();
@@ -563,8 +613,8 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, const uint8_t* __restrict__ 
       delta(sm + B_A0, sm + B_G0, 0.f, nullptr);                                 // d fc1
       publish();
       wait(&bar_w, pW); tc_fence_after();
-      drain(T_DW, H, part + PR_MID1 + row * H);
-      { uint32_t u[4]; tmem_ld4(tl + T_DO, u); tmem_ld_wait(); float v = __uint_as_float(u[0]); if (!first) v += part[PR_DB1 + row]; part[PR_DB1 + row] = v; }
+      drain(T_DW, H, part + PR_MID1 + row);
+      { uint32_t u[4]; tmem_ld4(tl + T_DO, u); tmem_ld_wait(); drain1(part + PR_DB1 + row, __uint_as_float(u[0])); }
       mark_drained();
       // ---- S5: in_layer
       wait(&bar_d, pD); tc_fence_after();
@@ -581,38 +631,36 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, const uint8_t* __restrict__ 
         }
       }
       wait(&bar_w, pW); tc_fence_after();
-      drain(T_DW, XG_C, part + PR_IN + row * XG_C);
+      drain(T_DW, XG_C, part + PR_IN + row);
       mark_drained();
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (tid < 4) part[PR_HB + tid] = s_hb[tid];
+  if (tid < 4) atomicAdd(&part[PR_HB + tid], s_hb[tid]);
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-// sum of the per-CTA partials, scattered into the flat nn.Linear-ordered gradient (OVERWRITES g_params)
+// accumulation buffer -> flat nn.Linear-ordered gradient (OVERWRITES g_params); one thread per slot, slot (column k, row o) of a
+// region lives at region + k * 128 + o.
 __global__ void reduce_kernel(int n_part, const float* __restrict__ partials, float* __restrict__ g_params) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= P_TOTAL) return;
-  int src;
-  if (i < P_INB) { const int n = i / E1, k = i - n * E1; src = PR_IN + n * XG_C + k; }
-  else if (i < P_M1W) src = PR_IN + (i - P_INB) * XG_C + XG_ONE;
-  else if (i < P_M1B) src = PR_MID1 + (i - P_M1W);
-  else if (i < P_CATW) src = PR_DB1 + (i - P_M1B);
-  else if (i < P_CATB) { const int j = i - P_CATW, n = j / (H + E1), k = j - n * (H + E1); src = PR_CAT + n * (H + XG_C) + k; }
-  else if (i < P_M2W) src = PR_CAT + (i - P_CATB) * (H + XG_C) + H + XG_ONE;
-  else if (i < P_M2B) src = PR_MID2 + (i - P_M2W);
-  else if (i < P_AW) src = PR_DB2 + (i - P_M2B);
-  else if (i < P_AB) src = PR_HEAD + (i - P_AW) * 32 + 16 + 3;
-  else if (i < P_COLW) src = PR_HB + 3;
-  else if (i < P_COLB) { const int j = i - P_COLW, n = j / (H + E2), k = j - n * (H + E2); src = PR_COL + n * (H + XC_C) + k; }
-  else if (i < P_OCW) src = PR_COL + (i - P_COLB) * (H + XC_C) + H + XC_ONE;
-  else if (i < P_OCB) { const int j = i - P_OCW, q = j / H, c = j - q * H; src = PR_HEAD + c * 32 + q; }
-  else src = PR_HB + (i - P_OCB);
+  const int s = blockIdx.x * 256 + threadIdx.x;
+  if (s >= PART_FLOATS) return;
+  int dst = -1;
+  if (s < PR_MID1) { const int k = s >> 7, o = s & 127; dst = k < E1 ? P_INW + o * E1 + k : (k == XG_ONE ? P_INB + o : -1); }
+  else if (s < PR_CAT) { const int t = s - PR_MID1, k = t >> 7, o = t & 127; dst = P_M1W + o * H + k; }
+  else if (s < PR_MID2) { const int t = s - PR_CAT, k = t >> 7, o = t & 127; dst = k < H + E1 ? P_CATW + o * (H + E1) + k : (k == H + XG_ONE ? P_CATB + o : -1); }
+  else if (s < PR_COL) { const int t = s - PR_MID2, k = t >> 7, o = t & 127; dst = P_M2W + o * H + k; }
+  else if (s < PR_DB1) { const int t = s - PR_COL, k = t >> 7, o = t & 127; dst = k < H + E2 ? P_COLW + o * (H + E2) + k : (k == H + XC_ONE ? P_COLB + o : -1); }
+  else if (s < PR_DB2) dst = P_M1B + (s - PR_DB1);
+  else if (s < PR_HEAD) dst = P_M2B + (s - PR_DB2);
+  else if (s < PR_HB) { const int t = s - PR_HEAD, j = t >> 7, c = t & 127; dst = j < 3 ? P_OCW + j * H + c : (j == 19 ? P_AW + c : -1); }
+  else { const int t = s - PR_HB; dst = t < 3 ? P_OCB + t : (t == 3 ? P_AB : -1); }
+  if (dst < 0) return;
   float a = 0.f;
-  for (int c = 0; c < n_part; ++c) a += partials[(size_t)c * PART_FLOATS + src];
-  g_params[i] = a;
+#pragma unroll 4
+  for (int c = 0; c < n_part; ++c) a += partials[(size_t)c * PART_FLOATS + s];
+  g_params[dst] = a;
 }
 
 }  // namespace otc
@@ -626,11 +674,10 @@ static size_t ws_imgs() { return align_up(PREP_BYTES, 1024); }
 static size_t ws_imgs_bytes(int P) { return (size_t)((P + TPT - 1) / TPT) * TILE_IMG_BYTES; }
 
 static size_t ws_parts(int P) { return ws_imgs() + align_up(ws_imgs_bytes(P), 1024); }
-constexpr int MAX_PARTS = 148;
 
 extern "C" size_t cnf_occmap_tc_workspace_bytes(int n_pts) {
   if (n_pts < 0) n_pts = 0;
-  return ws_parts(n_pts) + (size_t)MAX_PARTS * PART_FLOATS * sizeof(float);
+  return ws_parts(n_pts) + (size_t)PART_FLOATS * sizeof(float);
 }
 
 extern "C" int cnf_occmap_tc_fwd(int P, const float* params, const float* emb, float* alpha, float* rgb, void* ws, size_t ws_bytes,
@@ -672,9 +719,15 @@ extern "C" int cnf_occmap_tc_bwd(int P, const float* params, const float* rgb, c
   CNF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   const int n_tiles = (P + TPT - 1) / TPT;
   int grid = n_tiles < n_sm ? n_tiles : n_sm;
-  if (grid > MAX_PARTS) grid = MAX_PARTS;
   float* parts = reinterpret_cast<float*>(w8 + ws_parts(P));
+  CNF_CUDA(cudaMemsetAsync(parts, 0, PART_FLOATS * sizeof(float), st));
   bwd_kernel<<<grid, NT, B_SMEM, st>>>(P, w8 + ws_prep(), w8 + ws_imgs(), rgb, g_alpha, g_rgb, parts, g_emb);
-  reduce_kernel<<<(P_TOTAL + 255) / 256, 256, 0, st>>>(grid, parts, g_params);
+  reduce_kernel<<<(PART_FLOATS + 255) / 256, 256, 0, st>>>(1, parts, g_params);
   return check_launch("cnf_occmap_tc_bwd");
+}
+
+extern "C" int cnf_occmap_tc_set_debug(void* stamps /* device buffer of 64 int64, or NULL */) {
+  long long* p = reinterpret_cast<long long*>(stamps);
+  CNF_CUDA(cudaMemcpyToSymbol(cnf::otc::g_stamp, &p, sizeof(p)));
+  return CNF_OK;
 }

@@ -121,10 +121,12 @@ int cnf_occmap_bwd(int n_cat, int n_pts, int H, const float* params, const float
  *     fwd: emb [P,129] -> alpha [P] (already x10), rgb [P,3]; keeps bf16 activation images in ws for the backward.
  *     bwd (after fwd on the same ws, same params): rgb (fwd output), g_alpha [P], g_rgb [P,3] ->
  *          g_params [cnf_occmap_param_count(128)] OVERWRITTEN (not accumulated), g_emb [P,129] (may be NULL).
- *     ws >= cnf_occmap_tc_workspace_bytes(P) (1568 B/point of activation images + 58 MiB of per-CTA partial gradients). */
+ *     ws >= cnf_occmap_tc_workspace_bytes(P) (1568 B/point of activation images + 0.4 MiB). */
 size_t cnf_occmap_tc_workspace_bytes(int n_pts);
 int cnf_occmap_tc_fwd(int n_pts, const float* params, const float* emb, float* alpha, float* rgb,
                       void* ws, size_t ws_bytes, cnf_stream_t stream);
+/* development aid: SM-clock stamps of CTA 0's epilogue thread 0 (64 int64 device buffer; NULL switches it off) */
+int cnf_occmap_tc_set_debug(void* stamps);
 int cnf_occmap_tc_bwd(int n_pts, const float* params, const float* rgb, const float* g_alpha, const float* g_rgb,
                       void* ws, size_t ws_bytes, float* g_params, float* g_emb, cnf_stream_t stream);
 
