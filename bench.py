@@ -405,6 +405,32 @@ def main():
         except Exception as e:
             extra["render_512x512"] = {"error": repr(e)}
 
+    if rank == 0 and not args.no_large:
+        # background model step (train.py:172-180): 1200 rays x (5+9) samples, OccupancyMap W=128 on tensor cores, CUDA-graph replay
+        try:
+            from category_nerf_reconstruction_official_b200.background import FusedBackgroundTrainer
+            from category_nerf_reconstruction_official_b200.synthetic import synth_rays as _sr
+            gb = torch.Generator().manual_seed(11)
+            trb = FusedBackgroundTrainer(scale=5.0, device=dev, generator=gb)
+            rb = [t.to(dev) for t in _sr(1200, 1, gb)][:4]
+            replay_b = trb.capture(*rb)
+            for _ in range(3):
+                replay_b()
+            torch.cuda.synchronize()
+            tms = []
+            for _ in range(10):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); replay_b(); e1.record(); torch.cuda.synchronize(); tms.append(e0.elapsed_time(e1))
+            msb = sorted(tms)[5]
+            extra["background_step_1200x14"] = {"rays": 1200, "samples_per_ray": 14, "ms_per_step": msb, "rays_per_s": 1200 / (msb * 1e-3),
+                                                "algorithmic_flop_per_point": 562176.0,
+                                                "tensor_tflops_whole_step": 16800 * 562176.0 / (msb * 1e-3) / 1e12,
+                                                "note": "sampler + embed + OccupancyMap(128) fwd/bwd on tcgen05 + composite/loss, graph replay, L2 flushed"}
+            del trb, rb
+        except Exception as e:
+            extra["background_step_1200x14"] = {"error": repr(e)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -47,8 +47,9 @@ constexpr int P_INW = 0, P_INB = 11136, P_M1W = 11264, P_M1B = 27648, P_CATW = 2
               P_TOTAL = 94340;
 // activation images of one tile in the workspace
 constexpr int IMG_XG = 0, IMG_XC = 24576, IMG_FC1 = 36864, IMG_FC2 = 69632, IMG_FC3 = 102400, IMG_FC4 = 135168, IMG_H = 167936,
-              TILE_IMG_BYTES = 200704;
+              IMG_DXC = 200704 /* backward scratch: d xc, fp32 [48][128] */, TILE_IMG_BYTES = 225280;
 constexpr int ACT_BYTES = 32768;
+constexpr int EMB_TILE_BYTES = TPT * EMB * 4;    // 66048: one tile's contiguous fp32 [128 x 129] block of emb / g_emb
 
 // development aid: SM-clock stamps of CTA 0 (epilogue thread 0: slots 0..31, control lane 0: slots 32..63); NULL = off
 __device__ long long* g_stamp = nullptr;
@@ -114,7 +115,6 @@ __device__ __forceinline__ void issue_fwd(uint32_t d, uint32_t aAddr, int aCols,
 // forward
 // ---------------------------------------------------------------------------------------------------------
 // The fp32 embedding tile (128 x 129 floats = 66048 B, contiguous in global memory) is staged over A0 | A1 (+ 512 B of slack)
-constexpr int EMB_TILE_BYTES = TPT * EMB * 4;
 constexpr int F_XG = 0, F_XC = 24576, F_A0 = 36864, F_A1 = 69632, F_W = 103424, F_C = F_W + 3 * 32768, F_SMEM = F_C + C_FLOATS * 4;
 static_assert(F_A0 + EMB_TILE_BYTES <= F_W, "embedding staging overlaps the weight ring");
 
@@ -314,15 +314,17 @@ __device__ __forceinline__ void issue_wgrad(uint32_t d, uint32_t aAddr, int aCol
            ks > 0 ? 1u : 0u);
 }
 
-constexpr int B_A0 = 0, B_A1 = 32768, B_AX = 65536, B_G0 = 90112, B_G1 = 122880, B_W0 = 155648, B_W1 = 188416, B_ONES = 221184,
+// A0 | A1 | G1 are contiguous: in the last stage they are free and stage the tile's fp32 g_emb block (128 x 129 floats)
+constexpr int B_A0 = 0, B_A1 = 32768, B_G1 = 65536, B_G0 = 98304, B_AX = 131072, B_W0 = 155648, B_W1 = 188416, B_ONES = 221184,
               B_HD = 225280, B_C = 229376, B_SMEM = B_C + (128 + 384) * 4;
+static_assert(B_A0 + EMB_TILE_BYTES <= B_G0, "g_emb staging must fit A0 | A1 | G1");
 constexpr int T_DA = 0, T_DB = 128, T_DW = 224, T_DO = 448, T_DH = 464;
 // per-CTA partial weight gradients (fp32): rows = output feature (TMEM lane), row lengths 96 / 128 / 224 / 128 / 176 / 1 / 1 / 32
 constexpr int PR_IN = 0, PR_MID1 = 12288, PR_CAT = 28672, PR_MID2 = 57344, PR_COL = 73728, PR_DB1 = 96256, PR_DB2 = 96384,
               PR_HEAD = 96512, PR_HB = 100608, PART_FLOATS = 100616;
 
 __global__ void __launch_bounds__(NT, 1)
-bwd_kernel(int P, const uint8_t* __restrict__ prep, const uint8_t* __restrict__ imgs, const float* __restrict__ rgb,
+bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, const float* __restrict__ rgb,
            const float* __restrict__ g_alpha, const float* __restrict__ g_rgb, float* __restrict__ part /* [PART_FLOATS], zeroed */,
            float* __restrict__ g_emb) {
   extern __shared__ __align__(1024) uint8_t sm[];
@@ -574,16 +576,14 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, const uint8_t* __restrict__ 
       wait(&bar_d, pD); tc_fence_after();
       wait(&fullA1, pA1);
       delta(sm + B_A1, sm + B_G1, draw, wa);                                     // d fc4 = mask(fc4) (colour branch + alpha head)
-      if (g_emb != nullptr) {                                                    // d xc -> g_emb[:, 87:]
+      float* dxc = reinterpret_cast<float*>(imgs + (size_t)tile * TILE_IMG_BYTES + IMG_DXC) + row;      // [column][row]: coalesced
+      if (g_emb != nullptr) {                                                    // d xc: parked until the last stage
         uint32_t u[32], v[16];
         tmem_ld32(tl + T_DB, u); tmem_ld16(tl + T_DB + 32, v); tmem_ld_wait();
-        if (act) {
-          float* ge = g_emb + (size_t)p * EMB + E1;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) ge[c] = __uint_as_float(u[c]);
+        for (int c = 0; c < 32; ++c) dxc[c * 128] = __uint_as_float(u[c]);
 #pragma unroll
-          for (int c = 0; c < E2 - 32; ++c) ge[32 + c] = __uint_as_float(v[c]);
-        }
+        for (int c = 0; c < E2 - 32; ++c) dxc[(32 + c) * 128] = __uint_as_float(v[c]);
       }
       publish();
       wait(&bar_w, pW); tc_fence_after();
@@ -618,16 +618,29 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, const uint8_t* __restrict__ 
       mark_drained();
       // ---- S5: in_layer
       wait(&bar_d, pD); tc_fence_after();
-      if (g_emb != nullptr) {                                                    // d xg (cat part + in part) -> g_emb[:, :87]
-#pragma unroll 1
-        for (int ch = 0; ch < 3; ++ch) {
-          uint32_t u[32];
-          tmem_ld32(tl + T_DB + ch * 32, u); tmem_ld_wait();
-          if (act) {
-            float* ge = g_emb + (size_t)p * EMB + ch * 32;
+      if (g_emb != nullptr) {
+        // g_emb rows of the tile are one contiguous block: stage [128][129] fp32 in shared memory (row stride 129 words:
+        // conflict-free), then ONE bulk copy (ragged last tile: coalesced cooperative stores)
+        float* stg = reinterpret_cast<float*>(sm + B_A0) + row * EMB;
+        uint32_t uu[3][32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) if (ch * 32 + c < E1) ge[c] = __uint_as_float(u[c]);
-          }
+        for (int ch = 0; ch < 3; ++ch) tmem_ld32(tl + T_DB + ch * 32, uu[ch]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+          for (int c = 0; c < 32; ++c) if (ch * 32 + c < E1) stg[ch * 32 + c] = __uint_as_float(uu[ch][c]);   // d xg (cat part + in part)
+#pragma unroll
+        for (int c = 0; c < E2; ++c) stg[E1 + c] = dxc[c * 128];
+        fence_async_smem();
+        nbar_sync(5, TPT);
+        const int p0 = tile * TPT;
+        if (p0 + TPT <= P) {
+          if (tid == 0) { bulk_s2g(g_emb + (size_t)p0 * EMB, sm + B_A0, EMB_TILE_BYTES); bulk_commit(); bulk_wait_read<0>(); }
+        } else {
+          const float* all = reinterpret_cast<const float*>(sm + B_A0);
+          const int nvalid = (P - p0) * EMB;
+          for (int i = tid; i < nvalid; i += TPT) g_emb[(size_t)p0 * EMB + i] = all[i];
         }
       }
       wait(&bar_w, pW); tc_fence_after();
@@ -635,6 +648,7 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, const uint8_t* __restrict__ 
       mark_drained();
     }
   }
+  if (tid == 0) bulk_wait<0>();                  // g_emb bulk stores have landed
   tc_fence_before();
   __syncthreads();
   if (tid < 4) atomicAdd(&part[PR_HB + tid], s_hb[tid]);
