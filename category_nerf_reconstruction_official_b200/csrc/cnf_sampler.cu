@@ -254,8 +254,9 @@ sample_emit_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const 
              this_obj, bc[0], bc[1], bc[2], __int_as_float(stats[k * 8 + 7]), z, pcs, valid, labels);
 }
 
-// Single-launch sampler for small ray batches (R <= SAMPLE_SMALL_RAYS): one CTA per category counts the cases / loss masks and
-// the maximum depth, writes the stats row, then emits the category's ray blocks in order with running case offsets.
+// Single-launch sampler for small ray batches (R <= SAMPLE_SMALL_RAYS): grid (category, ray block).  Every CTA counts the cases /
+// loss masks and the maximum depth of its whole category (a few thousand rays: cheaper than a second launch), derives the running
+// case offsets of ITS block and emits that block; block 0 writes the stats row.
 constexpr int SAMPLE_SMALL_RAYS = 4096;
 __global__ void __launch_bounds__(EMIT_T)
 sample_small_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const float* __restrict__ depth,
@@ -315,17 +316,15 @@ sample_small_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const
     s_tot[0] = a0; s_tot[1] = a1; s_tot[2] = a2;
   }
   __syncthreads();
-  if (t == 0) {
+  if (t == 0 && blockIdx.y == 0) {
     int32_t* st = stats + k * 8;
     st[0] = s_tot[0]; st[1] = s_tot[1] + s_tot[2]; st[2] = s_tot[1]; st[3] = s_tot[2];
     st[4] = s_tot[3]; st[5] = s_tot[4]; st[6] = s_tot[5]; st[7] = __float_as_int(s_max);
   }
-  // ---- emit, block by block
-  for (int b = 0; b < nb; ++b) {
-    emit_block(sh, k, b, R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth, lin_S, lin_N, lin_M, min_bound, eps, stop_eps,
-               this_obj, s_blk[b][0], s_blk[b][1], s_blk[b][2], s_max, z, pcs, valid, labels);
-    __syncthreads();
-  }
+  // ---- emit this CTA's block
+  const int b = blockIdx.y;
+  emit_block(sh, k, b, R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth, lin_S, lin_N, lin_M, min_bound, eps, stop_eps,
+             this_obj, s_blk[b][0], s_blk[b][1], s_blk[b][2], s_max, z, pcs, valid, labels);
 }
 
 __global__ void stratified_bins_kernel(int n_rays, int n_bins, const float* __restrict__ mn, int mn_s,
@@ -361,7 +360,7 @@ extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, c
   float* blk_max = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align_up((size_t)K * nb * 8 * sizeof(int), 256));
   cudaStream_t st = as_stream(stream);
   if (R <= SAMPLE_SMALL_RAYS) {
-    sample_small_kernel<<<K, EMIT_T, 0, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth, lin_S, lin_N, lin_M, min_bound,
+    sample_small_kernel<<<dim3(K, nb), EMIT_T, 0, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth, lin_S, lin_N, lin_M, min_bound,
                                               eps, stop_eps, this_obj, max_depth_override, stats, z, pcs, valid, labels);
     return check_launch("cnf_sample_fwd");
   }

@@ -1,5 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_occmap_tc.py -m gpu -x -q 2>&1 | tail -3 > gpurun_out/t.log
-timeout 300 python scripts/time_otc.py staged >> gpurun_out/t.log 2>&1
-timeout 300 python scripts/stamps_otc.py 16800 2>&1 | sed -n '/backward/,$p' >> gpurun_out/t.log
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/t.log
+timeout 600 python bench.py > gpurun_out/bench.json 2>gpurun_out/bench.err; tail -3 gpurun_out/bench.err >> gpurun_out/t.log
 timeout 300 python scripts/time_bg.py tc 2>&1 | grep -E "Fused" >> gpurun_out/t.log
-cat gpurun_out/t.log
+cat gpurun_out/t.log; cat gpurun_out/bench.json
