@@ -336,9 +336,55 @@ __global__ void stratified_bins_kernel(int n_rays, int n_bins, const float* __re
   z[e] = strat(mn[mn_s ? 0 : r], mx[mx_s ? 0 : r], lin[i], u[e], (float)n_bins);
 }
 
+// origin_dirs_O / origin_dirs_W (scene_cateogries.py:24-47): per-ray camera pose -> ray origin and direction in the object
+// (invert = 1: T_OC = inv(T_CO), general 4x4 inverse by cofactors) or world (invert = 0) frame.  One thread per ray; each
+// thread reads its own 64-byte matrix as four float4 (full sectors).
+__global__ void origin_dirs_kernel(int n, int invert, const float4* __restrict__ T, const float* __restrict__ dirs_c,
+                                   float* __restrict__ origins, float* __restrict__ dirs_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float4 r0 = T[(size_t)r * 4 + 0], r1 = T[(size_t)r * 4 + 1], r2 = T[(size_t)r * 4 + 2], r3 = T[(size_t)r * 4 + 3];
+  float b[3][4];
+  if (invert) {
+    const float m00 = r0.x, m01 = r0.y, m02 = r0.z, m03 = r0.w, m10 = r1.x, m11 = r1.y, m12 = r1.z, m13 = r1.w;
+    const float m20 = r2.x, m21 = r2.y, m22 = r2.z, m23 = r2.w, m30 = r3.x, m31 = r3.y, m32 = r3.z, m33 = r3.w;
+    const float s0 = m00 * m11 - m10 * m01, s1 = m00 * m12 - m10 * m02, s2 = m00 * m13 - m10 * m03;
+    const float s3 = m01 * m12 - m11 * m02, s4 = m01 * m13 - m11 * m03, s5 = m02 * m13 - m12 * m03;
+    const float c5 = m22 * m33 - m32 * m23, c4 = m21 * m33 - m31 * m23, c3 = m21 * m32 - m31 * m22;
+    const float c2 = m20 * m33 - m30 * m23, c1 = m20 * m32 - m30 * m22, c0 = m20 * m31 - m30 * m21;
+    const float inv = 1.0f / (s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0);
+    b[0][0] = (m11 * c5 - m12 * c4 + m13 * c3) * inv;  b[0][1] = (-m01 * c5 + m02 * c4 - m03 * c3) * inv;
+    b[0][2] = (m31 * s5 - m32 * s4 + m33 * s3) * inv;  b[0][3] = (-m21 * s5 + m22 * s4 - m23 * s3) * inv;
+    b[1][0] = (-m10 * c5 + m12 * c2 - m13 * c1) * inv; b[1][1] = (m00 * c5 - m02 * c2 + m03 * c1) * inv;
+    b[1][2] = (-m30 * s5 + m32 * s2 - m33 * s1) * inv; b[1][3] = (m20 * s5 - m22 * s2 + m23 * s1) * inv;
+    b[2][0] = (m10 * c4 - m11 * c2 + m13 * c0) * inv;  b[2][1] = (-m00 * c4 + m01 * c2 - m03 * c0) * inv;
+    b[2][2] = (m30 * s4 - m31 * s2 + m33 * s0) * inv;  b[2][3] = (-m20 * s4 + m21 * s2 - m23 * s0) * inv;
+  } else {
+    b[0][0] = r0.x; b[0][1] = r0.y; b[0][2] = r0.z; b[0][3] = r0.w;
+    b[1][0] = r1.x; b[1][1] = r1.y; b[1][2] = r1.z; b[1][3] = r1.w;
+    b[2][0] = r2.x; b[2][1] = r2.y; b[2][2] = r2.z; b[2][3] = r2.w;
+  }
+  const float dx = dirs_c[(size_t)r * 3 + 0], dy = dirs_c[(size_t)r * 3 + 1], dz = dirs_c[(size_t)r * 3 + 2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    dirs_out[(size_t)r * 3 + i] = b[i][0] * dx + b[i][1] * dy + b[i][2] * dz;
+    origins[(size_t)r * 3 + i] = b[i][3];
+  }
+}
+
 }  // namespace cnf
 
 using namespace cnf;
+
+extern "C" int cnf_origin_dirs(int n_rays, int invert, const float* T, const float* dirs_c, float* origins, float* dirs_out,
+                               cnf_stream_t stream) {
+  CNF_REQUIRE(n_rays >= 0 && (n_rays == 0 || (T && dirs_c && origins && dirs_out)), "cnf_origin_dirs: bad arguments");
+  CNF_REQUIRE((reinterpret_cast<uintptr_t>(T) & 15) == 0, "cnf_origin_dirs: T must be 16-byte aligned");
+  if (n_rays == 0) return CNF_OK;
+  origin_dirs_kernel<<<(n_rays + 255) / 256, 256, 0, as_stream(stream)>>>(n_rays, invert, reinterpret_cast<const float4*>(T), dirs_c,
+                                                                           origins, dirs_out);
+  return check_launch("cnf_origin_dirs");
+}
 
 extern "C" size_t cnf_sample_workspace_bytes(int n_cat, int n_rays) {
   const size_t nb = (size_t)(n_rays + SB - 1) / SB;

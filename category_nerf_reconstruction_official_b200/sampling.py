@@ -20,6 +20,29 @@ def stratified_bins(min_depth, max_depth, n_bins, n_rays, type=torch.float32, de
     return ops.stratified_bins_op(min_depth, max_depth, n_bins, u)
 
 
+def _origin_dirs(T, dirs_C, invert):
+    assert T.shape[0] == dirs_C.shape[0] and T.shape[1:] == (4, 4) and dirs_C.shape[1] == 3
+    from ._lib import check, lib_for, ptr, stream
+    lib = lib_for(T)
+    T = T.float().contiguous(); dirs_C = dirs_C.float().contiguous()
+    n = T.shape[0]
+    origins = torch.empty(n, 3, device=T.device, dtype=torch.float32)
+    dirs = torch.empty(n, 3, device=T.device, dtype=torch.float32)
+    check(lib.cnf_origin_dirs(n, int(invert), ptr(T), ptr(dirs_C), ptr(origins), ptr(dirs), stream()))
+    return origins, dirs
+
+
+def origin_dirs_O(T_CO, dirs_C):
+    """Ray origins / directions in the object frame from per-ray object->camera poses (scene_cateogries.py:24-35):
+    T_OC = inv(T_CO); dirs_O = T_OC[:, :3, :3] @ dirs_C; origins = T_OC[:, :3, 3]."""
+    return _origin_dirs(T_CO, dirs_C, True)
+
+
+def origin_dirs_W(T_WC, dirs_C):
+    """Ray origins / directions in the world frame (scene_cateogries.py:37-47)."""
+    return _origin_dirs(T_WC, dirs_C, False)
+
+
 def normal_bins_sampling(depth, n_bins, n_rays, delta, device="cuda:0", n=None):
     """depth[:,None] + clip(sort(N(0, delta/3)), -delta, delta)  ->  [n_rays, n_bins]."""
     if n is None:

@@ -74,6 +74,12 @@ int cnf_stratified_bins(int n_rays, int n_bins, const float* min_d, int min_is_s
                         const float* max_d, int max_is_scalar, const float* u, const float* lin,
                         float* z, cnf_stream_t stream);
 
+/* origin_dirs_O / origin_dirs_W (src/scene_cateogries.py:24-47; called per step by get_training_samples :428-433):
+ * T [n_rays,4,4] (per-ray camera pose T_CO or T_WC, 16-byte aligned), dirs_c [n_rays,3] ->
+ * invert = 1: origins = inv(T)[:3,3], dirs_out = inv(T)[:3,:3] dirs_c (general 4x4 inverse);  invert = 0: the same with T itself. */
+int cnf_origin_dirs(int n_rays, int invert, const float* T, const float* dirs_c, float* origins, float* dirs_out,
+                    cnf_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (2) Embedding -- UniDirsEmbed.forward (src/embedding.py:82-92) and its backward.
  *     x [K,P,3], B [K,21,3], scale [K] -> emb [K,P,129] = cat(x/s, sin(pi * 2^f * (x/s) B^T)).

@@ -267,3 +267,24 @@ def test_umma_m64_wgrad_lane_mapping(mode, N):
     torch.testing.assert_close(D[lanes], ref, rtol=1e-4, atol=2e-3)
     other = torch.ones(128, dtype=torch.bool); other[lanes] = False
     assert torch.all(D[other] == -777.0)
+
+
+@pytest.mark.parametrize("n", [1, 255, 5000])
+def test_origin_dirs_vs_linalg_inv(n):
+    """origin_dirs_O / origin_dirs_W (scene_cateogries.py:24-47) against torch.linalg.inv in float64 on sim3-shaped per-ray poses
+    (rotation x scale in [0.3, 3], translations up to 5): 2e-5 relative to the largest entry."""
+    from category_nerf_reconstruction_official_b200 import sampling
+    g = torch.Generator().manual_seed(n)
+    q, _ = torch.linalg.qr(torch.randn(n, 3, 3, generator=g, dtype=torch.float64))
+    s = torch.rand(n, 1, 1, generator=g, dtype=torch.float64) * 2.7 + 0.3
+    T = torch.zeros(n, 4, 4, dtype=torch.float64)
+    T[:, :3, :3] = q * s; T[:, :3, 3] = (torch.rand(n, 3, generator=g, dtype=torch.float64) - 0.5) * 10; T[:, 3, 3] = 1
+    d = torch.randn(n, 3, generator=g, dtype=torch.float64)
+    Ti = torch.linalg.inv(T)
+    o_ref, d_ref = Ti[:, :3, 3], (Ti[:, :3, :3] @ d[..., None]).squeeze(-1)
+    o, dd = sampling.origin_dirs_O(T.float().to(DEV), d.float().to(DEV))
+    assert float((o.cpu().double() - o_ref).abs().max()) < 2e-5 * float(o_ref.abs().max())
+    assert float((dd.cpu().double() - d_ref).abs().max()) < 2e-5 * float(d_ref.abs().max())
+    o, dd = sampling.origin_dirs_W(T.float().to(DEV), d.float().to(DEV))
+    torch.testing.assert_close(o.cpu().double(), T[:, :3, 3], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(dd.cpu().double(), (T[:, :3, :3] @ d[..., None]).squeeze(-1), rtol=1e-5, atol=1e-5)
