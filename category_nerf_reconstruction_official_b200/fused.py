@@ -71,6 +71,8 @@ class FusedCategoryTrainer:
         self._ws_key = None
         self._opt_state = None
         self._side = None
+        self._side2 = None
+        self._rand_key = None
         self.launches_per_step = 0
 
     # ------------------------------------------------------------------------------------------ state import
@@ -168,15 +170,46 @@ class FusedCategoryTrainer:
                 self.prepare(indices, rgbs.shape[1])
         else:
             self.prepare(indices, rgbs.shape[1])
-        if rand is None:
+        prefetch = rand is None and overlap and os.environ.get("CNF_NO_RNG_PREFETCH") is None
+        if prefetch:
+            rand = self._prefetched_randoms(rgbs.shape[0], rgbs.shape[1])
+        elif rand is None:
             rand = sampling.draw_randoms(rgbs, depth, self.N, self.M, self.eps, self.min_bound, self.this_obj)
         z, _, valid, labels, stats = ops.sample_batched(rgbs, depth, origins, dirs, self.N, self.M, self.eps, self.stop_eps,
                                                        rand, self.min_bound, self.this_obj, want_pcs=False)
+        if prefetch:
+            # the NEXT step's offsets are drawn into the same buffers as soon as this step's sampler has read them, on a third
+            # stream next to the fused kernel (same generator, same order of draws: only their position in time changes)
+            if self._side2 is None:
+                self._side2 = torch.cuda.Stream(device=self.device)
+            self._side2.wait_stream(main)
+            with torch.cuda.stream(self._side2):
+                self._draw_randoms_into_buffers()
         if overlap:
             main.wait_stream(self._side)
         self.launches_per_step = 3 + 4
-        return self.step_from_samples(origins, dirs, z, depth, rgbs, valid.view(torch.uint8), indices, stats[:, 4:8], add_reg,
+        loss = self.step_from_samples(origins, dirs, z, depth, rgbs, valid.view(torch.uint8), indices, stats[:, 4:8], add_reg,
                                       prepared=True)
+        if prefetch:
+            main.wait_stream(self._side2)                    # join (a CUDA-graph capture needs every forked stream back)
+        return loss
+
+    def _draw_randoms_into_buffers(self):
+        self._rand_u.uniform_()
+        self._rand_n.normal_(mean=0., std=self.eps / 3.)
+
+    def _prefetched_randoms(self, K: int, R: int):
+        """Random offsets of this step: drawn by the previous step (or right now, the first time) into fixed buffers."""
+        N, M = self.N, self.M
+        n1, n2, n3 = K * R * (N + M), K * R * N, K * R * M
+        if self._rand_key != (K, R):
+            self._rand_u = torch.empty(n1 + n2 + n3, device=self.device)
+            self._rand_n = torch.empty(K, R, M, device=self.device)
+            self._rand_key = (K, R)
+            self._draw_randoms_into_buffers()
+        u = self._rand_u
+        return {"u_inv": u[:n1].view(K, R, N + M), "u_val": u[n1:n1 + n2].view(K, R, N), "n_obj": self._rand_n,
+                "u_oth": u[n1 + n2:].view(K, R, M)}
 
     def capture(self, rgbs, depth, origins, dirs, indices, add_reg=True):
         """Capture sampler + fused step over THESE (static) input tensors into a CUDA graph and return ``replay``.

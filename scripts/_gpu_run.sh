@@ -1,5 +1,6 @@
-timeout 600 python -m pytest tests/test_gpu_parity_v0.py -m gpu -x -q -k origin_dirs 2>&1 | tail -3 > gpurun_out/t.log
-timeout 300 python scripts/profile_bg.py 3 >> gpurun_out/t.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^bwd_kernel" --launch-skip 2 --launch-count 1 -f -o gpurun_out/otc_bwd python scripts/profile_bg.py 3 > gpurun_out/ncu_otc.log 2>&1
-tail -3 gpurun_out/ncu_otc.log >> gpurun_out/t.log
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/t.log
+for i in 1 2; do
+CNF_NO_RNG_PREFETCH=1 timeout 300 python bench.py --no-large --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('no-prefetch ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'])" >> gpurun_out/t.log
+timeout 300 python bench.py --no-large --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('prefetch    ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'])" >> gpurun_out/t.log
+done
 cat gpurun_out/t.log
