@@ -47,6 +47,9 @@ class FusedBackgroundTrainer:
         self.out_loss = torch.zeros(7, device=dev)          # {loss, e_depth, e_obj, e_sem, depth, color, opacity}
         self._one = torch.ones(1, device=dev)
         self._buf_key = None
+        self._side = None
+        self._side2 = None
+        self._rand_key = None
         self._opt_state = None
         self.launches_per_step = 0
 
@@ -95,42 +98,76 @@ class FusedBackgroundTrainer:
 
     def step_from_samples(self, pcs, z, gt_depth, gt_rgb_u8, labels, mask_depth):
         """Forward + backward given sampled points: pcs [R,S,3], z [R,S], gt_depth [R], gt_rgb_u8 u8 [R,3+] (first three channels),
-        labels u8 [R], mask_depth u8/bool [R].  Fills self.g_params / self.g_B / self.out_loss; returns the loss (0-d, async)."""
+        labels u8 [R], mask_depth u8/bool [R].  Fills self.g_params / self.g_B / self.out_loss; returns the loss (0-d, async).
+        The small input-only pieces (gt colours, mask counts, gradient clear) run on a side stream next to the embedding / MLP."""
         lib = lib_for(self.params)
         R, S = z.shape
         assert S == self.S
         P = R * S
         self._buffers(R)
-        st = stream()
         pcs = pcs.contiguous(); z = z.contiguous(); gt_depth = gt_depth.contiguous()
         labels = labels.contiguous()
         mask_depth = mask_depth.view(torch.uint8) if mask_depth.dtype == torch.bool else mask_depth
         mask_depth = mask_depth.contiguous()
-        torch.div(gt_rgb_u8[:, :3], 255.0, out=self._gt_color)                                   # train.py:128 (gt_rgb / 255)
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            torch.div(gt_rgb_u8[:, :3], 255.0, out=self._gt_color)                               # train.py:128 (gt_rgb / 255)
+            check(lib.cnf_mask_counts(1, R, ptr(labels), ptr(mask_depth), ptr(self._counts), stream()))
+            self.g_B.zero_()
+        st = stream()
         check(lib.cnf_embed_fwd(1, P, ptr(pcs), ptr(self.pe_B), ptr(self.pe_scale), ptr(self._emb), st))
         check(lib.cnf_occmap_tc_fwd(P, ptr(self.params), ptr(self._emb), ptr(self._alpha), ptr(self._rgb), ptr(self._ws),
                                     self._ws.numel(), st))
-        check(lib.cnf_mask_counts(1, R, ptr(labels), ptr(mask_depth), ptr(self._counts), st))
+        main.wait_stream(self._side)
         args = (1, R, S, ptr(self._alpha), ptr(self._rgb), ptr(z), ptr(gt_depth), ptr(self._gt_color), ptr(labels), ptr(mask_depth),
                 ptr(self._counts), float(self.cs), float(self.os))
         check(lib.cnf_composite_loss_fwd(*args, ptr(self._rays), ptr(self.out_loss), ptr(self._cws), self._cws.numel(), st))
         check(lib.cnf_composite_loss_bwd(*args, ptr(self._one), ptr(self._g_alpha), ptr(self._g_rgb), st))
         check(lib.cnf_occmap_tc_bwd(P, ptr(self.params), ptr(self._rgb), ptr(self._g_alpha), ptr(self._g_rgb), ptr(self._ws),
                                     self._ws.numel(), ptr(self.g_params), ptr(self._g_emb), st))
-        self.g_B.zero_()
         check(lib.cnf_embed_bwd(1, P, ptr(pcs), ptr(self.pe_B), ptr(self.pe_scale), ptr(self._g_emb), ptr(self.g_B), None, st))
         return self.out_loss[0]
 
     def step(self, rgbs, depth, origins, dirs, rand: Optional[Dict[str, torch.Tensor]] = None):
         """Sample + step: rgbs u8 [R,4] (rgb + label), depth [R], origins / dirs [R,3] (scene_cateogries.py:453-546 sampler)."""
-        if rand is None:
-            rand = sampling.draw_randoms(rgbs[None], depth[None], self.N, self.M, self.eps, self.min_bound, self.this_obj)
+        prefetch = rand is None
+        main = torch.cuda.current_stream(self.device)
+        if prefetch:
+            rand = self._prefetched_randoms(rgbs.shape[0])
         elif rand["u_inv"].dim() == 2:
             rand = {k: v[None] for k, v in rand.items()}
         z, pcs, valid, labels, _ = ops.sample_batched(rgbs[None], depth[None], origins[None], dirs[None], self.N, self.M, self.eps,
                                                        self.stop_eps, rand, self.min_bound, self.this_obj, want_pcs=True)
-        self.launches_per_step = 3 + 10
-        return self.step_from_samples(pcs[0], z[0], depth, rgbs, labels[0], valid[0])
+        if prefetch:          # the next step's offsets: drawn into the same buffers once this step's sampler has read them
+            if self._side2 is None:
+                self._side2 = torch.cuda.Stream(device=self.device)
+            self._side2.wait_stream(main)
+            with torch.cuda.stream(self._side2):
+                self._draw_randoms_into_buffers()
+        self.launches_per_step = 1 + 12
+        loss = self.step_from_samples(pcs[0], z[0], depth, rgbs, labels[0], valid[0])
+        if prefetch:
+            main.wait_stream(self._side2)
+        return loss
+
+    def _draw_randoms_into_buffers(self):
+        self._rand_u.uniform_()
+        self._rand_n.normal_(mean=0., std=self.eps / 3.)
+
+    def _prefetched_randoms(self, R: int):
+        N, M = self.N, self.M
+        n1, n2, n3 = R * (N + M), R * N, R * M
+        if self._rand_key != R:
+            self._rand_u = torch.empty(n1 + n2 + n3, device=self.device)
+            self._rand_n = torch.empty(1, R, M, device=self.device)
+            self._rand_key = R
+            self._draw_randoms_into_buffers()
+        u = self._rand_u
+        return {"u_inv": u[:n1].view(1, R, N + M), "u_val": u[n1:n1 + n2].view(1, R, N), "n_obj": self._rand_n,
+                "u_oth": u[n1 + n2:].view(1, R, M)}
 
     def capture(self, rgbs, depth, origins, dirs):
         """Capture sampler + step over THESE (static) input tensors into a CUDA graph; returns ``replay``."""

@@ -158,14 +158,10 @@ def test_fused_background_trainer_step_vs_oracle(well_conditioned):
     # graph replay == eager
     g_eager = tr.g_params.clone(); l_eager = tr.out_loss.clone()
     rgbs_d, depth_d, org_d, dirs_d = dv(rgbs), dv(depth), dv(org), dv(dirs)
-    import category_nerf_reconstruction_official_b200.sampling as sampling
-    rd = {k: dv(v)[None] for k, v in rand.items()}
-    orig = sampling.draw_randoms
-    sampling.draw_randoms = lambda *a, **k: rd           # same offsets inside the captured step
-    try:
-        replay = tr.capture(rgbs_d, depth_d, org_d, dirs_d)
-        tr.g_params.zero_(); replay(); torch.cuda.synchronize()
-    finally:
-        sampling.draw_randoms = orig
+    replay = tr.capture(rgbs_d, depth_d, org_d, dirs_d)
+    # the captured step reads its random offsets from the trainer's prefetch buffers: put the eager step's offsets there
+    tr._rand_u.copy_(torch.cat([rand["u_inv"].reshape(-1), rand["u_val"].reshape(-1), rand["u_oth"].reshape(-1)]).to(DEV))
+    tr._rand_n.copy_(rand["n_obj"].reshape(1, R, M).to(DEV))
+    tr.g_params.zero_(); replay(); torch.cuda.synchronize()
     torch.testing.assert_close(tr.out_loss, l_eager, rtol=1e-5, atol=1e-6)
     assert rel(tr.g_params, g_eager) < 1e-4
