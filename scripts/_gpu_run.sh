@@ -1,3 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_occmap_tc.py -m gpu -x -q 2>&1 | tail -3 > gpurun_out/t.log
-timeout 300 python scripts/time_bg.py tc 2>&1 | grep -E "Fused" >> gpurun_out/t.log
-cat gpurun_out/t.log
+timeout 300 python scripts/stamps_otc.py 16800 > gpurun_out/stamps_otc.txt 2>&1
+cat gpurun_out/stamps_otc.txt | tail -45
