@@ -147,7 +147,9 @@ class FusedBackgroundTrainer:
             self._side2.wait_stream(main)
             with torch.cuda.stream(self._side2):
                 self._draw_randoms_into_buffers()
-        self.launches_per_step = 1 + 12
+        # kernels of libcnf_sm100.so: sampler 1 | mask counts, embed fwd, prep, OccupancyMap fwd | composite fwd (tile + finalize), composite
+        # bwd | OccupancyMap bwd, gradient scatter, embed bwd
+        self.launches_per_step = 1 + 4 + 3 + 3
         loss = self.step_from_samples(pcs[0], z[0], depth, rgbs, labels[0], valid[0])
         if prefetch:
             main.wait_stream(self._side2)

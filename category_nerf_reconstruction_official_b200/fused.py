@@ -187,7 +187,10 @@ class FusedCategoryTrainer:
                 self._draw_randoms_into_buffers()
         if overlap:
             main.wait_stream(self._side)
-        self.launches_per_step = 3 + 4
+        # kernels of libcnf_sm100.so per step: sampler (1 launch up to 4096 rays per category, else count + scan + emit), prepare half
+        # (1 launch up to 32 ray blocks of 256, else prep + count + scan + scatter), fused fwd+bwd, finalize
+        R_ = rgbs.shape[1]
+        self.launches_per_step = (1 if R_ <= 4096 else 3) + (1 if (R_ + 255) // 256 <= 32 else 4) + 2
         loss = self.step_from_samples(origins, dirs, z, depth, rgbs, valid.view(torch.uint8), indices, stats[:, 4:8], add_reg,
                                       prepared=True)
         if prefetch:
