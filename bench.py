@@ -427,7 +427,23 @@ def main():
                                                 "algorithmic_flop_per_point": 562176.0,
                                                 "tensor_tflops_whole_step": 16800 * 562176.0 / (msb * 1e-3) / 1e12,
                                                 "note": "sampler + embed + OccupancyMap(128) fwd/bwd on tcgen05 + composite/loss, graph replay, L2 flushed"}
-            del trb, rb
+            # whole iteration of the reference: all object categories + the background model, one graph, two parallel branches
+            from category_nerf_reconstruction_official_b200.background import capture_iteration
+            tri = make_trainer(wl)
+            bi = synth_batch(wl, seed=5, device=dev)
+            replay_i = capture_iteration(tri, (bi["rgbs"], bi["depth"], bi["origins"], bi["dirs"], bi["indices"]), trb, tuple(rb))
+            for _ in range(3):
+                replay_i()
+            torch.cuda.synchronize()
+            tms = []
+            for _ in range(10):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); replay_i(); e1.record(); torch.cuda.synchronize(); tms.append(e0.elapsed_time(e1))
+            msi = sorted(tms)[5]
+            extra["iteration_objects_plus_background"] = {"rays": K * R + 1200, "ms_per_iteration": msi, "rays_per_s": (K * R + 1200) / (msi * 1e-3),
+                                                          "note": "C2 object step and background step as parallel branches of one CUDA graph (train.py:123-184 minus the optimizer)"}
+            del trb, rb, tri, bi
         except Exception as e:
             extra["background_step_1200x14"] = {"error": repr(e)}
 

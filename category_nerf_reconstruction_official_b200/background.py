@@ -200,3 +200,38 @@ class FusedBackgroundTrainer:
         st["t"] += 1
         for i, (p, g) in enumerate(((self.params, self.g_params), (self.pe_B, self.g_B))):
             ops.adamw_step_(p, g, st["m"][i], st["v"][i], lr, betas[0], betas[1], eps, weight_decay, st["t"])
+
+
+def capture_iteration(obj_trainer, obj_inputs, bg_trainer, bg_inputs, with_optimizer: bool = False, opt_kwargs=None):
+    """One training iteration of the reference (train.py:123-184: every object category, then the background model) as ONE CUDA
+    graph with the two steps on parallel branches: ``obj_inputs`` = (rgbs, depth, origins, dirs, indices) of
+    ``FusedCategoryTrainer.step``, ``bg_inputs`` = (rgbs, depth, origins, dirs) of ``FusedBackgroundTrainer.step``; static tensors,
+    updated in place between replays.  Returns ``replay``."""
+    opt_kwargs = opt_kwargs or {}
+    dev = obj_trainer.device
+    branch = torch.cuda.Stream(device=dev)
+
+    def iteration():
+        main = torch.cuda.current_stream(dev)
+        branch.wait_stream(main)
+        with torch.cuda.stream(branch):
+            bg_trainer.step(*bg_inputs)
+            if with_optimizer:
+                bg_trainer.adamw_step(**{k: v for k, v in opt_kwargs.items() if k in ("lr", "weight_decay", "betas", "eps")})
+        obj_trainer.step(*obj_inputs)
+        if with_optimizer:
+            obj_trainer.adamw_step(**opt_kwargs)
+        main.wait_stream(branch)
+
+    warm = torch.cuda.Stream(device=dev)
+    warm.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(warm):
+        for _ in range(2):
+            iteration()
+    torch.cuda.current_stream(dev).wait_stream(warm)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        iteration()
+    obj_trainer._iteration_graph = graph
+    return graph.replay
