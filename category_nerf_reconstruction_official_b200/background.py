@@ -3,9 +3,9 @@
 ``FusedBackgroundTrainer`` holds the background ``OccupancyMap`` (hidden size 128, src/model.py:86-154) and its positional
 embedding as flat fp32 buffers and runs one step per call through the C ABI only:
 
-    sampler (cnf_sample_fwd) -> embedding (cnf_embed_fwd) -> OccupancyMap forward (cnf_occmap_tc_fwd, tcgen05, bf16 operands)
-    -> compositing + losses forward / backward (cnf_composite_loss_fwd / _bwd) -> OccupancyMap backward (cnf_occmap_tc_bwd)
-    -> embedding backward (cnf_embed_bwd)
+    sampler (cnf_sample_fwd) -> embedding + OccupancyMap forward (cnf_occmap_tc_fwd_points: tcgen05, bf16 operands, the embedding
+    is computed inside the kernel) -> compositing + losses forward / backward (cnf_composite_loss_fwd / _bwd)
+    -> OccupancyMap + embedding backward (cnf_occmap_tc_bwd_points)
 
 Every buffer is preallocated, nothing is read back, so the step can be captured into a CUDA graph (``capture``).  Parameter
 order and shapes are the module's (``model.OccupancyMap(87, 42, 128)``), so state interchanges with the drop-in module path."""
@@ -86,8 +86,8 @@ class FusedBackgroundTrainer:
             dev, S = self.device, self.S
             P = R * S
             f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
-            self._emb, self._alpha, self._rgb = f(P, 129), f(P), f(P, 3)
-            self._g_alpha, self._g_rgb, self._g_emb = f(P), f(P, 3), f(P, 129)
+            self._alpha, self._rgb = f(P), f(P, 3)
+            self._g_alpha, self._g_rgb = f(P), f(P, 3)
             self._rays = f(R, 6)
             self._counts = torch.empty(1, 4, device=dev, dtype=torch.int32)
             self._gt_color = f(R, 3)
@@ -116,19 +116,16 @@ class FusedBackgroundTrainer:
         with torch.cuda.stream(self._side):
             torch.div(gt_rgb_u8[:, :3], 255.0, out=self._gt_color)                               # train.py:128 (gt_rgb / 255)
             check(lib.cnf_mask_counts(1, R, ptr(labels), ptr(mask_depth), ptr(self._counts), stream()))
-            self.g_B.zero_()
         st = stream()
-        check(lib.cnf_embed_fwd(1, P, ptr(pcs), ptr(self.pe_B), ptr(self.pe_scale), ptr(self._emb), st))
-        check(lib.cnf_occmap_tc_fwd(P, ptr(self.params), ptr(self._emb), ptr(self._alpha), ptr(self._rgb), ptr(self._ws),
-                                    self._ws.numel(), st))
+        check(lib.cnf_occmap_tc_fwd_points(P, ptr(self.params), ptr(self.pe_B), ptr(self.pe_scale), ptr(pcs), ptr(self._alpha),
+                                           ptr(self._rgb), ptr(self._ws), self._ws.numel(), st))
         main.wait_stream(self._side)
         args = (1, R, S, ptr(self._alpha), ptr(self._rgb), ptr(z), ptr(gt_depth), ptr(self._gt_color), ptr(labels), ptr(mask_depth),
                 ptr(self._counts), float(self.cs), float(self.os))
         check(lib.cnf_composite_loss_fwd(*args, ptr(self._rays), ptr(self.out_loss), ptr(self._cws), self._cws.numel(), st))
         check(lib.cnf_composite_loss_bwd(*args, ptr(self._one), ptr(self._g_alpha), ptr(self._g_rgb), st))
-        check(lib.cnf_occmap_tc_bwd(P, ptr(self.params), ptr(self._rgb), ptr(self._g_alpha), ptr(self._g_rgb), ptr(self._ws),
-                                    self._ws.numel(), ptr(self.g_params), ptr(self._g_emb), st))
-        check(lib.cnf_embed_bwd(1, P, ptr(pcs), ptr(self.pe_B), ptr(self.pe_scale), ptr(self._g_emb), ptr(self.g_B), None, st))
+        check(lib.cnf_occmap_tc_bwd_points(P, ptr(self.params), ptr(pcs), ptr(self._rgb), ptr(self._g_alpha), ptr(self._g_rgb),
+                                           ptr(self._ws), self._ws.numel(), ptr(self.g_params), ptr(self.g_B), st))
         return self.out_loss[0]
 
     def step(self, rgbs, depth, origins, dirs, rand: Optional[Dict[str, torch.Tensor]] = None):
@@ -147,9 +144,9 @@ class FusedBackgroundTrainer:
             self._side2.wait_stream(main)
             with torch.cuda.stream(self._side2):
                 self._draw_randoms_into_buffers()
-        # kernels of libcnf_sm100.so: sampler 1 | mask counts, embed fwd, prep, OccupancyMap fwd | composite fwd (tile + finalize), composite
-        # bwd | OccupancyMap bwd, gradient scatter, embed bwd
-        self.launches_per_step = 1 + 4 + 3 + 3
+        # kernels of libcnf_sm100.so: sampler 1 | mask counts, prep, OccupancyMap fwd | composite fwd (tile + finalize), composite bwd |
+        # OccupancyMap bwd, gradient scatter
+        self.launches_per_step = 1 + 3 + 3 + 2
         loss = self.step_from_samples(pcs[0], z[0], depth, rgbs, labels[0], valid[0])
         if prefetch:
             main.wait_stream(self._side2)

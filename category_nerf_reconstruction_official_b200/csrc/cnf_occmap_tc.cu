@@ -39,7 +39,8 @@ __host__ __device__ constexpr int blk_byte(int b) {
 }
 constexpr int WIMG_BYTES = 752 * 256;           // 192512
 // fp32 constants behind the images
-constexpr int C_BMID1 = 0, C_BMID2 = 128, C_WA = 256, C_WOC = 384, C_BA = 768, C_BOC = 769, C_FLOATS = 776;
+constexpr int C_BMID1 = 0, C_BMID2 = 128, C_WA = 256, C_WOC = 384, C_BA = 768, C_BOC = 769, C_PEB = 776 /* [21][3] */, C_ISCALE = 839,
+              C_FLOATS = 840;
 constexpr int PREP_BYTES = WIMG_BYTES + C_FLOATS * 4;
 // flat parameter offsets (named_parameters() order, H = 128)
 constexpr int P_INW = 0, P_INB = 11136, P_M1W = 11264, P_M1B = 27648, P_CATW = 27776, P_CATB = 55296, P_M2W = 55424,
@@ -78,7 +79,8 @@ __device__ __forceinline__ float wval(const float* __restrict__ P, int b, int n,
 }
 
 // fp32 nn.Linear parameters -> bf16 operand images + fp32 constants.  One thread per 16-byte chunk.
-__global__ void prep_kernel(const float* __restrict__ P, uint8_t* __restrict__ prep) {
+__global__ void prep_kernel(const float* __restrict__ P, const float* __restrict__ pe_B /* may be NULL */,
+                            const float* __restrict__ pe_scale, uint8_t* __restrict__ prep) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i < WIMG_BYTES / 16) {
     const int byte = i * 16;
@@ -100,8 +102,23 @@ __global__ void prep_kernel(const float* __restrict__ P, uint8_t* __restrict__ p
     else if (i < C_BA) v = P[P_OCW + i - C_WOC];
     else if (i == C_BA) v = P[P_AB];
     else if (i < C_BOC + 3) v = P[P_OCB + i - C_BOC];
+    else if (i >= C_PEB && i < C_PEB + 63 && pe_B != nullptr) v = pe_B[i - C_PEB];
+    else if (i == C_ISCALE && pe_scale != nullptr) v = 1.0f / pe_scale[0];
     reinterpret_cast<float*>(prep + WIMG_BYTES)[i] = v;
   }
+}
+
+constexpr float PI_F = 3.14159265358979f;
+// sin / cos of pi * proj (one MUFU pair after an exact range reduction), then the double-angle recurrence for the octaves
+__device__ __forceinline__ void pe_sincos(const float* __restrict__ b3, const float t[3], float& s, float& c) {
+  const float proj = fmaf(t[2], b3[2], fmaf(t[1], b3[1], t[0] * b3[0]));
+  const float r = proj - 2.0f * rintf(0.5f * proj);
+  __sincosf(PI_F * r, &s, &c);
+}
+__device__ __forceinline__ void pe_double(float& s, float& c) {
+  const float s2 = 2.0f * s * c;
+  c = fmaf(-2.0f * s, s, 1.0f);
+  s = s2;
 }
 
 // forward issue: D[128 x 128] (+)= A[128 x aCols] (K-major image) * W[128 x aCols]^T (K-major image)
@@ -118,10 +135,14 @@ __device__ __forceinline__ void issue_fwd(uint32_t d, uint32_t aAddr, int aCols,
 constexpr int F_XG = 0, F_XC = 24576, F_A0 = 36864, F_A1 = 69632, F_W = 103424, F_C = F_W + 3 * 32768, F_SMEM = F_C + C_FLOATS * 4;
 static_assert(F_A0 + EMB_TILE_BYTES <= F_W, "embedding staging overlaps the weight ring");
 
+// PTS = false: emb is the fp32 embedding [P,129] (module-level drop-in: OccupancyMap.forward takes the embedding);
+// PTS = true: emb is the POINTS [P,3] and the embedding (UniDirsEmbed, src/embedding.py:82-92) is computed here, straight into the
+// bf16 operand images (no [P,129] tensor exists).
+template <bool PTS>
 __global__ void __launch_bounds__(NT, 1)
 fwd_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ emb, uint8_t* __restrict__ imgs,
            float* __restrict__ alpha_out, float* __restrict__ rgb_out) {
-  extern __shared__ __align__(1024) uint8_t sm[];
+  extern __shared__ __align__(128) uint8_t sm[];   // no-swizzle operand images need 16-byte alignment only
   __shared__ uint64_t full[3];
   __shared__ uint64_t bar_mma, full_emb;
   __shared__ uint32_t tmem_base_s;
@@ -163,7 +184,7 @@ fwd_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ em
     for (int it = 0; it < nt; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       uint8_t* img = imgs + (size_t)tile * TILE_IMG_BYTES;
-      if ((tile + 1) * TPT <= P) {                       // full tile: one bulk copy of its contiguous fp32 embedding block
+      if (!PTS && (tile + 1) * TPT <= P) {               // full tile: one bulk copy of its contiguous fp32 embedding block
         if (lane == 0) {
           bulk_wait_read<0>();                           // the previous tile's spills out of A0 / A1 have been read
           mbar_expect_tx(&full_emb, EMB_TILE_BYTES);
@@ -241,8 +262,39 @@ fwd_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ em
       const int tile = blockIdx.x + it * gridDim.x;
       const int p0 = tile * TPT, p = p0 + row;
       mark();
-      // embedding tile -> xg | xc images (coalesced read of the tile's contiguous [128 x 129] block)
-      if (p0 + TPT <= P) {
+      if (PTS) {
+        // embedding in registers: t = x / scale, sin(pi 2^f t.B_d) for 21 directions x 6 octaves, column order of the reference
+        float t[3] = {0.f, 0.f, 0.f};
+        if (p < P) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) t[q] = emb[(size_t)p * 3 + q] * cs[C_ISCALE];
+        }
+        float v[EMB + 7];
+        v[0] = t[0]; v[1] = t[1]; v[2] = t[2];
+#pragma unroll
+        for (int d = 0; d < 21; ++d) {
+          float sn, cn;
+          pe_sincos(cs + C_PEB + d * 3, t, sn, cn);
+          v[3 + d] = sn;
+#pragma unroll
+          for (int f = 1; f < 6; ++f) { pe_double(sn, cn); v[3 + f * 21 + d] = sn; }
+        }
+        v[EMB] = 1.0f;                                   // the ones column follows xc in this array (xc column 42)
+#pragma unroll
+        for (int j = 1; j < 7; ++j) v[EMB + j] = 0.f;
+#pragma unroll
+        for (int cb = 0; cb < 11; ++cb)
+          *reinterpret_cast<uint4*>(rowblk(sm + F_XG, row, cb, XG_C)) =
+              make_uint4(pack2(v[8 * cb], v[8 * cb + 1]), pack2(v[8 * cb + 2], v[8 * cb + 3]), pack2(v[8 * cb + 4], v[8 * cb + 5]),
+                         pack2(v[8 * cb + 6], cb == 10 ? 1.0f : v[8 * cb + 7]));
+        *reinterpret_cast<uint4*>(rowblk(sm + F_XG, row, 11, XG_C)) = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int cb = 0; cb < 6; ++cb)
+          *reinterpret_cast<uint4*>(rowblk(sm + F_XC, row, cb, XC_C)) =
+              make_uint4(pack2(v[E1 + 8 * cb], v[E1 + 8 * cb + 1]), pack2(v[E1 + 8 * cb + 2], v[E1 + 8 * cb + 3]),
+                         pack2(v[E1 + 8 * cb + 4], v[E1 + 8 * cb + 5]), pack2(v[E1 + 8 * cb + 6], v[E1 + 8 * cb + 7]));
+      } else if (p0 + TPT <= P) {
+        // embedding tile -> xg | xc images: staged by one bulk copy (the tile's fp32 [128 x 129] block is contiguous)
         // staged tile: thread = row converts its 129 floats (row stride 129 words: conflict-free) into the two images
         mbar_wait(&full_emb, eph); eph ^= 1;
         const float* src = reinterpret_cast<const float*>(sm + F_A0) + row * EMB;
@@ -316,26 +368,31 @@ __device__ __forceinline__ void issue_wgrad(uint32_t d, uint32_t aAddr, int aCol
 
 // A0 | A1 | G1 are contiguous: in the last stage they are free and stage the tile's fp32 g_emb block (128 x 129 floats)
 constexpr int B_A0 = 0, B_A1 = 32768, B_G1 = 65536, B_G0 = 98304, B_AX = 131072, B_W0 = 155648, B_W1 = 188416, B_ONES = 221184,
-              B_HD = 225280, B_C = 229376, B_SMEM = B_C + (128 + 384) * 4;
+              B_HD = 225280, B_C = 229376, B_CPE = 128 + 384 /* [21][3] PE matrix, 1/scale at +63 */, B_SMEM = B_C + (128 + 384 + 64) * 4;
 static_assert(B_A0 + EMB_TILE_BYTES <= B_G0, "g_emb staging must fit A0 | A1 | G1");
 constexpr int T_DA = 0, T_DB = 128, T_DW = 224, T_DO = 448, T_DH = 464;
 // per-CTA partial weight gradients (fp32): rows = output feature (TMEM lane), row lengths 96 / 128 / 224 / 128 / 176 / 1 / 1 / 32
 constexpr int PR_IN = 0, PR_MID1 = 12288, PR_CAT = 28672, PR_MID2 = 57344, PR_COL = 73728, PR_DB1 = 96256, PR_DB2 = 96384,
-              PR_HEAD = 96512, PR_HB = 100608, PART_FLOATS = 100616;
+              PR_HEAD = 96512, PR_HB = 100608, PR_PE = 100612 /* [21][3] d B_layer */, PART_FLOATS = 100676;
 
+// PTS = false: writes g_emb [P,129] (may be NULL).  PTS = true: g_emb is the POINTS [P,3] (read), the embedding backward runs here
+// (d proj_d = sum_f d emb[3 + 21 f + d] pi 2^f cos(pi 2^f proj_d); d B_d += d proj_d t) and no [P,129] gradient exists.
+template <bool PTS>
 __global__ void __launch_bounds__(NT, 1)
 bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, const float* __restrict__ rgb,
            const float* __restrict__ g_alpha, const float* __restrict__ g_rgb, float* __restrict__ part /* [PART_FLOATS], zeroed */,
            float* __restrict__ g_emb) {
-  extern __shared__ __align__(1024) uint8_t sm[];
+  extern __shared__ __align__(128) uint8_t sm[];   // no-swizzle operand images need 16-byte alignment only
   __shared__ uint64_t fullA0, fullA1, fullAX, fullH, fullW0, fullW1, bar_d, bar_w;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_hb[4];
+  __shared__ float s_gB[64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {
     float* c = reinterpret_cast<float*>(sm + B_C);
     const float* src = reinterpret_cast<const float*>(prep + WIMG_BYTES);
     for (int i = tid; i < 128 + 384; i += NT) c[i] = src[C_WA + i];             // w_alpha | W_oc
+    if (tid < 64) { c[B_CPE + tid] = src[C_PEB + tid]; s_gB[tid] = 0.f; }        // PE matrix | 1/scale
     // constant-one image [128 points x 16]: column 0 = 1
     for (int i = tid; i < 4096 / 16; i += NT) {
       // chunk i: row-group i / 2, column block i % 2 ... rows x 16 B; column 0 lives in column block 0
@@ -577,7 +634,32 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
       wait(&fullA1, pA1);
       delta(sm + B_A1, sm + B_G1, draw, wa);                                     // d fc4 = mask(fc4) (colour branch + alpha head)
       float* dxc = reinterpret_cast<float*>(imgs + (size_t)tile * TILE_IMG_BYTES + IMG_DXC) + row;      // [column][row]: coalesced
-      if (g_emb != nullptr) {                                                    // d xc: parked until the last stage
+      const float* peB = wa + B_CPE;
+      float tpt[3] = {0.f, 0.f, 0.f};                                            // PTS: this row's t = x / scale
+      if (PTS && act) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) tpt[q] = g_emb[(size_t)p * 3 + q] * peB[63];
+      }
+      if (PTS) {
+        // octaves 4, 5 of d proj from d xc; parked (as d xc is in the other mode) until the last stage
+        uint32_t u[32], v[16];
+        tmem_ld32(tl + T_DB, u); tmem_ld16(tl + T_DB + 32, v); tmem_ld_wait();
+        float gx[48];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) gx[c] = __uint_as_float(u[c]);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) gx[32 + c] = __uint_as_float(v[c]);
+#pragma unroll
+        for (int d = 0; d < 21; ++d) {
+          float sn, cn;
+          pe_sincos(peB + d * 3, tpt, sn, cn);
+          pe_double(sn, cn); pe_double(sn, cn); pe_double(sn, cn); pe_double(sn, cn);        // octave 4
+          float gp = gx[d] * (16.0f * PI_F) * cn;
+          pe_double(sn, cn);
+          gp = fmaf(gx[21 + d] * (32.0f * PI_F), cn, gp);
+          dxc[d * 128] = gp;
+        }
+      } else if (g_emb != nullptr) {                                             // d xc: parked until the last stage
         uint32_t u[32], v[16];
         tmem_ld32(tl + T_DB, u); tmem_ld16(tl + T_DB + 32, v); tmem_ld_wait();
 #pragma unroll
@@ -618,7 +700,34 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
       mark_drained();
       // ---- S5: in_layer
       wait(&bar_d, pD); tc_fence_after();
-      if (g_emb != nullptr) {
+      if (PTS) {
+        // embedding backward: octaves 0..3 from d xg, plus the parked octaves 4, 5; d B_d += d proj_d * t, summed over the warp's
+        // 32 rows by shuffles, then over the CTA in shared memory (flushed with 63 REDs per CTA at the end)
+        uint32_t uu[3][32];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) tmem_ld32(tl + T_DB + ch * 32, uu[ch]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < 21; ++d) {
+          float sn, cn;
+          pe_sincos(peB + d * 3, tpt, sn, cn);
+          float gp = dxc[d * 128];
+          float w = PI_F;
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            const int col = 3 + f * 21 + d;
+            gp = fmaf(__uint_as_float(uu[col >> 5][col & 31]) * w, cn, gp);
+            pe_double(sn, cn);
+            w *= 2.0f;
+          }
+          if (!act) gp = 0.f;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const float r = warp_sum(gp * tpt[q]);
+            if (lane == 0) atomicAdd(&s_gB[d * 3 + q], r);
+          }
+        }
+      } else if (g_emb != nullptr) {
         // g_emb rows of the tile are one contiguous block: stage [128][129] fp32 in shared memory (row stride 129 words:
         // conflict-free), then ONE bulk copy (ragged last tile: coalesced cooperative stores)
         float* stg = reinterpret_cast<float*>(sm + B_A0) + row * EMB;
@@ -652,14 +761,20 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
   tc_fence_before();
   __syncthreads();
   if (tid < 4) atomicAdd(&part[PR_HB + tid], s_hb[tid]);
+  if (PTS && tid < 63) atomicAdd(&part[PR_PE + tid], s_gB[tid]);
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // accumulation buffer -> flat nn.Linear-ordered gradient (OVERWRITES g_params); one thread per slot, slot (column k, row o) of a
 // region lives at region + k * 128 + o.
-__global__ void reduce_kernel(int n_part, const float* __restrict__ partials, float* __restrict__ g_params) {
+__global__ void reduce_kernel(int n_part, const float* __restrict__ partials, float* __restrict__ g_params,
+                              float* __restrict__ g_B /* [21][3], may be NULL */) {
   const int s = blockIdx.x * 256 + threadIdx.x;
   if (s >= PART_FLOATS) return;
+  if (s >= PR_PE) {
+    if (g_B != nullptr && s < PR_PE + 63) g_B[s - PR_PE] = partials[s];
+    return;
+  }
   int dst = -1;
   if (s < PR_MID1) { const int k = s >> 7, o = s & 127; dst = k < E1 ? P_INW + o * E1 + k : (k == XG_ONE ? P_INB + o : -1); }
   else if (s < PR_CAT) { const int t = s - PR_MID1, k = t >> 7, o = t & 127; dst = P_M1W + o * H + k; }
@@ -694,50 +809,74 @@ extern "C" size_t cnf_occmap_tc_workspace_bytes(int n_pts) {
   return ws_parts(n_pts) + (size_t)PART_FLOATS * sizeof(float);
 }
 
-extern "C" int cnf_occmap_tc_fwd(int P, const float* params, const float* emb, float* alpha, float* rgb, void* ws, size_t ws_bytes,
-                                 cnf_stream_t stream) {
-  CNF_REQUIRE(P >= 0, "cnf_occmap_tc_fwd: bad size P=%d", P);
-  CNF_REQUIRE(params && ws && (P == 0 || (emb && alpha && rgb)), "cnf_occmap_tc_fwd: null pointer");
-  if (ws_bytes < cnf_occmap_tc_workspace_bytes(P)) { set_error("cnf_occmap_tc_fwd: workspace too small"); return CNF_ERR_WORKSPACE; }
+static int otc_forward(bool pts, const char* who, int P, const float* params, const float* pe_B, const float* pe_scale, const float* in,
+                       float* alpha, float* rgb, void* ws, size_t ws_bytes, cnf_stream_t stream) {
+  if (P < 0) { set_error("%s: bad size P=%d", who, P); return CNF_ERR_ARG; }
+  if (!(params && ws && (P == 0 || (in && alpha && rgb)) && (!pts || (pe_B && pe_scale)))) { set_error("%s: null pointer", who); return CNF_ERR_ARG; }
+  if (ws_bytes < cnf_occmap_tc_workspace_bytes(P)) { set_error("%s: workspace too small", who); return CNF_ERR_WORKSPACE; }
   if (P == 0) return CNF_OK;
   cudaStream_t st = as_stream(stream);
   uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
   static bool attr_set = false;
   if (!attr_set) {
-    CNF_CUDA(cudaFuncSetAttribute(fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+    CNF_CUDA(cudaFuncSetAttribute(fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+    CNF_CUDA(cudaFuncSetAttribute(fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
     attr_set = true;
   }
   int dev = 0, n_sm = 148;
   CNF_CUDA(cudaGetDevice(&dev));
   CNF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  prep_kernel<<<(WIMG_BYTES / 16 + 255) / 256, 256, 0, st>>>(params, w8 + ws_prep());
-  const int n_tiles = (P + TPT - 1) / TPT;
-  fwd_kernel<<<n_tiles < n_sm ? n_tiles : n_sm, NT, F_SMEM, st>>>(P, w8 + ws_prep(), emb, w8 + ws_imgs(), alpha, rgb);
-  return check_launch("cnf_occmap_tc_fwd");
+  prep_kernel<<<(WIMG_BYTES / 16 + 255) / 256, 256, 0, st>>>(params, pts ? pe_B : nullptr, pts ? pe_scale : nullptr, w8 + ws_prep());
+  const int n_tiles = (P + TPT - 1) / TPT, grid = n_tiles < n_sm ? n_tiles : n_sm;
+  if (pts) fwd_kernel<true><<<grid, NT, F_SMEM, st>>>(P, w8 + ws_prep(), in, w8 + ws_imgs(), alpha, rgb);
+  else fwd_kernel<false><<<grid, NT, F_SMEM, st>>>(P, w8 + ws_prep(), in, w8 + ws_imgs(), alpha, rgb);
+  return check_launch(who);
 }
 
-extern "C" int cnf_occmap_tc_bwd(int P, const float* params, const float* rgb, const float* g_alpha, const float* g_rgb, void* ws,
-                                 size_t ws_bytes, float* g_params, float* g_emb, cnf_stream_t stream) {
-  CNF_REQUIRE(P > 0, "cnf_occmap_tc_bwd: bad size P=%d", P);
-  CNF_REQUIRE(params && rgb && g_alpha && g_rgb && ws && g_params, "cnf_occmap_tc_bwd: null pointer");
-  if (ws_bytes < cnf_occmap_tc_workspace_bytes(P)) { set_error("cnf_occmap_tc_bwd: workspace too small"); return CNF_ERR_WORKSPACE; }
+extern "C" int cnf_occmap_tc_fwd(int P, const float* params, const float* emb, float* alpha, float* rgb, void* ws, size_t ws_bytes,
+                                 cnf_stream_t stream) {
+  return otc_forward(false, "cnf_occmap_tc_fwd", P, params, nullptr, nullptr, emb, alpha, rgb, ws, ws_bytes, stream);
+}
+
+extern "C" int cnf_occmap_tc_fwd_points(int P, const float* params, const float* pe_B, const float* pe_scale, const float* points,
+                                        float* alpha, float* rgb, void* ws, size_t ws_bytes, cnf_stream_t stream) {
+  return otc_forward(true, "cnf_occmap_tc_fwd_points", P, params, pe_B, pe_scale, points, alpha, rgb, ws, ws_bytes, stream);
+}
+
+static int otc_backward(bool pts, const char* who, int P, const float* params, const float* points, const float* rgb, const float* g_alpha,
+                        const float* g_rgb, void* ws, size_t ws_bytes, float* g_params, float* g_emb, float* g_B, cnf_stream_t stream) {
+  if (P <= 0) { set_error("%s: bad size P=%d", who, P); return CNF_ERR_ARG; }
+  if (!(params && rgb && g_alpha && g_rgb && ws && g_params && (!pts || (points && g_B)))) { set_error("%s: null pointer", who); return CNF_ERR_ARG; }
+  if (ws_bytes < cnf_occmap_tc_workspace_bytes(P)) { set_error("%s: workspace too small", who); return CNF_ERR_WORKSPACE; }
   cudaStream_t st = as_stream(stream);
   uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
   static bool attr_set = false;
   if (!attr_set) {
-    CNF_CUDA(cudaFuncSetAttribute(bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    CNF_CUDA(cudaFuncSetAttribute(bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+    CNF_CUDA(cudaFuncSetAttribute(bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
     attr_set = true;
   }
   int dev = 0, n_sm = 148;
   CNF_CUDA(cudaGetDevice(&dev));
   CNF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   const int n_tiles = (P + TPT - 1) / TPT;
-  int grid = n_tiles < n_sm ? n_tiles : n_sm;
+  const int grid = n_tiles < n_sm ? n_tiles : n_sm;
   float* parts = reinterpret_cast<float*>(w8 + ws_parts(P));
   CNF_CUDA(cudaMemsetAsync(parts, 0, PART_FLOATS * sizeof(float), st));
-  bwd_kernel<<<grid, NT, B_SMEM, st>>>(P, w8 + ws_prep(), w8 + ws_imgs(), rgb, g_alpha, g_rgb, parts, g_emb);
-  reduce_kernel<<<(PART_FLOATS + 255) / 256, 256, 0, st>>>(1, parts, g_params);
-  return check_launch("cnf_occmap_tc_bwd");
+  if (pts) bwd_kernel<true><<<grid, NT, B_SMEM, st>>>(P, w8 + ws_prep(), w8 + ws_imgs(), rgb, g_alpha, g_rgb, parts, const_cast<float*>(points));
+  else bwd_kernel<false><<<grid, NT, B_SMEM, st>>>(P, w8 + ws_prep(), w8 + ws_imgs(), rgb, g_alpha, g_rgb, parts, g_emb);
+  reduce_kernel<<<(PART_FLOATS + 255) / 256, 256, 0, st>>>(1, parts, g_params, pts ? g_B : nullptr);
+  return check_launch(who);
+}
+
+extern "C" int cnf_occmap_tc_bwd(int P, const float* params, const float* rgb, const float* g_alpha, const float* g_rgb, void* ws,
+                                 size_t ws_bytes, float* g_params, float* g_emb, cnf_stream_t stream) {
+  return otc_backward(false, "cnf_occmap_tc_bwd", P, params, nullptr, rgb, g_alpha, g_rgb, ws, ws_bytes, g_params, g_emb, nullptr, stream);
+}
+
+extern "C" int cnf_occmap_tc_bwd_points(int P, const float* params, const float* points, const float* rgb, const float* g_alpha,
+                                        const float* g_rgb, void* ws, size_t ws_bytes, float* g_params, float* g_B, cnf_stream_t stream) {
+  return otc_backward(true, "cnf_occmap_tc_bwd_points", P, params, points, rgb, g_alpha, g_rgb, ws, ws_bytes, g_params, nullptr, g_B, stream);
 }
 
 extern "C" int cnf_occmap_tc_set_debug(void* stamps /* device buffer of 64 int64, or NULL */) {

@@ -226,6 +226,27 @@ class OccMapTCFn(torch.autograd.Function):
         return g_emb, g_params
 
 
+def occmap_tc_points_fwd_bwd(points, params, pe_B, pe_scale, g_alpha_fn):
+    """Tensor-core OccupancyMap with the embedding computed in-kernel (cnf_occmap_tc_fwd_points / _bwd_points), forward then
+    backward: points [P,3], flat params (hidden 128), pe_B [21,3], pe_scale (0-d / [1]); ``g_alpha_fn(alpha, rgb) -> (g_alpha [P],
+    g_rgb [P,3])`` supplies the upstream gradients.  Returns alpha, rgb, g_params, g_B."""
+    lib = lib_for(points)
+    points = _f32c(points); params = _f32c(params); pe_B = _f32c(pe_B); pe_scale = _f32c(pe_scale.reshape(1))
+    P = points.shape[0]
+    dev = points.device
+    ws = torch.empty(lib.cnf_occmap_tc_workspace_bytes(P), device=dev, dtype=torch.uint8)
+    alpha = torch.empty(P, device=dev, dtype=torch.float32)
+    rgb = torch.empty(P, 3, device=dev, dtype=torch.float32)
+    check(lib.cnf_occmap_tc_fwd_points(P, ptr(params), ptr(pe_B), ptr(pe_scale), ptr(points), ptr(alpha), ptr(rgb), ptr(ws), ws.numel(),
+                                       stream()))
+    g_alpha, g_rgb = g_alpha_fn(alpha, rgb)
+    g_params = torch.empty_like(params)
+    g_B = torch.empty_like(pe_B)
+    check(lib.cnf_occmap_tc_bwd_points(P, ptr(params), ptr(points), ptr(rgb), ptr(_f32c(g_alpha)), ptr(_f32c(g_rgb)), ptr(ws), ws.numel(),
+                                       ptr(g_params), ptr(g_B), stream()))
+    return alpha, rgb, g_params, g_B
+
+
 # ------------------------------------------------------------------------------------------------
 # compositing + losses
 # ------------------------------------------------------------------------------------------------

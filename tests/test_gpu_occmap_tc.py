@@ -90,6 +90,41 @@ def test_occmap_tc_fwd_bwd(P):
         assert r_po < 0.15 and r_eo < 0.15
 
 
+@pytest.mark.parametrize("P", [77, 128, 1200 * 14, 2 * 148 * 128 + 9])
+def test_occmap_tc_points_variant(P):
+    """Embedding computed inside the kernels (cnf_occmap_tc_fwd_points / _bwd_points) against the embedding-in kernels fed with the
+    fp32 embedding of the same points: outputs 2e-2 / 2e-3 (fast sincos + double-angle recurrence vs libm, before the same bf16
+    rounding), parameter gradient 2e-2 relative L2, and the B_layer gradient against cnf_embed_bwd of the other path's g_emb
+    (5e-2; also against the fp32 oracle: 0.2)."""
+    from category_nerf_reconstruction_official_b200 import ops
+    g = torch.Generator().manual_seed(900 + P % 89)
+    params = O.init_params(O.occmap_param_shapes(128), g)
+    B = O.icosa_matrix() + 0.01 * torch.randn(21, 3, generator=g)
+    pts = (torch.rand(P, 3, generator=g) - 0.5) * 6.0
+    ga = torch.randn(P, generator=g) * 0.1; gc = torch.randn(P, 3, generator=g)
+    flat = torch.cat([p.reshape(-1) for p in params]).to(DEV)
+    scale = torch.tensor(5.0, device=DEV)
+    alpha, rgb, gp, gB = ops.occmap_tc_points_fwd_bwd(pts.to(DEV), flat, B.to(DEV), scale, lambda a, c: (ga.to(DEV), gc.to(DEV)))
+    # the embedding-in path on the same points
+    Bd = B.to(DEV).requires_grad_(True)
+    emb = ops.EmbedFn.apply(pts.to(DEV)[None], Bd[None], scale.reshape(1))[0]
+    flat_r = flat.clone().requires_grad_(True)
+    a2, c2 = ops.OccMapTCFn.apply(emb, flat_r)
+    ((a2 * ga.to(DEV)).sum() + (c2 * gc.to(DEV)).sum()).backward()
+    torch.cuda.synchronize()
+    # fp32 oracle for the B gradient
+    Bo = B.clone().requires_grad_(True)
+    a_o, c_o = O.occmap_forward([p.clone() for p in params], O.embed(pts[:, None, :], Bo, 5.0).reshape(P, 129))
+    ((a_o.reshape(-1) * ga).sum() + (c_o.reshape(-1, 3) * gc).sum()).backward()
+    e_a, e_c = float((alpha - a2).abs().max()), float((rgb - c2).abs().max())
+    r_p, r_B, r_Bo = rel(gp, flat_r.grad), rel(gB, Bd.grad), rel(gB.cpu(), Bo.grad)
+    print("P=%d points variant vs embedding-in: alpha %.2e rgb %.2e grads %.2e B %.2e | B vs fp32 oracle %.3f" % (P, e_a, e_c, r_p, r_B, r_Bo))
+    assert torch.isfinite(gp).all() and torch.isfinite(gB).all()
+    assert e_a < 5e-2 and e_c < 5e-3
+    if P >= 1000:
+        assert r_p < 2e-2 and r_B < 5e-2 and r_Bo < 0.2
+
+
 def test_occmap_module_tensor_core_background_step():
     """OccupancyMap module with use_tensor_cores: the reference's background step (train.py:172-180: embed -> OccupancyMap ->
     step_batch_loss -> backward) against the fp32 oracle step on a well-conditioned loss (all depths invalid -> depth term off)."""
