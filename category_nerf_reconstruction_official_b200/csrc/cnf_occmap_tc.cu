@@ -385,20 +385,17 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
   extern __shared__ __align__(128) uint8_t sm[];   // no-swizzle operand images need 16-byte alignment only
   __shared__ uint64_t fullA0, fullA1, fullAX, fullH, fullW0, fullW1, bar_d, bar_w;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_hb[4];
-  __shared__ float s_gB[64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {
     float* c = reinterpret_cast<float*>(sm + B_C);
     const float* src = reinterpret_cast<const float*>(prep + WIMG_BYTES);
     for (int i = tid; i < 128 + 384; i += NT) c[i] = src[C_WA + i];             // w_alpha | W_oc
-    if (tid < 64) { c[B_CPE + tid] = src[C_PEB + tid]; s_gB[tid] = 0.f; }        // PE matrix | 1/scale
+    if (tid < 64) c[B_CPE + tid] = src[C_PEB + tid];                            // PE matrix | 1/scale
     // constant-one image [128 points x 16]: column 0 = 1
     for (int i = tid; i < 4096 / 16; i += NT) {
       // chunk i: row-group i / 2, column block i % 2 ... rows x 16 B; column 0 lives in column block 0
       *reinterpret_cast<uint4*>(sm + B_ONES + i * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
-    if (tid < 4) s_hb[tid] = 0.f;
   }
   __syncthreads();
   if (tid < TPT) *reinterpret_cast<__nv_bfloat16*>(sm + B_ONES + blk_off(tid, 0, 16)) = __float2bfloat16_rn(1.0f);
@@ -540,6 +537,7 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
     const float* woc = wa + 128;
     uint32_t pA0 = 0, pA1 = 0, pH = 0, pD = 0, pW = 0;
     int sg = 0, sd = 0, si = 0;
+    float acc_hb = 0.f, acc_pe0 = 0.f, acc_pe1 = 0.f;    // per-lane partial sums of the head biases / the PE matrix gradient
     auto mark = [&]() { if (tid == 0) stamp(si); ++si; };
     auto wait = [&](uint64_t* bar, uint32_t& ph) { mbar_wait(bar, ph); ph ^= 1; mark(); };
     auto publish = [&]() { fence_async_smem(); tc_fence_before(); nbar_arrive(1 + (sg & 1), NT); ++sg; mark(); };
@@ -607,9 +605,9 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
       }
       *reinterpret_cast<uint4*>(rowblk(sm + B_HD, row, 0, 16)) = make_uint4(pack2(dp[0], dp[1]), pack2(dp[2], draw), 0u, 0u);
       *reinterpret_cast<uint4*>(rowblk(sm + B_HD, row, 1, 16)) = make_uint4(0u, 0u, 0u, 0u);
-      {
-        float s0 = warp_sum(dp[0]), s1 = warp_sum(dp[1]), s2 = warp_sum(dp[2]), s3 = warp_sum(draw);
-        if (lane == 0) { atomicAdd(&s_hb[0], s0); atomicAdd(&s_hb[1], s1); atomicAdd(&s_hb[2], s2); atomicAdd(&s_hb[3], s3); }
+      {   // head-bias gradients: lane q of each warp accumulates sum q in a register (shared-memory float atomics are CAS loops)
+        const float s0 = warp_sum(dp[0]), s1 = warp_sum(dp[1]), s2 = warp_sum(dp[2]), s3 = warp_sum(draw);
+        acc_hb += lane == 0 ? s0 : (lane == 1 ? s1 : (lane == 2 ? s2 : (lane == 3 ? s3 : 0.f)));
       }
       wait(&fullH, pH);
 #pragma unroll 1
@@ -724,7 +722,8 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
             const float r = warp_sum(gp * tpt[q]);
-            if (lane == 0) atomicAdd(&s_gB[d * 3 + q], r);
+            const int i = d * 3 + q;                     // lane i % 32 keeps sum i in a register
+            if (lane == (i & 31)) { if (i < 32) acc_pe0 += r; else acc_pe1 += r; }
           }
         }
       } else if (g_emb != nullptr) {
@@ -756,12 +755,15 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
       drain(T_DW, XG_C, part + PR_IN + row);
       mark_drained();
     }
+    if (lane < 4) atomicAdd(&part[PR_HB + lane], acc_hb);
+    if (PTS) {
+      atomicAdd(&part[PR_PE + lane], acc_pe0);
+      if (lane < 31) atomicAdd(&part[PR_PE + 32 + lane], acc_pe1);
+    }
   }
   if (tid == 0) bulk_wait<0>();                  // g_emb bulk stores have landed
   tc_fence_before();
   __syncthreads();
-  if (tid < 4) atomicAdd(&part[PR_HB + tid], s_hb[tid]);
-  if (PTS && tid < 63) atomicAdd(&part[PR_PE + tid], s_gB[tid]);
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
