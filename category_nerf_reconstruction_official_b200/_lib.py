@@ -106,6 +106,7 @@ SIGNATURES = {
     "cnf_eval_points": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     "cnf_render_rays_workspace_bytes": (c_size_t, [c_int, c_int]),
     "cnf_render_rays": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
+    "cnf_composite_loss_fwd_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_float, c_float, P, P, P, P, P, c_size_t, P]),
     "cnf_origin_dirs": (c_int, [c_int, c_int, P, P, P, P, P]),
     "cnf_occmap_tc_workspace_bytes": (c_size_t, [c_int]),
     "cnf_occmap_tc_fwd": (c_int, [c_int, P, P, P, P, P, c_size_t, P]),

@@ -122,8 +122,8 @@ class FusedBackgroundTrainer:
         main.wait_stream(self._side)
         args = (1, R, S, ptr(self._alpha), ptr(self._rgb), ptr(z), ptr(gt_depth), ptr(self._gt_color), ptr(labels), ptr(mask_depth),
                 ptr(self._counts), float(self.cs), float(self.os))
-        check(lib.cnf_composite_loss_fwd(*args, ptr(self._rays), ptr(self.out_loss), ptr(self._cws), self._cws.numel(), st))
-        check(lib.cnf_composite_loss_bwd(*args, ptr(self._one), ptr(self._g_alpha), ptr(self._g_rgb), st))
+        check(lib.cnf_composite_loss_fwd_bwd(*args, ptr(self._rays), ptr(self.out_loss), ptr(self._g_alpha), ptr(self._g_rgb),
+                                             ptr(self._cws), self._cws.numel(), st))
         check(lib.cnf_occmap_tc_bwd_points(P, ptr(self.params), ptr(pcs), ptr(self._rgb), ptr(self._g_alpha), ptr(self._g_rgb),
                                            ptr(self._ws), self._ws.numel(), ptr(self.g_params), ptr(self.g_B), st))
         return self.out_loss[0]
@@ -144,9 +144,9 @@ class FusedBackgroundTrainer:
             self._side2.wait_stream(main)
             with torch.cuda.stream(self._side2):
                 self._draw_randoms_into_buffers()
-        # kernels of libcnf_sm100.so: sampler 1 | mask counts, prep, OccupancyMap fwd | composite fwd (tile + finalize), composite bwd |
+        # kernels of libcnf_sm100.so: sampler 1 | mask counts, prep, OccupancyMap fwd | composite fwd+bwd (tile + finalize) |
         # OccupancyMap bwd, gradient scatter
-        self.launches_per_step = 1 + 3 + 3 + 2
+        self.launches_per_step = 1 + 3 + 2 + 2
         loss = self.step_from_samples(pcs[0], z[0], depth, rgbs, labels[0], valid[0])
         if prefetch:
             main.wait_stream(self._side2)

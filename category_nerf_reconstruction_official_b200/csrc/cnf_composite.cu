@@ -270,7 +270,10 @@ __device__ __forceinline__ void tile_store(float* __restrict__ dst, const float*
   }
 }
 
-template <bool BWD>
+// MODE 0: forward (rays + loss partials); 1: backward (gradients); 2: both in ONE pass (the backward only needs per-ray quantities
+// and the input-only mask counts, so the loss value and its gradients can leave the same kernel: small-batch steps save a launch
+// and a second read of alpha / colour / z).
+template <int MODE>
 __global__ void __launch_bounds__(TR)
 composite_tile_kernel(int K, int R, int S, const float* __restrict__ alpha, const float* __restrict__ color,
                       const float* __restrict__ z, const float* __restrict__ gt_depth, const float* __restrict__ gt_color,
@@ -278,6 +281,7 @@ composite_tile_kernel(int K, int R, int S, const float* __restrict__ alpha, cons
                       const int32_t* __restrict__ counts, float cs, float os, const float* __restrict__ g_loss,
                       float* __restrict__ out_rays, float* __restrict__ partial, float* __restrict__ g_alpha, float* __restrict__ g_color) {
   extern __shared__ float sm_t[];
+  constexpr bool BWD = MODE != 0, FWD = MODE != 1;
   const int k = blockIdx.y, t = threadIdx.x;
   const int SP = S | 1, CP = (3 * S) | 1;
   float* sA = sm_t;                    // alpha -> (fwd) weights w_i / (bwd) occupancy -> d alpha
@@ -324,13 +328,14 @@ composite_tile_kernel(int K, int R, int S, const float* __restrict__ alpha, cons
       const float md = (mask_depth[g] != 0 && lab != 0) ? 1.f : 0.f;
       const float info = 1.0f / (sqrtf(var) + 1e-4f);                          // render_rays.py:73-80
       const float gd = gt_depth[g], q0 = gt_color[g * 3], q1 = gt_color[g * 3 + 1], q2 = gt_color[g * 3 + 2];
-      if (!BWD) {
+      if (FWD) {
         float* orow = out_rays + g * 6;
         orow[0] = D; orow[1] = var; orow[2] = C0; orow[3] = C1; orow[4] = C2; orow[5] = O;
         ld += fabsf(D - gd) * md * info;                                       // loss.py:52-54
         lc += (fabsf(C0 - q0) + fabsf(C1 - q1) + fabsf(C2 - q2)) * mo;
         lo += fabsf(O - mo) * ms;                                              // loss.py:64-66
-      } else {
+      }
+      if (BWD) {
         auto sgn = [](float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); };
         const float gD = sgn(D - gd) * md * info * iNd;
         const float gC0 = sgn(C0 - q0) * mo * iNo, gC1 = sgn(C1 - q1) * mo * iNo, gC2 = sgn(C2 - q2) * mo * iNo;
@@ -354,7 +359,7 @@ composite_tile_kernel(int K, int R, int S, const float* __restrict__ alpha, cons
       __syncthreads();
     }
   }
-  if (!BWD) {
+  if (FWD) {
     __shared__ float s_p[TR / 32][3];
     const int lane = t & 31, warp = t >> 5;
     ld = warp_sum(ld); lc = warp_sum(lc); lo = warp_sum(lo);
@@ -529,8 +534,8 @@ extern "C" int cnf_composite_loss_fwd(int K, int R, int S, const float* alpha, c
     nb = tile_blocks(R);
     const int smem = tile_smem_floats(S, false) * 4;
     static bool attr = false;
-    if (!attr) { CNF_CUDA(cudaFuncSetAttribute(composite_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_floats(32, false) * 4)); attr = true; }
-    composite_tile_kernel<false><<<dim3(nb, K), TR, smem, as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth,
+    if (!attr) { CNF_CUDA(cudaFuncSetAttribute(composite_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_floats(32, false) * 4)); attr = true; }
+    composite_tile_kernel<0><<<dim3(nb, K), TR, smem, as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth,
                                                                               counts, cs, os, nullptr, out_rays, (float*)ws, nullptr, nullptr);
   } else {
     nb = comp_blocks(R, S);
@@ -551,14 +556,35 @@ extern "C" int cnf_composite_loss_bwd(int K, int R, int S, const float* alpha, c
   if (S <= 32) {
     const int smem = tile_smem_floats(S, true) * 4;
     static bool attr = false;
-    if (!attr) { CNF_CUDA(cudaFuncSetAttribute(composite_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_floats(32, true) * 4)); attr = true; }
-    composite_tile_kernel<true><<<dim3(tile_blocks(R), K), TR, smem, as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels,
+    if (!attr) { CNF_CUDA(cudaFuncSetAttribute(composite_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_floats(32, true) * 4)); attr = true; }
+    composite_tile_kernel<1><<<dim3(tile_blocks(R), K), TR, smem, as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels,
                                                                                         mask_depth, counts, cs, os, g_loss, nullptr, nullptr, g_alpha, g_color);
     return check_launch("cnf_composite_loss_bwd");
   }
   composite_bwd_kernel<<<dim3(comp_blocks(R, S), K), CT, 0, as_stream(stream)>>>(
       K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth, counts, cs, os, g_loss, g_alpha, g_color);
   return check_launch("cnf_composite_loss_bwd");
+}
+
+// forward and backward in one pass (upstream gradient of the loss = 1): S <= 32
+extern "C" int cnf_composite_loss_fwd_bwd(int K, int R, int S, const float* alpha, const float* color, const float* z,
+                                          const float* gt_depth, const float* gt_color, const uint8_t* labels,
+                                          const uint8_t* mask_depth, const int32_t* counts, float cs, float os,
+                                          float* out_rays, float* out_loss, float* g_alpha, float* g_color,
+                                          void* ws, size_t ws_bytes, cnf_stream_t stream) {
+  CNF_REQUIRE(K > 0 && R > 0 && S > 0, "cnf_composite_loss_fwd_bwd: bad sizes");
+  CNF_REQUIRE(alpha && color && z && gt_depth && gt_color && labels && mask_depth && counts && out_rays && out_loss && g_alpha && g_color && ws,
+              "cnf_composite_loss_fwd_bwd: null pointer");
+  if (S > 32) { set_error("cnf_composite_loss_fwd_bwd: S=%d > 32 (use the separate forward / backward entry points)", S); return CNF_ERR_UNSUPPORTED; }
+  if (ws_bytes < cnf_composite_workspace_bytes(K, R)) { set_error("cnf_composite_loss_fwd_bwd: workspace too small"); return CNF_ERR_WORKSPACE; }
+  const int nb = tile_blocks(R);
+  const int smem = tile_smem_floats(S, true) * 4;
+  static bool attr = false;
+  if (!attr) { CNF_CUDA(cudaFuncSetAttribute(composite_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_floats(32, true) * 4)); attr = true; }
+  composite_tile_kernel<2><<<dim3(nb, K), TR, smem, as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth,
+                                                                        counts, cs, os, nullptr, out_rays, (float*)ws, g_alpha, g_color);
+  composite_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(K, nb, (const float*)ws, counts, cs, os, out_loss);
+  return check_launch("cnf_composite_loss_fwd_bwd");
 }
 
 extern "C" int cnf_code_reg(int n_obj, int L, const float* codes, float weight, float* out, float* g_codes,

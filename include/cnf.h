@@ -170,6 +170,13 @@ int cnf_composite_loss_bwd(int n_cat, int n_rays, int S, const float* alpha, con
                            const uint8_t* labels, const uint8_t* mask_depth, const int32_t* counts,
                            float color_scaling, float opacity_scaling, const float* g_loss,
                            float* g_alpha, float* g_color, cnf_stream_t stream);
+/* forward and backward in ONE pass for S <= 32 (upstream gradient of the loss = 1): the backward only needs per-ray quantities and
+ * the input-only mask counts, so loss terms and gradients leave the same kernel.  Same arguments as the two calls above. */
+int cnf_composite_loss_fwd_bwd(int n_cat, int n_rays, int S, const float* alpha, const float* color,
+                               const float* z, const float* gt_depth, const float* gt_color,
+                               const uint8_t* labels, const uint8_t* mask_depth, const int32_t* counts,
+                               float color_scaling, float opacity_scaling, float* out_rays, float* out_loss,
+                               float* g_alpha, float* g_color, void* ws, size_t ws_bytes, cnf_stream_t stream);
 /* step_batch_loss_reg (src/loss.py:5-15): codes [n_obj,L] -> out[0] = sum_i ||codes_i||_2 (0 if n_obj==1);
  * g_codes (may be NULL) += weight * codes_i/||codes_i||. */
 int cnf_code_reg(int n_obj, int L, const float* codes, float weight, float* out, float* g_codes,

@@ -288,3 +288,34 @@ def test_origin_dirs_vs_linalg_inv(n):
     o, dd = sampling.origin_dirs_W(T.float().to(DEV), d.float().to(DEV))
     torch.testing.assert_close(o.cpu().double(), T[:, :3, 3], rtol=1e-6, atol=1e-6)
     torch.testing.assert_close(dd.cpu().double(), (T[:, :3, :3] @ d[..., None]).squeeze(-1), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("K,R,S", [(1, 1200, 14), (3, 333, 10), (2, 129, 32)])
+def test_composite_fwd_bwd_one_pass_matches_two_calls(K, R, S):
+    """cnf_composite_loss_fwd_bwd (one pass) against cnf_composite_loss_fwd + cnf_composite_loss_bwd (themselves checked against the
+    golden reference outputs above): identical arithmetic, so loss terms, rays and gradients must agree to 1e-6."""
+    from category_nerf_reconstruction_official_b200 import ops, _lib
+    from category_nerf_reconstruction_official_b200._lib import check, ptr, stream
+    g = torch.Generator().manual_seed(K * 100 + S)
+    alpha = (torch.randn(K, R, S, generator=g) * 3).to(DEV); color = torch.rand(K, R, S, 3, generator=g).to(DEV)
+    z = torch.sort(torch.rand(K, R, S, generator=g) * 4, dim=-1).values.to(DEV)
+    gd = (torch.rand(K, R, generator=g) * 4).to(DEV); gc = torch.rand(K, R, 3, generator=g).to(DEV)
+    lab = torch.randint(0, 3, (K, R), generator=g, dtype=torch.uint8).to(DEV)
+    md = (torch.rand(K, R, generator=g) > 0.2).to(torch.uint8).to(DEV)
+    lib = _lib.load()
+    counts = ops.mask_counts(lab, md)
+    ws = torch.empty(lib.cnf_composite_workspace_bytes(K, R), dtype=torch.uint8, device=DEV)
+    one = torch.ones(1, device=DEV)
+    f = lambda *s: torch.empty(*s, device=DEV)
+    rays1, out1, ga1, gc1 = f(K, R, 6), f(4 + 3 * K), f(K, R, S), f(K, R, S, 3)
+    rays2, out2, ga2, gc2 = f(K, R, 6), f(4 + 3 * K), f(K, R, S), f(K, R, S, 3)
+    args = (K, R, S, ptr(alpha), ptr(color), ptr(z), ptr(gd), ptr(gc), ptr(lab), ptr(md), ptr(counts), 5.0, 10.0)
+    check(lib.cnf_composite_loss_fwd(*args, ptr(rays1), ptr(out1), ptr(ws), ws.numel(), stream()))
+    check(lib.cnf_composite_loss_bwd(*args, ptr(one), ptr(ga1), ptr(gc1), stream()))
+    check(lib.cnf_composite_loss_fwd_bwd(*args, ptr(rays2), ptr(out2), ptr(ga2), ptr(gc2), ptr(ws), ws.numel(), stream()))
+    torch.cuda.synchronize()
+    assert float(out1[0]) > 0
+    torch.testing.assert_close(out2, out1, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(rays2, rays1, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(ga2, ga1, rtol=1e-6, atol=1e-9)
+    torch.testing.assert_close(gc2, gc1, rtol=1e-6, atol=1e-9)
