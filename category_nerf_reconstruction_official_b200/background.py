@@ -12,6 +12,7 @@ order and shapes are the module's (``model.OccupancyMap(87, 42, 128)``), so stat
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -49,6 +50,7 @@ class FusedBackgroundTrainer:
         self._buf_key = None
         self._side = None
         self._side2 = None
+        self._side3 = None
         self._rand_key = None
         self._opt_state = None
         self.launches_per_step = 0
@@ -96,7 +98,14 @@ class FusedBackgroundTrainer:
             self._buf_key = R
         return self._buf_key
 
-    def step_from_samples(self, pcs, z, gt_depth, gt_rgb_u8, labels, mask_depth):
+    def prepare(self, R: int):
+        """Parameter-only half of a step (cnf_occmap_tc_prepare): bf16 operand images, constants, zeroed gradient buffer."""
+        self._buffers(R)
+        lib = lib_for(self.params)
+        check(lib.cnf_occmap_tc_prepare(R * self.S, ptr(self.params), ptr(self.pe_B), ptr(self.pe_scale), ptr(self._ws),
+                                        self._ws.numel(), stream()))
+
+    def step_from_samples(self, pcs, z, gt_depth, gt_rgb_u8, labels, mask_depth, prepared: bool = False):
         """Forward + backward given sampled points: pcs [R,S,3], z [R,S], gt_depth [R], gt_rgb_u8 u8 [R,3+] (first three channels),
         labels u8 [R], mask_depth u8/bool [R].  Fills self.g_params / self.g_B / self.out_loss; returns the loss (0-d, async).
         The small input-only pieces (gt colours, mask counts, gradient clear) run on a side stream next to the embedding / MLP."""
@@ -117,21 +126,30 @@ class FusedBackgroundTrainer:
             torch.div(gt_rgb_u8[:, :3], 255.0, out=self._gt_color)                               # train.py:128 (gt_rgb / 255)
             check(lib.cnf_mask_counts(1, R, ptr(labels), ptr(mask_depth), ptr(self._counts), stream()))
         st = stream()
+        flags = 1 if prepared else 0
         check(lib.cnf_occmap_tc_fwd_points(P, ptr(self.params), ptr(self.pe_B), ptr(self.pe_scale), ptr(pcs), ptr(self._alpha),
-                                           ptr(self._rgb), ptr(self._ws), self._ws.numel(), st))
+                                           ptr(self._rgb), ptr(self._ws), self._ws.numel(), flags, st))
         main.wait_stream(self._side)
         args = (1, R, S, ptr(self._alpha), ptr(self._rgb), ptr(z), ptr(gt_depth), ptr(self._gt_color), ptr(labels), ptr(mask_depth),
                 ptr(self._counts), float(self.cs), float(self.os))
         check(lib.cnf_composite_loss_fwd_bwd(*args, ptr(self._rays), ptr(self.out_loss), ptr(self._g_alpha), ptr(self._g_rgb),
                                              ptr(self._cws), self._cws.numel(), st))
         check(lib.cnf_occmap_tc_bwd_points(P, ptr(self.params), ptr(pcs), ptr(self._rgb), ptr(self._g_alpha), ptr(self._g_rgb),
-                                           ptr(self._ws), self._ws.numel(), ptr(self.g_params), ptr(self.g_B), st))
+                                           ptr(self._ws), self._ws.numel(), ptr(self.g_params), ptr(self.g_B), flags, st))
         return self.out_loss[0]
 
     def step(self, rgbs, depth, origins, dirs, rand: Optional[Dict[str, torch.Tensor]] = None):
         """Sample + step: rgbs u8 [R,4] (rgb + label), depth [R], origins / dirs [R,3] (scene_cateogries.py:453-546 sampler)."""
         prefetch = rand is None
         main = torch.cuda.current_stream(self.device)
+        split = os.environ.get("CNF_BG_NO_PREPARE_SPLIT") is None
+        self._buffers(rgbs.shape[0])                         # allocate on the main stream
+        if split:
+            if self._side3 is None:
+                self._side3 = torch.cuda.Stream(device=self.device)
+            self._side3.wait_stream(main)
+            with torch.cuda.stream(self._side3):             # parameter-only half next to the sampler
+                self.prepare(rgbs.shape[0])
         if prefetch:
             rand = self._prefetched_randoms(rgbs.shape[0])
         elif rand["u_inv"].dim() == 2:
@@ -147,7 +165,9 @@ class FusedBackgroundTrainer:
         # kernels of libcnf_sm100.so: sampler 1 | mask counts, prep, OccupancyMap fwd | composite fwd+bwd (tile + finalize) |
         # OccupancyMap bwd, gradient scatter
         self.launches_per_step = 1 + 3 + 2 + 2
-        loss = self.step_from_samples(pcs[0], z[0], depth, rgbs, labels[0], valid[0])
+        if split:
+            main.wait_stream(self._side3)
+        loss = self.step_from_samples(pcs[0], z[0], depth, rgbs, labels[0], valid[0], prepared=split)
         if prefetch:
             main.wait_stream(self._side2)
         return loss

@@ -812,7 +812,7 @@ extern "C" size_t cnf_occmap_tc_workspace_bytes(int n_pts) {
 }
 
 static int otc_forward(bool pts, const char* who, int P, const float* params, const float* pe_B, const float* pe_scale, const float* in,
-                       float* alpha, float* rgb, void* ws, size_t ws_bytes, cnf_stream_t stream) {
+                       float* alpha, float* rgb, void* ws, size_t ws_bytes, cnf_stream_t stream, bool prepared = false) {
   if (P < 0) { set_error("%s: bad size P=%d", who, P); return CNF_ERR_ARG; }
   if (!(params && ws && (P == 0 || (in && alpha && rgb)) && (!pts || (pe_B && pe_scale)))) { set_error("%s: null pointer", who); return CNF_ERR_ARG; }
   if (ws_bytes < cnf_occmap_tc_workspace_bytes(P)) { set_error("%s: workspace too small", who); return CNF_ERR_WORKSPACE; }
@@ -828,7 +828,7 @@ static int otc_forward(bool pts, const char* who, int P, const float* params, co
   int dev = 0, n_sm = 148;
   CNF_CUDA(cudaGetDevice(&dev));
   CNF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  prep_kernel<<<(WIMG_BYTES / 16 + 255) / 256, 256, 0, st>>>(params, pts ? pe_B : nullptr, pts ? pe_scale : nullptr, w8 + ws_prep());
+  if (!prepared) prep_kernel<<<(WIMG_BYTES / 16 + 255) / 256, 256, 0, st>>>(params, pts ? pe_B : nullptr, pts ? pe_scale : nullptr, w8 + ws_prep());
   const int n_tiles = (P + TPT - 1) / TPT, grid = n_tiles < n_sm ? n_tiles : n_sm;
   if (pts) fwd_kernel<true><<<grid, NT, F_SMEM, st>>>(P, w8 + ws_prep(), in, w8 + ws_imgs(), alpha, rgb);
   else fwd_kernel<false><<<grid, NT, F_SMEM, st>>>(P, w8 + ws_prep(), in, w8 + ws_imgs(), alpha, rgb);
@@ -841,12 +841,25 @@ extern "C" int cnf_occmap_tc_fwd(int P, const float* params, const float* emb, f
 }
 
 extern "C" int cnf_occmap_tc_fwd_points(int P, const float* params, const float* pe_B, const float* pe_scale, const float* points,
-                                        float* alpha, float* rgb, void* ws, size_t ws_bytes, cnf_stream_t stream) {
-  return otc_forward(true, "cnf_occmap_tc_fwd_points", P, params, pe_B, pe_scale, points, alpha, rgb, ws, ws_bytes, stream);
+                                        float* alpha, float* rgb, void* ws, size_t ws_bytes, int flags, cnf_stream_t stream) {
+  return otc_forward(true, "cnf_occmap_tc_fwd_points", P, params, pe_B, pe_scale, points, alpha, rgb, ws, ws_bytes, stream, (flags & 1) != 0);
+}
+
+// the parameter-only half of a step (operand images, constants, zeroed gradient buffer): may run on another stream next to the sampler
+extern "C" int cnf_occmap_tc_prepare(int P, const float* params, const float* pe_B, const float* pe_scale, void* ws, size_t ws_bytes,
+                                     cnf_stream_t stream) {
+  CNF_REQUIRE(P >= 0 && params && ws, "cnf_occmap_tc_prepare: bad arguments");
+  if (ws_bytes < cnf_occmap_tc_workspace_bytes(P)) { set_error("cnf_occmap_tc_prepare: workspace too small"); return CNF_ERR_WORKSPACE; }
+  cudaStream_t st = as_stream(stream);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  CNF_CUDA(cudaMemsetAsync(w8 + ws_parts(P), 0, PART_FLOATS * sizeof(float), st));
+  prep_kernel<<<(WIMG_BYTES / 16 + 255) / 256, 256, 0, st>>>(params, pe_B, pe_B ? pe_scale : nullptr, w8 + ws_prep());
+  return check_launch("cnf_occmap_tc_prepare");
 }
 
 static int otc_backward(bool pts, const char* who, int P, const float* params, const float* points, const float* rgb, const float* g_alpha,
-                        const float* g_rgb, void* ws, size_t ws_bytes, float* g_params, float* g_emb, float* g_B, cnf_stream_t stream) {
+                        const float* g_rgb, void* ws, size_t ws_bytes, float* g_params, float* g_emb, float* g_B, cnf_stream_t stream,
+                        bool prepared = false) {
   if (P <= 0) { set_error("%s: bad size P=%d", who, P); return CNF_ERR_ARG; }
   if (!(params && rgb && g_alpha && g_rgb && ws && g_params && (!pts || (points && g_B)))) { set_error("%s: null pointer", who); return CNF_ERR_ARG; }
   if (ws_bytes < cnf_occmap_tc_workspace_bytes(P)) { set_error("%s: workspace too small", who); return CNF_ERR_WORKSPACE; }
@@ -864,7 +877,7 @@ static int otc_backward(bool pts, const char* who, int P, const float* params, c
   const int n_tiles = (P + TPT - 1) / TPT;
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
   float* parts = reinterpret_cast<float*>(w8 + ws_parts(P));
-  CNF_CUDA(cudaMemsetAsync(parts, 0, PART_FLOATS * sizeof(float), st));
+  if (!prepared) CNF_CUDA(cudaMemsetAsync(parts, 0, PART_FLOATS * sizeof(float), st));
   if (pts) bwd_kernel<true><<<grid, NT, B_SMEM, st>>>(P, w8 + ws_prep(), w8 + ws_imgs(), rgb, g_alpha, g_rgb, parts, const_cast<float*>(points));
   else bwd_kernel<false><<<grid, NT, B_SMEM, st>>>(P, w8 + ws_prep(), w8 + ws_imgs(), rgb, g_alpha, g_rgb, parts, g_emb);
   reduce_kernel<<<(PART_FLOATS + 255) / 256, 256, 0, st>>>(1, parts, g_params, pts ? g_B : nullptr);
@@ -877,8 +890,10 @@ extern "C" int cnf_occmap_tc_bwd(int P, const float* params, const float* rgb, c
 }
 
 extern "C" int cnf_occmap_tc_bwd_points(int P, const float* params, const float* points, const float* rgb, const float* g_alpha,
-                                        const float* g_rgb, void* ws, size_t ws_bytes, float* g_params, float* g_B, cnf_stream_t stream) {
-  return otc_backward(true, "cnf_occmap_tc_bwd_points", P, params, points, rgb, g_alpha, g_rgb, ws, ws_bytes, g_params, nullptr, g_B, stream);
+                                        const float* g_rgb, void* ws, size_t ws_bytes, float* g_params, float* g_B, int flags,
+                                        cnf_stream_t stream) {
+  return otc_backward(true, "cnf_occmap_tc_bwd_points", P, params, points, rgb, g_alpha, g_rgb, ws, ws_bytes, g_params, nullptr, g_B, stream,
+                      (flags & 1) != 0);
 }
 
 extern "C" int cnf_occmap_tc_set_debug(void* stamps /* device buffer of 64 int64, or NULL */) {

@@ -238,12 +238,12 @@ def occmap_tc_points_fwd_bwd(points, params, pe_B, pe_scale, g_alpha_fn):
     alpha = torch.empty(P, device=dev, dtype=torch.float32)
     rgb = torch.empty(P, 3, device=dev, dtype=torch.float32)
     check(lib.cnf_occmap_tc_fwd_points(P, ptr(params), ptr(pe_B), ptr(pe_scale), ptr(points), ptr(alpha), ptr(rgb), ptr(ws), ws.numel(),
-                                       stream()))
+                                       0, stream()))
     g_alpha, g_rgb = g_alpha_fn(alpha, rgb)
     g_params = torch.empty_like(params)
     g_B = torch.empty_like(pe_B)
     check(lib.cnf_occmap_tc_bwd_points(P, ptr(params), ptr(points), ptr(rgb), ptr(_f32c(g_alpha)), ptr(_f32c(g_rgb)), ptr(ws), ws.numel(),
-                                       ptr(g_params), ptr(g_B), stream()))
+                                       ptr(g_params), ptr(g_B), 0, stream()))
     return alpha, rgb, g_params, g_B
 
 

@@ -135,9 +135,14 @@ int cnf_occmap_tc_fwd(int n_pts, const float* params, const float* emb, float* a
  *     pe_scale [1] instead of emb; no [P,129] embedding or embedding gradient exists.  bwd_points: g_B [21,3] OVERWRITTEN
  *     (the B_layer gradient); same workspace contract (fwd_points first, same ws and params). */
 int cnf_occmap_tc_fwd_points(int n_pts, const float* params, const float* pe_B, const float* pe_scale, const float* points,
-                             float* alpha, float* rgb, void* ws, size_t ws_bytes, cnf_stream_t stream);
+                             float* alpha, float* rgb, void* ws, size_t ws_bytes, int flags, cnf_stream_t stream);
 int cnf_occmap_tc_bwd_points(int n_pts, const float* params, const float* points, const float* rgb, const float* g_alpha,
-                             const float* g_rgb, void* ws, size_t ws_bytes, float* g_params, float* g_B, cnf_stream_t stream);
+                             const float* g_rgb, void* ws, size_t ws_bytes, float* g_params, float* g_B, int flags,
+                             cnf_stream_t stream);
+/*     flags bit0: the workspace was prepared for this step by cnf_occmap_tc_prepare (operand images + constants from params / pe_B /
+ *     pe_scale, zeroed gradient buffer): the parameter-only half of a step, which may run on another stream next to the sampler. */
+int cnf_occmap_tc_prepare(int n_pts, const float* params, const float* pe_B, const float* pe_scale, void* ws, size_t ws_bytes,
+                          cnf_stream_t stream);
 /* development aid: SM-clock stamps of CTA 0's epilogue thread 0 (64 int64 device buffer; NULL switches it off) */
 int cnf_occmap_tc_set_debug(void* stamps);
 int cnf_occmap_tc_bwd(int n_pts, const float* params, const float* rgb, const float* g_alpha, const float* g_rgb,

@@ -19,8 +19,8 @@ def fwd(): check(lib.cnf_occmap_tc_fwd(P, flat.data_ptr(), emb.data_ptr(), alpha
 def bwd(): check(lib.cnf_occmap_tc_bwd(P, flat.data_ptr(), rgb.data_ptr(), ga.data_ptr(), gc.data_ptr(), ws.data_ptr(), ws.numel(), gp.data_ptr(), ge.data_ptr(), st))
 if len(sys.argv) > 2 and sys.argv[2] == "pts":      # embedding computed in-kernel
     pts = torch.rand(P, 3, device=dev) * 4 - 2; Bm = torch.randn(21, 3, device=dev); sc = torch.tensor([5.0], device=dev); gB = torch.empty(21, 3, device=dev)
-    def fwd(): check(lib.cnf_occmap_tc_fwd_points(P, flat.data_ptr(), Bm.data_ptr(), sc.data_ptr(), pts.data_ptr(), alpha.data_ptr(), rgb.data_ptr(), ws.data_ptr(), ws.numel(), st))
-    def bwd(): check(lib.cnf_occmap_tc_bwd_points(P, flat.data_ptr(), pts.data_ptr(), rgb.data_ptr(), ga.data_ptr(), gc.data_ptr(), ws.data_ptr(), ws.numel(), gp.data_ptr(), gB.data_ptr(), st))
+    def fwd(): check(lib.cnf_occmap_tc_fwd_points(P, flat.data_ptr(), Bm.data_ptr(), sc.data_ptr(), pts.data_ptr(), alpha.data_ptr(), rgb.data_ptr(), ws.data_ptr(), ws.numel(), 0, st))
+    def bwd(): check(lib.cnf_occmap_tc_bwd_points(P, flat.data_ptr(), pts.data_ptr(), rgb.data_ptr(), ga.data_ptr(), gc.data_ptr(), ws.data_ptr(), ws.numel(), gp.data_ptr(), gB.data_ptr(), 0, st))
 for _ in range(3): fwd(); bwd()
 check(lib.cnf_occmap_tc_set_debug(dbg.data_ptr()))
 FW = ["tile start", "input staged", "L0 mma done", "fc1 written", "L1 mma done", "fc2 written", "L2 mma done", "fc3 written",

@@ -18,8 +18,8 @@ for P in (16800, 148 * 128 * 4):
     def fwd(): check(lib.cnf_occmap_tc_fwd(P, flat.data_ptr(), emb.data_ptr(), alpha.data_ptr(), rgb.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
     def bwd(): check(lib.cnf_occmap_tc_bwd(P, flat.data_ptr(), rgb.data_ptr(), ga.data_ptr(), gc.data_ptr(), ws.data_ptr(), ws.numel(), gp.data_ptr(), ge.data_ptr(), torch.cuda.current_stream().cuda_stream))
     pts = torch.rand(P, 3, device=dev) * 4 - 2; Bm = torch.randn(21, 3, device=dev); sc = torch.tensor([5.0], device=dev); gB = torch.empty(21, 3, device=dev)
-    def fwdp(): check(lib.cnf_occmap_tc_fwd_points(P, flat.data_ptr(), Bm.data_ptr(), sc.data_ptr(), pts.data_ptr(), alpha.data_ptr(), rgb.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
-    def bwdp(): check(lib.cnf_occmap_tc_bwd_points(P, flat.data_ptr(), pts.data_ptr(), rgb.data_ptr(), ga.data_ptr(), gc.data_ptr(), ws.data_ptr(), ws.numel(), gp.data_ptr(), gB.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    def fwdp(): check(lib.cnf_occmap_tc_fwd_points(P, flat.data_ptr(), Bm.data_ptr(), sc.data_ptr(), pts.data_ptr(), alpha.data_ptr(), rgb.data_ptr(), ws.data_ptr(), ws.numel(), 0, torch.cuda.current_stream().cuda_stream))
+    def bwdp(): check(lib.cnf_occmap_tc_bwd_points(P, flat.data_ptr(), pts.data_ptr(), rgb.data_ptr(), ga.data_ptr(), gc.data_ptr(), ws.data_ptr(), ws.numel(), gp.data_ptr(), gB.data_ptr(), 0, torch.cuda.current_stream().cuda_stream))
     res = []
     for name, fn in (("fwd", fwd), ("bwd", bwd), ("fwd+bwd", lambda: (fwd(), bwd())), ("fwd_points", fwdp), ("bwd_points", bwdp), ("points fwd+bwd", lambda: (fwdp(), bwdp()))):
         with torch.cuda.stream(s):
