@@ -436,6 +436,16 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
   return check_launch("cnf_train_step");
 }
 
+static int eval_set_attrs() {
+  static bool done = false;
+  if (!done) {
+    CNF_CUDA(cudaFuncSetAttribute(eval_points_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EV_SMEM));
+    CNF_CUDA(cudaFuncSetAttribute(eval_points_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EV_SMEM));
+    done = true;
+  }
+  return CNF_OK;
+}
+
 // ---- forward-only evaluation at arbitrary points with one instance's codes (trainer.py:125-151)
 static size_t eval_ws_prep() { return 0; }
 static size_t eval_ws_ctab() { return align_up(PREP_BYTES, 256); }
@@ -450,6 +460,7 @@ extern "C" int cnf_eval_points(int P, int L, const float* params, const float* p
   CNF_REQUIRE(params && pe_B && pe_scale && shape_code && tex_code && ws && (P == 0 || (points && occ && rgb)), "cnf_eval_points: null pointer");
   if (ws_bytes < cnf_eval_points_workspace_bytes()) { set_error("cnf_eval_points: workspace too small"); return CNF_ERR_WORKSPACE; }
   if (P == 0) return CNF_OK;
+  if (int e = eval_set_attrs()) return e;
   cudaStream_t st = as_stream(stream);
   uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
   int32_t* n_obj = reinterpret_cast<int32_t*>(w8 + eval_ws_nobj());
@@ -484,6 +495,7 @@ extern "C" int cnf_render_rays(int R, int S, int L, const float* params, const f
               "cnf_render_rays: null pointer");
   if (ws_bytes < cnf_render_rays_workspace_bytes(R, S)) { set_error("cnf_render_rays: workspace too small"); return CNF_ERR_WORKSPACE; }
   if (R == 0) return CNF_OK;
+  if (int e = eval_set_attrs()) return e;
   cudaStream_t st = as_stream(stream);
   uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
   int32_t* n_obj = reinterpret_cast<int32_t*>(w8 + eval_ws_nobj());

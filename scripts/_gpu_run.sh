@@ -1,9 +1,9 @@
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/t.log
-timeout 600 python bench.py > gpurun_out/bench.json 2>gpurun_out/bench.err; tail -3 gpurun_out/bench.err >> gpurun_out/t.log
-python -c "
-import json; d=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
-print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], 'frac', d['roofline']['frac'], 'launches', d['gpu_launches'])
-for k in ('large_batch_c4','eval_points_256cube','render_512x512_S14','render_512x512_S96','background_step_1200x14','iteration_objects_plus_background'): print(k, d.get(k))
-" >> gpurun_out/t.log 2>&1
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" >> gpurun_out/t.log 2>&1
+V=category_nerf_reconstruction_official_b200/csrc/variants
+timeout 900 python -m pytest tests/test_gpu_fused.py -m gpu -x -q -k "render_rays or eval_points" 2>&1 | tail -3 > gpurun_out/t.log
+for r in 1 2; do
+CNF_LIB_PATH=$V/libcnf_ev3.so timeout 300 python scripts/time_render.py 2>&1 | sed 's/^/3 chains: /' >> gpurun_out/t.log
+timeout 300 python scripts/time_render.py 2>&1 | sed 's/^/4 chains: /' >> gpurun_out/t.log
+CNF_LIB_PATH=$V/libcnf_ev3.so timeout 300 python scripts/time_eval_points.py 2>&1 | tail -2 | sed 's/^/3 chains: /' >> gpurun_out/t.log
+timeout 300 python scripts/time_eval_points.py 2>&1 | tail -2 | sed 's/^/4 chains: /' >> gpurun_out/t.log
+done
 cat gpurun_out/t.log
