@@ -140,8 +140,8 @@ static_assert(F_A0 + EMB_TILE_BYTES <= F_W, "embedding staging overlaps the weig
 // bf16 operand images (no [P,129] tensor exists).
 template <bool PTS>
 __global__ void __launch_bounds__(NT, 1)
-fwd_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ emb, uint8_t* __restrict__ imgs,
-           float* __restrict__ alpha_out, float* __restrict__ rgb_out) {
+fwd_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ emb, uint8_t* __restrict__ imgs /* NULL: inference */,
+           float* __restrict__ alpha_out, float* __restrict__ rgb_out, int occ_act /* alpha_out = sigmoid(alpha) */) {
   extern __shared__ __align__(128) uint8_t sm[];   // no-swizzle operand images need 16-byte alignment only
   __shared__ uint64_t full[3];
   __shared__ uint64_t bar_mma, full_emb;
@@ -201,7 +201,7 @@ fwd_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ em
         const int sp_dst = (l == 0) ? IMG_XG : IMG_FC1 + (l - 1) * ACT_BYTES;
         nbar_sync(1 + (stage & 1), NT); ++stage;                                  // the layer's input image is complete
         for (int q = 0; q < nb; ++q) mbar_wait(&full[(consumed + q) % 3], ((consumed + q) / 3) & 1);
-        if (lane == 0) {
+        if (lane == 0 && imgs != nullptr) {
           bulk_s2g(img + sp_dst, sm + sp_src, sp_bytes);                         // spill for the backward
           bulk_commit();
           bulk_wait_read<1>();                                                   // the image spilled one layer ago is free again
@@ -219,7 +219,7 @@ fwd_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ em
         load_more();
       }
       nbar_sync(1 + (stage & 1), NT); ++stage;                                    // h is complete
-      if (lane == 0) { bulk_s2g(img + IMG_H, sm + F_A0, ACT_BYTES); bulk_commit(); }
+      if (lane == 0 && imgs != nullptr) { bulk_s2g(img + IMG_H, sm + F_A0, ACT_BYTES); bulk_commit(); }
       __syncwarp();
     }
     if (lane == 0) bulk_wait<0>();
@@ -338,7 +338,8 @@ fwd_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ em
       float hc[3] = {0.f, 0.f, 0.f};
       layer(sm + F_A0, nullptr, cs + C_WOC, 3, hc); publish();                    // h + colour head
       if (p < P) {
-        alpha_out[p] = 10.0f * (ha[0] + cs[C_BA]);                                // model.py:142-146
+        const float al = 10.0f * (ha[0] + cs[C_BA]);                              // model.py:142-146
+        alpha_out[p] = occ_act ? 1.0f / (1.0f + __expf(-al)) : al;                // render_rays.py:3-7 (occupancy_activation)
 #pragma unroll
         for (int q = 0; q < 3; ++q) rgb_out[(size_t)p * 3 + q] = 1.0f / (1.0f + __expf(-(hc[q] + cs[C_BOC + q])));
       }
@@ -830,9 +831,33 @@ static int otc_forward(bool pts, const char* who, int P, const float* params, co
   CNF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   if (!prepared) prep_kernel<<<(WIMG_BYTES / 16 + 255) / 256, 256, 0, st>>>(params, pts ? pe_B : nullptr, pts ? pe_scale : nullptr, w8 + ws_prep());
   const int n_tiles = (P + TPT - 1) / TPT, grid = n_tiles < n_sm ? n_tiles : n_sm;
-  if (pts) fwd_kernel<true><<<grid, NT, F_SMEM, st>>>(P, w8 + ws_prep(), in, w8 + ws_imgs(), alpha, rgb);
-  else fwd_kernel<false><<<grid, NT, F_SMEM, st>>>(P, w8 + ws_prep(), in, w8 + ws_imgs(), alpha, rgb);
+  if (pts) fwd_kernel<true><<<grid, NT, F_SMEM, st>>>(P, w8 + ws_prep(), in, w8 + ws_imgs(), alpha, rgb, 0);
+  else fwd_kernel<false><<<grid, NT, F_SMEM, st>>>(P, w8 + ws_prep(), in, w8 + ws_imgs(), alpha, rgb, 0);
   return check_launch(who);
+}
+
+// forward-only evaluation at arbitrary points (Trainer.eval_points of the background model, trainer.py:125-151): no activation
+// images are kept; occ = sigmoid(alpha)
+extern "C" size_t cnf_occmap_tc_eval_workspace_bytes(void) { return align_up(PREP_BYTES, 1024); }
+extern "C" int cnf_occmap_tc_eval_points(int P, const float* params, const float* pe_B, const float* pe_scale, const float* points,
+                                         float* occ, float* rgb, void* ws, size_t ws_bytes, cnf_stream_t stream) {
+  CNF_REQUIRE(P >= 0 && params && pe_B && pe_scale && ws && (P == 0 || (points && occ && rgb)), "cnf_occmap_tc_eval_points: bad arguments");
+  if (ws_bytes < cnf_occmap_tc_eval_workspace_bytes()) { set_error("cnf_occmap_tc_eval_points: workspace too small"); return CNF_ERR_WORKSPACE; }
+  if (P == 0) return CNF_OK;
+  cudaStream_t st = as_stream(stream);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CNF_CUDA(cudaFuncSetAttribute(fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+    attr_set = true;
+  }
+  int dev = 0, n_sm = 148;
+  CNF_CUDA(cudaGetDevice(&dev));
+  CNF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  prep_kernel<<<(WIMG_BYTES / 16 + 255) / 256, 256, 0, st>>>(params, pe_B, pe_scale, w8);
+  const int n_tiles = (P + TPT - 1) / TPT, grid = n_tiles < n_sm ? n_tiles : n_sm;
+  fwd_kernel<true><<<grid, NT, F_SMEM, st>>>(P, w8, points, nullptr, occ, rgb, 1);
+  return check_launch("cnf_occmap_tc_eval_points");
 }
 
 extern "C" int cnf_occmap_tc_fwd(int P, const float* params, const float* emb, float* alpha, float* rgb, void* ws, size_t ws_bytes,

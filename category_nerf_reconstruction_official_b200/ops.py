@@ -226,6 +226,20 @@ class OccMapTCFn(torch.autograd.Function):
         return g_emb, g_params
 
 
+def occmap_eval_points_fused(points, flat_params, pe_B, pe_scale):
+    """Forward-only tensor-core evaluation of the hidden-128 OccupancyMap (cnf_occmap_tc_eval_points): points [P,3] ->
+    (occupancy [P] = sigmoid(alpha), rgb [P,3])."""
+    lib = lib_for(points)
+    P = points.shape[0]
+    dev = points.device
+    occ = torch.empty(P, device=dev, dtype=torch.float32)
+    rgb = torch.empty(P, 3, device=dev, dtype=torch.float32)
+    ws = torch.empty(lib.cnf_occmap_tc_eval_workspace_bytes(), device=dev, dtype=torch.uint8)
+    check(lib.cnf_occmap_tc_eval_points(P, ptr(_f32c(flat_params.detach())), ptr(_f32c(pe_B.detach())), ptr(_f32c(pe_scale.detach().reshape(1))),
+                                        ptr(_f32c(points)), ptr(occ), ptr(rgb), ptr(ws), ws.numel(), stream()))
+    return occ, rgb
+
+
 def occmap_tc_points_fwd_bwd(points, params, pe_B, pe_scale, g_alpha_fn):
     """Tensor-core OccupancyMap with the embedding computed in-kernel (cnf_occmap_tc_fwd_points / _bwd_points), forward then
     backward: points [P,3], flat params (hidden 128), pe_B [21,3], pe_scale (0-d / [1]); ``g_alpha_fn(alpha, rgb) -> (g_alpha [P],

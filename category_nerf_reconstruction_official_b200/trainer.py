@@ -70,6 +70,15 @@ class Trainer:
                 print("no occ")
                 return None
             return (occ, color)
+        if self.cls_id == 0 and points.is_cuda and getattr(self.fc_occ_map, "hidden_size", 0) == 128 and self.use_tensor_cores:
+            # background model on tensor cores (embedding computed in-kernel): one launch for all points
+            from . import model as _model, ops
+            with torch.no_grad():
+                occ, color = ops.occmap_eval_points_fused(points, _model.flat_params(self.fc_occ_map), self.pe.B_layer.weight, self.pe.scale)
+            if occ.max() == 0:
+                print("no occ")
+                return None
+            return (occ, color)
         with torch.no_grad():
             for s in range(0, P, chunk_size):
                 emb = self.pe(points[s:s + chunk_size, ...])

@@ -143,6 +143,11 @@ int cnf_occmap_tc_bwd_points(int n_pts, const float* params, const float* points
  *     pe_scale, zeroed gradient buffer): the parameter-only half of a step, which may run on another stream next to the sampler. */
 int cnf_occmap_tc_prepare(int n_pts, const float* params, const float* pe_B, const float* pe_scale, void* ws, size_t ws_bytes,
                           cnf_stream_t stream);
+/*     Forward-only evaluation at arbitrary points (Trainer.eval_points of the background model, src/trainer.py:125-151):
+ *     occ [P] = sigmoid(alpha) (occupancy_activation), rgb [P,3]; no activation images are kept. */
+size_t cnf_occmap_tc_eval_workspace_bytes(void);
+int cnf_occmap_tc_eval_points(int n_pts, const float* params, const float* pe_B, const float* pe_scale, const float* points,
+                              float* occ, float* rgb, void* ws, size_t ws_bytes, cnf_stream_t stream);
 /* development aid: SM-clock stamps of CTA 0's epilogue thread 0 (64 int64 device buffer; NULL switches it off) */
 int cnf_occmap_tc_set_debug(void* stamps);
 int cnf_occmap_tc_bwd(int n_pts, const float* params, const float* rgb, const float* g_alpha, const float* g_rgb,

@@ -125,6 +125,26 @@ def test_occmap_tc_points_variant(P):
         assert r_p < 2e-2 and r_B < 5e-2 and r_Bo < 0.2
 
 
+def test_occmap_tc_eval_points_vs_oracle():
+    """cnf_occmap_tc_eval_points (Trainer.eval_points of the background model) against the fp32 oracle: occupancy = sigmoid(alpha)
+    and colour, 2e-2 absolute, ragged point count over several tiles per CTA."""
+    from category_nerf_reconstruction_official_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    P = 148 * 128 * 2 + 55
+    params = O.init_params(O.occmap_param_shapes(128), g)
+    B = O.icosa_matrix() + 0.01 * torch.randn(21, 3, generator=g)
+    pts = (torch.rand(P, 3, generator=g) - 0.5) * 8.0
+    flat = torch.cat([p.reshape(-1) for p in params]).to(DEV)
+    occ, rgb = ops.occmap_eval_points_fused(pts.to(DEV), flat, B.to(DEV), torch.tensor(5.0, device=DEV))
+    torch.cuda.synchronize()
+    a_o, c_o = O.occmap_forward(params, O.embed(pts[:, None, :], B, 5.0).reshape(P, 129))
+    occ_o = torch.sigmoid(a_o.reshape(-1))
+    e_o, e_c = float((occ.cpu() - occ_o).abs().max()), float((rgb.cpu() - c_o.reshape(-1, 3)).abs().max())
+    print("occmap eval_points: occupancy max abs err %.2e (range %.3f..%.3f) colour %.2e" % (e_o, float(occ_o.min()), float(occ_o.max()), e_c))
+    assert float(occ_o.max() - occ_o.min()) > 0.5
+    assert e_o < 2e-2 and e_c < 2e-2
+
+
 def test_occmap_module_tensor_core_background_step():
     """OccupancyMap module with use_tensor_cores: the reference's background step (train.py:172-180: embed -> OccupancyMap ->
     step_batch_loss -> backward) against the fp32 oracle step on a well-conditioned loss (all depths invalid -> depth term off)."""
