@@ -351,6 +351,170 @@ fwd_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ em
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// forward-only evaluation (Trainer.eval_points of the background model): TWO CTAs per SM
+// ---------------------------------------------------------------------------------------------------------
+// Nothing is kept for a backward, so a CTA needs ONE activation image (a layer's epilogue overwrites the image its own GEMM has
+// finished reading), the xg / xc operands live in tensor memory (A from TMEM), and the weight ring shrinks to two slots:
+// 100 KB of shared memory and 256 TMEM columns per CTA.  Two CTAs share an SM: while one waits for a GEMM round trip or a weight
+// block the other runs its epilogue -- the overlap the training kernels cannot have at one tile per SM.
+constexpr int E_ACT = 0, E_W = 32768, E_C = E_W + 2 * 32768, E_SMEM = E_C + C_FLOATS * 4;
+constexpr int ET_D = 0, ET_XG = 128, ET_XC = 176;     // TMEM columns: accumulator 128 | xg 96 bf16 | xc 48 bf16
+
+__device__ __forceinline__ void issue_fwd_ts(uint32_t d, uint32_t aTmem, int aCols, uint32_t wAddr, bool acc) {
+  const uint32_t id = idesc_bf16(128, 128, 0, 0);
+  for (int ks = 0; ks < aCols / 16; ++ks)
+    mma_ts(d, aTmem + ks * 8, smem_desc(wAddr + ks * 256, 128, 16 * aCols), id, (acc || ks > 0) ? 1u : 0u);
+}
+
+__global__ void __launch_bounds__(NT, 2)
+eval_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ points, float* __restrict__ occ_out,
+            float* __restrict__ rgb_out) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  __shared__ uint64_t full[2];
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < C_FLOATS; i += NT) reinterpret_cast<float*>(sm + E_C)[i] = reinterpret_cast<const float*>(prep + WIMG_BYTES)[i];
+  if (tid == 0) {
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int n_tiles = (P + TPT - 1) / TPT;
+  const int nt = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const uint32_t sbase = smem_u32(sm);
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ control warp: two-slot weight ring, MMA issue
+    int loaded = 0, consumed = 0, stage = 0;
+    uint32_t mph = 0;
+    const int total_blocks = nt * NBLK;
+    auto load_more = [&]() {
+      while (loaded < consumed + 2 && loaded < total_blocks) {
+        const int b = loaded % NBLK, slot = loaded & 1;
+        if (lane == 0) {
+          const uint32_t bytes = blk_cols(b) * 256;
+          mbar_expect_tx(&full[slot], bytes);
+          bulk_g2s(sm + E_W + slot * ACT_BYTES, prep + blk_byte(b), bytes, &full[slot]);
+        }
+        ++loaded;
+      }
+      __syncwarp();
+    };
+    load_more();
+    for (int it = 0; it < nt; ++it) {
+      for (int l = 0; l < 5; ++l) {
+        const int nb = (l == 2 || l == 4) ? 2 : 1;
+        nbar_sync(1 + (stage & 1), NT); ++stage;                                  // the layer's input operand is complete
+        for (int q = 0; q < nb; ++q) mbar_wait(&full[(consumed + q) & 1], ((consumed + q) >> 1) & 1);
+        if (elect_one()) {
+          tc_fence_after();
+          const uint32_t w0 = sbase + E_W + (consumed & 1) * ACT_BYTES, w1 = sbase + E_W + ((consumed + 1) & 1) * ACT_BYTES;
+          if (l == 0) {
+            issue_fwd_ts(tmem + ET_D, tmem + ET_XG, XG_C, w0, false);
+          } else {
+            issue_fwd(tmem + ET_D, sbase + E_ACT, H, w0, false);
+            if (l == 2) issue_fwd_ts(tmem + ET_D, tmem + ET_XG, XG_C, w1, true);
+            if (l == 4) issue_fwd_ts(tmem + ET_D, tmem + ET_XC, XC_C, w1, true);
+          }
+          mma_commit(&bar_mma);
+        }
+        __syncwarp();
+        mbar_wait(&bar_mma, mph); mph ^= 1;
+        consumed += nb;
+        load_more();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps: thread = tile row
+    const int row = tid;
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    const float* cs = reinterpret_cast<const float*>(sm + E_C);
+    uint32_t mph = 0;
+    int stage = 0;
+    auto publish = [&]() { fence_async_smem(); tmem_st_wait(); tc_fence_before(); nbar_arrive(1 + (stage & 1), NT); ++stage; };
+    auto layer = [&](uint8_t* dst, const float* bias, const float* hw, int nh, float* hacc) {
+      mbar_wait(&bar_mma, mph); mph ^= 1;
+      tc_fence_after();
+      uint32_t uu[4][32];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) tmem_ld32(tl + ET_D + ch * 32, uu[ch]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const uint32_t* u = uu[ch];
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a = __uint_as_float(u[2 * j]), b = __uint_as_float(u[2 * j + 1]);
+          if (bias != nullptr) { a += bias[ch * 32 + 2 * j]; b += bias[ch * 32 + 2 * j + 1]; }
+          a = fmaxf(a, 0.f); b = fmaxf(b, 0.f);
+          for (int q = 0; q < nh; ++q) hacc[q] = fmaf(hw[q * H + ch * 32 + 2 * j + 1], b, fmaf(hw[q * H + ch * 32 + 2 * j], a, hacc[q]));
+          w[j] = pack2(a, b);
+        }
+        if (dst != nullptr) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(rowblk(dst, row, ch * 4 + q, H)) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        }
+      }
+    };
+    for (int it = 0; it < nt; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int p = tile * TPT + row;
+      float t[3] = {0.f, 0.f, 0.f};
+      if (p < P) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) t[q] = points[(size_t)p * 3 + q] * cs[C_ISCALE];
+      }
+      float v[EMB + 7];
+      v[0] = t[0]; v[1] = t[1]; v[2] = t[2];
+#pragma unroll
+      for (int d = 0; d < 21; ++d) {
+        float sn, cn;
+        pe_sincos(cs + C_PEB + d * 3, t, sn, cn);
+        v[3 + d] = sn;
+#pragma unroll
+        for (int f = 1; f < 6; ++f) { pe_double(sn, cn); v[3 + f * 21 + d] = sn; }
+      }
+      v[EMB] = 1.0f;
+#pragma unroll
+      for (int j = 1; j < 7; ++j) v[EMB + j] = 0.f;
+#pragma unroll
+      for (int cb = 0; cb < 11; ++cb)
+        tmem_st4(tl + ET_XG + 4 * cb, pack2(v[8 * cb], v[8 * cb + 1]), pack2(v[8 * cb + 2], v[8 * cb + 3]), pack2(v[8 * cb + 4], v[8 * cb + 5]),
+                 pack2(v[8 * cb + 6], cb == 10 ? 1.0f : v[8 * cb + 7]));
+      tmem_st4(tl + ET_XG + 44, 0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int cb = 0; cb < 6; ++cb)
+        tmem_st4(tl + ET_XC + 4 * cb, pack2(v[E1 + 8 * cb], v[E1 + 8 * cb + 1]), pack2(v[E1 + 8 * cb + 2], v[E1 + 8 * cb + 3]),
+                 pack2(v[E1 + 8 * cb + 4], v[E1 + 8 * cb + 5]), pack2(v[E1 + 8 * cb + 6], v[E1 + 8 * cb + 7]));
+      publish();
+      layer(sm + E_ACT, nullptr, nullptr, 0, nullptr); publish();                 // fc1
+      layer(sm + E_ACT, cs + C_BMID1, nullptr, 0, nullptr); publish();            // fc2
+      layer(sm + E_ACT, nullptr, nullptr, 0, nullptr); publish();                 // fc3
+      float ha[1] = {0.f};
+      layer(sm + E_ACT, cs + C_BMID2, cs + C_WA, 1, ha); publish();               // fc4 + alpha head
+      float hc[3] = {0.f, 0.f, 0.f};
+      layer(nullptr, nullptr, cs + C_WOC, 3, hc);                                 // h (not stored) + colour head
+      tc_fence_before();
+      if (p < P) {
+        occ_out[p] = 1.0f / (1.0f + __expf(-10.0f * (ha[0] + cs[C_BA])));         // model.py:142-146, render_rays.py:3-7
+#pragma unroll
+        for (int q = 0; q < 3; ++q) rgb_out[(size_t)p * 3 + q] = 1.0f / (1.0f + __expf(-(hc[q] + cs[C_BOC + q])));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------------
 // data gradient: D[128 x Nout] (+)= G[128 x 128] (K-major image) * W[128 x Nout] (MN-major view of the weight image)
@@ -848,15 +1012,16 @@ extern "C" int cnf_occmap_tc_eval_points(int P, const float* params, const float
   uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
   static bool attr_set = false;
   if (!attr_set) {
-    CNF_CUDA(cudaFuncSetAttribute(fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+    CNF_CUDA(cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
+    CNF_CUDA(cudaFuncSetAttribute(eval_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
   int dev = 0, n_sm = 148;
   CNF_CUDA(cudaGetDevice(&dev));
   CNF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   prep_kernel<<<(WIMG_BYTES / 16 + 255) / 256, 256, 0, st>>>(params, pe_B, pe_scale, w8);
-  const int n_tiles = (P + TPT - 1) / TPT, grid = n_tiles < n_sm ? n_tiles : n_sm;
-  fwd_kernel<true><<<grid, NT, F_SMEM, st>>>(P, w8, points, nullptr, occ, rgb, 1);
+  const int n_tiles = (P + TPT - 1) / TPT, grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;       // two CTAs per SM
+  eval_kernel<<<grid, NT, E_SMEM, st>>>(P, w8, points, occ, rgb);
   return check_launch("cnf_occmap_tc_eval_points");
 }
 

@@ -1,20 +1,7 @@
-timeout 900 python -m pytest tests/test_gpu_occmap_tc.py -m gpu -x -q -s 2>&1 | grep -E "eval_points|passed|failed|^E  " > gpurun_out/t.log
-timeout 300 python - >> gpurun_out/t.log 2>&1 <<'PY'
-import torch, sys
-sys.path.insert(0, '.')
-from category_nerf_reconstruction_official_b200 import ops, model
-dev = torch.device('cuda:0')
-m = model.OccupancyMap(87, 42, hidden_size=128).to(dev); m.apply(model.init_weights)
-flat = model.flat_params(m).detach()
-B = torch.randn(21, 3, device=dev); sc = torch.tensor(5.0, device=dev)
-for P in (1 << 20, 1 << 24):
-    pts = (torch.rand(P, 3, device=dev) - 0.5) * 8
-    for _ in range(2): ops.occmap_eval_points_fused(pts, flat, B, sc)
-    torch.cuda.synchronize(); ts = []
-    for _ in range(5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); ops.occmap_eval_points_fused(pts, flat, B, sc); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
-    ms = sorted(ts)[2]
-    print("OccupancyMap(128) eval_points P=%d: %.3f ms, %.1f M points/s, %.0f TFLOP/s algorithmic (187392 FLOP/pt) = %.1f%% of bf16 peak" % (P, ms, P / ms / 1e3, P * 187392 / ms / 1e9, P * 187392 / ms / 1e9 / 1656.5 * 100))
-PY
+V=category_nerf_reconstruction_official_b200/csrc/variants
+timeout 600 python -m pytest tests/test_gpu_occmap_tc.py -m gpu -x -q -s -k eval_points 2>&1 | grep -E "eval_points|passed|failed|^E  " > gpurun_out/t.log
+for r in 1 2; do
+CNF_LIB_PATH=$V/libcnf_ev1cta.so timeout 300 python scripts/time_bg_eval.py 1cta >> gpurun_out/t.log 2>&1
+timeout 300 python scripts/time_bg_eval.py 2cta >> gpurun_out/t.log 2>&1
+done
 cat gpurun_out/t.log
