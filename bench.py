@@ -377,6 +377,31 @@ def main():
             extra["eval_points_256cube"] = {"error": repr(e)}
 
     if rank == 0 and not args.no_large:
+        # background model inference (Trainer.eval_points for cls 0): OccupancyMap W=128 forward on tensor cores, 256^3 grid
+        try:
+            from category_nerf_reconstruction_official_b200 import ops as _ops, model as _model
+            mb = _model.OccupancyMap(87, 42, hidden_size=128).to(dev); mb.apply(_model.init_weights)
+            flb = _model.flat_params(mb).detach()
+            P = 256 ** 3
+            pts = (torch.rand(P, 3, device=dev) - 0.5) * 8.0
+            for _ in range(2):
+                _ops.occmap_eval_points_fused(pts, flb, tr.pe_B[0], tr.pe_scale[0])
+            torch.cuda.synchronize()
+            tms = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); _ops.occmap_eval_points_fused(pts, flb, tr.pe_B[0], tr.pe_scale[0]); e1.record()
+                torch.cuda.synchronize(); tms.append(e0.elapsed_time(e1))
+            ms6 = sorted(tms)[2]
+            tf6 = P * 187392.0 / (ms6 * 1e-3) / 1e12
+            extra["occmap_eval_points_256cube"] = {"points": P, "ms": ms6, "points_per_s": P / (ms6 * 1e-3), "tensor_tflops": tf6,
+                                                   "tensor_frac_of_burst_peak": tf6 / pk["bf16_burst"],
+                                                   "note": "forward-only OccupancyMap W=128 (187392 FLOP/point), embedding in-kernel, two CTAs per SM"}
+            del pts, mb
+        except Exception as e:
+            extra["occmap_eval_points_256cube"] = {"error": repr(e)}
+
+    if rank == 0 and not args.no_large:
         # dense view rendering (BASELINE config 5): 512x512 rays of one instance, forward only, S = 14 and S = 96
         try:
             from category_nerf_reconstruction_official_b200 import ops as _ops
