@@ -115,6 +115,8 @@ SIGNATURES = {
     "cnf_occmap_tc_prepare": (c_int, [c_int, P, P, P, P, c_size_t, P]),
     "cnf_occmap_tc_eval_workspace_bytes": (c_size_t, []),
     "cnf_occmap_tc_eval_points": (c_int, [c_int, P, P, P, P, P, P, P, c_size_t, P]),
+    "cnf_occmap_tc_render_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "cnf_occmap_tc_render_rays": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     "cnf_occmap_tc_set_debug": (c_int, [P]),
     "cnf_occmap_tc_bwd": (c_int, [c_int, P, P, P, P, P, c_size_t, P, P, P]),
     "cnf_set_debug_buffer": (c_int, [P]),

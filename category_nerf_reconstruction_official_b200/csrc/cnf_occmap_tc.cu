@@ -366,9 +366,13 @@ __device__ __forceinline__ void issue_fwd_ts(uint32_t d, uint32_t aTmem, int aCo
     mma_ts(d, aTmem + ks * 8, smem_desc(wAddr + ks * 256, 128, 16 * aCols), id, (acc || ks > 0) ? 1u : 0u);
 }
 
+// RAYS = false: point p = points[p]; outputs occ_out [P], rgb_out [P,3].
+// RAYS = true: point p = sample p % S of ray p / S: origin + dir * z (points = origins, dirs / zs alongside); the result goes out as
+// one float4 {occupancy, r, g, b} per point (occ_out viewed as float4[P]) for the per-ray compositing kernel.
+template <bool RAYS>
 __global__ void __launch_bounds__(NT, 2)
 eval_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ points, float* __restrict__ occ_out,
-            float* __restrict__ rgb_out) {
+            float* __restrict__ rgb_out, int S, const float* __restrict__ dirs, const float* __restrict__ zs) {
   extern __shared__ __align__(128) uint8_t sm[];
   __shared__ uint64_t full[2];
   __shared__ uint64_t bar_mma;
@@ -468,8 +472,16 @@ eval_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ p
       const int p = tile * TPT + row;
       float t[3] = {0.f, 0.f, 0.f};
       if (p < P) {
+        if (RAYS) {
+          const int ray = p / S;
+          const float zz = zs[p];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) t[q] = points[(size_t)p * 3 + q] * cs[C_ISCALE];
+          for (int q = 0; q < 3; ++q)                                             // scene_cateogries.py:543-544 (mul, then add)
+            t[q] = __fadd_rn(points[(size_t)ray * 3 + q], __fmul_rn(dirs[(size_t)ray * 3 + q], zz)) * cs[C_ISCALE];
+        } else {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) t[q] = points[(size_t)p * 3 + q] * cs[C_ISCALE];
+        }
       }
       float v[EMB + 7];
       v[0] = t[0]; v[1] = t[1]; v[2] = t[2];
@@ -503,9 +515,16 @@ eval_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ p
       layer(nullptr, nullptr, cs + C_WOC, 3, hc);                                 // h (not stored) + colour head
       tc_fence_before();
       if (p < P) {
-        occ_out[p] = 1.0f / (1.0f + __expf(-10.0f * (ha[0] + cs[C_BA])));         // model.py:142-146, render_rays.py:3-7
+        const float occ = 1.0f / (1.0f + __expf(-10.0f * (ha[0] + cs[C_BA])));    // model.py:142-146, render_rays.py:3-7
+        float col[3];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) rgb_out[(size_t)p * 3 + q] = 1.0f / (1.0f + __expf(-(hc[q] + cs[C_BOC + q])));
+        for (int q = 0; q < 3; ++q) col[q] = 1.0f / (1.0f + __expf(-(hc[q] + cs[C_BOC + q])));
+        if (RAYS) {
+          reinterpret_cast<float4*>(occ_out)[p] = make_float4(occ, col[0], col[1], col[2]);
+        } else {
+          occ_out[p] = occ;
+          rgb_out[(size_t)p * 3 + 0] = col[0]; rgb_out[(size_t)p * 3 + 1] = col[1]; rgb_out[(size_t)p * 3 + 2] = col[2];
+        }
       }
     }
   }
@@ -1003,26 +1022,66 @@ static int otc_forward(bool pts, const char* who, int P, const float* params, co
 // forward-only evaluation at arbitrary points (Trainer.eval_points of the background model, trainer.py:125-151): no activation
 // images are kept; occ = sigmoid(alpha)
 extern "C" size_t cnf_occmap_tc_eval_workspace_bytes(void) { return align_up(PREP_BYTES, 1024); }
-extern "C" int cnf_occmap_tc_eval_points(int P, const float* params, const float* pe_B, const float* pe_scale, const float* points,
-                                         float* occ, float* rgb, void* ws, size_t ws_bytes, cnf_stream_t stream) {
-  CNF_REQUIRE(P >= 0 && params && pe_B && pe_scale && ws && (P == 0 || (points && occ && rgb)), "cnf_occmap_tc_eval_points: bad arguments");
-  if (ws_bytes < cnf_occmap_tc_eval_workspace_bytes()) { set_error("cnf_occmap_tc_eval_points: workspace too small"); return CNF_ERR_WORKSPACE; }
+static int otc_eval(const char* who, int P, const float* params, const float* pe_B, const float* pe_scale, const float* points, float* occ,
+                    float* rgb, int S, const float* dirs, const float* zs, void* ws, cnf_stream_t stream, bool do_prep = true) {
   if (P == 0) return CNF_OK;
   cudaStream_t st = as_stream(stream);
   uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
   static bool attr_set = false;
   if (!attr_set) {
-    CNF_CUDA(cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
-    CNF_CUDA(cudaFuncSetAttribute(eval_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CNF_CUDA(cudaFuncSetAttribute(eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
+    CNF_CUDA(cudaFuncSetAttribute(eval_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CNF_CUDA(cudaFuncSetAttribute(eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
+    CNF_CUDA(cudaFuncSetAttribute(eval_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
   int dev = 0, n_sm = 148;
   CNF_CUDA(cudaGetDevice(&dev));
   CNF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  prep_kernel<<<(WIMG_BYTES / 16 + 255) / 256, 256, 0, st>>>(params, pe_B, pe_scale, w8);
+  if (do_prep) prep_kernel<<<(WIMG_BYTES / 16 + 255) / 256, 256, 0, st>>>(params, pe_B, pe_scale, w8);
   const int n_tiles = (P + TPT - 1) / TPT, grid = n_tiles < 2 * n_sm ? n_tiles : 2 * n_sm;       // two CTAs per SM
-  eval_kernel<<<grid, NT, E_SMEM, st>>>(P, w8, points, occ, rgb);
-  return check_launch("cnf_occmap_tc_eval_points");
+  if (dirs == nullptr) {
+    eval_kernel<false><<<grid, NT, E_SMEM, st>>>(P, w8, points, occ, rgb, 1, nullptr, nullptr);
+  } else {
+    eval_kernel<true><<<grid, NT, E_SMEM, st>>>(P, w8, points, occ, nullptr, S, dirs, zs);
+  }
+  return check_launch(who);
+}
+
+extern "C" int cnf_occmap_tc_eval_points(int P, const float* params, const float* pe_B, const float* pe_scale, const float* points,
+                                         float* occ, float* rgb, void* ws, size_t ws_bytes, cnf_stream_t stream) {
+  CNF_REQUIRE(P >= 0 && params && pe_B && pe_scale && ws && (P == 0 || (points && occ && rgb)), "cnf_occmap_tc_eval_points: bad arguments");
+  if (ws_bytes < cnf_occmap_tc_eval_workspace_bytes()) { set_error("cnf_occmap_tc_eval_points: workspace too small"); return CNF_ERR_WORKSPACE; }
+  return otc_eval("cnf_occmap_tc_eval_points", P, params, pe_B, pe_scale, points, occ, rgb, 1, nullptr, nullptr, ws, stream);
+}
+
+// forward-only rendering of rays through the background model (dense views; any S): point kernel in chunks whose {occ, rgb} stay in
+// L2, then per-ray compositing -- the OccupancyMap counterpart of cnf_render_rays
+constexpr int OTC_RENDER_CHUNK_POINTS = 4 << 20;
+static size_t otc_render_chunk_rays(int R, int S) { size_t rc = (size_t)OTC_RENDER_CHUNK_POINTS / S; if (rc < 1) rc = 1; return rc < (size_t)R ? rc : (size_t)R; }
+extern "C" size_t cnf_occmap_tc_render_workspace_bytes(int R, int S) {
+  const size_t base = cnf_occmap_tc_eval_workspace_bytes();
+  if (R < 1 || S < 1) return base;
+  return base + otc_render_chunk_rays(R, S) * (size_t)S * 16;
+}
+extern "C" int cnf_occmap_tc_render_rays(int R, int S, const float* params, const float* pe_B, const float* pe_scale, const float* origins,
+                                         const float* dirs, const float* z, float* out_rays, float* out_w, void* ws, size_t ws_bytes,
+                                         cnf_stream_t stream) {
+  CNF_REQUIRE(R >= 0 && S >= 1 && params && pe_B && pe_scale && ws && (R == 0 || (origins && dirs && z && out_rays)),
+              "cnf_occmap_tc_render_rays: bad arguments");
+  if (ws_bytes < cnf_occmap_tc_render_workspace_bytes(R, S)) { set_error("cnf_occmap_tc_render_rays: workspace too small"); return CNF_ERR_WORKSPACE; }
+  if (R == 0) return CNF_OK;
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  float* pts = reinterpret_cast<float*>(w8 + cnf_occmap_tc_eval_workspace_bytes());
+  const size_t rc = otc_render_chunk_rays(R, S);
+  for (size_t r0 = 0; r0 < (size_t)R; r0 += rc) {
+    const int nr = (int)((size_t)R - r0 < rc ? (size_t)R - r0 : rc);
+    if (int e = otc_eval("cnf_occmap_tc_render_rays", nr * S, params, pe_B, pe_scale, origins + r0 * 3, pts, nullptr, S, dirs + r0 * 3,
+                         z + r0 * S, ws, stream, r0 == 0))
+      return e;
+    if (int e = render_composite_launch(nr, S, pts, z + r0 * S, out_rays + r0 * 6, out_w ? out_w + r0 * S : nullptr, as_stream(stream))) return e;
+  }
+  return CNF_OK;
 }
 
 extern "C" int cnf_occmap_tc_fwd(int P, const float* params, const float* emb, float* alpha, float* rgb, void* ws, size_t ws_bytes,

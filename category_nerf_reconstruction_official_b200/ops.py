@@ -240,6 +240,24 @@ def occmap_eval_points_fused(points, flat_params, pe_B, pe_scale):
     return occ, rgb
 
 
+def occmap_render_rays_fused(origins, dirs, z, flat_params, pe_B, pe_scale, want_weights: bool = False):
+    """Forward-only rendering through the hidden-128 OccupancyMap (cnf_occmap_tc_render_rays): origins/dirs [R,3], z [R,S] ->
+    dict(depth [R], var [R], rgb [R,3], opacity [R][, weights [R,S]])."""
+    lib = lib_for(origins)
+    R, S = z.shape
+    dev = origins.device
+    out = torch.empty(R, 6, device=dev, dtype=torch.float32)
+    w = torch.empty(R, S, device=dev, dtype=torch.float32) if want_weights else None
+    ws = torch.empty(lib.cnf_occmap_tc_render_workspace_bytes(R, S), device=dev, dtype=torch.uint8)
+    check(lib.cnf_occmap_tc_render_rays(R, S, ptr(_f32c(flat_params.detach())), ptr(_f32c(pe_B.detach())), ptr(_f32c(pe_scale.detach().reshape(1))),
+                                        ptr(_f32c(origins)), ptr(_f32c(dirs)), ptr(_f32c(z)), ptr(out), ptr(w) if want_weights else None,
+                                        ptr(ws), ws.numel(), stream()))
+    res = {"depth": out[:, 0], "var": out[:, 1], "rgb": out[:, 2:5], "opacity": out[:, 5]}
+    if want_weights:
+        res["weights"] = w
+    return res
+
+
 def occmap_tc_points_fwd_bwd(points, params, pe_B, pe_scale, g_alpha_fn):
     """Tensor-core OccupancyMap with the embedding computed in-kernel (cnf_occmap_tc_fwd_points / _bwd_points), forward then
     backward: points [P,3], flat params (hidden 128), pe_B [21,3], pe_scale (0-d / [1]); ``g_alpha_fn(alpha, rgb) -> (g_alpha [P],

@@ -99,9 +99,13 @@ class Trainer:
         scripts and builds its uncertainty fields inline, category_registration.py:146-152): origins/dirs [R,3], z_vals [R,S] ->
         dict(depth, var, rgb, opacity[, weights = termination probabilities]).  CodeNeRF categories on a CUDA device only
         (tensor-core kernel cnf_render_rays; there is no CPU path)."""
-        if self.cls_id == 0:
-            raise NotImplementedError("render_rays: background OccupancyMap is rendered through the module-level fp32 path")
         from . import model as _model, ops
+        if self.cls_id == 0:
+            if getattr(self.fc_occ_map, "hidden_size", 0) != 128:
+                raise NotImplementedError("render_rays: the tensor-core background path needs hidden_size == 128")
+            with torch.no_grad():
+                return ops.occmap_render_rays_fused(origins, dirs, z_vals, _model.flat_params(self.fc_occ_map), self.pe.B_layer.weight,
+                                                    self.pe.scale, want_weights)
         obj_idx = torch.from_numpy(np.array(self.inst_id_to_index[inst_id])).to(self.device)
         with torch.no_grad():
             return ops.render_rays_fused(origins, dirs, z_vals, _model.flat_params(self.fc_occ_map), self.pe.B_layer.weight,

@@ -148,6 +148,13 @@ int cnf_occmap_tc_prepare(int n_pts, const float* params, const float* pe_B, con
 size_t cnf_occmap_tc_eval_workspace_bytes(void);
 int cnf_occmap_tc_eval_points(int n_pts, const float* params, const float* pe_B, const float* pe_scale, const float* points,
                               float* occ, float* rgb, void* ws, size_t ws_bytes, cnf_stream_t stream);
+/*     Forward-only rendering of rays through the hidden-128 OccupancyMap (dense views of the background; any S): the counterpart
+ *     of cnf_render_rays.  origins/dirs [R,3], z [R,S] -> out_rays [R,6] = {depth, variance, r, g, b, opacity}, out_w [R,S]
+ *     termination probabilities (may be NULL). */
+size_t cnf_occmap_tc_render_workspace_bytes(int n_rays, int S);
+int cnf_occmap_tc_render_rays(int n_rays, int S, const float* params, const float* pe_B, const float* pe_scale,
+                              const float* origins, const float* dirs, const float* z, float* out_rays, float* out_w,
+                              void* ws, size_t ws_bytes, cnf_stream_t stream);
 /* development aid: SM-clock stamps of CTA 0's epilogue thread 0 (64 int64 device buffer; NULL switches it off) */
 int cnf_occmap_tc_set_debug(void* stamps);
 int cnf_occmap_tc_bwd(int n_pts, const float* params, const float* rgb, const float* g_alpha, const float* g_rgb,

@@ -145,6 +145,32 @@ def test_occmap_tc_eval_points_vs_oracle():
     assert e_o < 2e-2 and e_c < 2e-2
 
 
+@pytest.mark.parametrize("R,S", [(700, 14), (130, 96)])
+def test_occmap_tc_render_rays_vs_oracle(R, S):
+    """cnf_occmap_tc_render_rays (dense views of the background model) against the oracle chain embed -> OccupancyMap -> sigmoid ->
+    termination -> render: every output max-abs 5e-2 (bf16 operands, x10 occupancy logit), weights mean-abs 5e-3."""
+    from category_nerf_reconstruction_official_b200 import ops
+    g = torch.Generator().manual_seed(50 + S)
+    params = O.init_params(O.occmap_param_shapes(128), g)
+    B = O.icosa_matrix() + 0.01 * torch.randn(21, 3, generator=g)
+    org = (torch.rand(R, 3, generator=g) - 0.5) * 4.0
+    dirs = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    z = torch.sort(torch.rand(R, S, generator=g) * 5.0, dim=-1).values
+    flat = torch.cat([p.reshape(-1) for p in params]).to(DEV)
+    out = ops.occmap_render_rays_fused(org.to(DEV), dirs.to(DEV), z.to(DEV), flat, B.to(DEV), torch.tensor(5.0, device=DEV), want_weights=True)
+    torch.cuda.synchronize()
+    pcs = org[:, None, :] + dirs[:, None, :] * z[..., None]
+    a_o, c_o = O.occmap_forward(params, O.embed(pcs, B, 5.0))
+    occ = torch.sigmoid(a_o.reshape(R, S)); col = c_o.reshape(R, S, 3)
+    w = O.termination(occ)
+    D = (w * z).sum(-1); Cc = (w[..., None] * col).sum(-2); Op = w.sum(-1)
+    errs = [float((out["weights"].cpu() - w).abs().max()), float((out["depth"].cpu() - D).abs().max()),
+            float((out["rgb"].cpu() - Cc).abs().max()), float((out["opacity"].cpu() - Op).abs().max())]
+    print("occmap render_rays R=%d S=%d: max abs err weights %.2e depth %.2e colour %.2e opacity %.2e" % (R, S, *errs))
+    assert max(errs) < 5e-2 and float((out["weights"].cpu() - w).abs().mean()) < 5e-3
+    torch.testing.assert_close((out["weights"] * z.to(DEV)).sum(-1), out["depth"], rtol=1e-4, atol=1e-5)
+
+
 def test_occmap_module_tensor_core_background_step():
     """OccupancyMap module with use_tensor_cores: the reference's background step (train.py:172-180: embed -> OccupancyMap ->
     step_batch_loss -> backward) against the fp32 oracle step on a well-conditioned loss (all depths invalid -> depth term off)."""
