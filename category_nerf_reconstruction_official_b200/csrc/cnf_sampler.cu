@@ -55,24 +55,39 @@ __global__ void sample_count_kernel(int R, const uint8_t* __restrict__ rgbs, con
   }
 }
 
-// (B) one block (256 threads) per category: exclusive scan of the block counts (in place, cols 0..2), totals -> stats.
-// Each thread owns a contiguous chunk of blocks; chunk sums are scanned with warp shuffles + one smem hop.
-__global__ void __launch_bounds__(256)
+// (B) one block (1024 threads) per category: exclusive scan of the block counts (in place, cols 0..2), totals -> stats.
+// Each thread owns a contiguous chunk of blocks, read as int4 pairs in batches of 8 blocks with every load of a batch in flight
+// at once (the serial load -> add chain of the first version cost 32 us at 4096 blocks); chunk sums are scanned with warp
+// shuffles + one smem hop.
+constexpr int SCAN_T = 1024;
+__global__ void __launch_bounds__(SCAN_T)
 sample_scan_kernel(int nb, int* __restrict__ blk_counts, const float* __restrict__ blk_max,
                    const float* __restrict__ max_override, int32_t* __restrict__ stats) {
   const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  int* bc = blk_counts + (size_t)k * nb * 8;
-  const int per = (nb + 255) / 256;
-  const int b0 = t * per, b1 = min(nb, b0 + per);
+  int4* bc4 = reinterpret_cast<int4*>(blk_counts + (size_t)k * nb * 8);       // block b: {nI, nO, nT, Nd} {No, Ns, -, -}
+  const float* bm = blk_max + (size_t)k * nb;
+  const int per = (nb + SCAN_T - 1) / SCAN_T;
+  const int b0 = min(nb, t * per), b1 = min(nb, b0 + per);
   int sum[6] = {0, 0, 0, 0, 0, 0};
   float mx = -INFINITY;
-  for (int b = b0; b < b1; ++b) {
+  for (int bb = b0; bb < b1; bb += 8) {
+    int4 lo[8], hi[8];
+    float m[8];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) sum[c] += bc[b * 8 + c];
-    mx = fmaxf(mx, blk_max[(size_t)k * nb + b]);
+    for (int j = 0; j < 8; ++j) {
+      const bool in = bb + j < b1;
+      lo[j] = in ? bc4[(bb + j) * 2] : make_int4(0, 0, 0, 0);
+      hi[j] = in ? bc4[(bb + j) * 2 + 1] : make_int4(0, 0, 0, 0);
+      m[j] = in ? bm[bb + j] : -INFINITY;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sum[0] += lo[j].x; sum[1] += lo[j].y; sum[2] += lo[j].z; sum[3] += lo[j].w; sum[4] += hi[j].x; sum[5] += hi[j].y;
+      mx = fmaxf(mx, m[j]);
+    }
   }
-  __shared__ int s_w[8][6];
-  __shared__ float s_m[8];
+  __shared__ int s_w[SCAN_T / 32][6];
+  __shared__ float s_m[SCAN_T / 32];
   int excl[6];
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
@@ -89,18 +104,27 @@ sample_scan_kernel(int nb, int* __restrict__ blk_counts, const float* __restrict
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     int before = 0, all = 0;
-    for (int w = 0; w < 8; ++w) { if (w < warp) before += s_w[w][c]; all += s_w[w][c]; }
+    for (int w = 0; w < SCAN_T / 32; ++w) { const int v = s_w[w][c]; if (w < warp) before += v; all += v; }
     excl[c] += before;
     tot[c] = all;
   }
   int run[3] = {excl[0], excl[1], excl[2]};
-  for (int b = b0; b < b1; ++b) {
+  for (int bb = b0; bb < b1; bb += 8) {
+    int4 lo[8];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { const int v = bc[b * 8 + c]; bc[b * 8 + c] = run[c]; run[c] += v; }
+    for (int j = 0; j < 8; ++j) lo[j] = (bb + j < b1) ? bc4[(bb + j) * 2] : make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (bb + j < b1) {
+        const int4 v = lo[j];
+        bc4[(bb + j) * 2] = make_int4(run[0], run[1], run[2], v.w);
+        run[0] += v.x; run[1] += v.y; run[2] += v.z;
+      }
+    }
   }
   if (t == 0) {
     float m = s_m[0];
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, s_m[w]);
+    for (int w = 1; w < SCAN_T / 32; ++w) m = fmaxf(m, s_m[w]);
     int32_t* st = stats + k * 8;
     st[0] = tot[0];              // nI
     st[1] = tot[1] + tot[2];     // nV
@@ -121,6 +145,7 @@ __device__ __forceinline__ float strat(float mn, float mxv, float lin_k, float u
   return __fadd_rn(lower, __fmul_rn(u, len));
 }
 
+
 // (C) emit: one block of SB rays; `base` = number of earlier rays of the category in case 0 / 1 / 2 (ray order)
 constexpr int EMIT_T = 1024;      // threads of the single-launch small-batch kernel: the first SB rank the rays, all of them write samples
 constexpr int EMIT_BIG_T = 512;   // threads per 256-ray block of the large-batch emit kernel (4 blocks per SM hide each other's phases)
@@ -140,7 +165,8 @@ emit_block(EmitSmem& sh, int k, int b, int R, int N, int M, const uint8_t* __res
            const float* __restrict__ n_obj, const float* __restrict__ u_oth,
            const float* __restrict__ lin_S, const float* __restrict__ lin_N, const float* __restrict__ lin_M,
            float min_bound, float eps, float stop_eps, int this_obj, int base0_in, int base1_in, int base2_in, float max_bound,
-           float* __restrict__ z, float* __restrict__ pcs, uint8_t* __restrict__ valid, uint8_t* __restrict__ labels) {
+           float* __restrict__ z, float* __restrict__ pcs, uint8_t* __restrict__ valid, uint8_t* __restrict__ labels,
+           float* __restrict__ zbuf /* shared, [SB * S]: the block's depths, staged so that z AND pcs leave as linear coalesced streams */) {
   const int S = N + M;
   const int r0 = b * SB;
   int (&s_row)[SB] = sh.row; int (&s_rowv)[SB] = sh.rowv; uint8_t (&s_case)[SB] = sh.cs; float (&s_depth)[SB] = sh.depth;
@@ -194,8 +220,9 @@ emit_block(EmitSmem& sh, int k, int b, int R, int N, int M, const uint8_t* __res
   // ---- phase 2: thread per sample (coalesced z / pcs writes)
   const int nrays = min(SB, R - r0);
   const float fS = (float)S, fN = (float)N, fM = (float)M;
+  const unsigned invS = 0xFFFFFFFFu / (unsigned)S + 1u;      // e / S by multiplication (exact for e < SB * 32)
   for (int e = t; e < nrays * S; e += blockDim.x) {
-    const int rr = e / S, i = e - rr * S;
+    const int rr = (int)__umulhi((unsigned)e, invS), i = e - rr * S;
     const int cc = s_case[rr];
     const float dd = s_depth[rr];
     float zz;
@@ -215,24 +242,24 @@ emit_block(EmitSmem& sh, int k, int b, int R, int N, int M, const uint8_t* __res
         rank += (o < v) || (o == v && q < j);
       }
       const float cl = fminf(fmaxf(v, -eps), eps);
-      zz = __fadd_rn(dd, cl);
-      // scatter to the sorted position inside the same ray
-      const size_t zo = ((size_t)k * R + r0 + rr) * S + N + rank;
-      z[zo] = zz;
-      if (pcs) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) pcs[zo * 3 + a] = __fadd_rn(s_od[rr][a], __fmul_rn(s_od[rr][3 + a], zz));
-      }
+      zbuf[rr * S + N + rank] = __fadd_rn(dd, cl);           // the sorted position inside the same ray
       continue;
     } else {                                     // :536-539 other objects: [d-eps, d+stop_eps]
       const float u = u_oth[((size_t)k * R + s_row[rr]) * M + (i - N)];
       zz = strat(__fsub_rn(dd, eps), __fadd_rn(dd, stop_eps), lin_M[i - N], u, fM);
     }
-    const size_t zo = ((size_t)k * R + r0) * S + e;
-    z[zo] = zz;
-    if (pcs) {
-#pragma unroll
-      for (int a = 0; a < 3; ++a) pcs[zo * 3 + a] = __fadd_rn(s_od[rr][a], __fmul_rn(s_od[rr][3 + a], zz));
+    zbuf[e] = zz;
+  }
+  __syncthreads();
+  // ---- phase 3: the block's z [nrays * S] and pcs [nrays * S * 3] are contiguous in global memory: linear, coalesced stores
+  const size_t g0 = ((size_t)k * R + r0) * S;
+  const int nz = nrays * S;
+  for (int f = t; f < nz; f += blockDim.x) z[g0 + f] = zbuf[f];
+  if (pcs) {
+    for (int f = t; f < nz * 3; f += blockDim.x) {
+      const int smp = (int)(__umulhi((unsigned)f, 0xAAAAAAABu) >> 1), a = f - 3 * smp;
+      const int rr = (int)__umulhi((unsigned)smp, invS);
+      pcs[g0 * 3 + f] = __fadd_rn(s_od[rr][a], __fmul_rn(s_od[rr][3 + a], zbuf[smp]));      // scene_cateogries.py:543-544
     }
   }
 }
@@ -248,10 +275,11 @@ sample_emit_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const 
                    float* __restrict__ z, float* __restrict__ pcs, uint8_t* __restrict__ valid,
                    uint8_t* __restrict__ labels) {
   __shared__ EmitSmem sh;
+  extern __shared__ float zbuf_dyn[];
   const int k = blockIdx.y, nb = gridDim.x, b = blockIdx.x;
   const int* bc = blk_counts + ((size_t)k * nb + b) * 8;
   emit_block(sh, k, b, R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth, lin_S, lin_N, lin_M, min_bound, eps, stop_eps,
-             this_obj, bc[0], bc[1], bc[2], __int_as_float(stats[k * 8 + 7]), z, pcs, valid, labels);
+             this_obj, bc[0], bc[1], bc[2], __int_as_float(stats[k * 8 + 7]), z, pcs, valid, labels, zbuf_dyn);
 }
 
 // Single-launch sampler for small ray batches (R <= SAMPLE_SMALL_RAYS): grid (category, ray block).  Every CTA counts the cases /
@@ -268,6 +296,7 @@ sample_small_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const
                     int32_t* __restrict__ stats, float* __restrict__ z, float* __restrict__ pcs, uint8_t* __restrict__ valid,
                     uint8_t* __restrict__ labels) {
   __shared__ EmitSmem sh;
+  extern __shared__ float zbuf_dyn[];
   __shared__ int s_c[EMIT_T / 32][6];
   __shared__ float s_m[EMIT_T / 32];
   __shared__ int s_tot[6];
@@ -324,7 +353,7 @@ sample_small_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const
   // ---- emit this CTA's block
   const int b = blockIdx.y;
   emit_block(sh, k, b, R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth, lin_S, lin_N, lin_M, min_bound, eps, stop_eps,
-             this_obj, s_blk[b][0], s_blk[b][1], s_blk[b][2], s_max, z, pcs, valid, labels);
+             this_obj, s_blk[b][0], s_blk[b][1], s_blk[b][2], s_max, z, pcs, valid, labels, zbuf_dyn);
 }
 
 __global__ void stratified_bins_kernel(int n_rays, int n_bins, const float* __restrict__ mn, int mn_s,
@@ -405,14 +434,22 @@ extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, c
   int* blk_counts = reinterpret_cast<int*>(ws);
   float* blk_max = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align_up((size_t)K * nb * 8 * sizeof(int), 256));
   cudaStream_t st = as_stream(stream);
+  const size_t zbytes = (size_t)SB * (N + M) * sizeof(float);
+  CNF_REQUIRE(N + M <= 96, "cnf_sample_fwd: more than 96 samples per ray");
+  static bool attr = false;
+  if (!attr) {
+    CNF_CUDA(cudaFuncSetAttribute(sample_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB * 96 * (int)sizeof(float)));
+    CNF_CUDA(cudaFuncSetAttribute(sample_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB * 96 * (int)sizeof(float)));
+    attr = true;
+  }
   if (R <= SAMPLE_SMALL_RAYS) {
-    sample_small_kernel<<<dim3(K, nb), EMIT_T, 0, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth, lin_S, lin_N, lin_M, min_bound,
+    sample_small_kernel<<<dim3(K, nb), EMIT_T, zbytes, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth, lin_S, lin_N, lin_M, min_bound,
                                               eps, stop_eps, this_obj, max_depth_override, stats, z, pcs, valid, labels);
     return check_launch("cnf_sample_fwd");
   }
   sample_count_kernel<<<dim3(nb, K), SB, 0, st>>>(R, rgbs, depth, min_bound, this_obj, blk_counts, blk_max);
-  sample_scan_kernel<<<K, 256, 0, st>>>(nb, blk_counts, blk_max, max_depth_override, stats);
-  sample_emit_kernel<<<dim3(nb, K), EMIT_BIG_T, 0, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth,
+  sample_scan_kernel<<<K, SCAN_T, 0, st>>>(nb, blk_counts, blk_max, max_depth_override, stats);
+  sample_emit_kernel<<<dim3(nb, K), EMIT_BIG_T, zbytes, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth,
                                                  lin_S, lin_N, lin_M, min_bound, eps, stop_eps, this_obj,
                                                  blk_counts, stats, z, pcs, valid, labels);
   return check_launch("cnf_sample_fwd");
