@@ -55,11 +55,11 @@ __global__ void sample_count_kernel(int R, const uint8_t* __restrict__ rgbs, con
   }
 }
 
-// (B) one block (1024 threads) per category: exclusive scan of the block counts (in place, cols 0..2), totals -> stats.
+// (B) one block (256 threads) per category: exclusive scan of the block counts (in place, cols 0..2), totals -> stats.
 // Each thread owns a contiguous chunk of blocks, read as int4 pairs in batches of 8 blocks with every load of a batch in flight
 // at once (the serial load -> add chain of the first version cost 32 us at 4096 blocks); chunk sums are scanned with warp
 // shuffles + one smem hop.
-constexpr int SCAN_T = 1024;
+constexpr int SCAN_T = 256;
 __global__ void __launch_bounds__(SCAN_T)
 sample_scan_kernel(int nb, int* __restrict__ blk_counts, const float* __restrict__ blk_max,
                    const float* __restrict__ max_override, int32_t* __restrict__ stats) {
