@@ -1,6 +1,6 @@
-timeout 900 python -m pytest tests/test_gpu_parity_v0.py -m gpu -x -q 2>&1 | tail -1 > gpurun_out/t.log
-timeout 300 python scripts/bench_standalone.py > gpurun_out/sa.json 2> gpurun_out/sa.err && \
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"sample_" -c 6 --csv --log-file gpurun_out/sampler_launches.csv python scripts/bench_standalone.py > gpurun_out/ncu_sa.log 2>&1
-python -c "import json; d=json.load(open('gpurun_out/sa.json')); print(d['sampler'])" >> gpurun_out/t.log
-grep -E "sample_" gpurun_out/sampler_launches.csv | awk -F'","' '{print substr($5,1,24), $(NF)}' | tail -3 >> gpurun_out/t.log
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/t.log
+timeout 300 python scripts/bench_standalone.py > gpurun_out/sa.json 2>/dev/null; python -c "
+import json; d=json.load(open('gpurun_out/sa.json')); print({k: (round(v['ms'],4), round(v['gbs']), round(v['frac'],3)) for k,v in d.items() if isinstance(v, dict)})" >> gpurun_out/t.log
+timeout 300 python scripts/race_check.py 2>&1 | tail -3 >> gpurun_out/t.log
+timeout 300 python scripts/garbage_check.py 2>&1 | awk '{print $NF, $(NF-3)}' | sort | uniq -c | head -5 >> gpurun_out/t.log
 cat gpurun_out/t.log
