@@ -214,20 +214,29 @@ class FusedCategoryTrainer:
         return {"u_inv": u[:n1].view(K, R, N + M), "u_val": u[n1:n1 + n2].view(K, R, N), "n_obj": self._rand_n,
                 "u_oth": u[n1 + n2:].view(K, R, M)}
 
-    def capture(self, rgbs, depth, origins, dirs, indices, add_reg=True):
+    def capture(self, rgbs, depth, origins, dirs, indices, add_reg=True, pre=None, post=None):
         """Capture sampler + fused step over THESE (static) input tensors into a CUDA graph and return ``replay``.
         The step is ~15 launches of microsecond-scale work at Replica-sized batches, i.e. launch-bound from Python;
-        replaying the captured graph removes the host from the loop.  Update the input tensors in place between replays."""
+        replaying the captured graph removes the host from the loop.  Update the input tensors in place between replays.
+        ``pre`` / ``post``: optional callables captured before / after the step on the same stream, e.g. the upload of the step's
+        inputs from pinned host memory into the static tensors and the download of ``out_loss`` into a pinned host buffer
+        (``dst.copy_(src, non_blocking=True)``), so that a whole host-to-host step is ONE graph launch."""
+        def body():
+            if pre is not None:
+                pre()
+            self.step(rgbs, depth, origins, dirs, indices, add_reg=add_reg)
+            if post is not None:
+                post()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):                      # warm-up: allocations, function attributes, RNG state registration
-                self.step(rgbs, depth, origins, dirs, indices, add_reg=add_reg)
+                body()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self.step(rgbs, depth, origins, dirs, indices, add_reg=add_reg)
+            body()
         self._graph = graph
         return graph.replay
 

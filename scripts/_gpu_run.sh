@@ -1,6 +1,3 @@
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/t.log
-timeout 300 python scripts/bench_standalone.py > gpurun_out/sa.json 2>/dev/null; python -c "
-import json; d=json.load(open('gpurun_out/sa.json')); print({k: (round(v['ms'],4), round(v['gbs']), round(v['frac'],3)) for k,v in d.items() if isinstance(v, dict)})" >> gpurun_out/t.log
-timeout 300 python scripts/race_check.py 2>&1 | tail -3 >> gpurun_out/t.log
-timeout 300 python scripts/garbage_check.py 2>&1 | awk '{print $NF, $(NF-3)}' | sort | uniq -c | head -5 >> gpurun_out/t.log
+for i in 1 2; do timeout 300 python bench.py --no-large --no-cpu-baseline 2>gpurun_out/bench.err | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('ms_per_step', d['ms_per_step'], 'e2e', d['e2e'])"; done > gpurun_out/t.log 2>&1
+tail -3 gpurun_out/bench.err >> gpurun_out/t.log
 cat gpurun_out/t.log
