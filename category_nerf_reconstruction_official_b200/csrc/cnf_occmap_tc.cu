@@ -28,6 +28,7 @@ constexpr int H = 128, TPT = 128;
 constexpr int E1 = 87, E2 = 42, EMB = 129;
 constexpr int XG_C = 96, XC_C = 48, XG_ONE = 87, XC_ONE = 42;
 constexpr int NT = 160;                         // 4 epilogue warps (thread = tile row = TMEM lane) + 1 control warp
+constexpr int NT_B = 288;                       // backward: + 4 read-out warps (weight-gradient accumulators -> RED), control warp last
 
 // weight blocks (bf16 images [128 x cols]): in | mid1 | cat(fc2 part) | cat(xg part) | mid2 | color(fc4 part) | color(xc part)
 constexpr int NBLK = 7;
@@ -562,7 +563,7 @@ constexpr int PR_IN = 0, PR_MID1 = 12288, PR_CAT = 28672, PR_MID2 = 57344, PR_CO
 // PTS = false: writes g_emb [P,129] (may be NULL).  PTS = true: g_emb is the POINTS [P,3] (read), the embedding backward runs here
 // (d proj_d = sum_f d emb[3 + 21 f + d] pi 2^f cos(pi 2^f proj_d); d B_d += d proj_d t) and no [P,129] gradient exists.
 template <bool PTS>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT_B, 1)
 bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, const float* __restrict__ rgb,
            const float* __restrict__ g_alpha, const float* __restrict__ g_rgb, float* __restrict__ part /* [PART_FLOATS], zeroed */,
            float* __restrict__ g_emb) {
@@ -573,10 +574,10 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
   {
     float* c = reinterpret_cast<float*>(sm + B_C);
     const float* src = reinterpret_cast<const float*>(prep + WIMG_BYTES);
-    for (int i = tid; i < 128 + 384; i += NT) c[i] = src[C_WA + i];             // w_alpha | W_oc
+    for (int i = tid; i < 128 + 384; i += NT_B) c[i] = src[C_WA + i];           // w_alpha | W_oc
     if (tid < 64) c[B_CPE + tid] = src[C_PEB + tid];                            // PE matrix | 1/scale
     // constant-one image [128 points x 16]: column 0 = 1
-    for (int i = tid; i < 4096 / 16; i += NT) {
+    for (int i = tid; i < 4096 / 16; i += NT_B) {
       // chunk i: row-group i / 2, column block i % 2 ... rows x 16 B; column 0 lives in column block 0
       *reinterpret_cast<uint4*>(sm + B_ONES + i * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -598,20 +599,20 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
   const int nt = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const uint32_t sb = smem_u32(sm);
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ control warp
     uint32_t pA0 = 0, pA1 = 0, pAX = 0, pH = 0, pW0 = 0, pW1 = 0, pD = 0;
     int sg = 0, sd = 0;                                      // named-barrier stage counters: G-ready (ids 1,2), drained (ids 3,4)
     auto load = [&](int dst, const uint8_t* src, uint32_t bytes, uint64_t* bar) {
       if (lane == 0) { mbar_expect_tx(bar, bytes); bulk_g2s(sm + dst, src, bytes, bar); }
     };
-    auto g_ready = [&]() { nbar_sync(1 + (sg & 1), NT); ++sg; };
-    auto drained = [&]() { nbar_sync(3 + (sd & 1), NT); ++sd; };
+    auto g_ready = [&]() { nbar_sync(1 + (sg & 1), 160); ++sg; };
+    auto drained = [&]() { nbar_sync(3 + (sd & 1), 160); ++sd; };
     auto wait = [&](uint64_t* bar, uint32_t& ph) { mbar_wait(bar, ph); ph ^= 1; };
     for (int it = 0; it < nt; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const uint8_t* img = imgs + (size_t)tile * TILE_IMG_BYTES;
-      if (it > 0) drained();                                 // previous tile's last accumulators are read out
+      if (it > 0) { drained(); nbar_sync(6, 160); }          // previous tile: accumulators read out, epilogue done with the buffers
       load(B_G1, img + IMG_H, ACT_BYTES, &fullH);
       load(B_A1, img + IMG_FC4, ACT_BYTES, &fullA1);
       load(B_AX, img + IMG_XC, XC_C * 256, &fullAX);
@@ -712,55 +713,65 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
       __syncwarp();
       wait(&bar_d, pD);
     }
-    if (nt > 0) drained();
+    if (nt > 0) { drained(); nbar_sync(6, 160); }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ read-out warps: thread = accumulator lane (output row).
+    // Every stage's weight-gradient accumulators are added into the shared gradient buffer (stored TRANSPOSED, [column][row], so the
+    // 32 lanes of a warp hit 128 contiguous bytes per column: coalesced RED.ADD at the L2) off the delta epilogues' critical path.
+    const int row = tid - 128;
+    const uint32_t tl = tmem + ((uint32_t)((warp - 4) * 32) << 16);
+    uint32_t pW = 0;
+    int sd = 0;
+    auto drain = [&](int tcol, int ncols, float* dst) {
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t u[32];
+        const int n = min(32, ncols - c0);
+        if (n == 32) tmem_ld32(tl + tcol + c0, u); else tmem_ld16(tl + tcol + c0, u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < n) atomicAdd(dst + (size_t)(c0 + j) * 128, __uint_as_float(u[j]));
+      }
+    };
+    auto bias = [&](float* d) { uint32_t u[4]; tmem_ld4(tl + T_DO, u); tmem_ld_wait(); atomicAdd(d, __uint_as_float(u[0])); };
+    auto begin = [&]() { mbar_wait(&bar_w, pW); pW ^= 1; tc_fence_after(); };
+    auto done = [&]() { tc_fence_before(); nbar_arrive(3 + (sd & 1), 160); ++sd; };
+    for (int it = 0; it < nt; ++it) {
+      begin(); drain(T_DW, H + XC_C, part + PR_COL + row); drain(T_DH, 32, part + PR_HEAD + row); done();      // S1 color_linear + heads
+      begin(); drain(T_DW, H, part + PR_MID2 + row); bias(part + PR_DB2 + row); done();                        // S2 mid2
+      begin(); drain(T_DW, H + XG_C, part + PR_CAT + row); done();                                             // S3 cat_layer
+      begin(); drain(T_DW, H, part + PR_MID1 + row); bias(part + PR_DB1 + row); done();                        // S4 mid1
+      begin(); drain(T_DW, XG_C, part + PR_IN + row); done();                                                  // S5 in_layer
+    }
   } else {
-    // ------------------------------------------------------------------ epilogue warps: thread = tile row / accumulator lane
+    // ------------------------------------------------------------------ epilogue warps: thread = tile row
     const int row = tid;
     const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
     const float* wa = reinterpret_cast<const float*>(sm + B_C);
     const float* woc = wa + 128;
-    uint32_t pA0 = 0, pA1 = 0, pH = 0, pD = 0, pW = 0;
-    int sg = 0, sd = 0, si = 0;
+    uint32_t pA0 = 0, pA1 = 0, pH = 0, pD = 0;
+    int sg = 0, si = 0;
     float acc_hb = 0.f, acc_pe0 = 0.f, acc_pe1 = 0.f;    // per-lane partial sums of the head biases / the PE matrix gradient
     auto mark = [&]() { if (tid == 0) stamp(si); ++si; };
     auto wait = [&](uint64_t* bar, uint32_t& ph) { mbar_wait(bar, ph); ph ^= 1; mark(); };
-    auto publish = [&]() { fence_async_smem(); tc_fence_before(); nbar_arrive(1 + (sg & 1), NT); ++sg; mark(); };
-    auto mark_drained = [&]() { tc_fence_before(); nbar_arrive(3 + (sd & 1), NT); ++sd; mark(); };
+    auto publish = [&]() { fence_async_smem(); tc_fence_before(); nbar_arrive(1 + (sg & 1), 160); ++sg; mark(); };
     for (int it = 0; it < nt; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int p = tile * TPT + row;
       const bool act = p < P;
       mark();
-      // add one accumulator row segment (this thread = accumulator lane) into the shared gradient buffer
-      // (stored TRANSPOSED, [column][row], so that the 32 lanes of a warp write 128 contiguous bytes per column)
-      auto drain = [&](int tcol, int ncols, float* dst) {
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-          uint32_t u[32];
-          const int n = min(32, ncols - c0);
-          if (n == 32) tmem_ld32(tl + tcol + c0, u); else tmem_ld16(tl + tcol + c0, u);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j < n) {
-              float* d = dst + (size_t)(c0 + j) * 128;
-              float v = __uint_as_float(u[j]);
-              atomicAdd(d, v);                           // one shared, pre-zeroed accumulator: coalesced RED.ADD at the L2
-            }
-          }
-        }
-      };
-      auto drain1 = [&](float* d, float v) {
-        atomicAdd(d, v);
-      };
       // delta epilogue: D (+ extra * xw) masked by the layer's own activation (> 0) -> bf16 image
       auto delta = [&](const uint8_t* actImg, uint8_t* dst, float extra, const float* xw) {
-        uint32_t uu[4][32];
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {             // two rounds of 64 columns (register budget of the 288-thread kernel)
+        uint32_t uu[2][32];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) tmem_ld32(tl + T_DA + ch * 32, uu[ch]);
+        for (int c2 = 0; c2 < 2; ++c2) tmem_ld32(tl + T_DA + (half * 2 + c2) * 32, uu[c2]);
         tmem_ld_wait();
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const uint32_t* u = uu[ch];
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int ch = half * 2 + c2;
+          const uint32_t* u = uu[c2];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint4 a = *reinterpret_cast<const uint4*>(actImg + (row >> 3) * (16 * H) + (ch * 4 + q) * 128 + (row & 7) * 16);
@@ -778,6 +789,7 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
             }
             *reinterpret_cast<uint4*>(rowblk(dst, row, ch * 4 + q, H)) = make_uint4(w[0], w[1], w[2], w[3]);
           }
+        }
         }
       };
       // ---- S0: loss gradients of the heads -> d h (G0) and the head-delta image
@@ -850,36 +862,21 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
         for (int c = 0; c < E2 - 32; ++c) dxc[(32 + c) * 128] = __uint_as_float(v[c]);
       }
       publish();
-      wait(&bar_w, pW); tc_fence_after();
-      drain(T_DW, H + XC_C, part + PR_COL + row);
-      drain(T_DH, 32, part + PR_HEAD + row);
-      mark_drained();
       // ---- S2: mid2
       wait(&bar_d, pD); tc_fence_after();
       wait(&fullA0, pA0);
       delta(sm + B_A0, sm + B_G0, 0.f, nullptr);                                 // d fc3
       publish();
-      wait(&bar_w, pW); tc_fence_after();
-      drain(T_DW, H, part + PR_MID2 + row);
-      { uint32_t u[4]; tmem_ld4(tl + T_DO, u); tmem_ld_wait(); drain1(part + PR_DB2 + row, __uint_as_float(u[0])); }
-      mark_drained();
       // ---- S3: cat_layer
       wait(&bar_d, pD); tc_fence_after();
       wait(&fullA1, pA1);
       delta(sm + B_A1, sm + B_G1, 0.f, nullptr);                                 // d fc2
       publish();
-      wait(&bar_w, pW); tc_fence_after();
-      drain(T_DW, H + XG_C, part + PR_CAT + row);
-      mark_drained();
       // ---- S4: mid1
       wait(&bar_d, pD); tc_fence_after();
       wait(&fullA0, pA0);
       delta(sm + B_A0, sm + B_G0, 0.f, nullptr);                                 // d fc1
       publish();
-      wait(&bar_w, pW); tc_fence_after();
-      drain(T_DW, H, part + PR_MID1 + row);
-      { uint32_t u[4]; tmem_ld4(tl + T_DO, u); tmem_ld_wait(); drain1(part + PR_DB1 + row, __uint_as_float(u[0])); }
-      mark_drained();
       // ---- S5: in_layer
       wait(&bar_d, pD); tc_fence_after();
       if (PTS) {
@@ -935,9 +932,7 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
           for (int i = tid; i < nvalid; i += TPT) g_emb[(size_t)p0 * EMB + i] = all[i];
         }
       }
-      wait(&bar_w, pW); tc_fence_after();
-      drain(T_DW, XG_C, part + PR_IN + row);
-      mark_drained();
+      nbar_arrive(6, 160);                                   // this tile's shared-memory buffers may be reloaded
     }
     if (lane < 4) atomicAdd(&part[PR_HB + lane], acc_hb);
     if (PTS) {
@@ -1127,8 +1122,8 @@ static int otc_backward(bool pts, const char* who, int P, const float* params, c
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
   float* parts = reinterpret_cast<float*>(w8 + ws_parts(P));
   if (!prepared) CNF_CUDA(cudaMemsetAsync(parts, 0, PART_FLOATS * sizeof(float), st));
-  if (pts) bwd_kernel<true><<<grid, NT, B_SMEM, st>>>(P, w8 + ws_prep(), w8 + ws_imgs(), rgb, g_alpha, g_rgb, parts, const_cast<float*>(points));
-  else bwd_kernel<false><<<grid, NT, B_SMEM, st>>>(P, w8 + ws_prep(), w8 + ws_imgs(), rgb, g_alpha, g_rgb, parts, g_emb);
+  if (pts) bwd_kernel<true><<<grid, NT_B, B_SMEM, st>>>(P, w8 + ws_prep(), w8 + ws_imgs(), rgb, g_alpha, g_rgb, parts, const_cast<float*>(points));
+  else bwd_kernel<false><<<grid, NT_B, B_SMEM, st>>>(P, w8 + ws_prep(), w8 + ws_imgs(), rgb, g_alpha, g_rgb, parts, g_emb);
   reduce_kernel<<<(PART_FLOATS + 255) / 256, 256, 0, st>>>(1, parts, g_params, pts ? g_B : nullptr);
   return check_launch(who);
 }
