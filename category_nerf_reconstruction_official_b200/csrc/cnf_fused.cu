@@ -88,7 +88,9 @@ __device__ __forceinline__ FinJob fin_job(int j) {
   if (j < FIN_P_CODE) return {5, 0, j, FIN_P_CODE};
   return {6, 0, 0, 1};
 }
-__global__ void __launch_bounds__(256)
+// (256, 4): 4 CTAs per SM so that the K x FIN_JOBS grid (560 CTAs at K = 20) is ONE wave; at 108 registers only 2 CTAs per SM fit
+// and the second half of the jobs started 5-11 us late
+__global__ void __launch_bounds__(256, 4)
 fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, const float* __restrict__ pe_scale,
                       const float* __restrict__ shape_codes, const float* __restrict__ tex_codes,
                       const int32_t* __restrict__ n_obj_arr, const float* __restrict__ raw, const float* __restrict__ rawi,
@@ -96,8 +98,13 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
                       float reg_scaling, int add_reg, float* __restrict__ g_params, float* __restrict__ g_B,
                       float* __restrict__ g_shape, float* __restrict__ g_tex, float* __restrict__ reg_out,
                       const int32_t* __restrict__ counts, int cstride, float cs, float os, int* __restrict__ done_counter,
-                      float* __restrict__ out_loss) {
+                      float* __restrict__ out_loss, long long* __restrict__ dbg /* development aid: per-CTA %globaltimer {start, end} */) {
   const int k = blockIdx.x, tid = threadIdx.x;
+  struct Stamp {
+    long long* p;
+    __device__ Stamp(long long* q) : p(q) { if (p && threadIdx.x == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p[0] = t; } }
+    __device__ ~Stamp() { __syncthreads(); if (p && threadIdx.x == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p[1] = t; } }
+  } stamp_(dbg ? dbg + 16384 + 2 * (blockIdx.x * gridDim.y + blockIdx.y) : nullptr);
   const FinJob jb = fin_job(blockIdx.y);
   auto part_lo = [&](int n) { return (int)((long long)n * jb.part / jb.nparts); };
   auto part_hi = [&](int n) { return (int)((long long)n * (jb.part + 1) / jb.nparts); };
@@ -149,9 +156,11 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
   if (jb.kind == 0) {
     // PE projection matrix: dB[d][a] = sum_p d(proj)[p][d] * t[p][a]  (accumulated as [t0 t1 t2 ONE]^T d(proj))
     for (int i = tid; i < 63; i += 256) { const int d = i / 3, ax = i % 3; g_B[(size_t)k * 63 + i] = rk[RPE + ax * 32 + pe_col(d)]; }
-    // plain layers (transposed copies out of the raw accumulators; xg / xc lanes follow the tile column order)
-    for (int i = tid; i < 32 * 87; i += 256) { const int n = i / 87, e = i % 87; G[lay.o[0] + i] = rk[RW1 + xg_col(e) * 32 + n]; }
-    for (int i = tid; i < 16 * 32; i += 256) { const int n = i / 32, c = i % 32; G[lay.o[24] + i] = rk[RW89 + c * 16 + n]; }
+    // plain layers (transposed copies out of the raw accumulators; xg / xc lanes follow the tile column order).  Everywhere in this
+    // kernel consecutive threads READ consecutive addresses of the raw accumulators / parameters (or one broadcast address) and the
+    // strided side is the fire-and-forget store: the strided reads of the first version made the kernel L2-sector bound.
+    for (int i = tid; i < 32 * 87; i += 256) { const int e = i >> 5, n = i & 31; G[lay.o[0] + n * 87 + e] = rk[RW1 + xg_col(e) * 32 + n]; }
+    for (int i = tid; i < 16 * 32; i += 256) { const int c = i >> 4, n = i & 15; G[lay.o[24] + n * 32 + c] = rk[RW89 + c * 16 + n]; }
     for (int i = tid; i < 3 * 16; i += 256) { const int j = i / 16, c = i % 16; G[lay.o[26] + i] = rk[RW89 + (32 + c) * 16 + j]; }
     for (int j = tid; j < 32; j += 256) G[lay.o[1] + j] = rk[RW1 + XG_BIAS_COL * 32 + j];              // b_xyz (row of the ones column)
     for (int n = tid; n < 16; n += 256) G[lay.o[25] + n] = rk[RDB8 + n];
@@ -167,7 +176,7 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
     const float gbs = rk[RW6 + BL * 48 + 32];
     if (jb.kind == 1) {
       for (int i = part_lo(32 * 74) + tid; i < part_hi(32 * 74); i += 256) {
-        const int n = i / 74, j = i % 74;
+        const int j = i >> 5, n = i & 31;
         float a;
         if (j < 32) {
           a = rk[RW6 + BL * 48 + n] * P[lay.o[15] + j];
@@ -176,7 +185,7 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
         } else {
           a = rk[RW6 + (32 + xc_col(87 + (j - 32))) * 48 + n];
         }
-        G[lay.o[18] + i] = a;
+        G[lay.o[18] + n * 74 + j] = a;
       }
       if (jb.part == 0) {
         for (int j = tid; j < 32; j += 256) G[lay.o[19] + j] = rk[RW6 + BL * 48 + j];                    // b_vd
@@ -184,11 +193,11 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
       }
     } else {
       for (int i = tid; i < 32 * 32; i += 256) {                      // dW5[j][k]
-        const int j = i / 32, kk = i % 32;
+        const int kk = i >> 5, j = i & 31;
         float a = P[lay.o[16] + j] * rk[RW6 + kk * 48 + 32];
 #pragma unroll
         for (int n = 0; n < 32; ++n) a = fmaf(P[lay.o[18] + (size_t)n * 74 + j], rk[RW6 + kk * 48 + n], a);
-        G[lay.o[14] + i] = a;
+        G[lay.o[14] + j * 32 + kk] = a;
       }
       for (int j = tid; j < 32; j += 256) {
         float b5 = P[lay.o[16] + j] * gbs;                             // db5[j]
@@ -205,11 +214,11 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
     // layer with per-instance bias c = W[:, :32] z + b : slots (zsl1->s1), (zcl->cat), (zsl2->s2), (ztl->t1)
     const int s = jb.s, ld = cons_ld(s);
     for (int i = part_lo(32 * ld) + tid; i < part_hi(32 * ld); i += 256) {
-      const int n = i / ld, c = i % ld;
+      const int c = i >> 5, n = i & 31;
       float a = rk[rw(s) + (c < 32 ? c : 32 + xg_col(c - 32)) * 32 + n];     // only the cat layer (s = 1) has c >= 32
       if (c < 32)
         for (int inst = 0; inst < n_obj; ++inst) a = fmaf(ri[(inst * 4 + s) * 32 + n], z[((size_t)s * n_obj_max + inst) * NL + c], a);
-      G[lay.o[cons_w(s)] + i] = a;
+      G[lay.o[cons_w(s)] + n * ld + c] = a;
     }
     if (jb.part == 0)
       for (int n = tid; n < 32; n += 256) {
@@ -432,7 +441,8 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
   if (g_ev_start && g_ev_stop) { CNF_CUDA(cudaEventRecord(g_ev_stop, st)); g_ev_start = g_ev_stop = nullptr; }
   fused_finalize_kernel<<<dim3(K, FIN_JOBS), 256, 0, st>>>(L, nom, params, pe_scale, shape_codes, tex_codes, n_obj, raw, rawi,
                                                             reinterpret_cast<float*>(w8 + wl.zlat), reg_scaling, flags & 1, g_params, g_B,
-                                                            g_shape, g_tex, reg, counts, cstride, cs, os, reinterpret_cast<int*>(w8 + wl.done), out_loss);
+                                                            g_shape, g_tex, reg, counts, cstride, cs, os, reinterpret_cast<int*>(w8 + wl.done), out_loss,
+                                                            g_dbg);
   return check_launch("cnf_train_step");
 }
 
