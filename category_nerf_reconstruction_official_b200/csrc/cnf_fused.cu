@@ -108,7 +108,13 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
   const FinJob jb = fin_job(blockIdx.y);
   auto part_lo = [&](int n) { return (int)((long long)n * jb.part / jb.nparts); };
   auto part_hi = [&](int n) { return (int)((long long)n * (jb.part + 1) / jb.nparts); };
-  const PLay lay(L);
+  // parameter offsets: built once per CTA in shared memory (dynamically indexed below; a per-thread table lived on the stack and
+  // its construction was 12 % of the kernel's instructions)
+  __shared__ __align__(16) unsigned char s_lay_raw[sizeof(PLay)];
+  if (tid == 0) { const PLay tmp(L); *reinterpret_cast<PLay*>(s_lay_raw) = tmp; }
+  __syncthreads();
+  const PLay& lay = *reinterpret_cast<const PLay*>(s_lay_raw);
+  const unsigned invL = 0xFFFFFFFFu / (unsigned)L + 1u;      // i / L by multiplication (exact for i < 2^32 / (4 L): every index range below)
   const float* P = params + (size_t)k * lay.total;
   float* G = g_params + (size_t)k * lay.total;
   const float* rk = raw + (size_t)k * RAW_FLOATS;
@@ -236,9 +242,12 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
       compute_dpre(s, s + 1, i0, nc);
       __syncthreads();
       for (int i = part_lo(32 * L) + tid; i < part_hi(32 * L); i += 256) {
-        const int c = i / L, j = i % L;
+        const int c = (int)__umulhi((unsigned)i, invL), j = i - c * L;
         float a = i0 ? G[lay.o[lat_w(s)] + i] : 0.f;
-        for (int li = 0; li < nc; ++li) a = fmaf(s_dpre[s][li][c], codes[(size_t)(i0 + li) * L + j], a);
+        const float* dp = &s_dpre[s][0][c];
+        const float* cd = codes + (size_t)i0 * L + j;
+#pragma unroll 4
+        for (int li = 0; li < nc; ++li) a = fmaf(dp[li * NL], cd[(size_t)li * L], a);
         G[lay.o[lat_w(s)] + i] = a;
       }
       if (jb.part == 0)
@@ -261,7 +270,7 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
       __syncthreads();
       const int c_lo = max(lo, i0 * L), c_hi = min(hi, (i0 + MAXOBJ) * L);
       for (int i = c_lo + tid; i < c_hi; i += 256) {
-        const int inst = i / L, li = inst - i0, j = i % L;
+        const int inst = (int)__umulhi((unsigned)i, invL), li = inst - i0, j = i - inst * L;
         float gs = 0.f, gt = 0.f;
         if (inst < n_obj) {
 #pragma unroll 16

@@ -1,8 +1,6 @@
-V=category_nerf_reconstruction_official_b200/csrc/variants
-timeout 300 python scripts/finalize_timing.py > gpurun_out/t.log 2>&1
+timeout 300 python scripts/finalize_timing.py 2>&1 | head -1 > gpurun_out/t.log
 timeout 600 python -m pytest tests/test_gpu_fused.py tests/test_gpu_training.py -m gpu -x -q 2>&1 | tail -1 >> gpurun_out/t.log
 for i in 1 2; do
-CNF_LIB_PATH=$V/libcnf_fin2.so timeout 300 python bench.py --no-large --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('old ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'])" >> gpurun_out/t.log
 timeout 300 python bench.py --no-large --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('new ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'])" >> gpurun_out/t.log
 done
 cat gpurun_out/t.log
