@@ -371,7 +371,7 @@ static int train_step_prepare(int K, int R, int S, int L, int nom, const float* 
     // one launch: images + biases | instance sort | clear of raw, rawi and the finalize completion counter (16-byte chunks)
     prepare_small_kernel<<<dim3(K, PREP_IMG_PARTS + 4 + 1 + PREP_ZERO_PARTS), 256, nom * sizeof(int), st>>>(
         L, nom, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, prep, zlat, ctab, R, RPT, inst, seg_ray0, seg_tile0, perm,
-        reinterpret_cast<uint4*>(raw), (wl.reg - wl.raw) / 16);
+        reinterpret_cast<uint4*>(raw), (wl.reg - wl.raw) / 16, g_dbg);
     return check_launch("cnf_train_step_prepare");
   }
   CNF_CUDA(cudaMemsetAsync(raw, 0, wl.reg - wl.raw, st));            // raw, rawi and the finalize completion counter
