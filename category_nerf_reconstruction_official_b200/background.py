@@ -27,6 +27,7 @@ class FusedBackgroundTrainer:
                  surface_eps: float = 0.1, stop_eps: float = 0.05, min_bound: float = 0.0, this_obj: int = 1,
                  color_scaling: float = 5.0, opacity_scaling: float = 10.0, generator: Optional[torch.Generator] = None):
         self.device = torch.device(device)
+        lib_for(torch.empty(1, device=self.device))          # no CPU path: raises unless this is a CUDA (sm_100) device
         self.N, self.M = n_bins_cam2surface, n_bins
         self.S = self.N + self.M
         self.eps, self.stop_eps, self.min_bound, self.this_obj = surface_eps, stop_eps, min_bound, this_obj

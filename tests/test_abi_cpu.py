@@ -44,6 +44,36 @@ def test_no_cpu_fallback():
         m(torch.zeros(4, 2, 129), torch.zeros(4, 1, 32), torch.zeros(4, 1, 32))
 
 
+def test_no_cpu_fallback_tensor_core_paths():
+    """The tensor-core entry points (background model, evaluation / rendering, ray set-up) refuse CPU tensors loudly."""
+    from category_nerf_reconstruction_official_b200 import ops, sampling
+    bg = model.OccupancyMap(87, 42, hidden_size=128)
+    bg.use_tensor_cores = True
+    with pytest.raises(cnf.CnfError):
+        bg(torch.zeros(4, 129))
+    flat = model.flat_params(bg).detach()
+    with pytest.raises(cnf.CnfError):
+        ops.occmap_eval_points_fused(torch.zeros(4, 3), flat, torch.zeros(21, 3), torch.tensor(5.0))
+    with pytest.raises(cnf.CnfError):
+        ops.occmap_render_rays_fused(torch.zeros(4, 3), torch.zeros(4, 3), torch.zeros(4, 14), flat, torch.zeros(21, 3), torch.tensor(5.0))
+    with pytest.raises(cnf.CnfError):
+        sampling.origin_dirs_O(torch.eye(4).repeat(3, 1, 1), torch.zeros(3, 3))
+    with pytest.raises((cnf.CnfError, RuntimeError, AssertionError)):
+        from category_nerf_reconstruction_official_b200.background import FusedBackgroundTrainer
+        FusedBackgroundTrainer(device="cpu")
+
+
+def test_tensor_core_kernels_use_bulk_copies_and_tmem():
+    """The OccupancyMap kernels carry the TMA-engine bulk copies (UBLKCP) next to the tensor-core instructions."""
+    import subprocess
+    cnf.build()
+    out = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3cnf3otc11eval_kernelILb0EEEviPKhPKfPfS6_iS5_S5_", _lib.LIB_PATH],
+                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    if not out.strip():      # mangled name changed: scan the whole library
+        out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "UTCHMMA" in out and "UBLKCP" in out and "LDTM" in out
+
+
 def test_state_dict_keys_match_reference():
     from helpers import golden
     names = [str(s) for s in golden("step")["step/param_names"]]
