@@ -1,5 +1,6 @@
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29527 bench.py --gpus 8 --steps 20 --warmup 5 --no-large > gpurun_out/bench8.json 2> gpurun_out/bench8.err
-python -c "import json; d=json.loads(open('gpurun_out/bench8.json').read().strip().splitlines()[-1]); print({k: d[k] for k in ('value','n_gpus','ms_per_step','scaling')}, d['e2e'])" > gpurun_out/t.log 2>&1
-tail -2 gpurun_out/bench8.err >> gpurun_out/t.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29528 bench.py --gpus 8 --steps 10 --warmup 3 --ray-split 2>/dev/null | tail -1 | cut -c1-400 >> gpurun_out/t.log
+timeout 300 python scripts/finalize_timing.py 2>&1 | grep -E "finalize:|job 4 lat s0 p0|job 5 codes p0|job 0|job 3 cond s2" > gpurun_out/t.log
+timeout 600 python -m pytest tests/test_gpu_fused.py tests/test_gpu_training.py -m gpu -x -q 2>&1 | tail -1 >> gpurun_out/t.log
+for i in 1 2; do
+timeout 300 python bench.py --no-large --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'])" >> gpurun_out/t.log
+done
 cat gpurun_out/t.log
