@@ -1,6 +1,9 @@
-timeout 300 python scripts/finalize_timing.py 2>&1 | grep -E "finalize:|job 4 lat s0 p0|job 5 codes p0|job 0|job 3 cond s2" > gpurun_out/t.log
-timeout 600 python -m pytest tests/test_gpu_fused.py tests/test_gpu_training.py -m gpu -x -q 2>&1 | tail -1 >> gpurun_out/t.log
-for i in 1 2; do
-timeout 300 python bench.py --no-large --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'])" >> gpurun_out/t.log
-done
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -2 > gpurun_out/t.log
+timeout 600 python bench.py > gpurun_out/bench.json 2>gpurun_out/bench.err; tail -2 gpurun_out/bench.err >> gpurun_out/t.log
+python -c "
+import json; d=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
+print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], 'frac', d['roofline']['frac'], 'clocks', d['clocks'])
+" >> gpurun_out/t.log 2>&1
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" >> gpurun_out/t.log 2>&1
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 | cut -c1-260 >> gpurun_out/t.log
 cat gpurun_out/t.log
