@@ -1,9 +1,2 @@
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -2 > gpurun_out/t.log
-timeout 600 python bench.py > gpurun_out/bench.json 2>gpurun_out/bench.err; tail -2 gpurun_out/bench.err >> gpurun_out/t.log
-python -c "
-import json; d=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
-print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], 'frac', d['roofline']['frac'], 'clocks', d['clocks'])
-" >> gpurun_out/t.log 2>&1
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" >> gpurun_out/t.log 2>&1
-timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 | cut -c1-260 >> gpurun_out/t.log
+timeout 600 python -m pytest tests/test_gpu_occmap_tc.py -m gpu -x -q -k capture_iteration 2>&1 | tail -15 > gpurun_out/t.log
 cat gpurun_out/t.log

@@ -246,3 +246,35 @@ def test_fused_background_trainer_step_vs_oracle(well_conditioned):
     tr.g_params.zero_(); replay(); torch.cuda.synchronize()
     torch.testing.assert_close(tr.out_loss, l_eager, rtol=1e-5, atol=1e-6)
     assert rel(tr.g_params, g_eager) < 1e-4
+
+
+def test_capture_iteration_objects_plus_background():
+    """One whole iteration (object categories + background model as parallel branches of one CUDA graph): replays run, both
+    trainers' losses and gradients are finite and change from replay to replay (fresh random offsets every step), and the graph's
+    first replay matches an eager step fed with the same random offsets."""
+    from category_nerf_reconstruction_official_b200.background import FusedBackgroundTrainer, capture_iteration
+    from category_nerf_reconstruction_official_b200.fused import FusedCategoryTrainer
+    g = torch.Generator().manual_seed(3)
+    K, n_obj, R = 4, 3, 240
+    obj = FusedCategoryTrainer(K, n_obj, latent_dim=32, scale=2.0, device=DEV, n_bins_cam2surface=1, n_bins=9, generator=g)
+    bg = FusedBackgroundTrainer(scale=5.0, device=DEV, generator=g)
+    cats = [O.synth_rays(R, n_obj, g) for _ in range(K)]
+    dv = lambda t: t.to(DEV)
+    oi = (dv(torch.stack([c[0] for c in cats])), dv(torch.stack([c[1] for c in cats])), dv(torch.stack([c[2] for c in cats])),
+          dv(torch.stack([c[3] for c in cats])), dv(torch.stack([c[4] for c in cats]).to(torch.int32)))
+    bi = tuple(dv(t) for t in O.synth_rays(600, 1, g)[:4])
+    replay = capture_iteration(obj, oi, bg, bi)
+    # eager reference for the NEXT replay: same offsets (the prefetch buffers hold what the next step will consume)
+    ru, rn, bu, bn = obj._rand_u.clone(), obj._rand_n.clone(), bg._rand_u.clone(), bg._rand_n.clone()
+    replay(); torch.cuda.synchronize()
+    lo1, lb1 = obj.out_loss.clone(), bg.out_loss.clone()
+    go1, gb1 = obj.g_params.clone(), bg.g_params.clone()
+    assert torch.isfinite(lo1).all() and torch.isfinite(lb1).all() and torch.isfinite(go1).all() and torch.isfinite(gb1).all()
+    assert float(go1.abs().sum()) > 0 and float(gb1.abs().sum()) > 0
+    replay(); torch.cuda.synchronize()
+    assert float((obj.out_loss - lo1).abs().max()) > 0 and float((bg.out_loss - lb1).abs().max()) > 0      # new offsets every step
+    obj._rand_u.copy_(ru); obj._rand_n.copy_(rn); bg._rand_u.copy_(bu); bg._rand_n.copy_(bn)
+    obj.step(*oi); bg.step(*bi); torch.cuda.synchronize()
+    torch.testing.assert_close(obj.out_loss, lo1, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(bg.out_loss, lb1, rtol=1e-5, atol=1e-6)
+    assert rel(obj.g_params, go1) < 1e-4 and rel(bg.g_params, gb1) < 1e-4
