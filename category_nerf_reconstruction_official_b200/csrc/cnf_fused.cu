@@ -369,16 +369,16 @@ static int train_step_prepare(int K, int R, int S, int L, int nom, const float* 
   const int rpw = 32 / S, RPT = 4 * rpw, nblk = wl.nblk;
   if (nblk <= SORT_SMALL_BLOCKS) {
     // one launch: images + biases | instance sort | clear of raw, rawi and the finalize completion counter (16-byte chunks)
-    prepare_small_kernel<<<dim3(K, PREP_IMG_PARTS + 4 + 1 + PREP_ZERO_PARTS), 256, nom * sizeof(int), st>>>(
+    prepare_small_kernel<<<dim3(K, PREP_IMG_PARTS + prep_lat_parts(nom) + 1 + PREP_ZERO_PARTS), 256, nom * sizeof(int), st>>>(
         L, nom, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, prep, zlat, ctab, R, RPT, inst, seg_ray0, seg_tile0, perm,
         reinterpret_cast<uint4*>(raw), (wl.reg - wl.raw) / 16, g_dbg);
     return check_launch("cnf_train_step_prepare");
   }
   CNF_CUDA(cudaMemsetAsync(raw, 0, wl.reg - wl.raw, st));            // raw, rawi and the finalize completion counter
-  fused_prep_kernel<<<dim3(K, PREP_IMG_PARTS + 4), 256, 0, st>>>(L, nom, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, prep, zlat, ctab);
+  fused_prep_kernel<<<dim3(K, PREP_IMG_PARTS + prep_lat_parts(nom)), 256, 0, st>>>(L, nom, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, prep, zlat, ctab);
   {
     sort_count_kernel<<<dim3(nblk, K), 256, nom * sizeof(int), st>>>(R, nom, nblk, inst, n_obj, hist);
-    sort_scan_kernel<<<K, 256, nom * sizeof(int), st>>>(nom, nblk, RPT, hist, base, seg_ray0, seg_tile0);
+    sort_scan_kernel<<<K, SORT_SCAN_T, nom * sizeof(int), st>>>(nom, nblk, RPT, hist, base, seg_ray0, seg_tile0);
     sort_scatter_kernel<<<dim3(nblk, K), 256, 0, st>>>(R, nom, nblk, inst, n_obj, base, seg_ray0, perm);
   }
   return check_launch("cnf_train_step_prepare");
