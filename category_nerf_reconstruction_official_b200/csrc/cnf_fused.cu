@@ -70,22 +70,26 @@ __device__ __forceinline__ void loss_outputs(int K, const float* __restrict__ ra
 struct FinJob { int kind, s, part, nparts; };
 constexpr int FIN_P_VD = 3, FIN_P_CAT = 3, FIN_P_LAT = 3, FIN_P_CODE = 4;     // parts of the sliced jobs
 constexpr int FIN_JOBS = 1 + FIN_P_VD + 1 + (3 + FIN_P_CAT) + 4 * FIN_P_LAT + FIN_P_CODE + 1;     // 28: K = 20 categories fit one wave
-__device__ __forceinline__ FinJob fin_job(int j) {
+// pm = part multiplier: with few categories the sliced jobs are cut into pm x more parts so that the grid still fills the machine
+// (K = 1: 182 CTAs instead of 28); grid.y = fin_jobs(pm) = 6 + 22 pm
+__host__ __device__ constexpr int fin_jobs(int pm) { return 1 + FIN_P_VD * pm + 1 + (3 + FIN_P_CAT * pm) + 4 * FIN_P_LAT * pm + FIN_P_CODE * pm + 1; }
+static_assert(fin_jobs(1) == FIN_JOBS, "job table");
+__device__ __forceinline__ FinJob fin_job(int j, int pm) {
   if (j == 0) return {0, 0, 0, 1};
   j -= 1;
-  if (j < FIN_P_VD) return {1, 0, j, FIN_P_VD};
-  j -= FIN_P_VD;
+  if (j < FIN_P_VD * pm) return {1, 0, j, FIN_P_VD * pm};
+  j -= FIN_P_VD * pm;
   if (j == 0) return {2, 0, 0, 1};
   j -= 1;
   if (j == 0) return {3, 0, 0, 1};
   j -= 1;
-  if (j < FIN_P_CAT) return {3, 1, j, FIN_P_CAT};
-  j -= FIN_P_CAT;
+  if (j < FIN_P_CAT * pm) return {3, 1, j, FIN_P_CAT * pm};
+  j -= FIN_P_CAT * pm;
   if (j < 2) return {3, 2 + j, 0, 1};
   j -= 2;
-  if (j < 4 * FIN_P_LAT) return {4, j / FIN_P_LAT, j % FIN_P_LAT, FIN_P_LAT};
-  j -= 4 * FIN_P_LAT;
-  if (j < FIN_P_CODE) return {5, 0, j, FIN_P_CODE};
+  if (j < 4 * FIN_P_LAT * pm) return {4, j / (FIN_P_LAT * pm), j % (FIN_P_LAT * pm), FIN_P_LAT * pm};
+  j -= 4 * FIN_P_LAT * pm;
+  if (j < FIN_P_CODE * pm) return {5, 0, j, FIN_P_CODE * pm};
   return {6, 0, 0, 1};
 }
 // (256, 4): 4 CTAs per SM so that the K x FIN_JOBS grid (560 CTAs at K = 20) is ONE wave; at 108 registers only 2 CTAs per SM fit
@@ -105,7 +109,7 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
     __device__ Stamp(long long* q) : p(q) { if (p && threadIdx.x == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p[0] = t; } }
     __device__ ~Stamp() { __syncthreads(); if (p && threadIdx.x == 0) { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p[1] = t; } }
   } stamp_(dbg ? dbg + 16384 + 2 * (blockIdx.x * gridDim.y + blockIdx.y) : nullptr);
-  const FinJob jb = fin_job(blockIdx.y);
+  const FinJob jb = fin_job(blockIdx.y, ((int)gridDim.y - 6) / 22);
   auto part_lo = [&](int n) { return (int)((long long)n * jb.part / jb.nparts); };
   auto part_hi = [&](int n) { return (int)((long long)n * (jb.part + 1) / jb.nparts); };
   // parameter offsets: built once per CTA in shared memory (dynamically indexed below; a per-thread table lived on the stack and
@@ -448,7 +452,10 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
   if (g_dbg) fused_step_kernel<true><<<dim3(cpc, K), NT, SM_TOTAL, st>>>(fa);
   else fused_step_kernel<false><<<dim3(cpc, K), NT, SM_TOTAL, st>>>(fa);
   if (g_ev_start && g_ev_stop) { CNF_CUDA(cudaEventRecord(g_ev_stop, st)); g_ev_start = g_ev_stop = nullptr; }
-  fused_finalize_kernel<<<dim3(K, FIN_JOBS), 256, 0, st>>>(L, nom, params, pe_scale, shape_codes, tex_codes, n_obj, raw, rawi,
+  int pm = (2 * n_sm) / (K * FIN_JOBS);                 // part multiplier: fill the machine when there are few categories
+  if (pm < 1) pm = 1;
+  if (pm > 8) pm = 8;
+  fused_finalize_kernel<<<dim3(K, fin_jobs(pm)), 256, 0, st>>>(L, nom, params, pe_scale, shape_codes, tex_codes, n_obj, raw, rawi,
                                                             reinterpret_cast<float*>(w8 + wl.zlat), reg_scaling, flags & 1, g_params, g_B,
                                                             g_shape, g_tex, reg, counts, cstride, cs, os, reinterpret_cast<int*>(w8 + wl.done), out_loss,
                                                             g_dbg);
