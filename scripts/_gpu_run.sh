@@ -1,6 +1,7 @@
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29537 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench2.json 2> gpurun_out/bench2.err
-echo "rc=$?" > gpurun_out/t.log
-python -c "import json; d=json.loads(open('gpurun_out/bench2.json').read().strip().splitlines()[-1]); print({k: d[k] for k in ('value','n_gpus','ms_per_step','scaling')}, d['e2e']['value'], sorted(k for k in d if k.endswith('cube') or 'step' in k or 'c4' in k))" >> gpurun_out/t.log 2>&1
-tail -3 gpurun_out/bench2.err >> gpurun_out/t.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29538 bench.py --gpus 2 --impl reference --steps 2 --warmup 1 > gpurun_out/ref2.json 2>/dev/null; echo "ref rc=$? lines=$(wc -l < gpurun_out/ref2.json)" >> gpurun_out/t.log
+timeout 300 python scripts/finalize_timing.py 2>&1 | grep -E "finalize:|job 4 lat s0 p0|job 5 codes p0|job 5 codes p3" > gpurun_out/t.log
+timeout 900 python -m pytest tests/test_gpu_fused.py tests/test_gpu_training.py tests/test_gpu_parity_v0.py -m gpu -x -q 2>&1 | tail -1 >> gpurun_out/t.log
+timeout 300 python scripts/race_check.py 2>&1 | tail -3 >> gpurun_out/t.log
+for i in 1 2; do
+timeout 300 python bench.py --no-large --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'])" >> gpurun_out/t.log
+done
 cat gpurun_out/t.log
