@@ -1,7 +1,3 @@
-timeout 300 python scripts/finalize_timing.py 2>&1 | grep -E "finalize:|job 4 lat s0 p0|job 5 codes p0|job 5 codes p3" > gpurun_out/t.log
-timeout 900 python -m pytest tests/test_gpu_fused.py tests/test_gpu_training.py tests/test_gpu_parity_v0.py -m gpu -x -q 2>&1 | tail -1 >> gpurun_out/t.log
-timeout 300 python scripts/race_check.py 2>&1 | tail -3 >> gpurun_out/t.log
-for i in 1 2; do
-timeout 300 python bench.py --no-large --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'])" >> gpurun_out/t.log
-done
+timeout 300 python scripts/run_fused.py replica_room0 360 4 > gpurun_out/t.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused_finalize --launch-skip 2 --launch-count 1 -f -o gpurun_out/fin2 python scripts/run_fused.py replica_room0 360 4 > gpurun_out/ncu_fin.log 2>&1
 cat gpurun_out/t.log
