@@ -8,8 +8,8 @@ synthetic batch: the sampler's random draws (2 torch launches), depth-guided sam
 between steps, max over ranks); `e2e` = the same through FusedCategoryTrainer.step with pinned HOST buffers
 (one H2D copy of the step's inputs + the captured step + D2H of the loss terms, wall clock incl. the stream sync).  `roofline` = the fused kernel against the
 measured bf16 tensor peak (MEASURED_PEAKS.json), timed live with CUDA events recorded around that kernel only
-(cnf_set_kernel_events).  `cpu_baseline` / `--impl reference` = the CPU oracle port of the reference's PyTorch
-path on the box's host cores (the reference is pure Python and cannot travel to the GPU box).
+(cnf_set_kernel_events).  `cpu_baseline` / `--impl reference` = the reference's OWN modules (staged unmodified under
+oracle/_ref by oracle/make_ref.py, driven with functorch.vmap as train.py does) on the box's host cores.
 """
 from __future__ import annotations
 
@@ -40,6 +40,13 @@ WORKLOADS = {
     "c4": dict(K=1, n_obj=64, R=524288, N=1, M=9, L=256, scale=2.0,
                desc="large single category: 64 instances x 8192 rays, 1+9 samples"),
 }
+
+
+def config_of(name, wl):
+    """The workload description both arms print (identical keys and values, so the driver can match them)."""
+    return {"workload": name, "desc": wl["desc"], "categories_per_gpu": wl["K"], "instances_per_category": wl["n_obj"],
+            "rays_per_category": wl["R"], "samples_per_ray": wl["N"] + wl["M"], "latent_dim": wl["L"],
+            "l2": "b200 arm: flushed between timed steps (256 MB write)"}
 
 
 def peaks():
@@ -121,9 +128,9 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_arm(wl, steps, warmup, seed=0):
-    """The reference's PyTorch CPU path (oracle port: same ATen ops, batched over categories like functorch.vmap):
-    sample_3d_points + code gather + PE + MLP + step_batch_loss + reg + backward, fp32, all host threads."""
+def cpu_port_arm(wl, steps, warmup, seed=0):
+    """Fallback CPU arm when the reference's files are not staged (oracle/_ref absent): the oracle PORT of the reference's
+    PyTorch path (same ATen ops, one bmm per layer like functorch.vmap), fp32, all host threads."""
     from oracle import cnf_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     g = torch.Generator().manual_seed(seed)
@@ -155,6 +162,19 @@ def cpu_reference_arm(wl, steps, warmup, seed=0):
     return K * R / dt, dt, torch.get_num_threads()
 
 
+def cpu_reference_arm(wl, steps, warmup, seed=0):
+    """The reference's OWN CPU implementation of the path on this box's host cores: the unmodified modules staged under
+    oracle/_ref (oracle/make_ref.py), driven as train.py:123-182 -- sample_3d_points per category, code gather, functorch
+    vmap(PE), vmap(CodeNeRF), step_batch_loss, regulariser, backward; fp32, all host threads, no optimizer step.
+    Falls back to the oracle port (kind "port") only when no staged reference exists.  Returns (rays/s, s/step, threads, kind)."""
+    from oracle import ref_driver
+    if ref_driver.find_ref_src() is not None:
+        v, dt, cores = ref_driver.time_reference(wl, synth_batch(wl, seed), steps, warmup, seed)
+        return v, dt, cores, "reference"
+    v, dt, cores = cpu_port_arm(wl, steps, warmup, seed)
+    return v, dt, cores, "port"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -179,14 +199,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cpu_steps = max(1, min(args.steps, 20))
-        v, dt, cores = cpu_reference_arm(wl, cpu_steps, min(warmup, 3))
-        cb = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
+        cpu_steps = max(1, args.steps if wl["K"] * wl["R"] <= 20000 else min(args.steps, 3))     # bounded sample for the large batch
+        v, dt, cores, kind = cpu_reference_arm(wl, cpu_steps, warmup if wl["K"] * wl["R"] <= 20000 else 1)
+        cb = {"value": v, "unit": "rays/s", "cores": cores, "kind": kind,
               "sample": "%d steps of the full %s batch (%d rays/step)" % (cpu_steps, args.workload, wl["K"] * wl["R"])}
         print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "rays/s", "n_gpus": args.gpus,
-                          "steps": cpu_steps, "warmup": min(warmup, 3), "ms_per_step": dt * 1e3, "higher_is_better": True,
+                          "steps": cpu_steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": args.workload, "desc": wl["desc"]}, "cpu_baseline": cb,
+                          "config": config_of(args.workload, wl), "cpu_baseline": cb,
                           "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -480,18 +500,20 @@ def main():
     cb = None
     if not args.no_cpu_baseline and world == 1:
         cpu_steps = 10 if K * R <= 20000 else 1
-        v, dt, cores = cpu_reference_arm(wl, cpu_steps, 2)
-        cb = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "ms_per_step": dt * 1e3,
-              "sample": "%d steps of the full %s batch (%d rays/step), oracle port of the reference PyTorch CPU path"
-                        % (cpu_steps, args.workload, K * R)}
+        v, dt, cores, kind = cpu_reference_arm(wl, cpu_steps, 2)
+        cb = {"value": v, "unit": "rays/s", "cores": cores, "kind": kind, "ms_per_step": dt * 1e3,
+              "sample": "%d steps of the full %s batch (%d rays/step), %s" % (
+                  cpu_steps, args.workload, K * R,
+                  "unmodified reference modules (oracle/_ref) under functorch.vmap" if kind == "reference"
+                  else "oracle port of the reference PyTorch CPU path")}
 
     line = {"metric": metric, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": args.workload, "desc": wl["desc"], "categories_per_gpu": K, "rays_per_category": R,
-                       "samples_per_ray": S, "latent_dim": wl["L"], "l2": "flushed between timed steps (256 MB write)",
-                       "optimizer_in_step": bool(args.with_optimizer), "cuda_graph": bool(use_graph),
-                       "eager_ms_per_step": eager_ms, "parallelism": "categories sharded, %d per GPU" % K},
+            "config": config_of(args.workload, wl),
+            "run": {"optimizer_in_step": bool(args.with_optimizer),
+                    "cuda_graph": bool(use_graph), "eager_ms_per_step": eager_ms,
+                    "parallelism": "categories sharded, %d per GPU, no collective in the step" % K},
             "clocks": clk, "roofline": roof, "cpu_baseline": cb,
             "e2e": {"value": rays_per_step / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -224,9 +224,9 @@ def _lin(x, w, b):
     """y = x W^T + b.  With stacked parameters (w [K,out,in], b [K,out]) and x [K,...,in] this is the batched matmul
     functorch.vmap turns nn.Linear into (train.py:154-155)."""
     if w.dim() == 3:
-        exw = (slice(None),) + (None,) * (x.dim() - 3)
-        exb = (slice(None),) + (None,) * (x.dim() - 2)
-        return torch.matmul(x, w[exw].transpose(-1, -2)) + b[exb]
+        K = w.shape[0]
+        y = torch.baddbmm(b[:, None, :], x.reshape(K, -1, x.shape[-1]), w.transpose(1, 2))    # one bmm per layer, as vmap emits
+        return y.reshape(*x.shape[:-1], w.shape[1])
     return x @ w.transpose(-1, -2) + b
 
 
