@@ -125,7 +125,14 @@ SIGNATURES = {
     "cnf_umma_rate_probe": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     "cnf_umma_selftest": (c_int, [c_int, c_int, c_int, P, P, P, P]),
     "cnf_adamw_step": (c_int, [c_size_t, P, P, P, P, c_float, c_float, c_float, c_float, c_float, c_int, P]),
+    "cnf_adamw_groups": (c_int, [c_int, P, c_float, c_float, c_float, P, P]),
 }
+
+
+class AdamwGroup(ctypes.Structure):
+    """include/cnf.h: cnf_adamw_group"""
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("n", c_size_t),
+                ("lr", c_float), ("weight_decay", c_float)]
 
 
 def load(auto_build: bool = True):

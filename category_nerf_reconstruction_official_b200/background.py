@@ -189,6 +189,28 @@ class FusedBackgroundTrainer:
         return {"u_inv": u[:n1].view(1, R, N + M), "u_val": u[n1:n1 + n2].view(1, R, N), "n_obj": self._rand_n,
                 "u_oth": u[n1 + n2:].view(1, R, M)}
 
+    def _state_tensors(self):
+        return [self.params, self.pe_B]
+
+    def snapshot_state(self):
+        st = self._opt_state
+        return {"state": [t.clone() for t in self._state_tensors()],
+                "opt": None if st is None else {"t": st["t"].clone(), "m": [t.clone() for t in st["m"]], "v": [t.clone() for t in st["v"]]}}
+
+    def restore_state(self, snap):
+        for t, c in zip(self._state_tensors(), snap["state"]):
+            t.copy_(c)
+        if self._opt_state is not None:
+            st = self._opt_state
+            if snap["opt"] is None:
+                st["t"].zero_()
+                for t in st["m"] + st["v"]:
+                    t.zero_()
+            else:
+                st["t"].copy_(snap["opt"]["t"])
+                for t, c in zip(st["m"] + st["v"], snap["opt"]["m"] + snap["opt"]["v"]):
+                    t.copy_(c)
+
     def capture(self, rgbs, depth, origins, dirs):
         """Capture sampler + step over THESE (static) input tensors into a CUDA graph; returns ``replay``."""
         side = torch.cuda.Stream(device=self.device)
@@ -210,21 +232,23 @@ class FusedBackgroundTrainer:
 
     # ------------------------------------------------------------------------------------------ optimizer
     def adamw_step(self, lr=1e-3, weight_decay=0.013, betas=(0.9, 0.999), eps=1e-8):
-        """Fused AdamW over the flat buffers (train.py:40,54-64,183-184)."""
+        """Fused AdamW over the flat buffers (train.py:40,54-64,183-184): one launch, device-side step count (graph capturable)."""
         if self._opt_state is None:
             z = torch.zeros_like
-            self._opt_state = {"t": 0, "m": [z(self.params), z(self.pe_B)], "v": [z(self.params), z(self.pe_B)]}
+            self._opt_state = {"t": torch.zeros(2, dtype=torch.int32, device=self.device),
+                               "m": [z(self.params), z(self.pe_B)], "v": [z(self.params), z(self.pe_B)]}
         st = self._opt_state
-        st["t"] += 1
-        for i, (p, g) in enumerate(((self.params, self.g_params), (self.pe_B, self.g_B))):
-            ops.adamw_step_(p, g, st["m"][i], st["v"][i], lr, betas[0], betas[1], eps, weight_decay, st["t"])
+        ops.adamw_groups_([(self.params, self.g_params, st["m"][0], st["v"][0], lr, weight_decay),
+                           (self.pe_B, self.g_B, st["m"][1], st["v"][1], lr, weight_decay)], betas[0], betas[1], eps, st["t"])
 
 
 def capture_iteration(obj_trainer, obj_inputs, bg_trainer, bg_inputs, with_optimizer: bool = False, opt_kwargs=None):
     """One training iteration of the reference (train.py:123-184: every object category, then the background model) as ONE CUDA
     graph with the two steps on parallel branches: ``obj_inputs`` = (rgbs, depth, origins, dirs, indices) of
     ``FusedCategoryTrainer.step``, ``bg_inputs`` = (rgbs, depth, origins, dirs) of ``FusedBackgroundTrainer.step``; static tensors,
-    updated in place between replays.  Returns ``replay``."""
+    updated in place between replays.  Returns ``replay``.  With ``with_optimizer`` the fused AdamW updates are part of the graph;
+    their step count is a device counter that every replay advances (cnf_adamw_groups), and the warm-up iterations are rolled
+    back, so N replays == N steps of torch.optim.AdamW from the state at capture time."""
     opt_kwargs = opt_kwargs or {}
     dev = obj_trainer.device
     branch = torch.cuda.Stream(device=dev)
@@ -243,9 +267,11 @@ def capture_iteration(obj_trainer, obj_inputs, bg_trainer, bg_inputs, with_optim
 
     warm = torch.cuda.Stream(device=dev)
     warm.wait_stream(torch.cuda.current_stream(dev))
+    snaps = (obj_trainer.snapshot_state(), bg_trainer.snapshot_state())      # the warm-up iterations must not train
     with torch.cuda.stream(warm):
         for _ in range(2):
             iteration()
+        obj_trainer.restore_state(snaps[0]); bg_trainer.restore_state(snaps[1])
     torch.cuda.current_stream(dev).wait_stream(warm)
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()

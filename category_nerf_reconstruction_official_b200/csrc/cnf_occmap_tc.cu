@@ -59,10 +59,9 @@ __device__ __forceinline__ void stamp(int slot) {
   if (g_stamp != nullptr && blockIdx.x == 0) g_stamp[slot] = clock64();
 }
 
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
+// packed operand pairs / single operand elements (fp16 by default, bf16 with -DCNF_OPERAND_FP16=0: cnf_umma.cuh)
+__device__ __forceinline__ uint32_t pack2(float a, float b) { return op_pack2(a, b); }
+__device__ __forceinline__ unsigned short op_elem(float a) { return (unsigned short)(op_pack2(a, 0.f) & 0xFFFFu); }
 __device__ __forceinline__ uint8_t* rowblk(uint8_t* base, int row, int cb, int cols) {
   return base + (row >> 3) * (16 * cols) + cb * 128 + (row & 7) * 16;
 }
@@ -124,7 +123,7 @@ __device__ __forceinline__ void pe_double(float& s, float& c) {
 
 // forward issue: D[128 x 128] (+)= A[128 x aCols] (K-major image) * W[128 x aCols]^T (K-major image)
 __device__ __forceinline__ void issue_fwd(uint32_t d, uint32_t aAddr, int aCols, uint32_t wAddr, bool acc) {
-  const uint32_t id = idesc_bf16(128, 128, 0, 0);
+  const uint32_t id = idesc_op(128, 128, 0, 0);
   for (int ks = 0; ks < aCols / 16; ++ks)
     mma_ss(d, smem_desc(aAddr + ks * 256, 128, 16 * aCols), smem_desc(wAddr + ks * 256, 128, 16 * aCols), id, (acc || ks > 0) ? 1u : 0u);
 }
@@ -320,15 +319,15 @@ fwd_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ em
         const int nvalid = min(TPT, P - p0) * EMB;
         for (int i = tid; i < TPT * EMB; i += 128) {
           const int r = i / EMB, c = i - r * EMB;
-          const __nv_bfloat16 hv = __float2bfloat16_rn(i < nvalid ? e[i] : 0.f);
-          if (c < E1) *reinterpret_cast<__nv_bfloat16*>(sm + F_XG + blk_off(r, c, XG_C)) = hv;
-          else *reinterpret_cast<__nv_bfloat16*>(sm + F_XC + blk_off(r, c - E1, XC_C)) = hv;
+          const unsigned short hv = op_elem(i < nvalid ? e[i] : 0.f);
+          if (c < E1) *reinterpret_cast<unsigned short*>(sm + F_XG + blk_off(r, c, XG_C)) = hv;
+          else *reinterpret_cast<unsigned short*>(sm + F_XC + blk_off(r, c - E1, XC_C)) = hv;
         }
-        const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
-        *reinterpret_cast<__nv_bfloat16*>(sm + F_XG + blk_off(row, XG_ONE, XG_C)) = one;
+        const unsigned short one = (unsigned short)OP_ONE, zero = 0;
+        *reinterpret_cast<unsigned short*>(sm + F_XG + blk_off(row, XG_ONE, XG_C)) = one;
         *reinterpret_cast<uint4*>(rowblk(sm + F_XG, row, 11, XG_C)) = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<__nv_bfloat16*>(sm + F_XC + blk_off(row, XC_ONE, XC_C)) = one;
-        for (int c = XC_ONE + 1; c < XC_C; ++c) *reinterpret_cast<__nv_bfloat16*>(sm + F_XC + blk_off(row, c, XC_C)) = zero;
+        *reinterpret_cast<unsigned short*>(sm + F_XC + blk_off(row, XC_ONE, XC_C)) = one;
+        for (int c = XC_ONE + 1; c < XC_C; ++c) *reinterpret_cast<unsigned short*>(sm + F_XC + blk_off(row, c, XC_C)) = zero;
       }
       publish();
       layer(sm + F_A0, nullptr, nullptr, 0, nullptr); publish();                  // fc1
@@ -362,7 +361,7 @@ constexpr int E_ACT = 0, E_W = 32768, E_C = E_W + 2 * 32768, E_SMEM = E_C + C_FL
 constexpr int ET_D = 0, ET_XG = 128, ET_XC = 176;     // TMEM columns: accumulator 128 | xg 96 bf16 | xc 48 bf16
 
 __device__ __forceinline__ void issue_fwd_ts(uint32_t d, uint32_t aTmem, int aCols, uint32_t wAddr, bool acc) {
-  const uint32_t id = idesc_bf16(128, 128, 0, 0);
+  const uint32_t id = idesc_op(128, 128, 0, 0);
   for (int ks = 0; ks < aCols / 16; ++ks)
     mma_ts(d, aTmem + ks * 8, smem_desc(wAddr + ks * 256, 128, 16 * aCols), id, (acc || ks > 0) ? 1u : 0u);
 }
@@ -539,13 +538,13 @@ eval_kernel(int P, const uint8_t* __restrict__ prep, const float* __restrict__ p
 // ---------------------------------------------------------------------------------------------------------
 // data gradient: D[128 x Nout] (+)= G[128 x 128] (K-major image) * W[128 x Nout] (MN-major view of the weight image)
 __device__ __forceinline__ void issue_dgrad(uint32_t d, uint32_t gAddr, uint32_t wAddr, int Nout, bool acc) {
-  const uint32_t id = idesc_bf16(128, Nout, 0, 1);
+  const uint32_t id = idesc_op(128, Nout, 0, 1);
   for (int ks = 0; ks < H / 16; ++ks)
     mma_ss(d, smem_desc(gAddr + ks * 256, 128, 16 * H), smem_desc(wAddr + ks * 2 * (16 * Nout), 16 * Nout, 128), id, (acc || ks > 0) ? 1u : 0u);
 }
 // weight gradient: D[aCols (rows) x bCols] = A^T * B, both MN-major views of [128 points x cols] images (contraction over the points)
 __device__ __forceinline__ void issue_wgrad(uint32_t d, uint32_t aAddr, int aCols, uint32_t bAddr, int bCols) {
-  const uint32_t id = idesc_bf16(128, bCols, 1, 1);
+  const uint32_t id = idesc_op(128, bCols, 1, 1);
   for (int ks = 0; ks < TPT / 16; ++ks)
     mma_ss(d, smem_desc(aAddr + ks * 2 * (16 * aCols), 16 * aCols, 128), smem_desc(bAddr + ks * 2 * (16 * bCols), 16 * bCols, 128), id,
            ks > 0 ? 1u : 0u);
@@ -570,6 +569,11 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
   extern __shared__ __align__(128) uint8_t sm[];   // no-swizzle operand images need 16-byte alignment only
   __shared__ uint64_t fullA0, fullA1, fullAX, fullH, fullW0, fullW1, bar_d, bar_w;
   __shared__ uint32_t tmem_base_s;
+  // fp16 operands: every tile's incoming loss gradients (O(1 / rays): far below fp16's normal range at large batches) are scaled by
+  // a power of two chosen from the tile's own largest |gradient| (mapped to [64, 128): 9 binades of head room up the data-gradient
+  // chain, conversions saturate); everything downstream is linear in it, and the inverse is applied where fp32 results leave the
+  // tile (accumulator read-out, PE / head-bias sums, g_emb).  s_gmax: per-warp maxima; s_inv[it & 1]: the tile's 1 / scale.
+  __shared__ float s_gmax[4], s_inv[2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {
     float* c = reinterpret_cast<float*>(sm + B_C);
@@ -583,7 +587,7 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
     }
   }
   __syncthreads();
-  if (tid < TPT) *reinterpret_cast<__nv_bfloat16*>(sm + B_ONES + blk_off(tid, 0, 16)) = __float2bfloat16_rn(1.0f);
+  if (tid < TPT) *reinterpret_cast<unsigned short*>(sm + B_ONES + blk_off(tid, 0, 16)) = (unsigned short)OP_ONE;
   if (tid == 0) {
     mbar_init(&fullA0, 1); mbar_init(&fullA1, 1); mbar_init(&fullAX, 1); mbar_init(&fullH, 1); mbar_init(&fullW0, 1); mbar_init(&fullW1, 1);
     mbar_init(&bar_d, 1); mbar_init(&bar_w, 1);
@@ -722,6 +726,7 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
     const uint32_t tl = tmem + ((uint32_t)((warp - 4) * 32) << 16);
     uint32_t pW = 0;
     int sd = 0;
+    float inv = 1.0f;                                      // this tile's 1 / gradient scale
     auto drain = [&](int tcol, int ncols, float* dst) {
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t u[32];
@@ -730,14 +735,16 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j < n) atomicAdd(dst + (size_t)(c0 + j) * 128, __uint_as_float(u[j]));
+          if (j < n) atomicAdd(dst + (size_t)(c0 + j) * 128, __uint_as_float(u[j]) * inv);
       }
     };
-    auto bias = [&](float* d) { uint32_t u[4]; tmem_ld4(tl + T_DO, u); tmem_ld_wait(); atomicAdd(d, __uint_as_float(u[0])); };
+    auto bias = [&](float* d) { uint32_t u[4]; tmem_ld4(tl + T_DO, u); tmem_ld_wait(); atomicAdd(d, __uint_as_float(u[0]) * inv); };
     auto begin = [&]() { mbar_wait(&bar_w, pW); pW ^= 1; tc_fence_after(); };
     auto done = [&]() { tc_fence_before(); nbar_arrive(3 + (sd & 1), 160); ++sd; };
     for (int it = 0; it < nt; ++it) {
-      begin(); drain(T_DW, H + XC_C, part + PR_COL + row); drain(T_DH, 32, part + PR_HEAD + row); done();      // S1 color_linear + heads
+      // (s_inv[it & 1] was written before the epilogue published stage S1, which precedes the first bar_w completion of this tile)
+      begin(); inv = *reinterpret_cast<volatile float*>(&s_inv[it & 1]);
+      drain(T_DW, H + XC_C, part + PR_COL + row); drain(T_DH, 32, part + PR_HEAD + row); done();               // S1 color_linear + heads
       begin(); drain(T_DW, H, part + PR_MID2 + row); bias(part + PR_DB2 + row); done();                        // S2 mid2
       begin(); drain(T_DW, H + XG_C, part + PR_CAT + row); done();                                             // S3 cat_layer
       begin(); drain(T_DW, H, part + PR_MID1 + row); bias(part + PR_DB1 + row); done();                        // S4 mid1
@@ -799,12 +806,31 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
         for (int q = 0; q < 3; ++q) { const float c = rgb[(size_t)p * 3 + q]; dp[q] = g_rgb[(size_t)p * 3 + q] * c * (1.0f - c); }   // sigmoid head
         draw = 10.0f * g_alpha[p];                                                                                                     // alpha = 10 raw
       }
-      *reinterpret_cast<uint4*>(rowblk(sm + B_HD, row, 0, 16)) = make_uint4(pack2(dp[0], dp[1]), pack2(dp[2], draw), 0u, 0u);
-      *reinterpret_cast<uint4*>(rowblk(sm + B_HD, row, 1, 16)) = make_uint4(0u, 0u, 0u, 0u);
       {   // head-bias gradients: lane q of each warp accumulates sum q in a register (shared-memory float atomics are CAS loops)
         const float s0 = warp_sum(dp[0]), s1 = warp_sum(dp[1]), s2 = warp_sum(dp[2]), s3 = warp_sum(draw);
         acc_hb += lane == 0 ? s0 : (lane == 1 ? s1 : (lane == 2 ? s2 : (lane == 3 ? s3 : 0.f)));
       }
+      float tinv = 1.0f;                                                         // 1 / this tile's gradient scale
+#if CNF_OPERAND_FP16
+      {
+        float mx = fmaxf(fmaxf(fabsf(dp[0]), fabsf(dp[1])), fmaxf(fabsf(dp[2]), fabsf(draw)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) s_gmax[warp] = mx;
+        nbar_sync(5, TPT);
+        mx = fmaxf(fmaxf(s_gmax[0], s_gmax[1]), fmaxf(s_gmax[2], s_gmax[3]));
+        // finite non-zero maximum 2^e (1 + f) -> scale 2^(6 - e); zero / non-finite gradients are passed through unscaled
+        const int e = (int)((__float_as_uint(mx) >> 23) & 0xFFu);
+        float gs = 1.0f;
+        if (e > 0 && e < 255) { const int se = min(max(127 + 6 - (e - 127), 1), 254); gs = __uint_as_float((uint32_t)se << 23); }
+        tinv = 1.0f / gs;
+        if (tid == 0) s_inv[it & 1] = tinv;
+        dp[0] *= gs; dp[1] *= gs; dp[2] *= gs; draw *= gs;
+        nbar_sync(5, TPT);                                                       // s_gmax may be rewritten by the next tile
+      }
+#endif
+      *reinterpret_cast<uint4*>(rowblk(sm + B_HD, row, 0, 16)) = make_uint4(pack2(dp[0], dp[1]), pack2(dp[2], draw), 0u, 0u);
+      *reinterpret_cast<uint4*>(rowblk(sm + B_HD, row, 1, 16)) = make_uint4(0u, 0u, 0u, 0u);
       wait(&fullH, pH);
 #pragma unroll 1
       for (int cb = 0; cb < 16; ++cb) {
@@ -899,7 +925,7 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
             pe_double(sn, cn);
             w *= 2.0f;
           }
-          if (!act) gp = 0.f;
+          gp = act ? gp * tinv : 0.f;
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
             const float r = warp_sum(gp * tpt[q]);
@@ -918,9 +944,9 @@ bwd_kernel(int P, const uint8_t* __restrict__ prep, uint8_t* __restrict__ imgs, 
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch)
 #pragma unroll
-          for (int c = 0; c < 32; ++c) if (ch * 32 + c < E1) stg[ch * 32 + c] = __uint_as_float(uu[ch][c]);   // d xg (cat part + in part)
+          for (int c = 0; c < 32; ++c) if (ch * 32 + c < E1) stg[ch * 32 + c] = __uint_as_float(uu[ch][c]) * tinv;   // d xg (cat part + in part)
 #pragma unroll
-        for (int c = 0; c < E2; ++c) stg[E1 + c] = dxc[c * 128];
+        for (int c = 0; c < E2; ++c) stg[E1 + c] = dxc[c * 128] * tinv;
         fence_async_smem();
         nbar_sync(5, TPT);
         const int p0 = tile * TPT;

@@ -214,6 +214,30 @@ class FusedCategoryTrainer:
         return {"u_inv": u[:n1].view(K, R, N + M), "u_val": u[n1:n1 + n2].view(K, R, N), "n_obj": self._rand_n,
                 "u_oth": u[n1 + n2:].view(K, R, M)}
 
+    # ------------------------------------------------------------------------------------------ state snapshot (graph warm-up)
+    def _state_tensors(self):
+        return [self.params, self.pe_B, self.shape_codes, self.tex_codes]
+
+    def snapshot_state(self):
+        """Copies of the trainable state and the optimizer state (moments + device step counter; None if no step was taken yet)."""
+        st = self._opt_state
+        return {"state": [t.clone() for t in self._state_tensors()],
+                "opt": None if st is None else {"t": st["t"].clone(), "m": [t.clone() for t in st["m"]], "v": [t.clone() for t in st["v"]]}}
+
+    def restore_state(self, snap):
+        for t, c in zip(self._state_tensors(), snap["state"]):
+            t.copy_(c)
+        if self._opt_state is not None:
+            st = self._opt_state
+            if snap["opt"] is None:                  # the optimizer state was created after the snapshot: back to "no step taken"
+                st["t"].zero_()
+                for t in st["m"] + st["v"]:
+                    t.zero_()
+            else:
+                st["t"].copy_(snap["opt"]["t"])
+                for t, c in zip(st["m"] + st["v"], snap["opt"]["m"] + snap["opt"]["v"]):
+                    t.copy_(c)
+
     def capture(self, rgbs, depth, origins, dirs, indices, add_reg=True, pre=None, post=None):
         """Capture sampler + fused step over THESE (static) input tensors into a CUDA graph and return ``replay``.
         The step is ~15 launches of microsecond-scale work at Replica-sized batches, i.e. launch-bound from Python;
@@ -229,9 +253,11 @@ class FusedCategoryTrainer:
                 post()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
+        snap = self.snapshot_state()                # ``post`` may be an optimizer step: the warm-up must not train
         with torch.cuda.stream(side):
             for _ in range(2):                      # warm-up: allocations, function attributes, RNG state registration
                 body()
+            self.restore_state(snap)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
@@ -248,15 +274,22 @@ class FusedCategoryTrainer:
 
     # ------------------------------------------------------------------------------------------ optimizer
     def adamw_step(self, lr=1e-3, weight_decay=0.013, code_lr=1e-3, code_weight_decay=0.013, betas=(0.9, 0.999), eps=1e-8):
-        """Fused AdamW over the flat buffers (train.py:40,54-64,183): MLP + PE with (lr, wd), codes with the code group."""
+        """Fused AdamW over the flat buffers (train.py:40,54-64,183): MLP + PE with (lr, wd), codes with the code group -- ONE launch
+        for the four groups.  The step count is a device counter (``self.opt_steps``), so the call can be part of a captured CUDA
+        graph: every replay advances it (cnf_adamw_groups)."""
         if self._opt_state is None:
             z = torch.zeros_like
-            self._opt_state = {"t": 0, "m": [z(self.params), z(self.pe_B), z(self.shape_codes), z(self.tex_codes)],
+            self._opt_state = {"t": torch.zeros(2, dtype=torch.int32, device=self.device),
+                               "m": [z(self.params), z(self.pe_B), z(self.shape_codes), z(self.tex_codes)],
                                "v": [z(self.params), z(self.pe_B), z(self.shape_codes), z(self.tex_codes)]}
         st = self._opt_state
-        st["t"] += 1
-        groups = [(self.params, self.g_params, lr, weight_decay), (self.pe_B, self.g_B, lr, weight_decay),
-                  (self.shape_codes, self.g_shape, code_lr, code_weight_decay),
-                  (self.tex_codes, self.g_tex, code_lr, code_weight_decay)]
-        for i, (p, g, l, wd) in enumerate(groups):
-            ops.adamw_step_(p, g, st["m"][i], st["v"][i], l, betas[0], betas[1], eps, wd, st["t"])
+        groups = [(self.params, self.g_params, st["m"][0], st["v"][0], lr, weight_decay),
+                  (self.pe_B, self.g_B, st["m"][1], st["v"][1], lr, weight_decay),
+                  (self.shape_codes, self.g_shape, st["m"][2], st["v"][2], code_lr, code_weight_decay),
+                  (self.tex_codes, self.g_tex, st["m"][3], st["v"][3], code_lr, code_weight_decay)]
+        ops.adamw_groups_(groups, betas[0], betas[1], eps, st["t"])
+
+    @property
+    def opt_steps(self) -> int:
+        """Optimizer steps taken so far (reads the device counter: synchronises)."""
+        return 0 if self._opt_state is None else int(self._opt_state["t"][0])

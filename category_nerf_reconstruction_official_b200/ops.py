@@ -368,6 +368,20 @@ def adamw_step_(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_
                              float(beta2), float(eps), float(weight_decay), int(step), stream()))
 
 
+def adamw_groups_(groups, beta1, beta2, eps, state):
+    """cnf_adamw_groups: ``groups`` = [(param, grad, exp_avg, exp_avg_sq, lr, weight_decay), ...] (<= 8), all updated by ONE launch;
+    ``state`` = int32[2] device tensor {steps done, 0}: the step count lives on the device, so the call is CUDA-graph capturable."""
+    import ctypes
+    from ._lib import AdamwGroup
+    lib = lib_for(state)
+    assert state.dtype == torch.int32 and state.numel() >= 2
+    arr = (AdamwGroup * len(groups))()
+    for i, (p, g, m, v, lr, wd) in enumerate(groups):
+        assert p.numel() == g.numel() == m.numel() == v.numel()
+        arr[i] = AdamwGroup(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(wd))
+    check(lib.cnf_adamw_groups(len(groups), ctypes.cast(arr, ctypes.c_void_p), float(beta1), float(beta2), float(eps), ptr(state), stream()))
+
+
 def eval_points_fused(points: torch.Tensor, flat_params: torch.Tensor, pe_B: torch.Tensor, pe_scale: torch.Tensor,
                       shape_code: torch.Tensor, tex_code: torch.Tensor):
     """Forward-only tensor-core evaluation (cnf_eval_points): points [P,3], one category's flat CodeNeRF(W=32) parameters,

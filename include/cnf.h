@@ -295,6 +295,18 @@ int cnf_adamw_step(size_t n, float* param, const float* grad, float* exp_avg, fl
                    float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                    cnf_stream_t stream);
 
+/* Same update for up to CNF_ADAMW_MAX_GROUPS parameter groups (train.py:54-64: MLP + PE with lr / weight_decay, code tables
+ * with code_lr / code_weight_decay) in ONE launch, with the step count kept on the device: state = int32[2] {steps done, 0},
+ * zero-initialised by the caller; the kernel uses t = state[0] + 1 and increments it, so the call can be captured into a CUDA
+ * graph and replayed (cnf_adamw_step takes t from the host and would freeze it). `groups` is a host array. */
+#define CNF_ADAMW_MAX_GROUPS 8
+typedef struct {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+  size_t n; float lr; float weight_decay;
+} cnf_adamw_group;
+int cnf_adamw_groups(int n_groups, const cnf_adamw_group* groups, float beta1, float beta2, float eps,
+                     int32_t* state, cnf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

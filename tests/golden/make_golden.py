@@ -211,6 +211,117 @@ def golden_bg(out):
         out[p + kk] = npy(v)
 
 
+def golden_bg128(out):
+    """The reference's background step at its own size (train.py:172-180: OccupancyMap hidden 128, 1200 rays x (5+9) samples, scale 5),
+    un-vmapped, fp32.  Two variants: 'mixed' (the default ray mix, depth term on) and 'nodepth' (every depth invalid, so the depth term
+    is switched off by the empty-mask rule and the loss is well conditioned).  Parameters are shared by the variants."""
+    torch.manual_seed(4242)
+    H, R, N, M = 128, 1200, 5, 9
+    m = ref_model.OccupancyMap(O.EMB_SIZE1, O.EMB_SIZE2, hidden_size=H)
+    m.apply(ref_model.init_weights)
+    pe = ref_embedding.UniDirsEmbed(max_deg=5, scale=5.0)
+    pe.B_layer.weight.data = pe.B_layer.weight.data + 0.02 * torch.randn(21, 3)
+    out["bg128/cfg"] = np.array([H, R, N, M]); out["bg128/scale"] = np.array(5.0)
+    out["bg128/param_names"] = np.array([n for n, _ in m.named_parameters()])
+    for i, (n, t) in enumerate(m.named_parameters()):
+        out["bg128/fc%02d" % i] = npy(t)
+    out["bg128/B"] = npy(pe.B_layer.weight)
+    for name, inv in (("mixed", 0.15), ("nodepth", 1.0)):
+        m.zero_grad(set_to_none=True); pe.zero_grad(set_to_none=True)
+        pcs, z, gd, grgb, dm, om, idx = make_batch(1, 1, R, N, M, seed=500 + int(inv * 10), inv=inv)
+        emb = pe(pcs[0])
+        a, c = m(emb)
+        loss, ld, lcol = ref_loss.step_batch_loss(a[None], c[None], gd, grgb / 255.0, om, dm, z)
+        loss.backward()
+        p = "bg128/" + name + "/"
+        for i, (n, t) in enumerate(m.named_parameters()):
+            out[p + "gfc%02d" % i] = npy(t.grad)
+        out[p + "gB"] = npy(pe.B_layer.weight.grad)
+        for kk, v in dict(pcs=pcs[0], z=z[0], gt_depth=gd[0], gt_rgb=grgb[0], mask_depth=dm[0], labels=om[0],
+                          loss=loss, depth=ld["depth"], colorl=ld["color"], opacity=ld["opacity"]).items():
+            out[p + kk] = npy(v)
+        if name == "mixed":
+            out[p + "alpha"] = npy(a).astype(np.float16); out[p + "color"] = npy(c).astype(np.float16)   # coarse forward check only
+
+
+CURVE = dict(K=2, n_obj=2, R=240, N=1, M=9, L=32, scale=2.0, steps=1000, n_batches=4, lr=1e-3, wd=0.013, code_lr=1e-3, code_wd=0.013)
+
+
+def curve_batches():
+    """The fixed ray batches of the loss-curve fixture (pure data from the oracle's generator; regenerated identically by the test)."""
+    c = CURVE
+    out = []
+    for i in range(c["n_batches"]):
+        g = torch.Generator().manual_seed(9000 + i)
+        cats = [O.synth_rays(c["R"], c["n_obj"], g) for _ in range(c["K"])]
+        out.append(tuple(torch.stack([cat[j] for cat in cats]) for j in range(5)))
+    return out
+
+
+def golden_curve(out):
+    """1000 optimizer steps of the reference's training loop (train.py:40,54-64,88-89,123-184) on CPU: reference sampler, functorch vmap
+    of the reference PE / CodeNeRF, reference losses + regulariser, torch.optim.AdamW with the config's groups.  Step `it` seeds
+    torch's global RNG with 7000 + it before sampling, so the test replays the same random offsets.  Stores the initial state and the
+    loss trajectory (total + the three terms per category)."""
+    c = CURVE
+    K, n_obj, R, N, M, L = c["K"], c["n_obj"], c["R"], c["N"], c["M"], c["L"]
+    torch.manual_seed(31337)
+    fcs, pes, scs, tcs = [], [], [], []
+    for k in range(K):
+        m = ref_model.CodeNeRF(O.EMB_SIZE1, O.EMB_SIZE2, shape_blocks=2, texture_blocks=1, W=32, latent_dim=L)
+        m.apply(ref_model.init_weights)
+        fcs.append(m)
+        pes.append(ref_embedding.UniDirsEmbed(max_deg=5, scale=c["scale"]))
+        scs.append(torch.nn.Parameter(torch.randn(n_obj, L) / np.sqrt(L / 2)))
+        tcs.append(torch.nn.Parameter(torch.randn(n_obj, L) / np.sqrt(L / 2)))
+    opt = torch.optim.AdamW([torch.autograd.Variable(torch.tensor(0))], lr=c["lr"], weight_decay=c["wd"])      # train.py:40
+    for k in range(K):
+        opt.add_param_group({"params": [scs[k]], "lr": c["code_lr"], "weight_decay": c["code_wd"]})                # train.py:63-64
+        opt.add_param_group({"params": [tcs[k]], "lr": c["code_lr"], "weight_decay": c["code_wd"]})
+    fc_model, fc_param, fc_buffer = combine_state_for_ensemble(fcs)                                                  # utils.py:24-28
+    [p.requires_grad_() for p in fc_param]
+    opt.add_param_group({"params": fc_param})
+    pe_model, pe_param, pe_buffer = combine_state_for_ensemble(pes)
+    [p.requires_grad_() for p in pe_param]
+    opt.add_param_group({"params": pe_param})
+    out["curve/cfg"] = np.array([K, n_obj, R, N, M, L, c["steps"], c["n_batches"]])
+    out["curve/hyper"] = np.array([c["scale"], c["lr"], c["wd"], c["code_lr"], c["code_wd"]])
+    for i, t in enumerate(fc_param):                 # copies: the optimizer updates these tensors in place
+        out["curve/fc%02d" % i] = npy(t).copy()
+    out["curve/B"] = npy(pe_param[0]).copy()
+    for k in range(K):
+        out["curve/sc%d" % k] = npy(scs[k]).copy(); out["curve/tc%d" % k] = npy(tcs[k]).copy()
+    batches = curve_batches()
+    sc = bare_scene(N, M)
+    cls_dict = {}
+    for k in range(K):
+        cc = _FakeCls(); cc.trainer = _FakeTrainer(); cc.trainer.n_obj = n_obj; cc.training_device = "cpu"
+        cc.trainer.shape_codes = (lambda t: (lambda ids: t[ids]))(scs[k])
+        cc.trainer.texture_codes = (lambda t: (lambda ids: t[ids]))(tcs[k])
+        cc.obj_ids = list(range(n_obj))
+        cls_dict[k + 1] = cc
+    traj = np.zeros((c["steps"], 1 + 3 * K), dtype=np.float32)
+    for it in range(c["steps"]):
+        rgbs, depth, org, dirs, idx = batches[it % c["n_batches"]]
+        torch.manual_seed(7000 + it)
+        pcs, zs, gd, grgb, dm, om = [], [], [], [], [], []
+        for k in range(K):
+            rgb, d, valid, labels, pc, z = sc.sample_3d_points(rgbs[k], depth[k], org[k], dirs[k])
+            pcs.append(pc); zs.append(z); gd.append(d); grgb.append(rgb); dm.append(valid); om.append(labels)
+        st = torch.stack
+        sh = st([scs[k][idx[k]][:, None, :] for k in range(K)]); tx = st([tcs[k][idx[k]][:, None, :] for k in range(K)])
+        emb = vmap(pe_model)(pe_param, pe_buffer, st(pcs))
+        alpha, color = vmap(fc_model)(fc_param, fc_buffer, emb, sh, tx)
+        loss, ld, _ = ref_loss.step_batch_loss(alpha, color, st(gd), st(grgb) / 255.0, st(om), st(dm), st(zs))
+        rs, rt = ref_loss.step_batch_loss_reg(cls_dict, torch.arange(K))
+        loss = loss + 0.0005 * (rs + rt).sum()                                                                       # train.py:165-169
+        loss.backward()
+        opt.step(); opt.zero_grad(set_to_none=True)                                                                  # train.py:183-184
+        traj[it, 0] = float(loss)
+        traj[it, 1:1 + K] = npy(ld["depth"]); traj[it, 1 + K:1 + 2 * K] = npy(ld["color"]); traj[it, 1 + 2 * K:] = npy(ld["opacity"])
+    out["curve/traj"] = traj
+
+
 def golden_loss(out):
     """step_batch_loss on raw alpha/color incl. the empty-mask quirk (render_rays.py:67-72)."""
     g = torch.Generator().manual_seed(21)
@@ -244,8 +355,11 @@ def golden_loss(out):
 def main():
     torch.set_num_threads(1)
     groups = dict(sampler=golden_sampler, embed=golden_embed, step=golden_train_step, bg=golden_bg,
-                  loss=golden_loss)
+                  loss=golden_loss, bg128=golden_bg128, curve=golden_curve)
+    only = sys.argv[1:]
     for gname, fn in groups.items():
+        if only and gname not in only:
+            continue
         out = {}
         fn(out)
         path = os.path.join(HERE, gname + ".npz")

@@ -1,10 +1,10 @@
 """Tensor-core OccupancyMap (hidden size 128, the reference's background model; src/model.py:86-154, train.py:172-180).
 
 Two references:
-  * a torch fp32 restatement with the kernel's bf16 roundings made explicit (operands of every GEMM bf16, accumulation fp32):
-    the kernel must agree with it to accumulation-order noise (gradients 5e-3 relative L2; measured ~1e-3);
-  * the fp32 oracle (oracle/cnf_oracle.py): what the reference computes.  ReLU masks flip for pre-activations within the bf16
-    forward error of zero, which bounds the agreement of the gradients at a few percent (measured 5-7 %; bound 15 %).
+  * a torch fp32 restatement with the kernel's operand roundings made explicit (operands of every GEMM fp16, accumulation fp32):
+    the kernel must agree with it to accumulation-order noise;
+  * the fp32 oracle (oracle/cnf_oracle.py): what the reference computes.  ReLU masks flip for pre-activations within the fp16
+    forward error of zero, which bounds the agreement of the gradients.
 """
 import pytest
 import torch
@@ -16,7 +16,9 @@ DEV = "cuda"
 
 
 def bf(x):
-    return x.to(torch.bfloat16).to(torch.float32)
+    """Round to the kernels' GEMM operand type (IEEE fp16 by default: cnf_umma.cuh CNF_OPERAND_FP16; the gradient operands carry an
+    exact power-of-two scale per tile, which commutes with the rounding)."""
+    return x.to(torch.float16).to(torch.float32)
 
 
 def occmap_bf16_emulation(params, emb, g_alpha, g_rgb):

@@ -149,3 +149,45 @@ def test_fused_step_repeats_to_atomic_noise():
             worst = max(worst, float((g - ref).abs().max() / ref.abs().max()))
         assert torch.isfinite(ref).all()
         assert worst < 5e-6, "fused step is not repeatable: worst deviation %.3e" % worst
+
+
+def test_fused_adamw_matches_torch_adamw_eager_and_graph():
+    """cnf_adamw_groups (one launch, four groups, device-side step count) against torch.optim.AdamW with the
+    reference's groups (train.py:40,54-64) on identical gradients: 25 eager steps, then -- the ADVICE case -- the optimizer step
+    captured in a CUDA graph together with the training step and replayed: N replays must equal N torch steps (a host-side step
+    count would be frozen into the graph)."""
+    from category_nerf_reconstruction_official_b200.fused import FusedCategoryTrainer
+    K, n_obj, L = 3, 4, 32
+    tr = FusedCategoryTrainer(K, n_obj, latent_dim=L, device=DEV, generator=torch.Generator().manual_seed(4))
+    ref = [t.clone().requires_grad_(True) for t in (tr.params, tr.pe_B, tr.shape_codes, tr.tex_codes)]
+    opt = torch.optim.AdamW([{"params": ref[:2], "lr": 2e-3, "weight_decay": 0.013}, {"params": ref[2:], "lr": 5e-4, "weight_decay": 0.02}])
+    g = torch.Generator(device=DEV).manual_seed(9)
+    for it in range(25):
+        for buf, r in zip((tr.g_params, tr.g_B, tr.g_shape, tr.g_tex), ref):
+            buf.copy_(torch.randn(buf.shape, device=DEV, generator=g) * (0.1 + it % 3))
+            r.grad = buf.clone()
+        tr.adamw_step(lr=2e-3, weight_decay=0.013, code_lr=5e-4, code_weight_decay=0.02)
+        opt.step()
+    assert tr.opt_steps == 25
+    for a, r in zip((tr.params, tr.pe_B, tr.shape_codes, tr.tex_codes), ref):
+        torch.testing.assert_close(a, r.detach(), rtol=2e-5, atol=2e-7)
+    # graph: step + optimizer captured; replays advance the device step counter
+    rgbs, depth, org, dirs, idx = _batch(K, 240, n_obj, 5)
+    tr2 = FusedCategoryTrainer(K, n_obj, latent_dim=L, device=DEV, generator=torch.Generator().manual_seed(4))
+    kw = dict(lr=1e-3, weight_decay=0.013, code_lr=1e-3, code_weight_decay=0.013)
+    before = tr2.params.clone()
+    replay = tr2.capture(rgbs, depth, org, dirs, idx.to(torch.int32), post=lambda: tr2.adamw_step(**kw))
+    torch.cuda.synchronize()
+    assert torch.equal(tr2.params, before) and tr2.opt_steps == 0, "graph warm-up must not train"
+    ref2 = [t.clone().requires_grad_(True) for t in (tr2.params, tr2.pe_B, tr2.shape_codes, tr2.tex_codes)]
+    opt2 = torch.optim.AdamW([{"params": ref2[:2], "lr": 1e-3, "weight_decay": 0.013}, {"params": ref2[2:], "lr": 1e-3, "weight_decay": 0.013}])
+    for it in range(6):
+        # torch side first: gradients of the CURRENT fused state are produced by the replay itself, so feed torch the gradients the
+        # replay computed (the state both optimizers see is identical up to rounding)
+        replay(); torch.cuda.synchronize()
+        for r, gbuf in zip(ref2, (tr2.g_params, tr2.g_B, tr2.g_shape, tr2.g_tex)):
+            r.grad = gbuf.clone()
+        opt2.step()
+        for a, r in zip((tr2.params, tr2.pe_B, tr2.shape_codes, tr2.tex_codes), ref2):
+            torch.testing.assert_close(a, r.detach(), rtol=1e-4, atol=1e-6)
+    assert tr2.opt_steps == 6
