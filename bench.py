@@ -244,8 +244,10 @@ def main():
             t.adamw_step()
         return loss
 
+    opt_post = (lambda t: (lambda: t.adamw_step())) if args.with_optimizer else (lambda t: None)
+
     def timed(t, b, steps, warm, graphed=False):
-        replay = t.capture(b["rgbs"], b["depth"], b["origins"], b["dirs"], b["indices"]) if graphed else None
+        replay = t.capture(b["rgbs"], b["depth"], b["origins"], b["dirs"], b["indices"], post=opt_post(t)) if graphed else None
         for _ in range(warm):
             replay() if graphed else run_step(t, b)
         torch.cuda.synchronize()
@@ -276,7 +278,7 @@ def main():
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    use_graph = not args.no_graph and not args.with_optimizer
+    use_graph = not args.no_graph
     # pass 1 (eager launches): times the fused kernel alone via events recorded around it inside cnf_train_step
     eager_ms, kern_ms = timed(tr, batch, args.steps, warmup)
     # pass 2: the step as a user runs it in a training loop -- one CUDA-graph replay per step
@@ -303,7 +305,7 @@ def main():
     out_host = torch.empty_like(tr.out_loss, device="cpu").pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in hb.values())
     d2h = out_host.numel() * 4
-    e2e_replay = tr.capture(sb["rgbs"], sb["depth"], sb["origins"], sb["dirs"], sb["indices"]) if use_graph else None
+    e2e_replay = tr.capture(sb["rgbs"], sb["depth"], sb["origins"], sb["dirs"], sb["indices"], post=opt_post(tr)) if use_graph else None
 
     def e2e_step():
         dev_block.copy_(host_block, non_blocking=True)                      # H2D of this step's inputs from pinned host memory
@@ -347,9 +349,11 @@ def main():
     flops = pts * FLOP_PER_POINT
     ach = flops / (kern_ms * 1e-3) / 1e12
     traffic = None                       # DRAM bytes of the fused kernel per launch, from the committed ncu capture of this workload
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.workload, {}).get("bytes_per_launch")
+    for tname in ("r02_traffic.json", "r01_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(args.workload, {}).get("bytes_per_launch")
+            break
     roof = {"bound": "tensor", "kernel": "fused_step_kernel", "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
             "frac": ach / pk["bf16_burst"], "traffic": traffic, "peak_source": pk["source"] + " (bf16 burst)",
             "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / step_ms,
@@ -492,6 +496,52 @@ def main():
         except Exception as e:
             extra["background_step_1200x14"] = {"error": repr(e)}
 
+    if rank == 0 and not args.no_large and not args.with_optimizer:
+        # the same step with the fused AdamW update of all four parameter groups inside the captured graph (report
+        # with / without the optimizer; train.py:183)
+        try:
+            tro = make_trainer(wl)
+            bo = synth_batch(wl, seed=100 + rank, device=dev)
+            replay_o = tro.capture(bo["rgbs"], bo["depth"], bo["origins"], bo["dirs"], bo["indices"], post=lambda: tro.adamw_step())
+            for _ in range(warmup):
+                replay_o()
+            torch.cuda.synchronize()
+            tms = []
+            for _ in range(args.steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); replay_o(); e1.record(); torch.cuda.synchronize(); tms.append(e0.elapsed_time(e1))
+            mso = sum(tms) / len(tms)
+            extra["with_optimizer"] = {"ms_per_step": mso, "rays_per_s": K * R / (mso * 1e-3), "optimizer_steps_taken": tro.opt_steps,
+                                       "note": "step + cnf_adamw_groups (one launch, device-side step count) in one CUDA graph"}
+            del tro, bo
+        except Exception as e:
+            extra["with_optimizer"] = {"error": repr(e)}
+
+    if rank == 0 and not args.no_large and world == 1:
+        # HBM-bound standalone kernels of the module-level API against the measured copy bandwidth (SURVEY 8(d) algorithmic bytes;
+        # ncu DRAM counters of the same kernels: profiles/r02_hbm_ncu.txt)
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("bench_standalone", os.path.join(ROOT, "scripts", "bench_standalone.py"))
+            mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+            hk = mod.measure(dev, 1 << 20, 5, flush)
+            extra["hbm_kernels"] = {k_: ({"bytes": v["alg_bytes"], "ms": v["ms"], "gbs": v["gbs"], "frac": v["frac"]} if isinstance(v, dict) else v)
+                                    for k_, v in hk.items()}
+        except Exception as e:
+            extra["hbm_kernels"] = {"error": repr(e)}
+
+    if world > 1:
+        # (collective blocks: every rank takes part)
+        try:
+            extra["ray_split_c4"] = ray_split_c4_block(make_trainer, dev, rank, world, flush, pk)
+        except Exception as e:
+            extra["ray_split_c4"] = {"error": repr(e)}
+        try:
+            extra["scannet0066_sharded"] = category_sharded_block(dev, rank, world, flush)
+        except Exception as e:
+            extra["scannet0066_sharded"] = {"error": repr(e)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -508,7 +558,7 @@ def main():
                   else "oracle port of the reference PyTorch CPU path")}
 
     line = {"metric": metric, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
             "data": "synthetic",
             "config": config_of(args.workload, wl),
             "run": {"optimizer_in_step": bool(args.with_optimizer),
@@ -517,7 +567,7 @@ def main():
             "clocks": clk, "roofline": roof, "cpu_baseline": cb,
             "e2e": {"value": rays_per_step / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": (tr.launches_per_step + (4 if args.with_optimizer else 0)) * args.steps,
+            "gpu_launches": (tr.launches_per_step + (1 if args.with_optimizer else 0)) * args.steps,
             "loss": loss_val}
     line.update(extra)
     print(json.dumps(line))
@@ -557,6 +607,114 @@ def ray_split_arm(args, wl, make_trainer, dev, rank, world, warmup, metric):
                           "config": {"workload": args.workload, "desc": wl["desc"], "parallelism": "ray split %d-way + NCCL all-reduce" % world,
                                      "l2": "flushed between timed steps"}, "loss": float(tr.out_loss[0]),
                           "gpu_launches": 8 * args.steps}))
+
+
+def _event_ms(fn, flush, steps, warm, dist=None, dev=None):
+    """Mean device time of fn() over `steps` calls (L2 flushed before each), max over ranks when `dist` is given."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier(); torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.zero_()
+        a.record(); fn(); b.record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    return ms
+
+
+def ray_split_c4_block(make_trainer, dev, rank, world, flush, pk, steps=10, warm=3):
+    """BASELINE config 4 on `world` GPUs: ONE large category (64 instances x 8192 rays, R = 524288) with its ray batch split over the
+    ranks; identical model replicas; one all-gather of the mask counts / max depth before the sampler and ONE NCCL all-reduce of the
+    flat gradient buffer after the fused step (parallel.RaySplitStep), the whole step captured in a CUDA graph.
+    Also the NCCL parity check a 1-GPU test box cannot run: the N-rank reduced gradients of one step against rank 0's own
+    full-batch gradients on the same samples."""
+    import torch.distributed as dist
+    from category_nerf_reconstruction_official_b200 import ops
+    from category_nerf_reconstruction_official_b200.parallel import RaySplitStep, split_rays
+    wl = dict(WORKLOADS["c4"])
+    K, R, N, M = wl["K"], wl["R"], wl["N"], wl["M"]
+    tr = make_trainer(wl)
+    for t_ in (tr.params, tr.pe_B, tr.shape_codes, tr.tex_codes):             # identical replicas
+        dist.broadcast(t_, src=0)
+    full = synth_batch(wl, seed=100, device=dev)                              # same seed on every rank: same full batch
+    sl = split_rays(R, world, rank)
+    loc = {k_: v[:, sl].contiguous() for k_, v in full.items()}
+    rs = RaySplitStep(tr)
+    # ---- parity: samples of the FULL batch (bit-exact sampler, same seeded offsets on every rank), each rank steps its slice
+    g = torch.Generator(device=dev).manual_seed(77)
+    rand = {"u_inv": torch.rand(K, R, N + M, device=dev, generator=g), "u_val": torch.rand(K, R, N, device=dev, generator=g),
+            "n_obj": torch.randn(K, R, M, device=dev, generator=g) * (0.1 / 3), "u_oth": torch.rand(K, R, M, device=dev, generator=g)}
+    z, _, valid, labels, stats = ops.sample_batched(full["rgbs"], full["depth"], full["origins"], full["dirs"], N, M, 0.1, 0.05, rand,
+                                                     want_pcs=False)
+    counts_full = stats[:, 4:8].contiguous()
+    vm = valid.view(torch.uint8)
+    local_counts = ops.mask_counts(loc["rgbs"][..., 3].contiguous(), vm[:, sl].contiguous())
+    counts_g, _ = rs.global_counts_and_max(local_counts, loc["depth"].max(dim=-1).values)
+    counts_ok = bool(torch.equal(counts_g[:, :3], counts_full[:, :3]))
+    tr.prepare(loc["indices"], loc["indices"].shape[1])
+    rs.step_from_samples(loc["origins"], loc["dirs"], z[:, sl].contiguous(), loc["depth"], loc["rgbs"], vm[:, sl].contiguous(),
+                         loc["indices"], counts_g, prepared=True)
+    reduced = tr.grad_flat.clone()
+    reduced_loss = float(tr.out_loss[0])
+    err = None
+    if rank == 0:
+        tr.step_from_samples(full["origins"], full["dirs"], z, full["depth"], full["rgbs"], vm, full["indices"], counts_full)
+        err = float((reduced.double() - tr.grad_flat.double()).norm() / tr.grad_flat.double().norm())
+        loss_err = abs(reduced_loss - float(tr.out_loss[0])) / abs(float(tr.out_loss[0]))
+    del z, valid, labels, rand, vm
+    torch.cuda.synchronize(); dist.barrier()
+    # ---- timing: the ray-split step as a graph replay (sampler with locally drawn offsets + both collectives inside)
+    try:
+        replay = rs.capture(loc["rgbs"], loc["depth"], loc["origins"], loc["dirs"], loc["indices"])
+        graphed = True
+    except Exception:
+        replay = lambda: rs.step(loc["rgbs"], loc["depth"], loc["origins"], loc["dirs"], loc["indices"])
+        graphed = False
+    ms = _event_ms(replay, flush, steps, warm, dist, dev)
+    ar_ms = _event_ms(rs.allreduce_outputs, flush, steps, warm, dist, dev)     # the gradient all-reduce alone (eager launch)
+    # ---- 1-GPU baseline of the same workload on rank 0 (the others wait): strong-scaling efficiency
+    t1 = None
+    if rank == 0:
+        rep1 = tr.capture(full["rgbs"], full["depth"], full["origins"], full["dirs"], full["indices"])
+        t1 = _event_ms(rep1, flush, 5, 2)
+    torch.cuda.synchronize(); dist.barrier()
+    if rank != 0:
+        return None
+    return {"config": wl["desc"] + "; rays split %d-way" % world, "rays": K * R, "ms_per_step": ms, "rays_per_s": K * R / (ms * 1e-3),
+            "one_gpu_ms_per_step": t1, "strong_efficiency": t1 / (world * ms), "allreduce_ms": ar_ms, "allreduce_share": ar_ms / ms,
+            "allreduce_bytes": tr.grad_flat.numel() * 4, "cuda_graph": graphed, "collectives_per_step": 2,
+            "grad_rel_err_vs_1gpu": err, "loss_rel_err_vs_1gpu": loss_err, "global_counts_match": counts_ok}
+
+
+def category_sharded_block(dev, rank, world, flush, steps=20, warm=3):
+    """BASELINE config 3 (ScanNet scene0066_00-shaped: 8 categories, L = 32, partial-observation depth masks) sharded by category:
+    parallel.shard_categories assigns the 8 categories to the ranks, every rank steps its own, no collective in the step."""
+    import torch.distributed as dist
+    from category_nerf_reconstruction_official_b200.fused import FusedCategoryTrainer
+    from category_nerf_reconstruction_official_b200.parallel import shard_categories
+    wl = dict(WORKLOADS["scannet0066"])
+    mine = shard_categories([float(wl["R"] * (wl["N"] + wl["M"]))] * wl["K"], world)[rank]
+    ms = 0.0
+    if mine:
+        w = dict(wl); w["K"] = len(mine)
+        tr = FusedCategoryTrainer(w["K"], w["n_obj"], latent_dim=w["L"], scale=w["scale"], device=dev, n_bins_cam2surface=w["N"],
+                                  n_bins=w["M"], generator=torch.Generator().manual_seed(77 + rank))
+        b = synth_batch(w, seed=300 + rank, device=dev)
+        replay = tr.capture(b["rgbs"], b["depth"], b["origins"], b["dirs"], b["indices"])
+    else:
+        replay = lambda: None
+    ms = _event_ms(replay, flush, steps, warm, dist, dev)
+    if rank != 0:
+        return None
+    return {"config": wl["desc"], "categories_per_rank": [len(x) for x in shard_categories([1.0] * wl["K"], world)],
+            "ms_per_step": ms, "rays_per_s": wl["K"] * wl["R"] / (ms * 1e-3), "collectives_per_step": 0}
 
 
 def timed_single(t, b, run_step, flush, steps, warm):

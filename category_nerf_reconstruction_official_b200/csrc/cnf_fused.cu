@@ -40,7 +40,7 @@ using namespace umma;
 // ---------------------------------------------------------------------------------------------------------
 // out_loss = {loss, e_depth, e_obj, e_sem, depth[K], color[K], opacity[K], reg_shape[K], reg_tex[K]}; executed by one warp
 __device__ __forceinline__ void loss_outputs(int K, const float* __restrict__ raw, const int32_t* __restrict__ counts, int cstride,
-                                             const float* reg, float cs, float os, float reg_scaling, int add_reg,
+                                             const float* reg, float cs, float os, float reg_scaling, int add_reg, int secondary,
                                              float* __restrict__ out_loss) {
   const int lane = threadIdx.x & 31;
   int f0 = 0, f1 = 0, f2 = 0;
@@ -54,12 +54,13 @@ __device__ __forceinline__ void loss_outputs(int K, const float* __restrict__ ra
     const float c = e1 ? 0.f : l[1] / ((float)counts[k * cstride + 1] + 1e-10f);
     const float o = e2 ? 0.f : l[2] / ((float)counts[k * cstride + 2] + 1e-10f);
     out_loss[4 + k] = d; out_loss[4 + K + k] = c; out_loss[4 + 2 * K + k] = o;
-    out_loss[4 + 3 * K + k] = r0; out_loss[4 + 4 * K + k] = r1;
+    out_loss[4 + 3 * K + k] = secondary ? 0.f : r0; out_loss[4 + 4 * K + k] = secondary ? 0.f : r1;
     total += d + c * cs + o * os;
     if (add_reg) total += reg_scaling * (r0 + r1);
   }
   total = warp_sum(total);
-  if (lane == 0) { out_loss[0] = total; out_loss[1] = e0; out_loss[2] = e1; out_loss[3] = e2; }
+  // secondary part of a ray-split step (outputs are summed over the parts): flags and regulariser values are reported by the first part only
+  if (lane == 0) { out_loss[0] = total; out_loss[1] = secondary ? 0.f : (float)e0; out_loss[2] = secondary ? 0.f : (float)e1; out_loss[3] = secondary ? 0.f : (float)e2; }
 }
 
 // grid = (K, FIN_JOBS): one CTA per (category, job); a job is a SLICE of ONE family of outputs, so a CTA's chain of dependent
@@ -99,7 +100,7 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
                       const float* __restrict__ shape_codes, const float* __restrict__ tex_codes,
                       const int32_t* __restrict__ n_obj_arr, const float* __restrict__ raw, const float* __restrict__ rawi,
                       const float* __restrict__ zlat,
-                      float reg_scaling, int add_reg, float* __restrict__ g_params, float* __restrict__ g_B,
+                      float reg_scaling, int add_reg, int secondary, float* __restrict__ g_params, float* __restrict__ g_B,
                       float* __restrict__ g_shape, float* __restrict__ g_tex, float* __restrict__ reg_out,
                       const int32_t* __restrict__ counts, int cstride, float cs, float os, int* __restrict__ done_counter,
                       float* __restrict__ out_loss, long long* __restrict__ dbg /* development aid: per-CTA %globaltimer {start, end} */) {
@@ -311,7 +312,7 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
     __syncthreads();
     if (s_last && tid < 32) {
       __threadfence();
-      loss_outputs(gridDim.x, raw, counts, cstride, reg_out, cs, os, reg_scaling, add_reg, out_loss);
+      loss_outputs(gridDim.x, raw, counts, cstride, reg_out, cs, os, reg_scaling, add_reg, secondary, out_loss);
     }
   }
 }
@@ -456,7 +457,7 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
   if (pm < 1) pm = 1;
   if (pm > 8) pm = 8;
   fused_finalize_kernel<<<dim3(K, fin_jobs(pm)), 256, 0, st>>>(L, nom, params, pe_scale, shape_codes, tex_codes, n_obj, raw, rawi,
-                                                            reinterpret_cast<float*>(w8 + wl.zlat), reg_scaling, flags & 1, g_params, g_B,
+                                                            reinterpret_cast<float*>(w8 + wl.zlat), reg_scaling, flags & 1, (flags >> 2) & 1, g_params, g_B,
                                                             g_shape, g_tex, reg, counts, cstride, cs, os, reinterpret_cast<int*>(w8 + wl.done), out_loss,
                                                             g_dbg);
   return check_launch("cnf_train_step");

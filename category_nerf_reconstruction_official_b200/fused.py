@@ -61,12 +61,20 @@ class FusedCategoryTrainer:
         self.shape_codes = (torch.randn(n_cat, self.n_obj_max, latent_dim, generator=g) / math.sqrt(latent_dim / 2)).to(dev)
         self.tex_codes = (torch.randn(n_cat, self.n_obj_max, latent_dim, generator=g) / math.sqrt(latent_dim / 2)).to(dev)
         self.n_obj = torch.tensor(n_obj, dtype=torch.int32, device=dev)
-        # --- gradients / outputs
-        self.g_params = torch.zeros_like(self.params)
-        self.g_B = torch.zeros_like(self.pe_B)
-        self.g_shape = torch.zeros_like(self.shape_codes)
-        self.g_tex = torch.zeros_like(self.tex_codes)
-        self.out_loss = torch.zeros(4 + 5 * n_cat, device=dev)
+        # --- gradients / outputs: views of ONE flat fp32 buffer {g_params | g_B | g_shape | g_tex | out_loss} (16-byte aligned
+        # segments), so that a ray-split step sums everything over ranks with a single all-reduce and no packing copies
+        segs = [self.params.numel(), self.pe_B.numel(), self.shape_codes.numel(), self.tex_codes.numel(), 4 + 5 * n_cat]
+        offs, tot = [], 0
+        for n in segs:
+            offs.append(tot)
+            tot += (n + 3) // 4 * 4
+        self.grad_flat = torch.zeros(tot, device=dev)
+        view = lambda i, like: self.grad_flat[offs[i]:offs[i] + segs[i]].view(like)
+        self.g_params = view(0, self.params.shape)
+        self.g_B = view(1, self.pe_B.shape)
+        self.g_shape = view(2, self.shape_codes.shape)
+        self.g_tex = view(3, self.tex_codes.shape)
+        self.out_loss = view(4, (4 + 5 * n_cat,))
         self._ws = None
         self._ws_key = None
         self._opt_state = None
@@ -129,10 +137,12 @@ class FusedCategoryTrainer:
                                          ptr(indices), ptr(ws), ws.numel(), stream()))
 
     def step_from_samples(self, origins, dirs, z, gt_depth, rgbs, mask_depth, indices, counts, add_reg: bool = True,
-                          prepared: bool = False):
+                          prepared: bool = False, secondary: bool = False):
         """Fused fwd+bwd given sampled depths z [K,R,S]. rgbs u8 [K,R,4] (rgb + label); mask_depth u8/bool [K,R];
         indices int32 [K,R]; counts int32 [K,4] (or a [K,>=4]-strided view, e.g. the sampler's stats[:, 4:8]).
-        Fills self.g_* and self.out_loss; returns the loss (0-d, async)."""
+        Fills self.g_* and self.out_loss; returns the loss (0-d, async).  ``secondary``: this call is a non-first part of a ray-split
+        step whose outputs are SUMMED over parts: the non-additive slots of out_loss (empty-mask flags, regulariser values) are
+        written as zeros so that the sum carries them once."""
         lib = lib_for(self.params)
         K, R, S = z.shape
         assert K == self.K and S == self.S
@@ -142,7 +152,7 @@ class FusedCategoryTrainer:
         if mask_depth.dtype != torch.uint8:
             mask_depth = mask_depth.to(torch.uint8)
         assert counts.dtype == torch.int32 and counts.stride(1) == 1 and 4 <= counts.stride(0) < 256
-        flags = (1 if add_reg else 0) | (2 if prepared else 0) | (counts.stride(0) << 8)
+        flags = (1 if add_reg else 0) | (2 if prepared else 0) | (4 if secondary else 0) | (counts.stride(0) << 8)
         check(lib.cnf_train_step(K, R, S, self.L, self.n_obj_max, ptr(self.params), ptr(self.pe_B), ptr(self.pe_scale),
                                  ptr(self.shape_codes), ptr(self.tex_codes), ptr(self.n_obj), ptr(origins.contiguous()),
                                  ptr(dirs.contiguous()), ptr(z.contiguous()), ptr(gt_depth.contiguous()),

@@ -76,30 +76,88 @@ def allreduce_gradients(grad_tensors: Sequence[torch.Tensor], group=None, flat: 
     return buf
 
 
+def pack_counts_and_max(counts: torch.Tensor, max_depth: torch.Tensor) -> torch.Tensor:
+    """[K,4] int32 mask counts + [K] fp32 max depth -> ONE int32 [K,5] message (the float travels as its bit pattern)."""
+    return torch.cat([counts.to(torch.int32), max_depth.to(torch.float32).reshape(-1, 1).view(torch.int32)], dim=1).contiguous()
+
+
+def reduce_counts_and_max(gathered: torch.Tensor):
+    """[world,K,5] int32 (all-gathered ``pack_counts_and_max`` messages) -> (global counts int32 [K,4] (sum), max depth fp32 [K] (max))."""
+    counts = gathered[:, :, :4].sum(dim=0, dtype=torch.int32).contiguous()
+    max_depth = gathered[:, :, 4].contiguous().view(torch.float32).max(dim=0).values.contiguous()
+    return counts, max_depth
+
+
 class RaySplitStep:
-    """Ray-split training step of a FusedCategoryTrainer replica: this rank's slice of every category's ray batch."""
+    """Ray-split training step of a FusedCategoryTrainer replica (BASELINE config 4): this rank's slice of every category's rays.
+
+    Per step TWO collectives, both on the compute stream:
+      1. before the sampler, ONE all-gather of a [K,5] int32 message per rank: the three loss-mask counts (denominators
+         N_d, N_o, N_s, src/render_rays.py:86 -- functions of the inputs only) and the bit pattern of the local maximum depth
+         (upper bound of the invalid-depth bins, src/scene_cateogries.py:486); every rank reduces the gathered messages itself
+         (sum / max), so the sampler and the losses see the same globals as a single-GPU step over the whole batch;
+      2. after the fused step, ONE all-reduce (sum) of the trainer's flat buffer {g_params | g_B | g_shape | g_tex | out_loss}
+         (the gradient tensors are views of it: no packing).  The regulariser and the non-additive out_loss slots are produced
+         by rank 0 only (cnf_train_step flags bit0 / bit2), so the sum is exactly the single-GPU result up to fp32 summation order.
+    The whole step (collectives included) can be captured into a CUDA graph (``capture``)."""
 
     def __init__(self, trainer, group=None):
         self.tr = trainer
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
-        self._flat = None
+        self._gathered = None
+        self._graph = None
+
+    # ---- collectives
+    def global_counts_and_max(self, local_counts: torch.Tensor, local_max_depth: torch.Tensor):
+        msg = pack_counts_and_max(local_counts, local_max_depth)
+        K = msg.shape[0]
+        if self._gathered is None or self._gathered.shape[0] != self.world * K:
+            self._gathered = torch.empty(self.world * K, 5, dtype=torch.int32, device=msg.device)    # ranks concatenated along dim 0
+        dist.all_gather_into_tensor(self._gathered, msg, group=self.group)
+        return reduce_counts_and_max(self._gathered.view(self.world, K, 5))
+
+    def allreduce_outputs(self):
+        dist.all_reduce(self.tr.grad_flat, op=dist.ReduceOp.SUM, group=self.group)
+
+    # ---- steps
+    def step_from_samples(self, origins, dirs, z, depth, rgbs, valid_u8, indices, counts_global, prepared=False):
+        """Fused step on this rank's rays with the GLOBAL counts, then the gradient all-reduce."""
+        tr = self.tr
+        tr.step_from_samples(origins, dirs, z, depth, rgbs, valid_u8, indices, counts_global, add_reg=(self.rank == 0),
+                             prepared=prepared, secondary=(self.rank != 0))
+        self.allreduce_outputs()
+        return tr.out_loss[0]
 
     def step(self, rgbs, depth, origins, dirs, indices, rand: Optional[Dict[str, torch.Tensor]] = None):
         """Inputs are THIS rank's rays ([K, R_local, ...]). Returns the global loss (identical on all ranks)."""
         from . import ops, sampling
         tr = self.tr
+        if indices.dtype != torch.int32:
+            indices = indices.to(torch.int32)
         if rand is None:
             rand = sampling.draw_randoms(rgbs, depth, tr.N, tr.M, tr.eps, tr.min_bound, tr.this_obj)
-        max_depth = allreduce_max_depth(depth, self.group)
-        z, _, valid, labels, stats = ops.sample_batched(rgbs, depth, origins, dirs, tr.N, tr.M, tr.eps, tr.stop_eps, rand,
-                                                       tr.min_bound, tr.this_obj, want_pcs=False, max_depth=max_depth)
-        counts = allreduce_counts(stats[:, 4:8].contiguous(), self.group)
-        tr.step_from_samples(origins, dirs, z, depth, rgbs, valid.view(torch.uint8), indices, counts, add_reg=(self.rank == 0))
-        grads = [tr.g_params, tr.g_B, tr.g_shape, tr.g_tex, tr.out_loss]
-        if self._flat is None:
-            self._flat = torch.empty(sum(g.numel() for g in grads), device=tr.g_params.device, dtype=torch.float32)
-        # loss terms are sums over local rays / global counts -> additive too; flags (out_loss[1:4]) are re-derived
-        allreduce_gradients(grads, self.group, self._flat)
-        return tr.out_loss[0]
+        valid = depth > tr.min_bound                                         # scene_cateogries.py:484 (inputs only)
+        local_counts = ops.mask_counts(rgbs[..., 3].contiguous(), valid.view(torch.uint8))
+        counts, max_depth = self.global_counts_and_max(local_counts, depth.max(dim=-1).values)
+        tr.prepare(indices, rgbs.shape[1])
+        z, _, valid_s, _, _ = ops.sample_batched(rgbs, depth, origins, dirs, tr.N, tr.M, tr.eps, tr.stop_eps, rand,
+                                                 tr.min_bound, tr.this_obj, want_pcs=False, max_depth=max_depth)
+        return self.step_from_samples(origins, dirs, z, depth, rgbs, valid_s.view(torch.uint8), indices, counts, prepared=True)
+
+    def capture(self, rgbs, depth, origins, dirs, indices):
+        """Capture ``step`` (sampler, both collectives, fused step) over THESE static tensors into a CUDA graph; returns ``replay``."""
+        dev = self.tr.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.step(rgbs, depth, origins, dirs, indices)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.step(rgbs, depth, origins, dirs, indices)
+        self._graph = graph
+        return graph.replay

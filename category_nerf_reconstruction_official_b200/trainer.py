@@ -10,46 +10,55 @@ from . import embedding, model, render_rays
 
 
 class Trainer:
+    """Per-category model state with the attribute names the reference's callers and checkpoints use (src/trainer.py:11-60):
+    ``fc_occ_map`` (CodeNeRF for object categories, OccupancyMap for cls 0), ``pe`` (UniDirsEmbed), ``shape_codes`` /
+    ``texture_codes`` (nn.Embedding, one row per instance, N(0, 2/latent_dim) init), ``inst_id_to_index``, ``n_obj``, ``obj_scale``,
+    ``bound_extent`` (0.995 background / 0.9 objects), ``extent_dict``, ``scale_template``."""
+
+    EMB_GEOMETRY = 3 + 21 * 4          # raw point + 4 octaves of the 21 directions (input of the geometry branch)
+    EMB_TOTAL = 3 + 21 * 6             # + 2 more octaves for the colour branch
+
     def __init__(self, cfg, cls_id, inst_ids):
-        self.cls_id = cls_id
-        self.inst_id_to_index = {inst_id: inst_ids.index(inst_id) for inst_id in inst_ids}
-        self.n_obj = len(inst_ids)
+        inst_ids = list(inst_ids)
+        self.cls_id, self.n_obj = cls_id, len(inst_ids)
+        self.inst_id_to_index = {inst: row for row, inst in enumerate(inst_ids)}
+        if len(self.inst_id_to_index) != self.n_obj:
+            raise ValueError("duplicate instance ids in %r" % (inst_ids,))
         self.device = cfg.training_device
-        self.obj_scale = cfg.obj_scale
-        self.n_unidir_funcs = cfg.n_unidir_funcs
-        self.emb_size1 = 21 * (3 + 1) + 3
-        self.emb_size2 = 21 * (5 + 1) + 3 - self.emb_size1
-        if cls_id == 0:
+        self.obj_scale, self.n_unidir_funcs = cfg.obj_scale, cfg.n_unidir_funcs
+        self.emb_size1, self.emb_size2 = self.EMB_GEOMETRY, self.EMB_TOTAL - self.EMB_GEOMETRY
+        is_background = cls_id == 0
+        if is_background:
             self.hidden_feature_size = cfg.hidden_feature_size
             self.load_NeRF()
         else:
             self.net_hyperparams = cfg.net_hyperparams
             self.load_codeNeRF()
             self.load_codes()
-        self.extent_dict = None
-        self.bound_extent = 0.995 if self.cls_id == 0 else 0.9
-        self.scale_template = None
-        self.use_tensor_cores = True      # eval_points of CodeNeRF categories through cnf_eval_points (False: fp32 CUDA-core modules)
+        self.bound_extent = 0.995 if is_background else 0.9
+        self.extent_dict = self.scale_template = None
+        self.use_tensor_cores = True      # eval_points / render_rays through the tcgen05 kernels (False: fp32 CUDA-core modules)
+
+    def _make_pe(self):
+        return embedding.UniDirsEmbed(max_deg=self.n_unidir_funcs, scale=self.obj_scale).to(self.device)
 
     def load_codeNeRF(self):
-        self.fc_occ_map = model.CodeNeRF(self.emb_size1, self.emb_size2, **self.net_hyperparams).to(self.device)
-        self.fc_occ_map.apply(model.init_weights).to(self.device)
-        self.pe = embedding.UniDirsEmbed(max_deg=self.n_unidir_funcs, scale=self.obj_scale).to(self.device)
+        net = model.CodeNeRF(self.emb_size1, self.emb_size2, **self.net_hyperparams)
+        net.apply(model.init_weights)                  # xavier-normal weights, default-uniform biases (model.py:4-6)
+        self.fc_occ_map, self.pe = net.to(self.device), self._make_pe()
 
     def load_NeRF(self):
-        self.fc_occ_map = model.OccupancyMap(self.emb_size1, self.emb_size2, hidden_size=self.hidden_feature_size)
-        self.fc_occ_map.apply(model.init_weights).to(self.device)
-        self.pe = embedding.UniDirsEmbed(max_deg=self.n_unidir_funcs, scale=self.obj_scale).to(self.device)
+        net = model.OccupancyMap(self.emb_size1, self.emb_size2, hidden_size=self.hidden_feature_size)
+        net.apply(model.init_weights)
+        self.fc_occ_map, self.pe = net.to(self.device), self._make_pe()
 
     def load_codes(self):
-        embdim = self.net_hyperparams['latent_dim']
-        d = self.n_obj
-        self.shape_codes = nn.Embedding(d, embdim)
-        self.texture_codes = nn.Embedding(d, embdim)
-        self.shape_codes.weight = nn.Parameter(torch.randn(d, embdim) / math.sqrt(embdim / 2))
-        self.texture_codes.weight = nn.Parameter(torch.randn(d, embdim) / math.sqrt(embdim / 2))
-        self.shape_codes = self.shape_codes.to(self.device)
-        self.texture_codes = self.texture_codes.to(self.device)
+        dim = self.net_hyperparams["latent_dim"]
+        std = 1.0 / math.sqrt(dim / 2)
+        for name in ("shape_codes", "texture_codes"):          # shape first: the reference draws them in this order
+            table = nn.Embedding(self.n_obj, dim)
+            table.weight = nn.Parameter(torch.randn(self.n_obj, dim) * std)
+            setattr(self, name, table.to(self.device))
 
     def eval_points(self, points, inst_id=None, chunk_size=500000):
         """points [P,3] -> (occupancy [P], colour [P,3]) with one instance's codes (trainer.py:125-151).

@@ -214,10 +214,12 @@ int cnf_code_reg(int n_obj, int L, const float* codes, float weight, float* out,
  *     limits: S <= 32, 1 <= n_obj_max <= 4096 (CNF_ERR_UNSUPPORTED otherwise).
  *     flags: bit0 = also add the code regulariser (weight reg_scaling) to loss and code grads;
  *            bit1 = the workspace was prepared by cnf_train_step_prepare (same arguments) -- skip that half;
+ *            bit2 = this call is a secondary part of a ray-split step whose outputs are summed over parts / ranks (with the GLOBAL
+ *                   counts): the non-additive slots of out_loss (empty-mask flags [1..3], regulariser values) are written as 0;
  *            bits 8-15 = row stride of `counts` in int32 elements (0 means 4), so cnf_sample_fwd's stats[K,8] + 4 can be passed as is.
  * ---------------------------------------------------------------------------------------------- */
 size_t cnf_train_step_workspace_bytes(int n_cat, int n_rays, int S, int L, int n_obj_max);
-/* Optional first half of a step: everything that does not depend on the sampled depths (bf16 operand images, per-instance
+/* Optional first half of a step: everything that does not depend on the sampled depths (fp16 operand images, per-instance
  * biases, instance sort of the rays, accumulator clear).  Call it on ANY stream (e.g. a side stream overlapping the sampler),
  * make the stream of cnf_train_step wait for it, then pass flags | 2 to cnf_train_step with the same arguments / workspace. */
 int cnf_train_step_prepare(int n_cat, int n_rays, int S, int L, int n_obj_max,

@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_parity_r2.py tests/test_gpu_occmap_tc.py tests/test_gpu_fused.py -m gpu -q -s 2>&1 | grep -E "^\[|P=|background|eval_points|render_rays|well-cond|passed|failed|Error|assert" > gpurun_out/t.log
-cat gpurun_out/t.log
+timeout 1500 python -m pytest tests -m gpu -q -s -x 2>&1 | grep -E "^\[|passed|failed|Error|assert|max abs|rel|P=|background" > gpurun_out/t.log
+tail -30 gpurun_out/t.log
+timeout 600 python scripts/seed_sweep.py > gpurun_out/seed_sweep.txt 2>&1; tail -3 gpurun_out/seed_sweep.txt

@@ -1,5 +1,6 @@
 """GPU parity of the fused tcgen05 training step (cnf_train_step) against the golden vectors (reference outputs)
-and the CPU oracle.  bf16 operands / fp32 accumulation: stated tolerances below."""
+and the CPU oracle.  fp16 operands (power-of-two scaled gradients) / fp32 accumulation.  Every bound below is <= 2x the value
+measured on B200 (profiles/r02_parity.txt), so an arithmetic regression fails the suite."""
 import pytest
 import torch
 
@@ -9,14 +10,18 @@ from oracle import cnf_oracle as O
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
-# Tolerances of the bf16 tensor-core path (north_star: "within a stated relative tolerance, e.g. 1e-3 for the
-# tf32/bf16 MLP" on rendered quantities / loss; gradients are compared by relative L2 error over each tensor).
-LOSS_RTOL = 2e-2
-# Gradients: bf16 rounds every operand to 2^-9 relative, and the depth loss weights rays by 1/(sqrt(var)+1e-4), which on
-# these tiny fixtures (24-60 rays, random-init nets, loss values up to ~2600) amplifies that noise; measured relative L2
-# errors are 0.003-0.12 with cosine similarity >= 0.993 (scripts/diag_fused.py).  The fp32 CUDA-core path is held to 2e-3.
-GRAD_REL_L2 = 0.2
-GRAD_COS = 0.985
+# Tolerances of the tensor-core path (north_star: "within a stated relative tolerance, e.g. 1e-3 for the tf32/bf16 MLP").
+# Loss terms: measured 8e-6 .. 9e-4 relative over all fixtures of this file.
+LOSS_RTOL = 2e-3
+# Gradients, per TENSOR, relative L2: fp16 rounds every GEMM operand to 2^-12 relative; the L1 losses and ReLUs turn that into a few
+# flipped signs / masks, which on these tiny fixtures (24-2400 rays; the depth term weights rays by 1/(sqrt(var)+1e-4)) is up to a
+# few percent of a small bias-like tensor: measured median 0.1-0.6 %, worst 4.4 % (a 32-element bias), cosine >= 0.99903.
+# At the batch sizes the path is built for the same quantity is 0.08-0.9 % (tests/test_gpu_parity_r2.py).
+GRAD_REL_L2 = 0.09
+GRAD_COS = 0.998
+
+
+_SEEN = []          # (name, rel L2, cosine) of every tensor compared since the last _summary()
 
 
 def _grad_ok(actual, expected, name, rel_tol=GRAD_REL_L2, cos_tol=GRAD_COS):
@@ -26,7 +31,20 @@ def _grad_ok(actual, expected, name, rel_tol=GRAD_REL_L2, cos_tol=GRAD_COS):
         return
     rel = float((a - e).norm() / e.norm())
     cos = float(torch.nn.functional.cosine_similarity(a, e, dim=0))
+    _SEEN.append((name, rel, cos))
     assert rel <= rel_tol and cos >= cos_tol, "%s: rel L2 %.3f cos %.4f" % (name, rel, cos)
+
+
+def _summary(tag, loss=None, ref_loss=None):
+    """Print what was measured (pytest -s; copied into profiles/r02_parity.txt) and reset."""
+    if _SEEN:
+        w = max(_SEEN, key=lambda t: t[1]); c = min(_SEEN, key=lambda t: t[2])
+        rels = sorted(t[1] for t in _SEEN)
+        msg = "[fused %s] %d tensors: rel L2 median %.4f worst %.4f (%s), min cosine %.5f (%s)" % (tag, len(_SEEN), rels[len(rels) // 2], w[1], w[0], c[2], c[0])
+        if loss is not None:
+            msg += " | loss rel err %.2e" % (abs(float(loss) - float(ref_loss)) / abs(float(ref_loss)))
+        print("\n" + msg)
+    del _SEEN[:]
 
 
 def _trainer_from_case(c):
@@ -58,10 +76,10 @@ def test_fused_step_vs_golden(name):
     K = c["K"]
     torch.testing.assert_close(lt["reg_shape"].cpu(), c["reg_shape"], rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(lt["reg_texture"].cpu(), c["reg_texture"], rtol=1e-4, atol=1e-5)
-    torch.testing.assert_close(lt["depth"].cpu(), c["depth"], rtol=5e-2, atol=5e-3)
-    torch.testing.assert_close(lt["color"].cpu(), c["colorl"], rtol=LOSS_RTOL, atol=2e-3)
-    torch.testing.assert_close(lt["opacity"].cpu(), c["opacity"], rtol=LOSS_RTOL, atol=2e-3)
-    torch.testing.assert_close(loss.cpu(), c["loss"], rtol=LOSS_RTOL, atol=1e-2)
+    torch.testing.assert_close(lt["depth"].cpu(), c["depth"], rtol=3e-3, atol=1e-3)
+    torch.testing.assert_close(lt["color"].cpu(), c["colorl"], rtol=LOSS_RTOL, atol=2e-4)
+    torch.testing.assert_close(lt["opacity"].cpu(), c["opacity"], rtol=LOSS_RTOL, atol=2e-4)
+    torch.testing.assert_close(loss.cpu(), c["loss"], rtol=LOSS_RTOL, atol=1e-3)
     names = [n for n, _ in O.codenerf_param_shapes(32, c["L"])]
     for k in range(K):
         gv = tr.grad_views(k)
@@ -71,6 +89,7 @@ def test_fused_step_vs_golden(name):
         n = c["n_obj"]
         _grad_ok(tr.g_shape[k, :n], c["gsc"][k], "shape_codes")
         _grad_ok(tr.g_tex[k, :n], c["gtc"][k], "texture_codes")
+    _summary("golden " + name, loss, c["loss"])
 
 
 def test_fused_step_multi_tile_vs_oracle():
@@ -95,7 +114,7 @@ def test_fused_step_multi_tile_vs_oracle():
     fc = [torch.stack([tr.param_views(k)[i].cpu() for k in range(K)]) for i in range(28)]
     out = O.train_step(fc, tr.pe_B.cpu(), 2.0, [tr.shape_codes[k].cpu() for k in range(K)], [tr.tex_codes[k].cpu() for k in range(K)],
                        st(pcs), st(zz), depth, rgbs[..., :3], st(labels), st(valid), idx)
-    torch.testing.assert_close(loss.cpu(), out["loss"], rtol=LOSS_RTOL, atol=1e-2)
+    torch.testing.assert_close(loss.cpu(), out["loss"], rtol=LOSS_RTOL, atol=1e-3)
     for k in range(K):
         gv = tr.grad_views(k)
         for i in range(28):
@@ -103,16 +122,19 @@ def test_fused_step_multi_tile_vs_oracle():
         _grad_ok(tr.g_B[k], out["g_B"][k], "B")
         _grad_ok(tr.g_shape[k], out["g_shape"][k], "sc")
         _grad_ok(tr.g_tex[k], out["g_texture"][k], "tc")
+    _summary("multi_tile", loss, out["loss"])
 
 
 def test_fused_gradients_well_conditioned_vs_oracle(capsys):
-    """bf16 tensor-core path against the fp32 oracle on a WELL-CONDITIONED loss: every ray has an invalid depth, so the depth term
-    (whose 1/(sqrt(var)+1e-4) weighting amplifies rounding noise without bound) is switched off by the reference's empty-mask rule
-    and the loss is 5*colour + 10*opacity.  Tolerances: loss 2e-3 relative; the WHOLE MLP gradient (all tensors concatenated)
-    relative L2 <= 0.03; every single gradient tensor relative L2 <= 0.2 and cosine >= 0.98.  Over 12 weight / data seeds
-    (scripts/seed_sweep.py, profiles/r01_parity_seed_sweep.txt) the whole gradient measured 0.4-2.0 %, the worst single tensor
-    (always B_layer or encoding_xyz.weight) 6-14.5 %, cosine >= 0.9895.  The residual is not only bf16 rounding (2^-9 per operand over a 7-layer chain): the
-    losses are L1, so a ray whose rendered colour / opacity is within the forward error of its target flips the SIGN of its gradient."""
+    """Tensor-core path (fp16 operands) against the fp32 oracle on a WELL-CONDITIONED loss: every ray has an invalid depth, so the
+    depth term (whose 1/(sqrt(var)+1e-4) weighting amplifies rounding noise without bound) is switched off by the reference's
+    empty-mask rule and the loss is 5*colour + 10*opacity.  Bounds (2x the measured values of this seed): loss 2e-4 relative
+    (measured 6.9e-5); the WHOLE MLP gradient (all tensors concatenated) relative L2 <= 2e-3 (9e-4); every single gradient tensor
+    relative L2 <= 0.05 (0.025, B_layer) and cosine >= 0.9993 (0.99969).  Over 12 weight / data seeds (scripts/seed_sweep.py,
+    profiles/r02_parity_seed_sweep.txt): whole gradient 0.10-0.50 %, worst single tensor 1.6-5.8 % (bf16 operands, round 1:
+    0.4-2.0 % / 6-14.5 %).  The residual is not plain rounding (the fp32 reference itself is 1e-6 from fp64,
+    scripts/fp32_noise_floor.py): the losses are L1 and the units ReLUs, so a ray / unit within the forward error of its
+    kink flips the sign / mask of its whole gradient path."""
     from category_nerf_reconstruction_official_b200.fused import FusedCategoryTrainer
     g = torch.Generator().manual_seed(11)
     K, n_obj, R, N, M, L = 2, 4, 1536, 1, 9, 32
@@ -135,7 +157,7 @@ def test_fused_gradients_well_conditioned_vs_oracle(capsys):
     out = O.train_step(fc, tr.pe_B.cpu(), 2.0, [tr.shape_codes[k].cpu() for k in range(K)], [tr.tex_codes[k].cpu() for k in range(K)],
                        pcs, zc, depth, rgbs[..., :3], labels.cpu(), valid.cpu().bool(), idx)
     assert float(out["loss"]) > 1.0
-    torch.testing.assert_close(loss.cpu(), out["loss"], rtol=2e-3, atol=1e-4)
+    torch.testing.assert_close(loss.cpu(), out["loss"], rtol=2e-4, atol=1e-5)
     worst_rel, worst_cos = 0.0, 1.0
     errs = []
     def chk(a, e, name):
@@ -146,7 +168,7 @@ def test_fused_gradients_well_conditioned_vs_oracle(capsys):
         rel = float((a - e).norm() / e.norm()); cos = float(torch.nn.functional.cosine_similarity(a, e, dim=0))
         worst_rel, worst_cos = max(worst_rel, rel), min(worst_cos, cos)
         errs.append("%s %.4f" % (name.split(".")[0], rel))
-        assert rel <= 0.2 and cos >= 0.98, "%s: rel L2 %.4f cos %.5f" % (name, rel, cos)
+        assert rel <= 0.05 and cos >= 0.9993, "%s: rel L2 %.4f cos %.5f" % (name, rel, cos)
     names = [n for n, _ in O.codenerf_param_shapes(32, L)]
     for k in range(K):
         gv = tr.grad_views(k)
@@ -158,7 +180,7 @@ def test_fused_gradients_well_conditioned_vs_oracle(capsys):
     A = tr.g_params.flatten().cpu().double()
     E = torch.cat([torch.cat([out["g_fc"][i][k].flatten() for i in range(28)]) for k in range(K)]).double()
     whole = float((A - E).norm() / E.norm())
-    assert whole <= 0.03, "whole MLP gradient rel L2 %.4f" % whole
+    assert whole <= 2e-3, "whole MLP gradient rel L2 %.4f" % whole
     with capsys.disabled():
         print("\n[well-conditioned parity] whole MLP gradient rel L2 %.4f" % whole)
         print("[well-conditioned parity] loss rel err %.2e, worst gradient rel L2 %.4f, worst cosine %.6f"
@@ -168,7 +190,8 @@ def test_fused_gradients_well_conditioned_vs_oracle(capsys):
 
 def test_eval_points_tensor_core_vs_oracle():
     """cnf_eval_points (forward-only tcgen05 path behind Trainer.eval_points) against the fp32 oracle: ragged point count
-    (3 chains x several tiles + a partial tile).  Tolerance: occupancy / colour 2e-2 absolute (bf16 operands; measured ~3e-3)."""
+    (3 chains x several tiles + a partial tile).  Bound: occupancy 4e-3, colour 1e-3 absolute (fp16 operands, a x10 occupancy logit;
+    measured 1.7e-3 / 3.1e-4)."""
     from category_nerf_reconstruction_official_b200 import ops
     g = torch.Generator().manual_seed(21)
     L, P = 32, 128 * 7 + 37
@@ -186,14 +209,14 @@ def test_eval_points_tensor_core_vs_oracle():
     err_o = float((occ.cpu() - occ_o).abs().max()); err_c = float((rgb.cpu() - c_o).abs().max())
     print("eval_points: max abs err occupancy %.2e colour %.2e (occupancy range %.3f..%.3f)" % (err_o, err_c, float(occ_o.min()), float(occ_o.max())))
     assert float(occ_o.max() - occ_o.min()) > 0.05
-    assert err_o < 2e-2 and err_c < 2e-2
+    assert err_o < 4e-3 and err_c < 1e-3
 
 
 @pytest.mark.parametrize("R,S,L", [(1000, 14, 64), (333, 96, 32), (257, 1, 32), (70000, 10, 256), (40, 200, 32)])
 def test_render_rays_tensor_core_vs_oracle(R, S, L):
     """cnf_render_rays (BASELINE config 5: forward-only dense rendering; S = 96 as category_registration.py:146) against the oracle
-    chain embed -> CodeNeRF -> sigmoid -> occupancy_to_termination -> render.  bf16 operands and a x10 occupancy logit: every output max-abs 5e-2
-    over up to 700k points (measured worst 2.2e-2), termination weights mean-abs 5e-3."""
+    chain embed -> CodeNeRF -> sigmoid -> occupancy_to_termination -> render.  fp16 operands and a x10 occupancy logit: every output
+    max-abs 7e-3 over up to 700k points (measured worst 3.5e-3: depth, on a 0..2.5 range), termination weights max-abs 5e-3 (2.4e-3)."""
     from category_nerf_reconstruction_official_b200 import ops
     g = torch.Generator().manual_seed(77 + S)
     params = O.init_params(O.codenerf_param_shapes(32, L), g)
@@ -224,7 +247,7 @@ def test_render_rays_tensor_core_vs_oracle(R, S, L):
           % (R, S, err_w, err_D, err_C, err_O, err_v, float(Op.min()), float(Op.max())))
     assert float(Op.max() - Op.min()) > 0.02
     mean_w = float((out["weights"].cpu() - w).abs().mean())
-    assert err_w < 5e-2 and mean_w < 5e-3 and err_D < 5e-2 and err_C < 5e-2 and err_O < 5e-2 and err_v < 5e-2
+    assert err_w < 5e-3 and mean_w < 5e-4 and err_D < 7e-3 and err_C < 3e-3 and err_O < 5e-3 and err_v < 5e-3
     # properties independent of the MLP: weights are a sub-probability distribution and reproduce the outputs exactly
     wk = out["weights"]
     assert float(wk.min()) >= 0.0 and float(wk.sum(-1).max()) <= 1.0 + 1e-5
@@ -243,10 +266,9 @@ def test_render_rays_tensor_core_vs_oracle(R, S, L):
 ])
 def test_fused_step_shapes_vs_oracle(K, n_obj, R, N, M, L, empty_inst):
     """Shape / edge-case sweep of the fused step against the oracle.  These 64-2400-ray fixtures include the ill-conditioned depth
-    term (1/(sqrt(var)+1e-4) weights amplify the bf16 forward error), so the bounds only separate "right mapping" from "wrong
-    mapping" (cosine ~ 0): per tensor rel L2 <= 0.6 and cosine >= 0.85, whole MLP gradient of a category rel L2 <= 0.3 and
-    cosine >= 0.95; the tight bounds live in the well-conditioned test above.  (The suite seeds torch's global RNG per test, so
-    the measured values repeat to atomic-order noise.)"""
+    term (1/(sqrt(var)+1e-4) weights).  Bounds = 2x measured: per tensor rel L2 <= 0.09 (worst 0.044) and cosine >= 0.998
+    (0.99903), whole MLP gradient of a category rel L2 <= 0.03.  (The suite seeds torch's global RNG per test, so the measured
+    values repeat to atomic-order noise.)"""
     from category_nerf_reconstruction_official_b200.fused import FusedCategoryTrainer
     n_objs = list(n_obj) if isinstance(n_obj, tuple) else [n_obj] * K
     g = torch.Generator().manual_seed(1000 + K * 7 + n_objs[0])
@@ -270,16 +292,17 @@ def test_fused_step_shapes_vs_oracle(K, n_obj, R, N, M, L, empty_inst):
                        [tr.tex_codes[k, :n_objs[k]].cpu() for k in range(K)],
                        st(pcs), st(zz), depth, rgbs[..., :3], st(labels), st(valid), idx)
     assert torch.isfinite(tr.g_params).all() and torch.isfinite(tr.g_shape).all() and torch.isfinite(tr.g_B).all()
-    torch.testing.assert_close(loss.cpu(), out["loss"], rtol=LOSS_RTOL, atol=1e-2)
+    torch.testing.assert_close(loss.cpu(), out["loss"], rtol=LOSS_RTOL, atol=1e-3)
     for k in range(K):
         gv = tr.grad_views(k)
         for i in range(28):
-            _grad_ok(gv[i], out["g_fc"][i][k], "p%d" % i, 0.6, 0.85)
-        _grad_ok(tr.g_B[k], out["g_B"][k], "B", 0.6, 0.85)
-        _grad_ok(tr.g_shape[k, :n_objs[k]], out["g_shape"][k], "sc", 0.6, 0.85)
-        _grad_ok(tr.g_tex[k, :n_objs[k]], out["g_texture"][k], "tc", 0.6, 0.85)
-        _grad_ok(tr.g_params[k], torch.cat([out["g_fc"][i][k].flatten() for i in range(28)]), "whole MLP gradient", 0.3, 0.95)
+            _grad_ok(gv[i], out["g_fc"][i][k], "p%d" % i)
+        _grad_ok(tr.g_B[k], out["g_B"][k], "B")
+        _grad_ok(tr.g_shape[k, :n_objs[k]], out["g_shape"][k], "sc")
+        _grad_ok(tr.g_tex[k, :n_objs[k]], out["g_texture"][k], "tc")
+        _grad_ok(tr.g_params[k], torch.cat([out["g_fc"][i][k].flatten() for i in range(28)]), "whole MLP gradient", 0.03, 0.9995)
         assert float(tr.g_shape[k, n_objs[k]:].abs().sum()) == 0.0 and float(tr.g_tex[k, n_objs[k]:].abs().sum()) == 0.0
+    _summary("shapes K=%d n_obj=%s R=%d S=%d L=%d" % (K, n_obj, R, N + M, L), loss, out["loss"])
     if empty_inst is not None:      # an instance without rays only gets the regulariser gradient
         reg_only = 0.0005 * tr.shape_codes[:, empty_inst] / tr.shape_codes[:, empty_inst].norm(dim=-1, keepdim=True)
         torch.testing.assert_close(tr.g_shape[:, empty_inst], reg_only, rtol=1e-4, atol=1e-8)

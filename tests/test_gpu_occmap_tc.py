@@ -72,7 +72,7 @@ def test_occmap_tc_fwd_bwd(P):
     torch.cuda.synchronize()
     # (1) bf16 emulation
     a_e, c_e, gp_e, ge_e = occmap_bf16_emulation(params, emb, ga, gc)
-    assert float((alpha.detach().cpu() - a_e).abs().max()) < 5e-2 and float((rgb.detach().cpu() - c_e).abs().max()) < 2e-3
+    assert float((alpha.detach().cpu() - a_e).abs().max()) < 2e-2 and float((rgb.detach().cpu() - c_e).abs().max()) < 5e-4
     r_p, r_e = rel(flat.grad.cpu(), gp_e), rel(emb_d.grad.cpu(), ge_e)
     # (2) fp32 oracle
     fc = [p.clone().requires_grad_(True) for p in params]
@@ -83,13 +83,14 @@ def test_occmap_tc_fwd_bwd(P):
     err_a = float((alpha.detach().cpu() - a_o.detach().reshape(-1)).abs().max())
     err_c = float((rgb.detach().cpu() - c_o.detach().reshape(-1, 3)).abs().max())
     r_po, r_eo = rel(flat.grad.cpu(), gp_o), rel(emb_d.grad.cpu(), emb_o.grad)
-    print("P=%d: vs bf16 emulation grads %.2e g_emb %.2e | vs fp32 oracle alpha %.2e rgb %.2e grads %.3f g_emb %.3f"
+    print("P=%d: vs fp16 emulation grads %.2e g_emb %.2e | vs fp32 oracle alpha %.2e rgb %.2e grads %.3f g_emb %.3f"
           % (P, r_p, r_e, err_a, err_c, r_po, r_eo))
     assert torch.isfinite(flat.grad).all() and torch.isfinite(emb_d.grad).all()
-    assert r_p < 5e-3 and r_e < 5e-3
-    assert err_a < 0.25 and err_c < 1e-2          # alpha = 10 x raw, |alpha| up to ~15
-    if P >= 1000:                                 # few-point gradients are dominated by single ReLU flips
-        assert r_po < 0.15 and r_eo < 0.15
+    # bounds = 2x measured (B200, fp16 operands): vs emulation 3.0e-3; vs fp32 oracle alpha 9.2e-3 (|alpha| up to ~15), rgb 2.3e-4,
+    # gradients 2.2 %
+    assert r_p < 6e-3 and r_e < 6e-3
+    assert err_a < 2e-2 and err_c < 5e-4
+    assert r_po < 0.045 and r_eo < 0.045
 
 
 @pytest.mark.parametrize("P", [77, 128, 1200 * 14, 2 * 148 * 128 + 9])
@@ -122,9 +123,8 @@ def test_occmap_tc_points_variant(P):
     r_p, r_B, r_Bo = rel(gp, flat_r.grad), rel(gB, Bd.grad), rel(gB.cpu(), Bo.grad)
     print("P=%d points variant vs embedding-in: alpha %.2e rgb %.2e grads %.2e B %.2e | B vs fp32 oracle %.3f" % (P, e_a, e_c, r_p, r_B, r_Bo))
     assert torch.isfinite(gp).all() and torch.isfinite(gB).all()
-    assert e_a < 5e-2 and e_c < 5e-3
-    if P >= 1000:
-        assert r_p < 2e-2 and r_B < 5e-2 and r_Bo < 0.2
+    assert e_a < 1.4e-2 and e_c < 3e-4          # measured 6.8e-3 / 1.4e-4
+    assert r_p < 1e-2 and r_B < 1.4e-2 and r_Bo < 0.05          # measured 5.0e-3 / 7.0e-3 / 0.023
 
 
 def test_occmap_tc_eval_points_vs_oracle():
@@ -144,7 +144,7 @@ def test_occmap_tc_eval_points_vs_oracle():
     e_o, e_c = float((occ.cpu() - occ_o).abs().max()), float((rgb.cpu() - c_o.reshape(-1, 3)).abs().max())
     print("occmap eval_points: occupancy max abs err %.2e (range %.3f..%.3f) colour %.2e" % (e_o, float(occ_o.min()), float(occ_o.max()), e_c))
     assert float(occ_o.max() - occ_o.min()) > 0.5
-    assert e_o < 2e-2 and e_c < 2e-2
+    assert e_o < 4e-3 and e_c < 5e-4          # measured 1.6e-3 / 2.0e-4
 
 
 @pytest.mark.parametrize("R,S", [(700, 14), (130, 96)])
@@ -169,7 +169,7 @@ def test_occmap_tc_render_rays_vs_oracle(R, S):
     errs = [float((out["weights"].cpu() - w).abs().max()), float((out["depth"].cpu() - D).abs().max()),
             float((out["rgb"].cpu() - Cc).abs().max()), float((out["opacity"].cpu() - Op).abs().max())]
     print("occmap render_rays R=%d S=%d: max abs err weights %.2e depth %.2e colour %.2e opacity %.2e" % (R, S, *errs))
-    assert max(errs) < 5e-2 and float((out["weights"].cpu() - w).abs().mean()) < 5e-3
+    assert max(errs) < 3e-3 and float((out["weights"].cpu() - w).abs().mean()) < 1.2e-3          # measured max 1.24e-3
     torch.testing.assert_close((out["weights"] * z.to(DEV)).sum(-1), out["depth"], rtol=1e-4, atol=1e-5)
 
 
@@ -199,12 +199,12 @@ def test_occmap_module_tensor_core_background_step():
     l.backward()
     torch.cuda.synchronize()
     out = O.bg_train_step(params, B, 5.0, pcs, z, gt_d, gt_rgb, labels, md)
-    torch.testing.assert_close(l.detach().cpu(), out["loss"], rtol=5e-3, atol=1e-4)
+    torch.testing.assert_close(l.detach().cpu(), out["loss"], rtol=1e-4, atol=1e-5)
     gp = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).cpu()
     gp_o = torch.cat([t.reshape(-1) for t in out["g_fc"]])
     r_p, r_B = rel(gp, gp_o), rel(pe.B_layer.weight.grad.cpu(), out["g_B"])
     print("background step: loss %.5f vs %.5f, whole MLP gradient rel L2 %.3f, B_layer gradient rel L2 %.3f" % (float(l), float(out["loss"]), r_p, r_B))
-    assert r_p < 0.15 and r_B < 0.2
+    assert r_p < 0.02 and r_B < 0.03          # measured 0.010 / 0.015
 
 
 @pytest.mark.parametrize("well_conditioned", [True, False])
@@ -233,11 +233,11 @@ def test_fused_background_trainer_step_vs_oracle(well_conditioned):
     cos = float(torch.nn.functional.cosine_similarity(tr.g_params.cpu().double(), gp_o.double(), dim=0))
     print("background trainer (well_conditioned=%s): loss %.5f vs %.5f, gradient rel L2 %.3f cos %.4f, B rel L2 %.3f"
           % (well_conditioned, float(loss), float(out["loss"]), r_p, cos, r_B))
-    torch.testing.assert_close(loss.cpu(), out["loss"], rtol=2e-2, atol=1e-3)
+    torch.testing.assert_close(loss.cpu(), out["loss"], rtol=2e-4, atol=1e-5)
     if well_conditioned:
-        assert r_p < 0.1 and r_B < 0.2
+        assert r_p < 0.005 and r_B < 0.012          # measured 0.002 / 0.006
     else:
-        assert r_p < 0.35 and cos > 0.93
+        assert r_p < 0.004 and cos > 0.9999 and r_B < 0.014          # measured 0.001 / 1.0000 / 0.007
     # graph replay == eager
     g_eager = tr.g_params.clone(); l_eager = tr.out_loss.clone()
     rgbs_d, depth_d, org_d, dirs_d = dv(rgbs), dv(depth), dv(org), dv(dirs)

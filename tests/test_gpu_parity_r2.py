@@ -79,19 +79,20 @@ def _oracle_step(tr, n_objs, rgbs, depth, org, dirs, idx, rand, N, M, scale):
                         st(valid), idx)
 
 
-# name -> (K, n_obj, R, N, M, L, scale, invalid_frac, no_depth,   bounds: loss_rel, whole-gradient rel L2, worst tensor rel L2)
+# name -> (K, n_obj, R, N, M, L, scale, invalid_frac, no_depth,   bounds (2x measured): loss rel err, rel L2 of the step's whole
+#          gradient vector, median over categories of the per-category MLP gradient rel L2)
 SHAPES = {
     # BASELINE config 2, the shape bench.py times
-    "c2_replica_room0": (20, 3, 360, 1, 9, 256, 2.0, 0.15, False, (2e-3, 0.05, 0.3)),
-    "c2_replica_room0_nodepth": (20, 3, 360, 1, 9, 256, 2.0, 0.15, True, (5e-4, 0.01, 0.1)),
+    "c2_replica_room0": (20, 3, 360, 1, 9, 256, 2.0, 0.15, False, (5e-4, 0.007, 0.008)),
+    "c2_replica_room0_nodepth": (20, 3, 360, 1, 9, 256, 2.0, 0.15, True, (1e-4, 0.009, 0.013)),
     # BASELINE config 3 (C3): 14 objects over 8 categories, L = 32, scale 3, 15 % invalid depths
-    "c3_scannet_0066": (8, (1, 1, 2, 2, 2, 2, 2, 2), 210, 1, 9, 32, 3.0, 0.15, False, (2e-3, 0.05, 0.3)),
-    "c3_scannet_0066_nodepth": (8, (1, 1, 2, 2, 2, 2, 2, 2), 210, 1, 9, 32, 3.0, 0.15, True, (5e-4, 0.01, 0.1)),
+    "c3_scannet_0066": (8, (1, 1, 2, 2, 2, 2, 2, 2), 210, 1, 9, 32, 3.0, 0.15, False, (2e-4, 0.006, 0.007)),
+    "c3_scannet_0066_nodepth": (8, (1, 1, 2, 2, 2, 2, 2, 2), 210, 1, 9, 32, 3.0, 0.15, True, (1e-4, 0.005, 0.006)),
     # the large-batch path of config 4: nblk = 64 > SORT_SMALL_BLOCKS, K = 1 -> finalize part multiplier 8, 64 instances
-    "c4_large_16k": (1, 64, 16384, 1, 9, 256, 2.0, 0.15, False, (2e-3, 0.05, 0.3)),
-    "c4_large_16k_nodepth": (1, 64, 16384, 1, 9, 256, 2.0, 0.15, True, (5e-4, 0.01, 0.1)),
+    "c4_large_16k": (1, 64, 16384, 1, 9, 256, 2.0, 0.15, False, (1e-3, 0.002, 0.002)),
+    "c4_large_16k_nodepth": (1, 64, 16384, 1, 9, 256, 2.0, 0.15, True, (1e-4, 0.0025, 0.002)),
     # same path, two categories, ray count not a multiple of the 256-ray sort block, S = 14
-    "large_ragged_2x9001": (2, (40, 17), 9001, 5, 9, 64, 2.0, 0.15, True, (5e-4, 0.01, 0.1)),
+    "large_ragged_2x9001": (2, (40, 17), 9001, 5, 9, 64, 2.0, 0.15, True, (1e-4, 0.008, 0.018)),
 }
 MEASURED = {}
 
@@ -145,12 +146,12 @@ def test_fused_step_baseline_shapes_vs_oracle(name):
     # tensors only have to be clearly the right quantity (an L1-loss gradient is a sum of +-1-weighted terms: for a small category a
     # bias-like tensor can nearly cancel, and then a handful of flipped signs is a large RELATIVE error of a tiny number)
     assert rep["loss_rel"] <= bounds[0] and rep["step"] <= bounds[1] and rep["whole_med"] <= bounds[2], rep
-    assert rep["step_cos"] >= 0.999 and rep["whole"] <= 0.25, rep
+    assert rep["step_cos"] >= 0.9999 and rep["whole"] <= 0.2, rep
     for k in range(K):      # padding rows of ragged categories stay untouched
         assert float(tr.g_shape[k, n_objs[k]:].abs().sum()) == 0.0 and float(tr.g_tex[k, n_objs[k]:].abs().sum()) == 0.0
 
 
-@pytest.mark.parametrize("variant,bounds", [("mixed", (5e-3, 0.1, 0.15)), ("nodepth", (5e-4, 0.02, 0.05))])
+@pytest.mark.parametrize("variant,bounds", [("mixed", (3e-4, 0.002, 0.006)), ("nodepth", (1e-4, 0.005, 0.014))])    # 2x measured
 def test_background_trainer_vs_reference_golden_h128(variant, bounds):
     """FusedBackgroundTrainer.step_from_samples (tensor-core OccupancyMap hidden 128 + in-kernel embedding + compositing / losses
     fwd+bwd) on the reference's own background batch against the golden written by the unmodified reference modules."""
@@ -171,7 +172,7 @@ def test_background_trainer_vs_reference_golden_h128(variant, bounds):
           % (variant, float(loss), float(G[p + "loss"]), lr, r_p, cosine(tr.g_params, gp_ref), r_B, worst[1], worst[0]))
     lt = tr.loss_terms()
     for key, ref in (("depth", "depth"), ("color", "colorl"), ("opacity", "opacity")):
-        torch.testing.assert_close(lt[key].cpu(), gt("bg128", p + ref).reshape(1), rtol=bounds[0] * 2, atol=1e-4)
+        torch.testing.assert_close(lt[key].cpu(), gt("bg128", p + ref).reshape(1), rtol=1e-3, atol=1e-5)
     assert lr <= bounds[0] and r_p <= bounds[1] and r_B <= bounds[2], (lr, r_p, r_B)
     if variant == "mixed":
         a_ref = gt("bg128", p + "alpha").float().reshape(-1); c_ref = gt("bg128", p + "color").float().reshape(-1, 3)
@@ -229,14 +230,16 @@ def test_loss_curve_vs_reference_trajectory():
     win = 50
     sa = la.unfold(0, win, win).median(-1).values; sb = lb.unfold(0, win, win).median(-1).values
     relw = (sa - sb).abs() / sb.abs()
-    print("\n[loss curve vs reference] first 20 steps max rel diff %.2e | 50-step window medians: first 4 windows max %.4f, all windows median %.4f q90 %.4f max %.4f | start %.3f -> best window %.3f (reference %.3f -> %.3f)"
-          % (float(first.max()), float(relw[:4].max()), float(relw.median()), float(relw.quantile(0.9)), float(relw.max()),
+    print("\n[loss curve vs reference] step 0 rel diff %.2e, first 20 steps max %.2e | 50-step window medians: first 4 windows max %.4f, all windows median %.4f q90 %.4f max %.4f | start %.3f -> best window %.3f (reference %.3f -> %.3f)"
+          % (float(first[0]), float(first.max()), float(relw[:4].max()), float(relw.median()), float(relw.quantile(0.9)), float(relw.max()),
              float(sa[0]), float(sa.min()), float(sb[0]), float(sb.min())))
     assert float(sb.min()) < 0.7 * float(sb[0]) and float(sa.min()) < 0.7 * float(sa[0]), "no training progress"
-    assert float(first[0]) < 1e-3, "step 0 (identical state and inputs) differs from the reference"
-    assert float(first.max()) < 0.02
-    assert float(relw[:4].max()) < 0.05
-    assert float(relw.median()) < 0.10 and float(relw.quantile(0.9)) < 0.30
+    # measured on B200: first 20 steps max 1.9e-3; first four windows max 0.0063; all windows median 0.012-0.016, q90 0.07-0.13 over runs (the two
+    # trajectories decorrelate slowly: Adam on a loss with 1/(sqrt(var)+1e-4) spikes amplifies every rounding difference)
+    assert float(first[0]) < 2e-3, "step 0 (identical state and inputs) differs from the reference"
+    assert float(first.max()) < 4e-3
+    assert float(relw[:4].max()) < 0.013
+    assert float(relw.median()) < 0.05 and float(relw.quantile(0.9)) < 0.3
 
 
 def test_zz_write_measurements():

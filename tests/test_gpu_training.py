@@ -42,7 +42,7 @@ def test_ray_split_additivity_one_gpu():
         if name == "loss":
             a, f = a[:1], f[:1]          # flags / regs are not additive by design
         rel = float((a - f).norm() / (f.norm() + 1e-12))
-        assert rel < 2e-3, (name, rel)   # identical bf16 math per ray; only fp32 summation order differs
+        assert rel < 1e-4, (name, rel)   # identical fp16 math per ray; only fp32 summation order differs
 
 
 def test_graph_replay_matches_eager():
@@ -121,11 +121,12 @@ def test_loss_curves_overlap_1k_steps():
     print("loss-curve rel diff per 50-step window (medians): median %.4f q90 %.4f max %.4f"
           % (float(rel.median()), float(rel.quantile(0.9)), float(rel.max())))
     # deterministic regime: the first 200 steps agree closely
-    assert float(rel[1:4].max()) < 0.03 and float(rel[0]) < 0.10, ("early loss curves differ", rel[:4].tolist())   # window 0 holds the initial transient
+    assert float(rel[1:4].max()) < 0.02 and float(rel[0]) < 0.05, ("early loss curves differ", rel[:4].tolist())   # window 0 holds the initial transient
     # afterwards the two trajectories decorrelate slowly: the optimisation is chaotic (Adam on a loss with 1/(sqrt(var)+1e-4)
     # spikes) and amplifies bf16 rounding and even the 1e-7 run-to-run noise of the fp32 atomics (scripts/race_check.py shows the
     # fused step itself repeats to 1e-7).  Measured over repeated runs on B200: median 0.03-0.10, q90 0.13-0.35, max 0.18-0.40.
-    assert float(rel.median()) < 0.2 and float(rel.quantile(0.9)) < 0.6, \
+    # fp16 operands (round 2): median 0.018, q90 0.097, max 0.13
+    assert float(rel.median()) < 0.06 and float(rel.quantile(0.9)) < 0.3, \
         ("smoothed loss curves diverge", rel.tolist(), sa.tolist(), sb.tolist())
 
 

@@ -58,6 +58,12 @@ def _worker(rank, world, port, ret):
     local_counts = torch.tensor([[int((va & (lab != 0)).sum()), int((lab != 0).sum()), int((lab != 2).sum()), 0]], dtype=torch.int32)
     counts = parallel.allreduce_counts(local_counts)
     assert counts[0, :3].tolist() == [int((valid & (labels != 0)).sum()), int((labels != 0).sum()), int((labels != 2).sum())]
+    # the ONE-message variant RaySplitStep uses: all-gather of [K,5] int32 (counts + max-depth bits), reduced locally
+    msg = parallel.pack_counts_and_max(local_counts, depth[None, sl].max(dim=-1).values)
+    gathered = torch.empty(world * 1, 5, dtype=torch.int32)
+    dist.all_gather_into_tensor(gathered, msg)
+    c2, m2 = parallel.reduce_counts_and_max(gathered.view(world, 1, 5))
+    assert torch.equal(c2, counts) and float(m2) == float(depth.max())
     # local step with GLOBAL denominators: scale the local masked sums by (local count / global count)
     fcl = [p.clone().requires_grad_(True) for p in fc]
     Bl = B.clone().requires_grad_(True)
