@@ -396,6 +396,26 @@ __global__ void termination_kernel(int n_rays, int S, const float* __restrict__ 
   }
 }
 
+// Backward of occupancy_to_termination (src/render_rays.py:25-33 under autograd): w_i = occ_i T_i, T_i = prod_{j<i} f_j,
+// f_j = 1 - occ_j + 1e-10.  d occ_j = T_j (g_j - Q_j) with Q_j = sum_{i>j} g_i occ_i prod_{j<m<i} f_m, i.e. the reverse recurrence
+// Q_{j} = g_{j+1} occ_{j+1} + f_{j+1} Q_{j+1} -- division-free, so saturated samples (f = 1e-10) need no special case.  One thread
+// per ray (module-level API, off the training hot path): pass 1 parks T_j in the output, pass 2 walks backwards.
+__global__ void termination_bwd_kernel(int n_rays, int S, const float* __restrict__ occ_in, const float* __restrict__ g_w,
+                                       float* __restrict__ g_occ) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rays) return;
+  const float* occ = occ_in + (size_t)r * S;
+  const float* g = g_w + (size_t)r * S;
+  float* out = g_occ + (size_t)r * S;
+  float T = 1.0f;
+  for (int i = 0; i < S; ++i) { out[i] = T; T *= __fadd_rn(__fsub_rn(1.0f, occ[i]), 1e-10f); }
+  float Q = 0.f;
+  for (int j = S - 1; j >= 0; --j) {
+    out[j] = out[j] * (g[j] - Q);
+    Q = fmaf(__fadd_rn(__fsub_rn(1.0f, occ[j]), 1e-10f), Q, g[j] * occ[j]);
+  }
+}
+
 // Inference compositing of points whose occupancy is already activated: pt[r*S+i] = {occ, r, g, b}; one ray per G-lane warp
 // segment, exclusive cumprod by shuffle scans over chunks of G samples with a carry (render_rays.py:25-50, loss.py:44-48).
 __global__ void __launch_bounds__(CT)
@@ -508,6 +528,13 @@ extern "C" int cnf_termination_fwd(int n_rays, int S, const float* occ, float* w
   if (n_rays == 0) return CNF_OK;
   termination_kernel<<<comp_blocks(n_rays, S), CT, 0, as_stream(stream)>>>(n_rays, S, occ, w);
   return check_launch("cnf_termination_fwd");
+}
+
+extern "C" int cnf_termination_bwd(int n_rays, int S, const float* occ, const float* g_w, float* g_occ, cnf_stream_t stream) {
+  CNF_REQUIRE(n_rays >= 0 && S > 0 && occ && g_w && g_occ, "cnf_termination_bwd: bad arguments");
+  if (n_rays == 0) return CNF_OK;
+  termination_bwd_kernel<<<(n_rays + 127) / 128, 128, 0, as_stream(stream)>>>(n_rays, S, occ, g_w, g_occ);
+  return check_launch("cnf_termination_bwd");
 }
 
 extern "C" int cnf_mask_counts(int K, int R, const uint8_t* labels, const uint8_t* mask_depth, int32_t* counts,

@@ -339,6 +339,16 @@ def termination(occ: torch.Tensor) -> torch.Tensor:
     return w
 
 
+def termination_bwd(occ: torch.Tensor, g_w: torch.Tensor) -> torch.Tensor:
+    """Gradient of occupancy_to_termination w.r.t. the occupancies (cnf_termination_bwd)."""
+    lib = lib_for(occ)
+    occ = _f32c(occ); g_w = _f32c(g_w)
+    S = occ.shape[-1]
+    g_occ = torch.empty_like(occ)
+    check(lib.cnf_termination_bwd(occ.numel() // S, S, ptr(occ), ptr(g_w), ptr(g_occ), stream()))
+    return g_occ
+
+
 class CodeRegFn(torch.autograd.Function):
     """sum_i ||codes_i||_2 (0 when n_obj == 1), loss.py:5-15."""
 

@@ -15,12 +15,13 @@ def occupancy_activation(alpha, distances=None):
 class _TerminationFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, occupancy):
+        ctx.save_for_backward(occupancy)
         return ops.termination(occupancy)
 
     @staticmethod
     def backward(ctx, g):
-        raise NotImplementedError("occupancy_to_termination is forward-only here; the differentiable path is "
-                                  "loss.step_batch_loss (fused compositing + loss backward)")
+        (occupancy,) = ctx.saved_tensors
+        return ops.termination_bwd(occupancy, g.contiguous())
 
 
 def occupancy_to_termination(occupancy, is_batch=False):

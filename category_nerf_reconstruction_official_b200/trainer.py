@@ -54,10 +54,12 @@ class Trainer:
 
     def load_codes(self):
         dim = self.net_hyperparams["latent_dim"]
-        std = 1.0 / math.sqrt(dim / 2)
-        for name in ("shape_codes", "texture_codes"):          # shape first: the reference draws them in this order
-            table = nn.Embedding(self.n_obj, dim)
-            table.weight = nn.Parameter(torch.randn(self.n_obj, dim) * std)
+        inv_std = math.sqrt(dim / 2)
+        # RNG consumption as the reference (trainer.py:52-60), so that the same seed gives the same initial codes: both tables are
+        # constructed first (nn.Embedding draws its own, discarded, init), then the N(0, 2/dim) weights, shape before texture
+        tables = {name: nn.Embedding(self.n_obj, dim) for name in ("shape_codes", "texture_codes")}
+        for name, table in tables.items():
+            table.weight = nn.Parameter(torch.randn(self.n_obj, dim) / inv_std)
             setattr(self, name, table.to(self.device))
 
     def eval_points(self, points, inst_id=None, chunk_size=500000):
