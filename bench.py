@@ -46,7 +46,8 @@ def config_of(name, wl):
     """The workload description both arms print (identical keys and values, so the driver can match them)."""
     return {"workload": name, "desc": wl["desc"], "categories_per_gpu": wl["K"], "instances_per_category": wl["n_obj"],
             "rays_per_category": wl["R"], "samples_per_ray": wl["N"] + wl["M"], "latent_dim": wl["L"],
-            "l2": "b200 arm: flushed between timed steps (256 MB write)"}
+            "l2": "b200 arm: flushed between timed steps (256 MB write)",
+            "operands": "b200 arm: fp16 operand images of the parameters are refreshed by the optimizer step (with_optimizer block), not per pass"}
 
 
 def peaks():
@@ -223,9 +224,14 @@ def main():
     K, R, S = wl["K"], wl["R"], wl["N"] + wl["M"]
 
     def make_trainer(w):
-        return FusedCategoryTrainer(w["K"], w["n_obj"], latent_dim=w["L"], scale=w["scale"], device=dev,
-                                    n_bins_cam2surface=w["N"], n_bins=w["M"],
-                                    generator=torch.Generator().manual_seed(1234 + rank))
+        t = FusedCategoryTrainer(w["K"], w["n_obj"], latent_dim=w["L"], scale=w["scale"], device=dev,
+                                 n_bins_cam2surface=w["N"], n_bins=w["M"],
+                                 generator=torch.Generator().manual_seed(1234 + rank))
+        # the fp16 operand images / per-instance latent biases are functions of the parameters: refreshed by the optimizer step
+        # (inside the timed step with --with-optimizer / the with_optimizer block), not rebuilt by every forward+backward pass
+        t.operands_follow_optimizer = True
+        t.refresh_operands(w["R"])
+        return t
 
     # weak scaling: every rank owns its own K categories (categories shard across GPUs; no data-path collective)
     if args.ray_split and world > 1:

@@ -102,7 +102,7 @@ SIGNATURES = {
     "cnf_train_step_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "cnf_train_step": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P, P,
                                c_float, c_float, c_float, c_int, P, P, P, P, P, P, c_size_t, P]),
-    "cnf_train_step_prepare": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_size_t, P]),
+    "cnf_train_step_prepare": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, P, c_size_t, P]),
     "cnf_eval_points_workspace_bytes": (c_size_t, []),
     "cnf_eval_points": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     "cnf_render_rays_workspace_bytes": (c_size_t, [c_int, c_int]),

@@ -358,10 +358,12 @@ extern "C" size_t cnf_train_step_workspace_bytes(int K, int R, int S, int L, int
   return FusedWs(K, R, n_obj_max).total;
 }
 
-// prep + instance sort + accumulator clear: everything of a step that does not depend on the sampled depths
+// prep + instance sort + accumulator clear: everything of a step that does not depend on the sampled depths.
+// what: bit0 = operand half (fp16 weight images, constants, per-instance latent biases: functions of the PARAMETERS only, so a
+// training loop refreshes them once per optimizer step), bit1 = input half (instance sort of this step's rays, accumulator clear).
 static int train_step_prepare(int K, int R, int S, int L, int nom, const float* params, const float* pe_B, const float* pe_scale,
                               const float* shape_codes, const float* tex_codes, const int32_t* n_obj, const int32_t* inst,
-                              uint8_t* w8, const FusedWs& wl, cudaStream_t st) {
+                              uint8_t* w8, const FusedWs& wl, cudaStream_t st, int what = 3) {
   uint8_t* prep = w8 + wl.prep;
   float* ctab = reinterpret_cast<float*>(w8 + wl.ctab);
   float* zlat = reinterpret_cast<float*>(w8 + wl.zlat);
@@ -372,15 +374,22 @@ static int train_step_prepare(int K, int R, int S, int L, int nom, const float* 
   int32_t* seg_tile0 = reinterpret_cast<int32_t*>(w8 + wl.seg_tile0);
   int32_t* perm = reinterpret_cast<int32_t*>(w8 + wl.perm);
   const int rpw = 32 / S, RPT = 4 * rpw, nblk = wl.nblk;
+  const int n_prep = PREP_IMG_PARTS + prep_lat_parts(nom);
+  if (what == 1) {                                         // operand half only
+    fused_prep_kernel<<<dim3(K, n_prep), 256, 0, st>>>(L, nom, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, prep, zlat, ctab);
+    return check_launch("cnf_train_step_refresh");
+  }
   if (nblk <= SORT_SMALL_BLOCKS) {
-    // one launch: images + biases | instance sort | clear of raw, rawi and the finalize completion counter (16-byte chunks)
-    prepare_small_kernel<<<dim3(K, PREP_IMG_PARTS + prep_lat_parts(nom) + 1 + PREP_ZERO_PARTS), 256, nom * sizeof(int), st>>>(
+    // one launch: [images + biases] | instance sort | clear of raw, rawi and the finalize completion counter (16-byte chunks)
+    const int first = (what & 1) ? 0 : n_prep;             // input half only: skip the operand parts
+    prepare_small_kernel<<<dim3(K, n_prep + 1 + PREP_ZERO_PARTS - first), 256, nom * sizeof(int), st>>>(
         L, nom, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, prep, zlat, ctab, R, RPT, inst, seg_ray0, seg_tile0, perm,
-        reinterpret_cast<uint4*>(raw), (wl.reg - wl.raw) / 16, g_dbg);
+        reinterpret_cast<uint4*>(raw), (wl.reg - wl.raw) / 16, first, g_dbg);
     return check_launch("cnf_train_step_prepare");
   }
   CNF_CUDA(cudaMemsetAsync(raw, 0, wl.reg - wl.raw, st));            // raw, rawi and the finalize completion counter
-  fused_prep_kernel<<<dim3(K, PREP_IMG_PARTS + prep_lat_parts(nom)), 256, 0, st>>>(L, nom, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, prep, zlat, ctab);
+  if (what & 1)
+    fused_prep_kernel<<<dim3(K, n_prep), 256, 0, st>>>(L, nom, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, prep, zlat, ctab);
   {
     sort_count_kernel<<<dim3(nblk, K), 256, nom * sizeof(int), st>>>(R, nom, nblk, inst, n_obj, hist);
     sort_scan_kernel<<<K, SORT_SCAN_T, nom * sizeof(int), st>>>(nom, nblk, RPT, hist, base, seg_ray0, seg_tile0);
@@ -398,13 +407,16 @@ static int check_step_sizes(const char* who, int K, int R, int S, int L, int n_o
 
 extern "C" int cnf_train_step_prepare(int K, int R, int S, int L, int n_obj_max, const float* params, const float* pe_B,
                                       const float* pe_scale, const float* shape_codes, const float* tex_codes,
-                                      const int32_t* n_obj, const int32_t* inst, void* ws, size_t ws_bytes, cnf_stream_t stream) {
+                                      const int32_t* n_obj, const int32_t* inst, int what, void* ws, size_t ws_bytes,
+                                      cnf_stream_t stream) {
   if (int e = check_step_sizes("cnf_train_step_prepare", K, R, S, L, n_obj_max)) return e;
-  CNF_REQUIRE(params && pe_B && pe_scale && shape_codes && tex_codes && n_obj && inst && ws, "cnf_train_step_prepare: null pointer");
+  CNF_REQUIRE(what >= 1 && what <= 3, "cnf_train_step_prepare: what = %d (1 operands, 2 inputs, 3 both)", what);
+  CNF_REQUIRE(params && pe_B && pe_scale && shape_codes && tex_codes && n_obj && ((what & 2) == 0 || inst) && ws,
+              "cnf_train_step_prepare: null pointer");
   const FusedWs wl(K, R, n_obj_max);
   if (ws_bytes < wl.total) { set_error("cnf_train_step_prepare: workspace too small (%zu < %zu)", ws_bytes, wl.total); return CNF_ERR_WORKSPACE; }
   return train_step_prepare(K, R, S, L, n_obj_max, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, inst,
-                            reinterpret_cast<uint8_t*>(ws), wl, as_stream(stream));
+                            reinterpret_cast<uint8_t*>(ws), wl, as_stream(stream), what);
 }
 
 extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const float* params, const float* pe_B,

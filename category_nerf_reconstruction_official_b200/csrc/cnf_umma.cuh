@@ -129,6 +129,11 @@ __device__ __forceinline__ uint32_t op_relu2(uint32_t w) {
   const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&w), __float2half2_rn(0.f));
   return *reinterpret_cast<const uint32_t*>(&r);
 }
+__device__ __forceinline__ uint32_t op_pack2_relu(float lo, float hi) {     // relu fused into the conversion (one instruction)
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ uint32_t op_pos_mask2(uint32_t w) { return __hgt2_mask(*reinterpret_cast<const __half2*>(&w), __float2half2_rn(0.f)); }
 __device__ __forceinline__ float op_lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
 __device__ __forceinline__ float op_hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
@@ -142,6 +147,7 @@ __device__ __forceinline__ uint32_t op_relu2(uint32_t w) {
   const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&w), __floats2bfloat162_rn(0.f, 0.f));
   return *reinterpret_cast<const uint32_t*>(&r);
 }
+__device__ __forceinline__ uint32_t op_pack2_relu(float lo, float hi) { return op_relu2(op_pack2(lo, hi)); }
 __device__ __forceinline__ uint32_t op_pos_mask2(uint32_t w) { return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&w), __floats2bfloat162_rn(0.f, 0.f)); }
 __device__ __forceinline__ float op_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float op_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }

@@ -82,6 +82,10 @@ class FusedCategoryTrainer:
         self._side2 = None
         self._rand_key = None
         self.launches_per_step = 0
+        # False: every step rebuilds the fp16 operand images from the fp32 parameters (safe if parameters are edited by hand).
+        # True: they are rebuilt when the parameters change through this class (adamw_step, load_category, refresh_operands).
+        self.operands_follow_optimizer = False
+        self._operands_R = None
 
     # ------------------------------------------------------------------------------------------ state import
     def load_category(self, k: int, fc_params: Sequence[torch.Tensor], B: torch.Tensor, shape_codes: torch.Tensor,
@@ -95,6 +99,7 @@ class FusedCategoryTrainer:
         self.shape_codes[k].zero_(); self.tex_codes[k].zero_()
         self.shape_codes[k, :n].copy_(shape_codes.to(self.device))
         self.tex_codes[k, :n].copy_(tex_codes.to(self.device))
+        self._operands_R = None                     # operand images are stale
 
     def param_views(self, k: int) -> List[torch.Tensor]:
         """The 28 nn.Linear-shaped views of category k's flat parameter buffer (and same for grads via grad_views)."""
@@ -127,14 +132,28 @@ class FusedCategoryTrainer:
             self._ws_key = key
         return self._ws
 
-    def prepare(self, indices, R: int):
-        """First half of a step (cnf_train_step_prepare): operand images, per-instance biases, instance sort, accumulator clear.
-        Independent of the sampled depths, so ``step`` runs it on a side stream next to the sampler."""
+    def prepare(self, indices, R: int, what: Optional[int] = None):
+        """First half of a step (cnf_train_step_prepare), independent of the sampled depths, so ``step`` runs it on a side stream
+        next to the sampler.  Two parts: the OPERAND half (fp16 weight images, per-instance latent biases: functions of the
+        parameters only) and the INPUT half (instance sort of this step's rays, accumulator clear).  With
+        ``operands_follow_optimizer`` the operand half is refreshed by ``adamw_step`` / ``refresh_operands`` (once per parameter
+        change, like the low-precision weight copy of mixed-precision training) and a step only runs the input half."""
         lib = lib_for(self.params)
         ws = self._workspace(R)
+        if what is None:
+            what = 2 if (self.operands_follow_optimizer and self._operands_R == R) else 3
         check(lib.cnf_train_step_prepare(self.K, R, self.S, self.L, self.n_obj_max, ptr(self.params), ptr(self.pe_B),
                                          ptr(self.pe_scale), ptr(self.shape_codes), ptr(self.tex_codes), ptr(self.n_obj),
-                                         ptr(indices), ptr(ws), ws.numel(), stream()))
+                                         ptr(indices) if indices is not None else None, int(what), ptr(ws), ws.numel(), stream()))
+        if what & 1:
+            self._operands_R = R
+
+    def refresh_operands(self, R: Optional[int] = None):
+        """Rebuild the operand half of the step's workspace from the current parameters / codes (call after changing them by hand
+        when ``operands_follow_optimizer`` is set; ``adamw_step`` and ``load_category`` do it themselves)."""
+        R = R if R is not None else (self._ws_key[0] if self._ws_key else None)
+        if R is not None:
+            self.prepare(None, R, what=1)
 
     def step_from_samples(self, origins, dirs, z, gt_depth, rgbs, mask_depth, indices, counts, add_reg: bool = True,
                           prepared: bool = False, secondary: bool = False):
@@ -200,7 +219,8 @@ class FusedCategoryTrainer:
         # kernels of libcnf_sm100.so per step: sampler (1 launch up to 4096 rays per category, else count + scan + emit), prepare half
         # (1 launch up to 32 ray blocks of 256, else prep + count + scan + scatter), fused fwd+bwd, finalize
         R_ = rgbs.shape[1]
-        self.launches_per_step = (1 if R_ <= 4096 else 3) + (1 if (R_ + 255) // 256 <= 32 else 4) + 2
+        skip_ops = self.operands_follow_optimizer and self._operands_R == R_
+        self.launches_per_step = (1 if R_ <= 4096 else 3) + (1 if (R_ + 255) // 256 <= 32 else (3 if skip_ops else 4)) + 2
         loss = self.step_from_samples(origins, dirs, z, depth, rgbs, valid.view(torch.uint8), indices, stats[:, 4:8], add_reg,
                                       prepared=True)
         if prefetch:
@@ -247,6 +267,8 @@ class FusedCategoryTrainer:
                 st["t"].copy_(snap["opt"]["t"])
                 for t, c in zip(st["m"] + st["v"], snap["opt"]["m"] + snap["opt"]["v"]):
                     t.copy_(c)
+        if self.operands_follow_optimizer:
+            self.refresh_operands()
 
     def capture(self, rgbs, depth, origins, dirs, indices, add_reg=True, pre=None, post=None):
         """Capture sampler + fused step over THESE (static) input tensors into a CUDA graph and return ``replay``.
@@ -298,6 +320,8 @@ class FusedCategoryTrainer:
                   (self.shape_codes, self.g_shape, st["m"][2], st["v"][2], code_lr, code_weight_decay),
                   (self.tex_codes, self.g_tex, st["m"][3], st["v"][3], code_lr, code_weight_decay)]
         ops.adamw_groups_(groups, betas[0], betas[1], eps, st["t"])
+        if self.operands_follow_optimizer:
+            self.refresh_operands()
 
     @property
     def opt_steps(self) -> int:

@@ -221,13 +221,17 @@ int cnf_code_reg(int n_obj, int L, const float* codes, float weight, float* out,
  *            bits 8-15 = row stride of `counts` in int32 elements (0 means 4), so cnf_sample_fwd's stats[K,8] + 4 can be passed as is.
  * ---------------------------------------------------------------------------------------------- */
 size_t cnf_train_step_workspace_bytes(int n_cat, int n_rays, int S, int L, int n_obj_max);
-/* Optional first half of a step: everything that does not depend on the sampled depths (fp16 operand images, per-instance
- * biases, instance sort of the rays, accumulator clear).  Call it on ANY stream (e.g. a side stream overlapping the sampler),
- * make the stream of cnf_train_step wait for it, then pass flags | 2 to cnf_train_step with the same arguments / workspace. */
+/* Optional first half of a step: everything that does not depend on the sampled depths.  `what` selects
+ *   1 = the OPERAND half: fp16 weight images, constants and per-instance latent biases -- functions of the parameters only, so a
+ *       training loop refreshes them once per optimizer step (like the low-precision weight copy of mixed-precision training);
+ *   2 = the INPUT half: instance sort of this step's rays (inst) and the accumulator clear;   3 = both.
+ * Call it on ANY stream (e.g. a side stream overlapping the sampler), make the stream of cnf_train_step wait for it, then pass
+ * flags | 2 to cnf_train_step with the same arguments / workspace (both halves must have run since the last parameter change /
+ * for this step's rays). */
 int cnf_train_step_prepare(int n_cat, int n_rays, int S, int L, int n_obj_max,
                            const float* params, const float* pe_B, const float* pe_scale,
                            const float* shape_codes, const float* tex_codes, const int32_t* n_obj,
-                           const int32_t* inst, void* ws, size_t ws_bytes, cnf_stream_t stream);
+                           const int32_t* inst, int what, void* ws, size_t ws_bytes, cnf_stream_t stream);
 int cnf_train_step(int n_cat, int n_rays, int S, int L, int n_obj_max,
                    const float* params, const float* pe_B, const float* pe_scale,
                    const float* shape_codes, const float* tex_codes, const int32_t* n_obj,

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_wrappers.py tests/test_gpu_training.py -m gpu -q -s 2>&1 | grep -E "^\[|passed|failed|Error|assert|^E " | head -60 > gpurun_out/t.log
+for i in 1 2 3; do timeout 600 python -m pytest tests/test_gpu_training.py tests/test_gpu_parity_r2.py -m gpu -q -s -k "curve" 2>&1 | grep -E "loss-curve|loss curve|passed|failed|early|diverge" ; done > gpurun_out/t.log
 cat gpurun_out/t.log

@@ -24,8 +24,8 @@ d = dbg.cpu()
 fn = ["start", "PE done (publish)"]
 for st in ["L1", "L2", "L3", "L4", "L6", "L7"]:
     fn += [st + " wait-begin", st + " mma-done", st + " epi-done (publish)"]
-fn += ["L8 wait-begin", "L8 mma-done", "  h3 stored", "  colours", "  compositing", "tile done (arrive full)"]
-bn = ["start (rays loaded)", "PE recompute done"]
+fn += ["part 1b done (half 0)", "xg | xc copied (tile done)"]
+bn = ["start (rays loaded)", "previous tile drained", "full[b] arrived (forward done)", "prologue done (publish)"]
 for st in ["B8", "B7", "B6", "B4", "B3", "B2"]:
     bn += [st + " wait-begin", st + " mma-done", st + " epi-done (publish)"]
 bn += ["B1 wait-begin", "B1 mma-done", "PE bwd done (publish)"]

