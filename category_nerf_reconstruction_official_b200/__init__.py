@@ -8,6 +8,6 @@ Taekbum/category-nerf-reconstruction-official, behind the reference's own Python
 All compute goes through ``csrc/libcnf_sm100.so`` (C ABI in ``include/cnf.h``); there is no CPU fallback.
 """
 from . import _lib  # noqa: F401
-from ._lib import CnfError, build, load  # noqa: F401
+from ._lib import CnfError, build, build_dev, load, load_dev  # noqa: F401
 
-__all__ = ["build", "load", "CnfError"]
+__all__ = ["build", "load", "build_dev", "load_dev", "CnfError"]

@@ -17,42 +17,44 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libcnf_sm100.so")
-SOURCES = ["cnf_api.cu", "cnf_sampler.cu", "cnf_embed.cu", "cnf_composite.cu", "cnf_mlp_simt.cu",
-           "cnf_selftest.cu", "cnf_fused.cu", "cnf_occmap_tc.cu"]
-HEADERS = ["cnf_common.cuh", "cnf_umma.cuh", "cnf_fused_a.inc", "cnf_fused_b.inc", "cnf_fused_c.inc", os.path.join("..", "..", "include", "cnf.h")]
+# development build: the same sources + cnf_selftest.cu with -DCNF_DEV (include/cnf_dev.h: descriptor self-tests, probes, clock stamps)
+DEV_LIB_PATH = os.path.join(CSRC, "libcnf_sm100_dev.so")
+SOURCES = ["cnf_api.cu", "cnf_sampler.cu", "cnf_embed.cu", "cnf_composite.cu", "cnf_mlp_simt.cu", "cnf_fused.cu", "cnf_occmap_tc.cu"]
+DEV_SOURCES = SOURCES + ["cnf_selftest.cu"]
+HEADERS = ["cnf_common.cuh", "cnf_umma.cuh", "cnf_fused_a.inc", "cnf_fused_b.inc", "cnf_fused_c.inc", os.path.join("..", "..", "include", "cnf.h"),
+           os.path.join("..", "..", "include", "cnf_dev.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
 _lock = threading.Lock()
 _lib = None
+_dev_lib = None
 
 
 class CnfError(RuntimeError):
     pass
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+def _stale(lib_path=None, sources=None) -> bool:
+    lib_path = lib_path or LIB_PATH
+    if not os.path.exists(lib_path):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    for f in SOURCES + HEADERS:
+    t = os.path.getmtime(lib_path)
+    for f in (sources or SOURCES) + HEADERS:
         p = os.path.join(CSRC, f)
         if os.path.exists(p) and os.path.getmtime(p) > t:
             return True
     return False
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu for sm_100a and link libcnf_sm100.so in-tree (nvcc cross-compiles without a GPU)."""
-    if not force and not _stale():
-        return LIB_PATH
+def _compile(lib_path, sources, extra, tag, verbose):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
     os.makedirs(os.path.join(CSRC, "build"), exist_ok=True)
-    for src in SOURCES:
-        obj = os.path.join(CSRC, "build", src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    for src in sources:
+        obj = os.path.join(CSRC, "build", src.replace(".cu", tag + ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -63,11 +65,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise CnfError("nvcc failed for %s:\n%s" % (src, out))
         if verbose and out:
             print(out)
-    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-cudart", "static"]
+    cmd = [nvcc, "-shared", "-o", lib_path] + objs + ["-cudart", "static"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise CnfError("link failed:\n" + r.stdout)
-    return LIB_PATH
+    return lib_path
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu for sm_100a and link libcnf_sm100.so in-tree (nvcc cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    return _compile(LIB_PATH, SOURCES, [], "", verbose)
+
+
+def build_dev(force: bool = False, verbose: bool = False) -> str:
+    """The development build (-DCNF_DEV): product ABI + include/cnf_dev.h.  Used by the hardware self-tests and tuning scripts."""
+    if not force and not _stale(DEV_LIB_PATH, DEV_SOURCES):
+        return DEV_LIB_PATH
+    return _compile(DEV_LIB_PATH, DEV_SOURCES, ["-DCNF_DEV"], ".dev", verbose)
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/cnf.h
@@ -80,6 +96,8 @@ SIGNATURES = {
     "cnf_sample_fwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P,
                                c_float, c_float, c_float, c_int, P, P, P, P, P, P, P, c_size_t, P]),
     "cnf_stratified_bins": (c_int, [c_int, c_int, P, c_int, P, c_int, P, P, P, P]),
+    "cnf_pool_gather": (c_int, [c_int, c_int, c_int] + [P] * 15),
+    "cnf_pool_compose": (c_int, [ctypes.c_int64, P, P, P, P]),
     "cnf_embed_fwd": (c_int, [c_int, c_int, P, P, P, P, P]),
     "cnf_embed_bwd": (c_int, [c_int, c_int, P, P, P, P, P, P, P]),
     "cnf_codenerf_param_count": (c_size_t, [c_int, c_int]),
@@ -118,15 +136,20 @@ SIGNATURES = {
     "cnf_occmap_tc_eval_points": (c_int, [c_int, P, P, P, P, P, P, P, c_size_t, P]),
     "cnf_occmap_tc_render_workspace_bytes": (c_size_t, [c_int, c_int]),
     "cnf_occmap_tc_render_rays": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, c_size_t, P]),
-    "cnf_occmap_tc_set_debug": (c_int, [P]),
     "cnf_occmap_tc_bwd": (c_int, [c_int, P, P, P, P, P, c_size_t, P, P, P]),
-    "cnf_set_debug_buffer": (c_int, [P]),
     "cnf_set_kernel_events": (c_int, [P, P]),
+    "cnf_adamw_step": (c_int, [c_size_t, P, P, P, P, c_float, c_float, c_float, c_float, c_float, c_int, P]),
+    "cnf_adamw_groups": (c_int, [c_int, P, c_float, c_float, c_float, P, P]),
+}
+
+
+# include/cnf_dev.h (development build only)
+DEV_SIGNATURES = {
+    "cnf_occmap_tc_set_debug": (c_int, [P]),
+    "cnf_set_debug_buffer": (c_int, [P]),
     "cnf_umma_m64_probe": (c_int, [c_int, c_int, c_int, P, P, P, P]),
     "cnf_umma_rate_probe": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     "cnf_umma_selftest": (c_int, [c_int, c_int, c_int, P, P, P, P]),
-    "cnf_adamw_step": (c_int, [c_size_t, P, P, P, P, c_float, c_float, c_float, c_float, c_float, c_int, P]),
-    "cnf_adamw_groups": (c_int, [c_int, P, c_float, c_float, c_float, P, P]),
 }
 
 
@@ -148,13 +171,32 @@ def load(auto_build: bool = True):
         if not os.path.exists(path):
             raise CnfError("libcnf_sm100.so is missing (%s): run __graft_entry__.build(); there is no fallback path"
                            % path)
-        lib = ctypes.CDLL(path)
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(lib, name)       # AttributeError if a declared symbol is not exported
-            fn.restype = res
-            fn.argtypes = args
-        _lib = lib
-        return lib
+        _lib = _bind(ctypes.CDLL(path))
+        return _lib
+
+
+def _bind(lib, dev: bool = False):
+    sigs = dict(SIGNATURES)
+    if dev or hasattr(lib, "cnf_set_debug_buffer"):       # a development build loaded through CNF_LIB_PATH
+        sigs.update(DEV_SIGNATURES)
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)       # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def load_dev(auto_build: bool = True):
+    """dlopen the development build (product ABI + include/cnf_dev.h); built on demand."""
+    global _dev_lib
+    with _lock:
+        if _dev_lib is None:
+            if auto_build and _stale(DEV_LIB_PATH, DEV_SOURCES):
+                build_dev()
+            if not os.path.exists(DEV_LIB_PATH):
+                raise CnfError("libcnf_sm100_dev.so is missing: run category_nerf_reconstruction_official_b200.build_dev()")
+            _dev_lib = _bind(ctypes.CDLL(DEV_LIB_PATH), dev=True)
+        return _dev_lib
 
 
 _checked_devices = set()

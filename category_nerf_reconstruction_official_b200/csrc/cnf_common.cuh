@@ -6,6 +6,9 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include "../../include/cnf.h"
+#ifdef CNF_DEV
+#include "../../include/cnf_dev.h"
+#endif
 
 namespace cnf {
 
@@ -36,6 +39,22 @@ inline int check_launch(const char* what) {
       return (int)e__;                                                     \
     }                                                                      \
   } while (0)
+
+// "Has this call site configured the CURRENT device yet?"  Function attributes (the > 48 KB dynamic shared-memory opt-in) are per
+// device, so a process that drives several GPUs must set them once on each; a plain `static bool` would skip every device but
+// the first.  One bit per device ordinal, relaxed atomics (setting an attribute twice is harmless).
+struct DeviceOnce {
+  unsigned long long bits[4] = {0, 0, 0, 0};
+  bool pending() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 256) return true;
+    return ((__atomic_load_n(&bits[dev >> 6], __ATOMIC_RELAXED) >> (dev & 63)) & 1ull) == 0;
+  }
+  void done() {
+    int d = 0;
+    if (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 256) __atomic_fetch_or(&bits[d >> 6], 1ull << (d & 63), __ATOMIC_RELAXED);
+  }
+};
 
 inline cudaStream_t as_stream(cnf_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -560,8 +560,8 @@ extern "C" int cnf_composite_loss_fwd(int K, int R, int S, const float* alpha, c
   if (S <= 32) {
     nb = tile_blocks(R);
     const int smem = tile_smem_floats(S, false) * 4;
-    static bool attr = false;
-    if (!attr) { CNF_CUDA(cudaFuncSetAttribute(composite_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_floats(32, false) * 4)); attr = true; }
+    static DeviceOnce attr;
+    if (attr.pending()) { CNF_CUDA(cudaFuncSetAttribute(composite_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_floats(32, false) * 4)); attr.done(); }
     composite_tile_kernel<0><<<dim3(nb, K), TR, smem, as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth,
                                                                               counts, cs, os, nullptr, out_rays, (float*)ws, nullptr, nullptr);
   } else {
@@ -582,8 +582,8 @@ extern "C" int cnf_composite_loss_bwd(int K, int R, int S, const float* alpha, c
               "cnf_composite_loss_bwd: null pointer");
   if (S <= 32) {
     const int smem = tile_smem_floats(S, true) * 4;
-    static bool attr = false;
-    if (!attr) { CNF_CUDA(cudaFuncSetAttribute(composite_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_floats(32, true) * 4)); attr = true; }
+    static DeviceOnce attr;
+    if (attr.pending()) { CNF_CUDA(cudaFuncSetAttribute(composite_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_floats(32, true) * 4)); attr.done(); }
     composite_tile_kernel<1><<<dim3(tile_blocks(R), K), TR, smem, as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels,
                                                                                         mask_depth, counts, cs, os, g_loss, nullptr, nullptr, g_alpha, g_color);
     return check_launch("cnf_composite_loss_bwd");
@@ -606,8 +606,8 @@ extern "C" int cnf_composite_loss_fwd_bwd(int K, int R, int S, const float* alph
   if (ws_bytes < cnf_composite_workspace_bytes(K, R)) { set_error("cnf_composite_loss_fwd_bwd: workspace too small"); return CNF_ERR_WORKSPACE; }
   const int nb = tile_blocks(R);
   const int smem = tile_smem_floats(S, true) * 4;
-  static bool attr = false;
-  if (!attr) { CNF_CUDA(cudaFuncSetAttribute(composite_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_floats(32, true) * 4)); attr = true; }
+  static DeviceOnce attr;
+  if (attr.pending()) { CNF_CUDA(cudaFuncSetAttribute(composite_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_floats(32, true) * 4)); attr.done(); }
   composite_tile_kernel<2><<<dim3(nb, K), TR, smem, as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth,
                                                                         counts, cs, os, nullptr, out_rays, (float*)ws, g_alpha, g_color);
   composite_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(K, nb, (const float*)ws, counts, cs, os, out_loss);

@@ -345,8 +345,12 @@ struct FusedWs {
 using namespace cnf;
 
 static thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+#ifdef CNF_DEV      // development build only (include/cnf_dev.h): clock-stamp buffer and the instrumented kernel variant
 static thread_local long long* g_dbg = nullptr;
 extern "C" int cnf_set_debug_buffer(void* p) { g_dbg = reinterpret_cast<long long*>(p); return CNF_OK; }
+#else
+static constexpr long long* g_dbg = nullptr;
+#endif
 extern "C" int cnf_set_kernel_events(void* ev_start, void* ev_stop) {
   g_ev_start = reinterpret_cast<cudaEvent_t>(ev_start);
   g_ev_stop = reinterpret_cast<cudaEvent_t>(ev_stop);
@@ -441,11 +445,13 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
   float* raw = reinterpret_cast<float*>(w8 + wl.raw);
   float* rawi = reinterpret_cast<float*>(w8 + wl.rawi);
   float* reg = reinterpret_cast<float*>(w8 + wl.reg);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.pending()) {
     CNF_CUDA(cudaFuncSetAttribute(fused_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+#ifdef CNF_DEV
     CNF_CUDA(cudaFuncSetAttribute(fused_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    attr_set = true;
+#endif
+    attr_set.done();
   }
   int dev = 0, n_sm = 148;
   CNF_CUDA(cudaGetDevice(&dev));
@@ -462,8 +468,11 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
   fa.cstride = cstride;
   fa.cs = cs; fa.os = os; fa.raw = raw; fa.rawi = rawi; fa.dbg = g_dbg;
   if (g_ev_start && g_ev_stop) CNF_CUDA(cudaEventRecord(g_ev_start, st));
+#ifdef CNF_DEV
   if (g_dbg) fused_step_kernel<true><<<dim3(cpc, K), NT, SM_TOTAL, st>>>(fa);
-  else fused_step_kernel<false><<<dim3(cpc, K), NT, SM_TOTAL, st>>>(fa);
+  else
+#endif
+  fused_step_kernel<false><<<dim3(cpc, K), NT, SM_TOTAL, st>>>(fa);
   if (g_ev_start && g_ev_stop) { CNF_CUDA(cudaEventRecord(g_ev_stop, st)); g_ev_start = g_ev_stop = nullptr; }
   int pm = (2 * n_sm) / (K * FIN_JOBS);                 // part multiplier: fill the machine when there are few categories
   if (pm < 1) pm = 1;
@@ -476,11 +485,11 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
 }
 
 static int eval_set_attrs() {
-  static bool done = false;
-  if (!done) {
+  static DeviceOnce done;
+  if (done.pending()) {
     CNF_CUDA(cudaFuncSetAttribute(eval_points_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EV_SMEM));
     CNF_CUDA(cudaFuncSetAttribute(eval_points_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EV_SMEM));
-    done = true;
+    done.done();
   }
   return CNF_OK;
 }

@@ -54,10 +54,15 @@ constexpr int ACT_BYTES = 32768;
 constexpr int EMB_TILE_BYTES = TPT * EMB * 4;    // 66048: one tile's contiguous fp32 [128 x 129] block of emb / g_emb
 
 // development aid: SM-clock stamps of CTA 0 (epilogue thread 0: slots 0..31, control lane 0: slots 32..63); NULL = off
+// (compiled only into the development build, -DCNF_DEV: include/cnf_dev.h)
+#ifdef CNF_DEV
 __device__ long long* g_stamp = nullptr;
 __device__ __forceinline__ void stamp(int slot) {
   if (g_stamp != nullptr && blockIdx.x == 0) g_stamp[slot] = clock64();
 }
+#else
+__device__ __forceinline__ void stamp(int) {}
+#endif
 
 // packed operand pairs / single operand elements (fp16 by default, bf16 with -DCNF_OPERAND_FP16=0: cnf_umma.cuh)
 __device__ __forceinline__ uint32_t pack2(float a, float b) { return op_pack2(a, b); }
@@ -1024,11 +1029,11 @@ static int otc_forward(bool pts, const char* who, int P, const float* params, co
   if (P == 0) return CNF_OK;
   cudaStream_t st = as_stream(stream);
   uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.pending()) {
     CNF_CUDA(cudaFuncSetAttribute(fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
     CNF_CUDA(cudaFuncSetAttribute(fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
-    attr_set = true;
+    attr_set.done();
   }
   int dev = 0, n_sm = 148;
   CNF_CUDA(cudaGetDevice(&dev));
@@ -1048,13 +1053,13 @@ static int otc_eval(const char* who, int P, const float* params, const float* pe
   if (P == 0) return CNF_OK;
   cudaStream_t st = as_stream(stream);
   uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.pending()) {
     CNF_CUDA(cudaFuncSetAttribute(eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
     CNF_CUDA(cudaFuncSetAttribute(eval_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CNF_CUDA(cudaFuncSetAttribute(eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
     CNF_CUDA(cudaFuncSetAttribute(eval_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set = true;
+    attr_set.done();
   }
   int dev = 0, n_sm = 148;
   CNF_CUDA(cudaGetDevice(&dev));
@@ -1135,11 +1140,11 @@ static int otc_backward(bool pts, const char* who, int P, const float* params, c
   if (ws_bytes < cnf_occmap_tc_workspace_bytes(P)) { set_error("%s: workspace too small", who); return CNF_ERR_WORKSPACE; }
   cudaStream_t st = as_stream(stream);
   uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.pending()) {
     CNF_CUDA(cudaFuncSetAttribute(bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
     CNF_CUDA(cudaFuncSetAttribute(bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-    attr_set = true;
+    attr_set.done();
   }
   int dev = 0, n_sm = 148;
   CNF_CUDA(cudaGetDevice(&dev));
@@ -1166,8 +1171,10 @@ extern "C" int cnf_occmap_tc_bwd_points(int P, const float* params, const float*
                       (flags & 1) != 0);
 }
 
+#ifdef CNF_DEV
 extern "C" int cnf_occmap_tc_set_debug(void* stamps /* device buffer of 64 int64, or NULL */) {
   long long* p = reinterpret_cast<long long*>(stamps);
   CNF_CUDA(cudaMemcpyToSymbol(cnf::otc::g_stamp, &p, sizeof(p)));
   return CNF_OK;
 }
+#endif

@@ -368,12 +368,7 @@ __global__ void stratified_bins_kernel(int n_rays, int n_bins, const float* __re
 // origin_dirs_O / origin_dirs_W (scene_cateogries.py:24-47): per-ray camera pose -> ray origin and direction in the object
 // (invert = 1: T_OC = inv(T_CO), general 4x4 inverse by cofactors) or world (invert = 0) frame.  One thread per ray; each
 // thread reads its own 64-byte matrix as four float4 (full sectors).
-__global__ void origin_dirs_kernel(int n, int invert, const float4* __restrict__ T, const float* __restrict__ dirs_c,
-                                   float* __restrict__ origins, float* __restrict__ dirs_out) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  const float4 r0 = T[(size_t)r * 4 + 0], r1 = T[(size_t)r * 4 + 1], r2 = T[(size_t)r * 4 + 2], r3 = T[(size_t)r * 4 + 3];
-  float b[3][4];
+__device__ __forceinline__ void pose_rows(int invert, const float4 r0, const float4 r1, const float4 r2, const float4 r3, float b[3][4]) {
   if (invert) {
     const float m00 = r0.x, m01 = r0.y, m02 = r0.z, m03 = r0.w, m10 = r1.x, m11 = r1.y, m12 = r1.z, m13 = r1.w;
     const float m20 = r2.x, m21 = r2.y, m22 = r2.z, m23 = r2.w, m30 = r3.x, m31 = r3.y, m32 = r3.z, m33 = r3.w;
@@ -393,12 +388,56 @@ __global__ void origin_dirs_kernel(int n, int invert, const float4* __restrict__
     b[1][0] = r1.x; b[1][1] = r1.y; b[1][2] = r1.z; b[1][3] = r1.w;
     b[2][0] = r2.x; b[2][1] = r2.y; b[2][2] = r2.z; b[2][3] = r2.w;
   }
+}
+
+__global__ void origin_dirs_kernel(int n, int invert, const float4* __restrict__ T, const float* __restrict__ dirs_c,
+                                   float* __restrict__ origins, float* __restrict__ dirs_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float b[3][4];
+  pose_rows(invert, T[(size_t)r * 4 + 0], T[(size_t)r * 4 + 1], T[(size_t)r * 4 + 2], T[(size_t)r * 4 + 3], b);
   const float dx = dirs_c[(size_t)r * 3 + 0], dy = dirs_c[(size_t)r * 3 + 1], dz = dirs_c[(size_t)r * 3 + 2];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     dirs_out[(size_t)r * 3 + i] = b[i][0] * dx + b[i][1] * dy + b[i][2] * dz;
     origins[(size_t)r * 3 + i] = b[i][3];
   }
+}
+
+// Device-resident ray pools (sceneCategory.get_training_samples, scene_cateogries.py:352-451): one launch cuts this step's
+// rays of EVERY category out of the pools and turns camera poses into ray origins / directions.  The pools of all categories
+// are concatenated structure-of-arrays (rgbs u8x4 | depth | camera-frame direction | pose index | instance index); the
+// reference's epoch reshuffle `pool = pool[randperm]` (:439-449) is kept as a permutation `perm` over pool rows instead of
+// moving 100 B per ray, so the k-th category's r-th ray of the step is pool row perm[seg[k] + start[k] + r].  `pose_index`
+// NULL = one pose per pool row (t_co_batch_all / t_wc_batch_all, :424-431), else a row of the pose table (the per-frame
+// t_wc_batch_dict[frame_batch] of the background category, :373-379).  Same arithmetic as origin_dirs_kernel.
+__global__ void pool_gather_kernel(int R, int invert, const int64_t* __restrict__ seg, const int64_t* __restrict__ start,
+                                   const int32_t* __restrict__ perm, const uint32_t* __restrict__ rgbs, const float* __restrict__ depth,
+                                   const float* __restrict__ dirs_c, const float4* __restrict__ poses, const int32_t* __restrict__ pose_index,
+                                   const int64_t* __restrict__ inst, uint32_t* __restrict__ o_rgbs, float* __restrict__ o_depth,
+                                   float* __restrict__ o_origins, float* __restrict__ o_dirs, int64_t* __restrict__ o_inst) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+  if (r >= R) return;
+  const size_t j = (size_t)perm[seg[k] + start[k] + r];
+  const size_t o = (size_t)k * R + r;
+  const size_t pj = pose_index ? (size_t)pose_index[j] : j;
+  float b[3][4];
+  pose_rows(invert, poses[pj * 4 + 0], poses[pj * 4 + 1], poses[pj * 4 + 2], poses[pj * 4 + 3], b);
+  const float dx = dirs_c[j * 3 + 0], dy = dirs_c[j * 3 + 1], dz = dirs_c[j * 3 + 2];
+  o_rgbs[o] = rgbs[j];
+  o_depth[o] = depth[j];
+  if (o_inst) o_inst[o] = inst ? inst[j] : 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    o_dirs[o * 3 + i] = b[i][0] * dx + b[i][1] * dy + b[i][2] * dz;
+    o_origins[o * 3 + i] = b[i][3];
+  }
+}
+
+// perm'[i] = perm[seg + idx[i]] for one category's segment (the composition that `pool = pool[rand_idx]` performs).
+__global__ void pool_compose_kernel(int64_t n, const int32_t* __restrict__ perm_in, const int64_t* __restrict__ idx, int32_t* __restrict__ perm_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) perm_out[i] = perm_in[idx[i]];
 }
 
 }  // namespace cnf
@@ -413,6 +452,31 @@ extern "C" int cnf_origin_dirs(int n_rays, int invert, const float* T, const flo
   origin_dirs_kernel<<<(n_rays + 255) / 256, 256, 0, as_stream(stream)>>>(n_rays, invert, reinterpret_cast<const float4*>(T), dirs_c,
                                                                            origins, dirs_out);
   return check_launch("cnf_origin_dirs");
+}
+
+extern "C" int cnf_pool_gather(int n_cat, int n_rays, int invert, const int64_t* seg, const int64_t* start, const int32_t* perm,
+                               const uint8_t* rgbs, const float* depth, const float* dirs_c, const float* poses, const int32_t* pose_index,
+                               const int64_t* inst, uint8_t* out_rgbs, float* out_depth, float* out_origins, float* out_dirs,
+                               int64_t* out_inst, cnf_stream_t stream) {
+  CNF_REQUIRE(n_cat >= 0 && n_rays >= 0, "cnf_pool_gather: bad sizes");
+  if (n_cat == 0 || n_rays == 0) return CNF_OK;
+  CNF_REQUIRE(seg && start && perm && rgbs && depth && dirs_c && poses && out_rgbs && out_depth && out_origins && out_dirs,
+              "cnf_pool_gather: null pointer");
+  CNF_REQUIRE((reinterpret_cast<uintptr_t>(poses) & 15) == 0 && (reinterpret_cast<uintptr_t>(rgbs) & 3) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out_rgbs) & 3) == 0,
+              "cnf_pool_gather: poses must be 16-byte aligned, rgbs 4-byte aligned");
+  CNF_REQUIRE(n_cat <= 65535, "cnf_pool_gather: more than 65535 categories");
+  pool_gather_kernel<<<dim3((n_rays + 255) / 256, n_cat), 256, 0, as_stream(stream)>>>(
+      n_rays, invert, seg, start, perm, reinterpret_cast<const uint32_t*>(rgbs), depth, dirs_c, reinterpret_cast<const float4*>(poses),
+      pose_index, inst, reinterpret_cast<uint32_t*>(out_rgbs), out_depth, out_origins, out_dirs, out_inst);
+  return check_launch("cnf_pool_gather");
+}
+
+extern "C" int cnf_pool_compose(int64_t n, const int32_t* perm_in, const int64_t* idx, int32_t* perm_out, cnf_stream_t stream) {
+  CNF_REQUIRE(n >= 0 && (n == 0 || (perm_in && idx && perm_out && perm_in != perm_out)), "cnf_pool_compose: bad arguments (out of place only)");
+  if (n == 0) return CNF_OK;
+  pool_compose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(n, perm_in, idx, perm_out);
+  return check_launch("cnf_pool_compose");
 }
 
 extern "C" size_t cnf_sample_workspace_bytes(int n_cat, int n_rays) {
@@ -436,11 +500,11 @@ extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, c
   cudaStream_t st = as_stream(stream);
   const size_t zbytes = (size_t)SB * (N + M) * sizeof(float);
   CNF_REQUIRE(N + M <= 96, "cnf_sample_fwd: more than 96 samples per ray");
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.pending()) {
     CNF_CUDA(cudaFuncSetAttribute(sample_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB * 96 * (int)sizeof(float)));
     CNF_CUDA(cudaFuncSetAttribute(sample_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB * 96 * (int)sizeof(float)));
-    attr = true;
+    attr.done();
   }
   if (R <= SAMPLE_SMALL_RAYS) {
     sample_small_kernel<<<dim3(K, nb), EMIT_T, zbytes, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth, lin_S, lin_N, lin_M, min_bound,

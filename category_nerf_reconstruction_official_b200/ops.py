@@ -427,10 +427,3 @@ def render_rays_fused(origins: torch.Tensor, dirs: torch.Tensor, z: torch.Tensor
     if want_weights:
         res["weights"] = w
     return res
-
-
-def umma_selftest(mode: int, A: torch.Tensor, B: torch.Tensor, N: int, Kd: int) -> torch.Tensor:
-    lib = lib_for(A)
-    D = torch.empty(128, N, device=A.device, dtype=torch.float32)
-    check(lib.cnf_umma_selftest(mode, N, Kd, ptr(_f32c(A)), ptr(_f32c(B)), ptr(D), stream()))
-    return D

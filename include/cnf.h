@@ -80,6 +80,22 @@ int cnf_stratified_bins(int n_rays, int n_bins, const float* min_d, int min_is_s
 int cnf_origin_dirs(int n_rays, int invert, const float* T, const float* dirs_c, float* origins, float* dirs_out,
                     cnf_stream_t stream);
 
+/* Device-resident ray pools -- the per-step slicing of sceneCategory.get_training_samples
+ * (src/scene_cateogries.py:352-451) for all categories in one launch.  The pools of n_cat categories are
+ * concatenated structure-of-arrays: rgbs u8 [P,4], depth [P], dirs_c [P,3] (camera frame), inst i64 [P]
+ * (batch_indices_all, may be NULL), poses [F,4,4] (16-byte aligned) with pose_index i32 [P] (NULL = one pose per
+ * pool row, t_co_batch_all :424-431; else the per-frame table t_wc_batch_dict[frame_batch] :373-379).
+ * perm i32 [P]: pool row held at each (shuffled) position; seg i64 [n_cat] first position of each category;
+ * start i64 [n_cat] = i_batch of each category.  Ray r of category k is pool row perm[seg[k]+start[k]+r];
+ * outputs [n_cat,n_rays,...]: rgbs u8 x4, depth, origins, dirs (as cnf_origin_dirs), inst (may be NULL). */
+int cnf_pool_gather(int n_cat, int n_rays, int invert, const int64_t* seg, const int64_t* start, const int32_t* perm,
+                    const uint8_t* rgbs, const float* depth, const float* dirs_c, const float* poses,
+                    const int32_t* pose_index, const int64_t* inst, uint8_t* out_rgbs, float* out_depth,
+                    float* out_origins, float* out_dirs, int64_t* out_inst, cnf_stream_t stream);
+/* Epoch reshuffle `pool = pool[rand_idx]` (src/scene_cateogries.py:439-449) as a composition of permutations:
+ * perm_out[i] = perm_in[idx[i]], i < n (out of place; idx = randperm(n) of one category's segment). */
+int cnf_pool_compose(int64_t n, const int32_t* perm_in, const int64_t* idx, int32_t* perm_out, cnf_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (2) Embedding -- UniDirsEmbed.forward (src/embedding.py:82-92) and its backward.
  *     x [K,P,3], B [K,21,3], scale [K] -> emb [K,P,129] = cat(x/s, sin(pi * 2^f * (x/s) B^T)).
@@ -155,8 +171,6 @@ size_t cnf_occmap_tc_render_workspace_bytes(int n_rays, int S);
 int cnf_occmap_tc_render_rays(int n_rays, int S, const float* params, const float* pe_B, const float* pe_scale,
                               const float* origins, const float* dirs, const float* z, float* out_rays, float* out_w,
                               void* ws, size_t ws_bytes, cnf_stream_t stream);
-/* development aid: SM-clock stamps of CTA 0's epilogue thread 0 (64 int64 device buffer; NULL switches it off) */
-int cnf_occmap_tc_set_debug(void* stamps);
 int cnf_occmap_tc_bwd(int n_pts, const float* params, const float* rgb, const float* g_alpha, const float* g_rgb,
                       void* ws, size_t ws_bytes, float* g_params, float* g_emb, cnf_stream_t stream);
 
@@ -273,29 +287,6 @@ int cnf_render_rays(int n_rays, int S, int L, const float* params, const float* 
  * them on its stream immediately before / after the fused tcgen05 kernel (and only that kernel), then clears
  * the hook.  Lets bench.py time the dominant kernel live without a profiler. */
 int cnf_set_kernel_events(void* ev_start, void* ev_stop);
-
-/* Development aid: device buffer of 256 int64 receiving SM-clock timestamps of CTA (0,0): [0..59] / [64..127] stage stamps of
- * the third tile (forward / backward role), [60..63] loop ends / flush end / kernel start, [128..191] / [192..255] tile-start
- * clocks of the first 64 tiles of each role, [256 + 8*cta ..] per-CTA %globaltimer stamps {entry, setup done, forward end,
- * backward end, flush done, tiles} (buffer of 256 + 8 * #CTAs int64).  NULL (default) selects the production kernel without any of it. */
-int cnf_set_debug_buffer(void* dev_ptr);
-
-/* tcgen05 self-test: D[128,N] = A[128,K] * B[N,K]^T with bf16 operands staged in shared memory in the
- * canonical no-swizzle UMMA layout; mode 0: A,B K-major; 1: B MN-major (dgrad view); 2: A,B MN-major
- * (wgrad view).  Used by tests to pin the descriptor encodings on hardware.
- * mode 3: A [128,K] staged in TENSOR MEMORY (packed bf16 pairs), B [N,K] K-major in shared memory.
- * mode 4/5: M = 64 weight-gradient view: A given [K,64], B given [K,N], both MN-major; D address lane offset 0 / 16;
- *           D receives ALL 128 lanes x N (sentinel -777 where untouched): row r lands in lane 32*(r/16) + r%16 (+16). */
-int cnf_umma_selftest(int mode, int N, int Kdim, const float* A, const float* B, float* D, cnf_stream_t stream);
-
-/* Hardware probe (development aid): where does an M=64 UMMA put its 64 accumulator rows in TMEM, and does the lane
- * field of the D address offset them?  D [128,N] receives all 128 lanes (sentinel -777 where untouched). */
-int cnf_umma_m64_probe(int N, int Kdim, int lane_off, const float* A, const float* B, float* D, cnf_stream_t stream);
-
-/* Development probe: one thread per CTA issues `reps` back-to-back tcgen05.mma (M x N x 16, bf16) into `ndst` rotating
- * accumulators and the CTA reports {issue cycles, cycles until the commit arrives} per CTA in out_cycles[2 * n_cta].
- * mode 0: A,B shared memory K-major; 1: A from TMEM; 2: A,B MN-major (weight-gradient view); 3: B MN-major. */
-int cnf_umma_rate_probe(int mode, int M, int N, int reps, int ndst, int n_cta, long long* out_cycles, cnf_stream_t stream);
 
 /* Fused AdamW over a flat fp32 buffer (train.py:183): decoupled weight decay as
  * torch.optim.AdamW.  step is 1-based. */

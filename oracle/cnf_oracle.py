@@ -424,6 +424,78 @@ def bg_train_step(fc_params: Sequence[torch.Tensor], pe_B: torch.Tensor, scale,
 
 
 # --------------------------------------------------------------------------------------
+# ray pools: per-step slicing, ray set-up and epoch reshuffle
+# --------------------------------------------------------------------------------------
+def origin_dirs(T: torch.Tensor, dirs_C: torch.Tensor, invert: bool):
+    """src/scene_cateogries.py:24-35 (origin_dirs_O: invert the per-ray pose first) and :37-47 (origin_dirs_W)."""
+    if invert:
+        T = torch.linalg.inv(T)
+    return T[:, :3, -1], (T[:, :3, :3] @ dirs_C[..., None]).squeeze(-1)
+
+
+class RayPool:
+    """One category's shuffled CPU ray pool as sceneCategory keeps it, with the batch slicing of get_training_samples.
+
+    flat-pool branch (object categories), src/scene_cateogries.py:421-449: slice [i_batch, i_batch+n) of rgbs / depth / ray_dirs /
+    per-ray poses / instance indices, origin_dirs_O (several instances) or origin_dirs_W (one instance); `i_batch += n`; when
+    `i_batch >= P - n` every array is re-indexed by one `randperm(P)` and `i_batch = 0`.
+    background branch, :353-418 with its single pool: the pose of a ray is `t_wc[frame]` (:373-379), same epoch rule (:404-412).
+    ``rand_idx`` injects the permutation the reference draws with torch.randperm."""
+
+    def __init__(self, rgbs, depth, ray_dirs, poses, indices=None, frames=None, invert=True):
+        self.rgbs, self.depth, self.ray_dirs, self.poses = rgbs.clone(), depth.clone(), ray_dirs.clone(), poses.clone()
+        self.indices = None if indices is None else indices.clone()
+        self.frames = None if frames is None else frames.clone()
+        self.invert = invert
+        self.i_batch = 0
+
+    def get_batch(self, n: int, rand_idx: Optional[torch.Tensor] = None):
+        i = self.i_batch
+        sl = slice(i, i + n)
+        T = self.poses[self.frames[sl]] if self.frames is not None else self.poses[sl]
+        origins, dirs = origin_dirs(T, self.ray_dirs[sl], self.invert)
+        idx = self.indices[sl] if self.indices is not None else torch.zeros(n, dtype=torch.int64)
+        out = (self.rgbs[sl], self.depth[sl], origins, dirs, idx)
+        self.i_batch += n
+        P = self.rgbs.shape[0]
+        if self.i_batch >= P - n:
+            if rand_idx is None:
+                rand_idx = torch.randperm(P)
+            self.rgbs, self.depth, self.ray_dirs = self.rgbs[rand_idx], self.depth[rand_idx], self.ray_dirs[rand_idx]
+            if self.indices is not None:
+                self.indices = self.indices[rand_idx]
+            if self.frames is not None:
+                self.frames = self.frames[rand_idx]
+            else:
+                self.poses = self.poses[rand_idx]
+            self.i_batch = 0
+        return out
+
+
+def synth_pool(P: int, n_obj: int, n_frames: int, gen: torch.Generator):
+    """A synthetic ray pool: rays of `synth_rays` plus sim3-shaped object->camera poses (rotation * scale | translation), one per
+    (frame, instance), expanded per ray (t_co_batch_all) and also kept as a table with a per-ray frame index."""
+    rgbs, depth, _, _, idx = synth_rays(P, n_obj, gen)
+    u = torch.rand(P, generator=gen) * 1200; v = torch.rand(P, generator=gen) * 680
+    ray_dirs = torch.stack([(u - 599.5) / 600.0, (v - 339.5) / 600.0, torch.ones(P)], -1)
+    F = n_frames * n_obj
+    q = torch.randn(F, 4, generator=gen); q = q / q.norm(dim=-1, keepdim=True)
+    w_, x_, y_, z_ = q.unbind(-1)
+    Rm = torch.stack([1 - 2 * (y_ * y_ + z_ * z_), 2 * (x_ * y_ - z_ * w_), 2 * (x_ * z_ + y_ * w_),
+                      2 * (x_ * y_ + z_ * w_), 1 - 2 * (x_ * x_ + z_ * z_), 2 * (y_ * z_ - x_ * w_),
+                      2 * (x_ * z_ - y_ * w_), 2 * (y_ * z_ + x_ * w_), 1 - 2 * (x_ * x_ + y_ * y_)], -1).reshape(F, 3, 3)
+    s = torch.rand(F, 1, 1, generator=gen) * 0.7 + 0.3
+    T = torch.zeros(F, 4, 4)
+    T[:, :3, :3] = Rm * s
+    T[:, :3, 3] = torch.randn(F, 3, generator=gen)
+    T[:, 3, 3] = 1.0
+    frame = torch.randint(0, n_frames, (P,), generator=gen)
+    pose_index = frame * n_obj + idx
+    return dict(rgbs=rgbs, depth=depth, ray_dirs=ray_dirs.contiguous(), indices=idx, pose_table=T, pose_index=pose_index,
+                poses=T[pose_index].contiguous())
+
+
+# --------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY 8(d) value distributions); shared by tests and bench
 # --------------------------------------------------------------------------------------
 def synth_rays(R: int, n_obj: int, gen: torch.Generator, invalid_frac: float = 0.15,

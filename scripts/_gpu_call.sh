@@ -1,3 +1,8 @@
 mkdir -p gpurun_out
-for i in 1 2 3; do timeout 600 python -m pytest tests/test_gpu_training.py tests/test_gpu_parity_r2.py -m gpu -q -s -k "curve" 2>&1 | grep -E "loss-curve|loss curve|passed|failed|early|diverge" ; done > gpurun_out/t.log
-cat gpurun_out/t.log
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/tests.log
+cat gpurun_out/tests.log
+for tool in memcheck synccheck racecheck initcheck; do
+  timeout 400 compute-sanitizer --tool $tool --print-limit 20 python __graft_entry__.py smoke > gpurun_out/sanitizer_$tool.log 2>&1
+  echo "$tool rc=$?" >> gpurun_out/sanitizer_$tool.log
+  tail -5 gpurun_out/sanitizer_$tool.log
+done

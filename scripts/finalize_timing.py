@@ -2,6 +2,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from category_nerf_reconstruction_official_b200 import dev as _dev; _dev.use_dev_library()   # include/cnf_dev.h hooks live in the development build
 from bench import WORKLOADS, synth_batch
 from category_nerf_reconstruction_official_b200 import _lib
 from category_nerf_reconstruction_official_b200.fused import FusedCategoryTrainer

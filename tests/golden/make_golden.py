@@ -352,10 +352,65 @@ def golden_loss(out):
     out["loss/term2d/term"] = npy(ref_render.occupancy_to_termination(occ2))
 
 
+def golden_pool(out):
+    """sceneCategory.get_training_samples (scene_cateogries.py:352-451) on bare instances: the per-step pool slices, origin_dirs_O/W
+    and the epoch reshuffle are the reference's own code; only the instance's sample_3d_points is replaced by a pass-through so
+    that the sampler's INPUTS are recorded (the sampler itself is pinned by golden_sampler)."""
+    def passthrough(rgbs, depth, origins, dirs):
+        return rgbs, depth, origins, dirs, rgbs[:, :0], depth[:0]
+
+    def record(tag, sc, n, steps, P, seed):
+        torch.manual_seed(seed)
+        for t in range(steps):
+            rgbs, depth, origins, dirs, _, _, idx = sc.get_training_samples(n)
+            for kk, v in dict(rgbs=rgbs, depth=depth, origins=origins, dirs=dirs, idx=idx).items():
+                out["pool/%s/step%d/%s" % (tag, t, kk)] = npy(v)
+        torch.manual_seed(seed)                     # the only RNG consumer was randperm(P) at each epoch end: replay it
+        e = 0
+        i_batch = 0
+        for t in range(steps):
+            i_batch += n
+            if i_batch >= P - n:
+                out["pool/%s/perm%d" % (tag, e)] = npy(torch.randperm(P)); e += 1
+                i_batch = 0
+        out["pool/%s/meta" % tag] = np.array([P, n, steps, e])
+
+    g = torch.Generator().manual_seed(77)
+    P, n_obj = 1000, 4
+    pool = O.synth_pool(P, n_obj, 7, g)
+    for kk, v in pool.items():
+        out["pool/in/" + kk] = npy(v)
+    for tag, ids in (("multi", [1, 2, 3, 4]), ("single", [9])):
+        sc = bare_scene(1, 9)
+        sc.cls_id = 3
+        sc.obj_ids = ids
+        sc.i_batch = 0
+        sc.batch_indices_all = pool["indices"].clone()
+        sc.rgbs_batch_all = pool["rgbs"].clone()
+        sc.depth_batch_all = pool["depth"].clone()
+        sc.ray_dirs_batch_all = pool["ray_dirs"].clone()
+        sc.t_co_batch_all = pool["poses"].clone()
+        sc.t_wc_batch_all = pool["poses"].clone()
+        sc.sample_3d_points = passthrough
+        record(tag, sc, 96, 25, P, 5)
+    sc = bare_scene(5, 9)
+    sc.cls_id = 0
+    sc.obj_ids = [0]
+    sc.trainer = types.SimpleNamespace(inst_id_to_index={0: 0})
+    sc.rgbs_batch_dict = {0: pool["rgbs"].clone()}
+    sc.depth_batch_dict = {0: pool["depth"].clone()}
+    sc.frame_batch_dict = {0: pool["pose_index"].clone()}
+    sc.ray_dirs_batch_dict = {0: pool["ray_dirs"].clone()}
+    sc.t_wc_batch_dict = {0: pool["pose_table"].clone()}
+    sc.i_batch_dict = {0: 0}
+    sc.sample_3d_points = passthrough
+    record("background", sc, 120, 20, P, 6)
+
+
 def main():
     torch.set_num_threads(1)
     groups = dict(sampler=golden_sampler, embed=golden_embed, step=golden_train_step, bg=golden_bg,
-                  loss=golden_loss, bg128=golden_bg128, curve=golden_curve)
+                  loss=golden_loss, bg128=golden_bg128, curve=golden_curve, pool=golden_pool)
     only = sys.argv[1:]
     for gname, fn in groups.items():
         if only and gname not in only:

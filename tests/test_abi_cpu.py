@@ -12,17 +12,34 @@ from category_nerf_reconstruction_official_b200 import _lib, model, embedding, o
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _declared(header):
+    hdr = open(os.path.join(ROOT, "include", header)).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return set(re.findall(r"\b(cnf_[a-z0-9_]+)\s*\(", hdr))
+
+
 def test_build_and_load_exports_every_declared_symbol():
     cnf.build()
     lib = cnf.load()
-    hdr = open(os.path.join(ROOT, "include", "cnf.h")).read()
-    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(cnf_[a-z0-9_]+)\s*\(", hdr))
+    declared = _declared("cnf.h")
     assert declared, "no declarations parsed"
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.cnf_version() >= 100
+    if os.environ.get("CNF_LIB_PATH") is None:
+        for name in _lib.DEV_SIGNATURES:        # the product library exports no development hook
+            assert not hasattr(lib, name), name
+
+
+def test_development_build_exports_product_and_dev_symbols():
+    """include/cnf_dev.h (self-tests, probes, clock stamps) lives only in libcnf_sm100_dev.so = the same sources with -DCNF_DEV."""
+    cnf.build_dev()
+    lib = cnf.load_dev()
+    declared = _declared("cnf_dev.h")
+    assert declared == set(_lib.DEV_SIGNATURES), (declared ^ set(_lib.DEV_SIGNATURES))
+    for name in declared | set(_lib.SIGNATURES):
+        assert hasattr(lib, name), name
 
 
 def test_param_counts_match_reference_layout():

@@ -7,6 +7,8 @@ import torch
 from helpers import SAMPLER_CASES, STEP_CASES, assert_grad_close, golden, gt, step_case
 from oracle import cnf_oracle as O
 
+from category_nerf_reconstruction_official_b200 import dev as cnf_dev      # hardware self-tests: development build (cnf_dev.h)
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
@@ -236,7 +238,7 @@ def test_umma_descriptor_selftest(mode, N, Kd):
         A = bf(torch.randn(128, Kd, generator=g)); B = bf(torch.randn(Kd, N, generator=g)); ref = A @ B
     else:
         A = bf(torch.randn(Kd, 128, generator=g)); B = bf(torch.randn(Kd, N, generator=g)); ref = A.t() @ B
-    D = ops.umma_selftest(mode, A.to(DEV), B.to(DEV), N, Kd)
+    D = cnf_dev.umma_selftest(mode, A.to(DEV), B.to(DEV), N, Kd)
     torch.testing.assert_close(D.cpu(), ref, rtol=1e-4, atol=1e-3)
 
 
@@ -247,7 +249,7 @@ def test_umma_tmem_operand_selftest(N, Kd):
     g = torch.Generator().manual_seed(300 + N + Kd)
     bf = lambda t: t.bfloat16().float()
     A = bf(torch.randn(128, Kd, generator=g)); B = bf(torch.randn(N, Kd, generator=g))
-    D = ops.umma_selftest(3, A.to(DEV), B.to(DEV), N, Kd)
+    D = cnf_dev.umma_selftest(3, A.to(DEV), B.to(DEV), N, Kd)
     torch.testing.assert_close(D.cpu(), A @ B.t(), rtol=1e-4, atol=1e-3)
 
 
@@ -261,7 +263,7 @@ def test_umma_m64_wgrad_lane_mapping(mode, N):
     Kd = 128
     A = bf(torch.randn(Kd, 64, generator=g)); B = bf(torch.randn(Kd, N, generator=g))
     ref = A.t() @ B                                   # [64, N]
-    D = ops.umma_selftest(mode, A.to(DEV), B.to(DEV), N, Kd).cpu()
+    D = cnf_dev.umma_selftest(mode, A.to(DEV), B.to(DEV), N, Kd).cpu()
     off = 16 if mode == 5 else 0
     lanes = torch.tensor([32 * (r // 16) + r % 16 + off for r in range(64)])
     torch.testing.assert_close(D[lanes], ref, rtol=1e-4, atol=2e-3)
