@@ -7,6 +7,7 @@
 // cumprod of the free-space factors and the reverse (suffix) sum of the backward are warp-shuffle scans over 32-sample
 // chunks with a carry.  HBM-bound: 20 B/sample in, 24 B/ray out (fwd).
 #include "cnf_common.cuh"
+#include "cnf_umma.cuh"      // mbarrier + 1-D bulk-copy (TMA) helpers
 
 namespace cnf {
 
@@ -149,25 +150,34 @@ composite_fwd_kernel(int K, int R, int S, const float* __restrict__ alpha, const
 __global__ void composite_finalize_kernel(int K, int nblk, const float* __restrict__ partial,
                                           const int32_t* __restrict__ counts, float cs, float os,
                                           float* __restrict__ out_loss) {
-  // one warp; fixed summation order (lane-strided partial sums, then a shuffle tree) -> deterministic
-  const int lane = threadIdx.x;
+  // one CTA of 32 (few partials) or 1024 threads; fixed summation order (thread-strided partial sums, a shuffle tree per warp, the
+  // warp sums in warp order) -> deterministic.  One warp walking 8192 partials serially cost 13 us of a 78 us forward at 1 Mi rays.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  __shared__ float s_p[32][3];
   bool e0, e1, e2;
   empty_flags(K, counts, e0, e1, e2);
   float total = 0.f;
   for (int k = 0; k < K; ++k) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int b = lane; b < nblk; b += 32) {
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
       const float* p = partial + ((size_t)k * nblk + b) * 3;
       s0 += p[0]; s1 += p[1]; s2 += p[2];
     }
     s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (nwarp > 1) {
+      __syncthreads();                        // previous category's s_p has been read
+      if (lane == 0) { s_p[warp][0] = s0; s_p[warp][1] = s1; s_p[warp][2] = s2; }
+      __syncthreads();
+      s0 = s1 = s2 = 0.f;
+      for (int w = 0; w < nwarp; ++w) { s0 += s_p[w][0]; s1 += s_p[w][1]; s2 += s_p[w][2]; }
+    }
     const float d = e0 ? 0.f : s0 / ((float)counts[k * 4 + 0] + 1e-10f);      // render_rays.py:86
     const float c = e1 ? 0.f : s1 / ((float)counts[k * 4 + 1] + 1e-10f);
     const float o = e2 ? 0.f : s2 / ((float)counts[k * 4 + 2] + 1e-10f);
-    if (lane == 0) { out_loss[4 + k] = d; out_loss[4 + K + k] = c; out_loss[4 + 2 * K + k] = o; }
+    if (threadIdx.x == 0) { out_loss[4 + k] = d; out_loss[4 + K + k] = c; out_loss[4 + 2 * K + k] = o; }
     total += d + c * cs + o * os;                                             // loss.py:69-70
   }
-  if (lane == 0) { out_loss[0] = total; out_loss[1] = e0; out_loss[2] = e1; out_loss[3] = e2; }
+  if (threadIdx.x == 0) { out_loss[0] = total; out_loss[1] = e0; out_loss[2] = e1; out_loss[3] = e2; }
 }
 
 __global__ void __launch_bounds__(CT)
@@ -373,6 +383,174 @@ composite_tile_kernel(int K, int R, int S, const float* __restrict__ alpha, cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Dense, double-buffered variant of the tile kernel (the default whenever gcd(S, 32) <= 4, e.g. S = 10 and 14).
+// ncu of composite_tile_kernel<0> at 1 Mi rays x 10 samples: 45 % of its 1120 instructions per ray staged the tile -- one 4-byte
+// cp.async per element with a division to find the padded (odd-stride) row -- and a block alternated load / compute phases.
+// Here a tile keeps the GLOBAL layout (rows of S floats back to back), so each of alpha / z / colour of a 128-ray tile is ONE
+// contiguous chunk that thread 0 fetches with a 1-D bulk copy (TMA) completing on an mbarrier; two stages, so tile i + 1 arrives while
+// tile i is composited, and the backward's gradients leave as two bulk stores from the same buffers.  Row stride S words means a
+// gcd(S, 32)-way bank conflict on the per-thread row accesses (2-way at S = 10 / 14: ~5 M shared wavefronts per 1 Mi rays, far from
+// the limit); S with gcd > 4 (8, 16, 24, 32) keep the padded kernel above.  Tiles that a bulk copy cannot move (the category's base
+// offset not 16-byte aligned, or the ragged last tile) are staged with dense 4-byte cp.async (no division) and stored by a plain loop.
+// ---------------------------------------------------------------------------------------------------------
+__host__ __device__ inline int dense_stage_floats(int S, bool bwd) { return TR * S * (bwd ? 3 : 2) + TR * 3 * S; }
+
+template <int MODE>
+__global__ void __launch_bounds__(TR)
+composite_dense_kernel(int K, int R, int S, const float* __restrict__ alpha, const float* __restrict__ color,
+                       const float* __restrict__ z, const float* __restrict__ gt_depth, const float* __restrict__ gt_color,
+                       const uint8_t* __restrict__ labels, const uint8_t* __restrict__ mask_depth,
+                       const int32_t* __restrict__ counts, float cs, float os, const float* __restrict__ g_loss,
+                       float* __restrict__ out_rays, float* __restrict__ partial, float* __restrict__ g_alpha, float* __restrict__ g_color) {
+  using namespace umma;
+  extern __shared__ __align__(128) float sm_d[];
+  __shared__ __align__(8) uint64_t full[2];
+  constexpr bool BWD = MODE != 0, FWD = MODE != 1;
+  const int k = blockIdx.y, t = threadIdx.x;
+  const int stage_floats = dense_stage_floats(S, BWD);
+  const int ntiles = (R + TR - 1) / TR;
+  const size_t kbase = (size_t)k * R;
+  // bulk copies need 16-byte aligned global addresses: every full tile of this category qualifies iff its first one does
+  const bool aligned = ((reinterpret_cast<uintptr_t>(alpha + kbase * S) | reinterpret_cast<uintptr_t>(z + kbase * S) |
+                         reinterpret_cast<uintptr_t>(color + kbase * S * 3) |
+                         (BWD ? (reinterpret_cast<uintptr_t>(g_alpha + kbase * S) | reinterpret_cast<uintptr_t>(g_color + kbase * S * 3)) : 0)) & 15) == 0;
+  auto bulk_ok = [&](int tile) { return aligned && tile < ntiles && (tile + 1) * TR <= R; };
+  if (t == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); fence_mbar_init(); }
+  __syncthreads();
+  auto issue = [&](int tile, int st) {          // thread 0: the three chunks of a full tile -> stage st
+    float* base = sm_d + st * stage_floats;
+    const size_t g0 = kbase + (size_t)tile * TR;
+    const uint32_t bA = TR * S * 4u;
+    mbar_expect_tx(&full[st], 5u * bA);
+    bulk_g2s(base, alpha + g0 * S, bA, &full[st]);
+    bulk_g2s(base + TR * S, z + g0 * S, bA, &full[st]);
+    bulk_g2s(base + 2 * TR * S, color + g0 * S * 3, 3u * bA, &full[st]);
+  };
+  float iNd = 0.f, iNo = 0.f, iNs = 0.f;
+  if (BWD) {
+    bool e0, e1, e2;
+    empty_flags(K, counts, e0, e1, e2);
+    const float gl = g_loss ? g_loss[0] : 1.0f;
+    iNd = e0 ? 0.f : gl / ((float)counts[k * 4 + 0] + 1e-10f);
+    iNo = e1 ? 0.f : gl * cs / ((float)counts[k * 4 + 1] + 1e-10f);
+    iNs = e2 ? 0.f : gl * os / ((float)counts[k * 4 + 2] + 1e-10f);
+  }
+  float ld = 0.f, lc = 0.f, lo = 0.f;
+  uint32_t ph0 = 0, ph1 = 0;
+  int tile = blockIdx.x;
+  if (t == 0 && bulk_ok(tile)) issue(tile, 0);
+  for (int j = 0; tile < ntiles; ++j, tile += gridDim.x) {
+    const int st = j & 1;
+    float* sA = sm_d + st * stage_floats;          // alpha -> (fwd) weights w_i / (bwd) occupancy -> d alpha
+    float* sZ = sA + TR * S;
+    float* sC = sZ + TR * S;                       // colour -> (bwd) d colour
+    float* sT = sC + TR * 3 * S;                   // (bwd) transmittance T_i
+    const int r0 = tile * TR, n = min(TR, R - r0);
+    const size_t g0 = kbase + r0;
+    const int nxt = tile + gridDim.x;
+    if (t == 0 && bulk_ok(nxt)) {                  // prefetch: stage st^1 was released by the barrier that ended iteration j-1
+      if (BWD) bulk_wait_read<0>();                // ... and its gradient stores have finished reading it
+      issue(nxt, st ^ 1);
+    }
+    if (bulk_ok(tile)) {
+      mbar_wait(&full[st], st ? ph1 : ph0);
+      if (st) ph1 ^= 1; else ph0 ^= 1;
+    } else {
+      if (BWD && t == 0) bulk_wait_read<0>();      // an earlier bulk store may still read this stage
+      __syncthreads();
+      const uint32_t dA = smem_u32(sA), dZ = smem_u32(sZ), dC = smem_u32(sC);
+      const float* pa = alpha + g0 * S; const float* pz = z + g0 * S; const float* pc = color + g0 * S * 3;
+      for (int e = t; e < n * S; e += TR) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dA + 4u * e), "l"(pa + e) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dZ + 4u * e), "l"(pz + e) : "memory");
+      }
+      for (int e = t; e < n * S * 3; e += TR) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dC + 4u * e), "l"(pc + e) : "memory");
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+    }
+    if (t < n) {
+      const size_t g = g0 + t;
+      float* a = sA + t * S; const float* zz = sZ + t * S; float* c = sC + t * 3 * S; float* tt = sT + t * S;
+      // per-ray inputs first: their latency overlaps the compositing loop
+      const uint8_t lab = labels[g];
+      const uint8_t mdep = mask_depth[g];
+      const float gd = gt_depth[g], q0 = gt_color[g * 3], q1 = gt_color[g * 3 + 1], q2 = gt_color[g * 3 + 2];
+      float T = 1.0f, D = 0.f, O = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+      for (int i = 0; i < S; ++i) {
+        const float occ = sigmoid_acc(a[i]);
+        const float w = occ * T;                                               // render_rays.py:33
+        D += w * zz[i]; O += w; C0 += w * c[3 * i]; C1 += w * c[3 * i + 1]; C2 += w * c[3 * i + 2];
+        if (BWD) { tt[i] = T; a[i] = occ; } else a[i] = w;
+        T *= __fadd_rn(__fsub_rn(1.0f, occ), 1e-10f);                          // render_rays.py:28
+      }
+      float var = 0.f;
+      for (int i = 0; i < S; ++i) {
+        const float w = BWD ? a[i] * tt[i] : a[i];
+        const float dz = zz[i] - D;
+        var += w * dz * dz;                                                    // loss.py:45-46 (detached)
+      }
+      const float mo = (lab != 0) ? 1.f : 0.f, ms = (lab != 2) ? 1.f : 0.f;
+      const float md = (mdep != 0 && lab != 0) ? 1.f : 0.f;
+      const float info = 1.0f / (sqrtf(var) + 1e-4f);                          // render_rays.py:73-80
+      if (FWD) {
+        float* orow = out_rays + g * 6;
+        orow[0] = D; orow[1] = var; orow[2] = C0; orow[3] = C1; orow[4] = C2; orow[5] = O;
+        ld += fabsf(D - gd) * md * info;                                       // loss.py:52-54
+        lc += (fabsf(C0 - q0) + fabsf(C1 - q1) + fabsf(C2 - q2)) * mo;
+        lo += fabsf(O - mo) * ms;                                              // loss.py:64-66
+      }
+      if (BWD) {
+        auto sgn = [](float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); };
+        const float gD = sgn(D - gd) * md * info * iNd;
+        const float gC0 = sgn(C0 - q0) * mo * iNo, gC1 = sgn(C1 - q1) * mo * iNo, gC2 = sgn(C2 - q2) * mo * iNo;
+        const float gO = sgn(O - mo) * ms * iNs;
+        float suffix = 0.f;                                                    // sum_{i>j} G_i w_i
+        for (int jj = S - 1; jj >= 0; --jj) {
+          const float occ = a[jj], Tj = tt[jj], w = occ * Tj;
+          const float Gi = gD * zz[jj] + gC0 * c[3 * jj] + gC1 * c[3 * jj + 1] + gC2 * c[3 * jj + 2] + gO;
+          const float f = __fadd_rn(__fsub_rn(1.0f, occ), 1e-10f);
+          const float docc = Gi * Tj - suffix / f;
+          a[jj] = docc * occ * (1.0f - occ);
+          c[3 * jj] = w * gC0; c[3 * jj + 1] = w * gC1; c[3 * jj + 2] = w * gC2;
+          suffix += Gi * w;
+        }
+      }
+    }
+    if (BWD) {
+      if (bulk_ok(tile)) {
+        fence_async_smem();                        // generic-proxy writes of the gradients -> visible to the bulk-copy engine
+        __syncthreads();
+        if (t == 0) {
+          bulk_s2g(g_alpha + g0 * S, sA, TR * S * 4u);
+          bulk_s2g(g_color + g0 * S * 3, sC, TR * S * 12u);
+          bulk_commit();
+        }
+      } else {
+        __syncthreads();
+        for (int e = t; e < n * S; e += TR) g_alpha[g0 * S + e] = sA[e];
+        for (int e = t; e < n * S * 3; e += TR) g_color[g0 * S * 3 + e] = sC[e];
+        __syncthreads();
+      }
+    } else {
+      __syncthreads();                             // every thread is done with stage st before it is refilled
+    }
+  }
+  if (BWD && t == 0) bulk_wait<0>();               // the last gradient stores have left shared memory (and are complete) before exit
+  if (FWD) {
+    __shared__ float s_p[TR / 32][3];
+    const int lane = t & 31, warp = t >> 5;
+    ld = warp_sum(ld); lc = warp_sum(lc); lo = warp_sum(lo);
+    if (lane == 0) { s_p[warp][0] = ld; s_p[warp][1] = lc; s_p[warp][2] = lo; }
+    __syncthreads();
+    if (t < 3) {
+      float v = 0.f;
+      for (int i = 0; i < TR / 32; ++i) v += s_p[i][t];
+      partial[((size_t)k * gridDim.x + blockIdx.x) * 3 + t] = v;               // deterministic 2-stage reduce
+    }
+  }
+}
+
 __global__ void termination_kernel(int n_rays, int S, const float* __restrict__ occ_in, float* __restrict__ w_out) {
   const int G = seg_width(S), rpw = 32 / G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -517,6 +695,29 @@ static int comp_blocks(int R, int S) {
   return nb < 1 ? 1 : nb;
 }
 
+// dense double-buffered kernel: chosen when the row stride S gives at most a 4-way bank conflict
+static bool use_dense(int S) { int g = 1; while (g < 32 && S % (g * 2) == 0) g *= 2; return g <= 4; }
+static int dense_smem_bytes(int S, bool bwd) { return 2 * dense_stage_floats(S, bwd) * (int)sizeof(float); }
+static int dense_blocks(int R, int S, bool bwd) {
+  int per_sm = (220 * 1024) / (dense_smem_bytes(S, bwd) + 1024);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  int nb = (R + TR - 1) / TR;
+  if (nb > 148 * per_sm) nb = 148 * per_sm;      // persistent CTAs, grid-stride over the tiles (<= 1184: the partial-sum workspace)
+  return nb < 1 ? 1 : nb;
+}
+template <int MODE>
+static int dense_attr(int S) {
+  static DeviceOnce once;
+  if (once.pending()) {
+    CNF_CUDA(cudaFuncSetAttribute(composite_dense_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, dense_smem_bytes(30, MODE != 0)));
+    CNF_CUDA(cudaFuncSetAttribute(composite_dense_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    once.done();
+  }
+  (void)S;
+  return CNF_OK;
+}
+
 static int tile_blocks(int R) {
   int nb = (R + TR - 1) / TR;
   if (nb > 1184) nb = 1184;      // partial-sum workspace is sized for 8 x 148 blocks; grid-stride beyond
@@ -557,7 +758,12 @@ extern "C" int cnf_composite_loss_fwd(int K, int R, int S, const float* alpha, c
               "cnf_composite_loss_fwd: null pointer");
   if (ws_bytes < cnf_composite_workspace_bytes(K, R)) { set_error("cnf_composite_loss_fwd: workspace too small"); return CNF_ERR_WORKSPACE; }
   int nb;
-  if (S <= 32) {
+  if (S <= 32 && use_dense(S)) {
+    nb = dense_blocks(R, S, false);
+    if (int rc = dense_attr<0>(S)) return rc;
+    composite_dense_kernel<0><<<dim3(nb, K), TR, dense_smem_bytes(S, false), as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth,
+                                                                                                   counts, cs, os, nullptr, out_rays, (float*)ws, nullptr, nullptr);
+  } else if (S <= 32) {
     nb = tile_blocks(R);
     const int smem = tile_smem_floats(S, false) * 4;
     static DeviceOnce attr;
@@ -569,7 +775,7 @@ extern "C" int cnf_composite_loss_fwd(int K, int R, int S, const float* alpha, c
     composite_fwd_kernel<<<dim3(nb, K), CT, 0, as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels,
                                                                     mask_depth, out_rays, (float*)ws);
   }
-  composite_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(K, nb, (const float*)ws, counts, cs, os, out_loss);
+  composite_finalize_kernel<<<1, nb > 64 ? 1024 : 32, 0, as_stream(stream)>>>(K, nb, (const float*)ws, counts, cs, os, out_loss);
   return check_launch("cnf_composite_loss_fwd");
 }
 
@@ -580,6 +786,12 @@ extern "C" int cnf_composite_loss_bwd(int K, int R, int S, const float* alpha, c
   CNF_REQUIRE(K > 0 && R > 0 && S > 0, "cnf_composite_loss_bwd: bad sizes");
   CNF_REQUIRE(alpha && color && z && gt_depth && gt_color && labels && mask_depth && counts && g_alpha && g_color,
               "cnf_composite_loss_bwd: null pointer");
+  if (S <= 32 && use_dense(S)) {
+    if (int rc = dense_attr<1>(S)) return rc;
+    composite_dense_kernel<1><<<dim3(dense_blocks(R, S, true), K), TR, dense_smem_bytes(S, true), as_stream(stream)>>>(
+        K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth, counts, cs, os, g_loss, nullptr, nullptr, g_alpha, g_color);
+    return check_launch("cnf_composite_loss_bwd");
+  }
   if (S <= 32) {
     const int smem = tile_smem_floats(S, true) * 4;
     static DeviceOnce attr;
@@ -604,13 +816,21 @@ extern "C" int cnf_composite_loss_fwd_bwd(int K, int R, int S, const float* alph
               "cnf_composite_loss_fwd_bwd: null pointer");
   if (S > 32) { set_error("cnf_composite_loss_fwd_bwd: S=%d > 32 (use the separate forward / backward entry points)", S); return CNF_ERR_UNSUPPORTED; }
   if (ws_bytes < cnf_composite_workspace_bytes(K, R)) { set_error("cnf_composite_loss_fwd_bwd: workspace too small"); return CNF_ERR_WORKSPACE; }
+  if (use_dense(S)) {
+    const int nbd = dense_blocks(R, S, true);
+    if (int rc = dense_attr<2>(S)) return rc;
+    composite_dense_kernel<2><<<dim3(nbd, K), TR, dense_smem_bytes(S, true), as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth,
+                                                                                                   counts, cs, os, nullptr, out_rays, (float*)ws, g_alpha, g_color);
+    composite_finalize_kernel<<<1, nbd > 64 ? 1024 : 32, 0, as_stream(stream)>>>(K, nbd, (const float*)ws, counts, cs, os, out_loss);
+    return check_launch("cnf_composite_loss_fwd_bwd");
+  }
   const int nb = tile_blocks(R);
   const int smem = tile_smem_floats(S, true) * 4;
   static DeviceOnce attr;
   if (attr.pending()) { CNF_CUDA(cudaFuncSetAttribute(composite_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_floats(32, true) * 4)); attr.done(); }
   composite_tile_kernel<2><<<dim3(nb, K), TR, smem, as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth,
                                                                         counts, cs, os, nullptr, out_rays, (float*)ws, g_alpha, g_color);
-  composite_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(K, nb, (const float*)ws, counts, cs, os, out_loss);
+  composite_finalize_kernel<<<1, nb > 64 ? 1024 : 32, 0, as_stream(stream)>>>(K, nb, (const float*)ws, counts, cs, os, out_loss);
   return check_launch("cnf_composite_loss_fwd_bwd");
 }
 

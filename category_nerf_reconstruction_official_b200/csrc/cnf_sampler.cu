@@ -18,48 +18,88 @@ __device__ __forceinline__ int ray_case(float d, uint8_t label, float min_bound,
   return (label == this_obj) ? 1 : 2;
 }
 
-// (A) counts per block: {nI, nV, nO, nT} plus loss-mask counts {Nd, No, Ns} and block max depth.
-__global__ void sample_count_kernel(int R, const uint8_t* __restrict__ rgbs, const float* __restrict__ depth,
-                                    float min_bound, int this_obj, int* __restrict__ blk_counts,
-                                    float* __restrict__ blk_max) {
-  const int k = blockIdx.y, nb = gridDim.x, b = blockIdx.x;
-  const int r = b * SB + threadIdx.x;
-  int cI = 0, cO = 0, cT = 0, cD = 0, cObj = 0, cSem = 0;
-  float mx = -INFINITY;
-  if (r < R) {
-    const float d = depth[(size_t)k * R + r];
-    const uint8_t lab = rgbs[((size_t)k * R + r) * 4 + 3];
-    const int c = ray_case(d, lab, min_bound, this_obj);
-    cI = (c == 0); cO = (c == 1); cT = (c == 2);
-    const bool mo = lab != 0, ms = lab != 2;
-    cD = (c != 0) && mo; cObj = mo; cSem = ms;
-    mx = d;
-  }
-  __shared__ int s_c[SB / 32][6];
-  __shared__ float s_m[SB / 32];
+// (A) counts per 256-ray block: {nI, nO, nT} plus loss-mask counts {Nd, No, Ns} and block max depth.  One CTA covers COUNT_RB
+// consecutive ray blocks with all of a thread's loads in flight at once (one ray block per CTA made the kernel a chain of tiny
+// latency-bound CTAs: 770 GB/s); warp w counts the rays [32w, 32w + 32) of every ray block by ballots.
+constexpr int COUNT_RB = 8;
+__global__ void __launch_bounds__(SB)
+sample_count_kernel(int R, int nb, const uint8_t* __restrict__ rgbs, const float* __restrict__ depth,
+                    float min_bound, int this_obj, int* __restrict__ blk_counts, float* __restrict__ blk_max,
+                    int* __restrict__ sup /* [K][gridDim.x][8]: this CTA's totals {nI, nO, nT, Nd, No, Ns, bits(max depth), -} */) {
+  const int k = blockIdx.y, b0 = blockIdx.x * COUNT_RB;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  cI = warp_sum_i(cI); cO = warp_sum_i(cO); cT = warp_sum_i(cT);
-  cD = warp_sum_i(cD); cObj = warp_sum_i(cObj); cSem = warp_sum_i(cSem);
-  mx = warp_max(mx);
-  if (l == 0) { s_c[w][0] = cI; s_c[w][1] = cO; s_c[w][2] = cT; s_c[w][3] = cD; s_c[w][4] = cObj; s_c[w][5] = cSem; s_m[w] = mx; }
-  __syncthreads();
-  if (threadIdx.x < 6) {
-    int t = 0;
-    for (int i = 0; i < SB / 32; ++i) t += s_c[i][threadIdx.x];
-    blk_counts[((size_t)k * nb + b) * 8 + threadIdx.x] = t;
+  const uint32_t* px = reinterpret_cast<const uint32_t*>(rgbs);
+  float d[COUNT_RB];
+  uint32_t p[COUNT_RB];
+#pragma unroll
+  for (int j = 0; j < COUNT_RB; ++j) {
+    const int r = (b0 + j) * SB + threadIdx.x;
+    const bool in = r < R;
+    d[j] = in ? depth[(size_t)k * R + r] : 0.f;
+    p[j] = in ? px[(size_t)k * R + r] : 0u;
   }
-  if (threadIdx.x == 32) {
-    float m = s_m[0];
-    for (int i = 1; i < SB / 32; ++i) m = fmaxf(m, s_m[i]);
-    blk_max[(size_t)k * nb + b] = m;
+  __shared__ int s_c[COUNT_RB][SB / 32][6];
+  __shared__ float s_m[COUNT_RB][SB / 32];
+#pragma unroll
+  for (int j = 0; j < COUNT_RB; ++j) {
+    const int r = (b0 + j) * SB + threadIdx.x;
+    const bool in = r < R;
+    const uint8_t lab = (uint8_t)(p[j] >> 24);
+    const int c = in ? ray_case(d[j], lab, min_bound, this_obj) : 3;
+    const bool mo = in && lab != 0, ms = in && lab != 2;
+    const unsigned q0 = __ballot_sync(0xffffffffu, c == 0), q1 = __ballot_sync(0xffffffffu, c == 1), q2 = __ballot_sync(0xffffffffu, c == 2);
+    const unsigned q3 = __ballot_sync(0xffffffffu, c != 0 && mo), q4 = __ballot_sync(0xffffffffu, mo), q5 = __ballot_sync(0xffffffffu, ms);
+    const float mx = warp_max(in ? d[j] : -INFINITY);
+    if (l == 0) {
+      s_c[j][w][0] = __popc(q0); s_c[j][w][1] = __popc(q1); s_c[j][w][2] = __popc(q2);
+      s_c[j][w][3] = __popc(q3); s_c[j][w][4] = __popc(q4); s_c[j][w][5] = __popc(q5);
+      s_m[j][w] = mx;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < COUNT_RB * 8) {
+    const int j = threadIdx.x >> 3, cc = threadIdx.x & 7;
+    if (b0 + j < nb) {
+      if (cc < 6) {
+        int tt = 0;
+#pragma unroll
+        for (int i = 0; i < SB / 32; ++i) tt += s_c[j][i][cc];
+        blk_counts[((size_t)k * nb + b0 + j) * 8 + cc] = tt;
+      } else if (cc == 6) {
+        float m = s_m[j][0];
+#pragma unroll
+        for (int i = 1; i < SB / 32; ++i) m = fmaxf(m, s_m[j][i]);
+        blk_max[(size_t)k * nb + b0 + j] = m;
+      }
+    }
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 7) {           // totals of the CTA's COUNT_RB ray blocks (rays beyond R counted nothing)
+    const int cc = threadIdx.x - 64;
+    int* o = sup + ((size_t)k * gridDim.x + blockIdx.x) * 8;
+    if (cc < 6) {
+      int tt = 0;
+#pragma unroll
+      for (int j = 0; j < COUNT_RB; ++j)
+#pragma unroll
+        for (int i = 0; i < SB / 32; ++i) tt += s_c[j][i][cc];
+      o[cc] = tt;
+    } else {
+      float m = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < COUNT_RB; ++j)
+#pragma unroll
+        for (int i = 0; i < SB / 32; ++i) m = fmaxf(m, s_m[j][i]);
+      o[6] = __float_as_int(m);
+    }
   }
 }
 
-// (B) one block (256 threads) per category: exclusive scan of the block counts (in place, cols 0..2), totals -> stats.
+// (B) one block (1024 threads) per category: exclusive scan of the block counts (in place, cols 0..2), totals -> stats.
 // Each thread owns a contiguous chunk of blocks, read as int4 pairs in batches of 8 blocks with every load of a batch in flight
 // at once (the serial load -> add chain of the first version cost 32 us at 4096 blocks); chunk sums are scanned with warp
 // shuffles + one smem hop.
-constexpr int SCAN_T = 256;
+constexpr int SCAN_T = 1024;
+constexpr int SCAN_BATCH = 4;   // blocks per thread whose loads are in flight together (1024 threads x 4 = the 4096 blocks of 1 Mi rays)
 __global__ void __launch_bounds__(SCAN_T)
 sample_scan_kernel(int nb, int* __restrict__ blk_counts, const float* __restrict__ blk_max,
                    const float* __restrict__ max_override, int32_t* __restrict__ stats) {
@@ -70,18 +110,18 @@ sample_scan_kernel(int nb, int* __restrict__ blk_counts, const float* __restrict
   const int b0 = min(nb, t * per), b1 = min(nb, b0 + per);
   int sum[6] = {0, 0, 0, 0, 0, 0};
   float mx = -INFINITY;
-  for (int bb = b0; bb < b1; bb += 8) {
-    int4 lo[8], hi[8];
-    float m[8];
+  for (int bb = b0; bb < b1; bb += SCAN_BATCH) {
+    int4 lo[SCAN_BATCH], hi[SCAN_BATCH];
+    float m[SCAN_BATCH];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < SCAN_BATCH; ++j) {
       const bool in = bb + j < b1;
       lo[j] = in ? bc4[(bb + j) * 2] : make_int4(0, 0, 0, 0);
       hi[j] = in ? bc4[(bb + j) * 2 + 1] : make_int4(0, 0, 0, 0);
       m[j] = in ? bm[bb + j] : -INFINITY;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < SCAN_BATCH; ++j) {
       sum[0] += lo[j].x; sum[1] += lo[j].y; sum[2] += lo[j].z; sum[3] += lo[j].w; sum[4] += hi[j].x; sum[5] += hi[j].y;
       mx = fmaxf(mx, m[j]);
     }
@@ -109,12 +149,12 @@ sample_scan_kernel(int nb, int* __restrict__ blk_counts, const float* __restrict
     tot[c] = all;
   }
   int run[3] = {excl[0], excl[1], excl[2]};
-  for (int bb = b0; bb < b1; bb += 8) {
-    int4 lo[8];
+  for (int bb = b0; bb < b1; bb += SCAN_BATCH) {
+    int4 lo[SCAN_BATCH];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) lo[j] = (bb + j < b1) ? bc4[(bb + j) * 2] : make_int4(0, 0, 0, 0);
+    for (int j = 0; j < SCAN_BATCH; ++j) lo[j] = (bb + j < b1) ? bc4[(bb + j) * 2] : make_int4(0, 0, 0, 0);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < SCAN_BATCH; ++j) {
       if (bb + j < b1) {
         const int4 v = lo[j];
         bc4[(bb + j) * 2] = make_int4(run[0], run[1], run[2], v.w);
@@ -281,6 +321,233 @@ sample_emit_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const 
   emit_block(sh, k, b, R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth, lin_S, lin_N, lin_M, min_bound, eps, stop_eps,
              this_obj, bc[0], bc[1], bc[2], __int_as_float(stats[k * 8 + 7]), z, pcs, valid, labels, zbuf_dyn);
 }
+
+// (C') emit, fast path for M <= 16 surface bins (every training / rendering shape of the reference except the 96-bin uncertainty
+// sweep): ONE THREAD PER RAY.  The generic kernel above spends ~340 instructions per SAMPLE (index arithmetic per element, an
+// O(M) rank loop per sample, one IEEE division per sample) and is issue-bound at 21 % of the HBM roofline (ncu: issue slots 79 %
+// busy).  Here a block of 256 rays
+//   1. loads its ray data (one coalesced round) and ranks the rays inside their case by warp ballots,
+//   2. copies its rows of the four random tensors -- rows of one case are consecutive in ray order, so each is ONE contiguous chunk --
+//      into shared memory with coalesced loads (nrays * S floats in total, whatever the case mix),
+//   3. each thread turns its row into the ray's S depths: the two IEEE divisions of `stratified_bins` once per ray, the M normal
+//      draws sorted by a compile-time odd-even transposition network in registers (any correct sort gives the reference's values),
+//      and stages z [S] and pcs [S,3] of its ray in shared memory,
+//   4. the block's z and pcs leave as linear 16-byte stores.
+// Same separately rounded fp32 operations as the reference (bit-exact); ~400 instructions per RAY.
+template <int M>
+__device__ __forceinline__ void sort_network(float (&v)[M]) {
+#pragma unroll
+  for (int p = 0; p < M; ++p) {
+#pragma unroll
+    for (int i = (p & 1); i + 1 < M; i += 2) {
+      const float a = v[i], b = v[i + 1];
+      v[i] = fminf(a, b); v[i + 1] = fmaxf(a, b);
+    }
+  }
+}
+
+template <int M>
+__global__ void __launch_bounds__(SB, 5)
+sample_emit_fast_kernel(int R, int N, const uint8_t* __restrict__ rgbs, const float* __restrict__ depth,
+                        const float* __restrict__ origins, const float* __restrict__ dirs,
+                        const float* __restrict__ u_inv, const float* __restrict__ u_val,
+                        const float* __restrict__ n_obj, const float* __restrict__ u_oth,
+                        const float* __restrict__ lin_S, const float* __restrict__ lin_N, const float* __restrict__ lin_M,
+                        float min_bound, float eps, float stop_eps, int this_obj,
+                        const int* __restrict__ blk_counts, int32_t* __restrict__ stats, const int* __restrict__ sup, int nsup,
+                        const float* __restrict__ max_override,
+                        float* __restrict__ z, float* __restrict__ pcs, uint8_t* __restrict__ valid, uint8_t* __restrict__ labels) {
+  extern __shared__ __align__(16) float sm_f[];
+  __shared__ int s_w[SB / 32][3];
+  __shared__ float s_lin[99];                 // linspace tables: [0, 33) S bins | [33, 66) N bins | [66, 99) M bins (S <= 32)
+  const int S = N + M;
+  const int k = blockIdx.y, nb = gridDim.x, b = blockIdx.x, t = threadIdx.x, w = t >> 5, l = t & 31;
+  if (t <= S) s_lin[t] = lin_S[t];
+  else if (t >= 64 && t - 64 <= N) s_lin[33 + t - 64] = lin_N[t - 64];
+  else if (t >= 128 && t - 128 <= M) s_lin[66 + t - 128] = lin_M[t - 128];
+  const int r0 = b * SB, r = r0 + t, nrays = min(SB, R - r0);
+  float* rbuf = sm_f;                         // [nrays * S]: random rows, then the block's z
+  float* pbuf = sm_f + SB * S;                // [nrays * 3S]: the block's pcs
+  // ---- 0. running case counts before this block + the category's maximum depth.  sup == NULL: blk_counts was scanned by
+  //      sample_scan_kernel (exclusive prefixes) and stats holds the maximum.  Otherwise (R up to a few Mi rays) there is no scan
+  //      launch: every block sums the totals of the count kernel's CTAs in front of it (nsup x 32 B, L2-resident) and the raw counts
+  //      of the ray blocks of its own count CTA; block 0 also writes the category's stats row.
+  int base0, base1, base2;
+  float max_bound;
+  if (sup == nullptr) {
+    const int* bc = blk_counts + ((size_t)k * nb + b) * 8;
+    base0 = bc[0]; base1 = bc[1]; base2 = bc[2];
+    max_bound = __int_as_float(stats[k * 8 + 7]);
+  } else {
+    __shared__ int s_red[SB / 32][10];
+    const int4* sup4 = reinterpret_cast<const int4*>(sup + (size_t)k * nsup * 8);
+    const int my_sup = b / COUNT_RB;
+    int acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};        // prefix {nI, nO, nT}, totals {nI, nO, nT, Nd, No, Ns}
+    float mx = -INFINITY;
+    for (int i = t; i < nsup; i += SB) {
+      const int4 lo = sup4[i * 2], hi = sup4[i * 2 + 1];
+      if (i < my_sup) { acc[0] += lo.x; acc[1] += lo.y; acc[2] += lo.z; }
+      acc[3] += lo.x; acc[4] += lo.y; acc[5] += lo.z; acc[6] += lo.w; acc[7] += hi.x; acc[8] += hi.y;
+      mx = fmaxf(mx, __int_as_float(hi.z));
+    }
+    if (t < b - my_sup * COUNT_RB) {                 // earlier ray blocks of my count CTA (raw per-block counts)
+      const int* bc = blk_counts + ((size_t)k * nb + my_sup * COUNT_RB + t) * 8;
+      acc[0] += bc[0]; acc[1] += bc[1]; acc[2] += bc[2];
+    }
+    const bool first = (b == 0);                     // block 0 also needs the category totals (stats row)
+#pragma unroll
+    for (int q = 0; q < 9; ++q) if (q < 3 || first) acc[q] = warp_sum_i(acc[q]);
+    mx = warp_max(mx);
+    if (l == 0) {
+#pragma unroll
+      for (int q = 0; q < 9; ++q) if (q < 3 || first) s_red[w][q] = acc[q];
+      s_red[w][9] = __float_as_int(mx);
+    }
+    __syncthreads();
+    int tot[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < SB / 32; ++i) {
+#pragma unroll
+      for (int q = 0; q < 9; ++q) if (q < 3 || first) tot[q] += s_red[i][q];
+      mx = fmaxf(mx, __int_as_float(s_red[i][9]));
+    }
+    base0 = tot[0]; base1 = tot[1]; base2 = tot[2];
+    max_bound = max_override ? max_override[k] : mx;
+    if (b == 0 && t == 0) {
+      int32_t* st = stats + k * 8;
+      st[0] = tot[3]; st[1] = tot[4] + tot[5]; st[2] = tot[4]; st[3] = tot[5];
+      st[4] = tot[6]; st[5] = tot[7]; st[6] = tot[8]; st[7] = __float_as_int(max_bound);
+    }
+  }
+
+  // ---- 1. ray data, case, rank inside the case (ray order)
+  int c = 3;
+  float d = 0.f, o[3] = {0.f, 0.f, 0.f}, dr[3] = {0.f, 0.f, 0.f};
+  const size_t gi = (size_t)k * R + r;
+  if (r < R) {
+    d = depth[gi];
+    const uint32_t px = reinterpret_cast<const uint32_t*>(rgbs)[gi];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { o[j] = origins[gi * 3 + j]; dr[j] = dirs[gi * 3 + j]; }
+    const uint8_t lab = (uint8_t)(px >> 24);
+    c = ray_case(d, lab, min_bound, this_obj);
+    valid[gi] = (c != 0);
+    labels[gi] = lab;
+  }
+  const unsigned m0 = __ballot_sync(0xffffffffu, c == 0), m1 = __ballot_sync(0xffffffffu, c == 1), m2 = __ballot_sync(0xffffffffu, c == 2);
+  const unsigned lt = (1u << l) - 1u;
+  if (l == 0) { s_w[w][0] = __popc(m0); s_w[w][1] = __popc(m1); s_w[w][2] = __popc(m2); }
+  __syncthreads();
+  int before[3] = {0, 0, 0}, cnt[3] = {0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < SB / 32; ++i) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { const int v = s_w[i][q]; cnt[q] += v; if (i < w) before[q] += v; }
+  }
+  // rank of this ray inside the block's rays of its case / of the valid rays
+  const int rk0 = before[0] + __popc(m0 & lt), rk1 = before[1] + __popc(m1 & lt), rk2 = before[2] + __popc(m2 & lt);
+
+  // ---- 2. the block's rows of the random tensors: four contiguous chunks -> rbuf (asynchronous 4-byte copies, all in flight)
+  //      [0, a0) u_inv rows | [a0, a1) u_val rows of the valid rays | [a1, a2) normal draws | [a2, a3) u_oth rows
+  const int nv = cnt[1] + cnt[2];
+  const int a0 = cnt[0] * S, a1 = a0 + nv * N, a2 = a1 + cnt[1] * M, a3 = a2 + cnt[2] * M;
+  {
+    const size_t kr = (size_t)k * R;
+    const float* p0 = u_inv + (kr + base0) * S;
+    const float* p1 = u_val + (kr + base1 + base2) * N;
+    const float* p2 = n_obj + (kr + base1) * M;
+    const float* p3 = u_oth + (kr + base2) * M;
+    const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(rbuf);
+    auto copy = [&](const float* src, int lo, int hi) {
+      for (int e = t; e < hi - lo; e += SB)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst0 + 4u * (lo + e)), "l"(src + e) : "memory");
+    };
+    copy(p0, 0, a0); copy(p1, a0, a1); copy(p2, a1, a2); copy(p3, a2, a3);
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ---- 3. this thread's ray, branch-free over the three cases (rays of different cases share a warp): both segments of a ray are
+  //      z_i = (range * lin_i + mn) + u_i * (range / n) with per-case {range, mn, n, lin table, row of draws}; the this-object case
+  //      replaces its surface segment by depth + clip(sorted normals).  z goes to the first S slots of the thread's pbuf row
+  //      (rbuf is still being read by other threads).
+  float* mine = pbuf + t * 3 * S;
+  {
+    const bool inval = (c == 0);
+    // segment A = samples [0, N): invalid rays use bins 0..N-1 of their S-bin stratification (:484-493), valid rays camera -> surface - eps (:502-504)
+    const float rangeI = __fsub_rn(max_bound, min_bound), lenI = __fdiv_rn(rangeI, (float)S);
+    const float rangeV = __fsub_rn(__fsub_rn(d, eps), min_bound), lenV = __fdiv_rn(rangeV, (float)N);
+    const float mn2 = __fsub_rn(d, eps), range2 = __fsub_rn(__fadd_rn(d, stop_eps), mn2), len2 = __fdiv_rn(range2, (float)M);
+    const float* rowI = rbuf + rk0 * S;                          // only dereferenced by the case that owns it (others read in-bounds junk)
+    const float* uA = inval ? rowI : rbuf + a0 + (rk1 + rk2) * N;
+    const float* linA = inval ? s_lin : s_lin + 33;
+    const float rangeA = inval ? rangeI : rangeV, lenA = inval ? lenI : lenV;
+    for (int i = 0; i < N; ++i) mine[i] = __fadd_rn(__fadd_rn(__fmul_rn(rangeA, linA[i]), min_bound), __fmul_rn(uA[i], lenA));
+    // segment B = samples [N, S): invalid: bins N..S-1; this object: sorted normals (:519-524); other objects: [d - eps, d + stop_eps] (:536-539)
+    const float* uB = inval ? rowI + N : (c == 1 ? rbuf + a1 + rk1 * M : rbuf + a2 + rk2 * M);
+    const float* linB = inval ? s_lin + N : s_lin + 66;
+    const float rangeB = inval ? rangeI : range2, lenB = inval ? lenI : len2, mnB = inval ? min_bound : mn2;
+    float v[M];
+    if (c == 3) uB = rbuf;                                       // rays beyond R: any valid address
+#pragma unroll
+    for (int j = 0; j < M; ++j) v[j] = uB[j];
+    float sv[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) sv[j] = v[j];
+    sort_network<M>(sv);
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      const float strat_z = __fadd_rn(__fadd_rn(__fmul_rn(rangeB, linB[j]), mnB), __fmul_rn(v[j], lenB));
+      const float norm_z = __fadd_rn(d, fminf(fmaxf(sv[j], -eps), eps));
+      mine[N + j] = (c == 1) ? norm_z : strat_z;
+    }
+  }
+  __syncthreads();
+  if (c != 3) {
+    // in place, last sample first: pcs of sample i go to slots 3i..3i+2, the unread depths sit in slots < i
+    for (int i = S - 1; i >= 0; --i) {
+      const float zz = mine[i];
+      rbuf[t * S + i] = zz;
+      if (pcs) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) mine[3 * i + q] = __fadd_rn(o[q], __fmul_rn(dr[q], zz));      // scene_cateogries.py:543-544
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 4. linear copy-out (16-byte stores when the block's output offset allows)
+  const size_t g0 = ((size_t)k * R + r0) * S;
+  const int nz = nrays * S;
+  float* zo = z + g0;
+  if ((reinterpret_cast<uintptr_t>(zo) & 15) == 0) {
+    for (int f = t; f < (nz >> 2); f += SB) reinterpret_cast<float4*>(zo)[f] = reinterpret_cast<const float4*>(rbuf)[f];
+    for (int f = (nz & ~3) + t; f < nz; f += SB) zo[f] = rbuf[f];
+  } else {
+    for (int f = t; f < nz; f += SB) zo[f] = rbuf[f];
+  }
+  if (pcs) {
+    float* po = pcs + g0 * 3;
+    const int np = nz * 3;
+    if ((reinterpret_cast<uintptr_t>(po) & 15) == 0) {
+      for (int f = t; f < (np >> 2); f += SB) reinterpret_cast<float4*>(po)[f] = reinterpret_cast<const float4*>(pbuf)[f];
+      for (int f = (np & ~3) + t; f < np; f += SB) po[f] = pbuf[f];
+    } else {
+      for (int f = t; f < np; f += SB) po[f] = pbuf[f];
+    }
+  }
+}
+
+typedef void (*emit_fast_fn)(int, int, const uint8_t*, const float*, const float*, const float*, const float*, const float*, const float*,
+                             const float*, const float*, const float*, const float*, float, float, float, int, const int*, int32_t*, const int*, int,
+                             const float*, float*, float*, uint8_t*, uint8_t*);
+template <int M> struct EmitFastTable {
+  static void fill(emit_fast_fn* tab) { tab[M] = sample_emit_fast_kernel<M>; EmitFastTable<M - 1>::fill(tab); }
+};
+template <> struct EmitFastTable<0> { static void fill(emit_fast_fn*) {} };
+constexpr int EMIT_FAST_MAX_M = 16;
+constexpr int EMIT_FAST_MAX_SUP = 2048;
 
 // Single-launch sampler for small ray batches (R <= SAMPLE_SMALL_RAYS): grid (category, ray block).  Every CTA counts the cases /
 // loss masks and the maximum depth of its whole category (a few thousand rays: cheaper than a second launch), derives the running
@@ -481,7 +748,9 @@ extern "C" int cnf_pool_compose(int64_t n, const int32_t* perm_in, const int64_t
 
 extern "C" size_t cnf_sample_workspace_bytes(int n_cat, int n_rays) {
   const size_t nb = (size_t)(n_rays + SB - 1) / SB;
-  return align_up((size_t)n_cat * nb * 8 * sizeof(int), 256) + align_up((size_t)n_cat * nb * sizeof(float), 256);
+  const size_t nsup = (nb + COUNT_RB - 1) / COUNT_RB;
+  return align_up((size_t)n_cat * nb * 8 * sizeof(int), 256) + align_up((size_t)n_cat * nb * sizeof(float), 256) +
+         align_up((size_t)n_cat * nsup * 8 * sizeof(int), 256);
 }
 
 extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, const float* depth,
@@ -497,6 +766,8 @@ extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, c
   const int nb = (R + SB - 1) / SB;
   int* blk_counts = reinterpret_cast<int*>(ws);
   float* blk_max = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align_up((size_t)K * nb * 8 * sizeof(int), 256));
+  const int nsup = (nb + COUNT_RB - 1) / COUNT_RB;
+  int* sup = reinterpret_cast<int*>(reinterpret_cast<char*>(blk_max) + align_up((size_t)K * nb * sizeof(float), 256));
   cudaStream_t st = as_stream(stream);
   const size_t zbytes = (size_t)SB * (N + M) * sizeof(float);
   CNF_REQUIRE(N + M <= 96, "cnf_sample_fwd: more than 96 samples per ray");
@@ -511,8 +782,26 @@ extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, c
                                               eps, stop_eps, this_obj, max_depth_override, stats, z, pcs, valid, labels);
     return check_launch("cnf_sample_fwd");
   }
-  sample_count_kernel<<<dim3(nb, K), SB, 0, st>>>(R, rgbs, depth, min_bound, this_obj, blk_counts, blk_max);
-  sample_scan_kernel<<<K, SCAN_T, 0, st>>>(nb, blk_counts, blk_max, max_depth_override, stats);
+  sample_count_kernel<<<dim3(nsup, K), SB, 0, st>>>(R, nb, rgbs, depth, min_bound, this_obj, blk_counts, blk_max, sup);
+  const bool fast = M <= EMIT_FAST_MAX_M && N + M <= 32;
+  // up to 2048 count CTAs per category (4 Mi rays) the fast emit kernel sums the count totals itself: no scan launch
+  const bool no_scan = fast && nsup <= EMIT_FAST_MAX_SUP;
+  if (!no_scan) sample_scan_kernel<<<K, SCAN_T, 0, st>>>(nb, blk_counts, blk_max, max_depth_override, stats);
+  if (fast) {       // thread-per-ray fast path
+    static emit_fast_fn tab[EMIT_FAST_MAX_M + 1] = {nullptr};
+    if (!tab[1]) EmitFastTable<EMIT_FAST_MAX_M>::fill(tab);
+    const int fbytes = SB * 4 * (N + M) * (int)sizeof(float);
+    static DeviceOnce fattr[EMIT_FAST_MAX_M + 1];
+    if (fattr[M].pending()) {
+      CNF_CUDA(cudaFuncSetAttribute((const void*)tab[M], cudaFuncAttributeMaxDynamicSharedMemorySize, SB * 4 * 32 * (int)sizeof(float)));
+      CNF_CUDA(cudaFuncSetAttribute((const void*)tab[M], cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      fattr[M].done();
+    }
+    tab[M]<<<dim3(nb, K), SB, fbytes, st>>>(R, N, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth, lin_S, lin_N, lin_M, min_bound,
+                                             eps, stop_eps, this_obj, blk_counts, stats, no_scan ? sup : nullptr, nsup, max_depth_override, z, pcs, valid,
+                                             labels);
+    return check_launch("cnf_sample_fwd");
+  }
   sample_emit_kernel<<<dim3(nb, K), EMIT_BIG_T, zbytes, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth,
                                                  lin_S, lin_N, lin_M, min_bound, eps, stop_eps, this_obj,
                                                  blk_counts, stats, z, pcs, valid, labels);

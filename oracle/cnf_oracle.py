@@ -146,8 +146,10 @@ def normal_bins(depth: torch.Tensor, n: torch.Tensor, delta: float) -> torch.Ten
 
 def sample_points(rgbs: torch.Tensor, depth: torch.Tensor, origins: torch.Tensor, dirs: torch.Tensor,
                   n_cam2surf: int, n_surf: int, eps: float, stop_eps: float,
-                  rand: Dict[str, torch.Tensor], min_bound: float = 0.0, this_obj: int = 1):
+                  rand: Dict[str, torch.Tensor], min_bound: float = 0.0, this_obj: int = 1, max_depth: Optional[float] = None):
     """sceneCategory.sample_3d_points (src/scene_cateogries.py:453-546).
+    ``max_depth`` (not in the reference): upper bound of the invalid-depth rays when this batch is one part of a larger batch
+    whose maximum depth (:486) has been computed over all parts (ray split across GPUs).
 
     ``rand`` holds the injected draws, consumed in the reference's order:
       'u_inv' [nI, N+M], 'u_val' [nV, N], 'n_obj' [nO, M] (already N(0, eps/3)), 'u_oth' [nT, M],
@@ -158,7 +160,7 @@ def sample_points(rgbs: torch.Tensor, depth: torch.Tensor, origins: torch.Tensor
     N, M = n_cam2surf, n_surf
     z = torch.zeros(R, N + M, dtype=depth.dtype)                                   # :478-482
     invalid = (depth <= min_bound).view(-1)                                        # :484
-    max_bound = torch.max(depth)                                                   # :486
+    max_bound = torch.max(depth) if max_depth is None else torch.tensor(max_depth, dtype=depth.dtype)   # :486
     nI = int(invalid.count_nonzero())
     if nI:
         z[invalid, :] = stratified_bins(min_bound, max_bound, N + M, rand["u_inv"][:nI])   # :489-493

@@ -1,8 +1,4 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/tests.log
+timeout 1500 python -m pytest tests/test_gpu_hbm_kernels.py tests/test_gpu_parity_v0.py tests/test_pool.py tests/test_gpu_occmap_tc.py tests/test_gpu_training.py -m gpu -x -q 2>&1 | tail -12 > gpurun_out/tests.log
 cat gpurun_out/tests.log
-for tool in memcheck synccheck racecheck initcheck; do
-  timeout 400 compute-sanitizer --tool $tool --print-limit 20 python __graft_entry__.py smoke > gpurun_out/sanitizer_$tool.log 2>&1
-  echo "$tool rc=$?" >> gpurun_out/sanitizer_$tool.log
-  tail -5 gpurun_out/sanitizer_$tool.log
-done
+timeout 600 python scripts/bench_standalone.py > gpurun_out/standalone.json 2> gpurun_out/standalone.err; cat gpurun_out/standalone.json; tail -3 gpurun_out/standalone.err

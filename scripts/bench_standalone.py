@@ -23,6 +23,9 @@ def measure(dev, R=1 << 20, iters=5, flush=None):
     def timeit(fn):
         """Device time of one call, as a CUDA-graph replay (the ops are a few launches of ~100 us: eager launches from Python
         would measure the host, not the kernels); L2 flushed before every timed replay."""
+        if os.environ.get("CNF_PROFILE_ONCE"):        # under ncu: two plain launches per op, no graph, no timing
+            fn(); fn(); torch.cuda.synchronize()
+            return 1.0
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
