@@ -34,6 +34,8 @@ __device__ __forceinline__ float seg_scan_add_rev(float v, int G, int sl) {
   return v;
 }
 __device__ __forceinline__ float sigmoid_acc(float a) { return 1.0f / (1.0f + expf(-a)); }
+// <= 3 ulp (ex2.approx of a pre-scaled argument + a correctly rounded reciprocal); saturates to exactly 0 / 1 like the accurate form
+__device__ __forceinline__ float sigmoid_fast(float a) { return __frcp_rn(1.0f + __expf(-a)); }
 
 struct RayOut { float D, var, C0, C1, C2, O; };
 
@@ -147,11 +149,11 @@ composite_fwd_kernel(int K, int R, int S, const float* __restrict__ alpha, const
 }
 
 // out_loss = {loss, e_depth, e_obj, e_sem, depth[K], color[K], opacity[K]}
-__global__ void composite_finalize_kernel(int K, int nblk, const float* __restrict__ partial,
-                                          const int32_t* __restrict__ counts, float cs, float os,
-                                          float* __restrict__ out_loss) {
-  // one CTA of 32 (few partials) or 1024 threads; fixed summation order (thread-strided partial sums, a shuffle tree per warp, the
-  // warp sums in warp order) -> deterministic.  One warp walking 8192 partials serially cost 13 us of a 78 us forward at 1 Mi rays.
+// Loss outputs from the per-CTA partial sums, by ONE CTA of any size (a multiple of 32 threads, <= 1024): fixed summation order
+// (thread-strided partial sums, a shuffle tree per warp, the warp sums in warp order) -> deterministic.  Called by the finalize
+// kernel, and by the LAST CTA of the dense tile kernel (ticket counter), which saves the second launch.
+__device__ __forceinline__ void finalize_block(int K, int nblk, const float* __restrict__ partial, const int32_t* __restrict__ counts,
+                                               float cs, float os, float* __restrict__ out_loss) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   __shared__ float s_p[32][3];
   bool e0, e1, e2;
@@ -161,7 +163,7 @@ __global__ void composite_finalize_kernel(int K, int nblk, const float* __restri
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
       const float* p = partial + ((size_t)k * nblk + b) * 3;
-      s0 += p[0]; s1 += p[1]; s2 += p[2];
+      s0 += __ldcg(p); s1 += __ldcg(p + 1); s2 += __ldcg(p + 2);             // written by other CTAs: bypass L1
     }
     s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
     if (nwarp > 1) {
@@ -178,6 +180,12 @@ __global__ void composite_finalize_kernel(int K, int nblk, const float* __restri
     total += d + c * cs + o * os;                                             // loss.py:69-70
   }
   if (threadIdx.x == 0) { out_loss[0] = total; out_loss[1] = e0; out_loss[2] = e1; out_loss[3] = e2; }
+}
+
+__global__ void composite_finalize_kernel(int K, int nblk, const float* __restrict__ partial,
+                                          const int32_t* __restrict__ counts, float cs, float os,
+                                          float* __restrict__ out_loss) {
+  finalize_block(K, nblk, partial, counts, cs, os, out_loss);
 }
 
 __global__ void __launch_bounds__(CT)
@@ -402,7 +410,8 @@ composite_dense_kernel(int K, int R, int S, const float* __restrict__ alpha, con
                        const float* __restrict__ z, const float* __restrict__ gt_depth, const float* __restrict__ gt_color,
                        const uint8_t* __restrict__ labels, const uint8_t* __restrict__ mask_depth,
                        const int32_t* __restrict__ counts, float cs, float os, const float* __restrict__ g_loss,
-                       float* __restrict__ out_rays, float* __restrict__ partial, float* __restrict__ g_alpha, float* __restrict__ g_color) {
+                       float* __restrict__ out_rays, float* __restrict__ partial, float* __restrict__ g_alpha, float* __restrict__ g_color,
+                       unsigned* __restrict__ ticket /* zeroed by the host; the last CTA to finish writes out_loss */, float* __restrict__ out_loss) {
   using namespace umma;
   extern __shared__ __align__(128) float sm_d[];
   __shared__ __align__(8) uint64_t full[2];
@@ -478,7 +487,7 @@ composite_dense_kernel(int K, int R, int S, const float* __restrict__ alpha, con
       const float gd = gt_depth[g], q0 = gt_color[g * 3], q1 = gt_color[g * 3 + 1], q2 = gt_color[g * 3 + 2];
       float T = 1.0f, D = 0.f, O = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
       for (int i = 0; i < S; ++i) {
-        const float occ = sigmoid_acc(a[i]);
+        const float occ = sigmoid_fast(a[i]);
         const float w = occ * T;                                               // render_rays.py:33
         D += w * zz[i]; O += w; C0 += w * c[3 * i]; C1 += w * c[3 * i + 1]; C2 += w * c[3 * i + 2];
         if (BWD) { tt[i] = T; a[i] = occ; } else a[i] = w;
@@ -510,7 +519,7 @@ composite_dense_kernel(int K, int R, int S, const float* __restrict__ alpha, con
           const float occ = a[jj], Tj = tt[jj], w = occ * Tj;
           const float Gi = gD * zz[jj] + gC0 * c[3 * jj] + gC1 * c[3 * jj + 1] + gC2 * c[3 * jj + 2] + gO;
           const float f = __fadd_rn(__fsub_rn(1.0f, occ), 1e-10f);
-          const float docc = Gi * Tj - suffix / f;
+          const float docc = Gi * Tj - __fdividef(suffix, f);
           a[jj] = docc * occ * (1.0f - occ);
           c[3 * jj] = w * gC0; c[3 * jj + 1] = w * gC1; c[3 * jj + 2] = w * gC2;
           suffix += Gi * w;
@@ -547,6 +556,15 @@ composite_dense_kernel(int K, int R, int S, const float* __restrict__ alpha, con
       float v = 0.f;
       for (int i = 0; i < TR / 32; ++i) v += s_p[i][t];
       partial[((size_t)k * gridDim.x + blockIdx.x) * 3 + t] = v;               // deterministic 2-stage reduce
+      __threadfence();
+    }
+    __shared__ int s_last;
+    __syncthreads();
+    if (t == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+    __syncthreads();
+    if (s_last) {                                  // every other CTA's partial sums are visible (fence + ticket)
+      __threadfence();
+      finalize_block(K, gridDim.x, partial, counts, cs, os, out_loss);
     }
   }
 }
@@ -747,7 +765,7 @@ extern "C" int cnf_mask_counts(int K, int R, const uint8_t* labels, const uint8_
   return check_launch("cnf_mask_counts");
 }
 
-extern "C" size_t cnf_composite_workspace_bytes(int K, int R) { return (size_t)K * 1184 * 3 * sizeof(float); }
+extern "C" size_t cnf_composite_workspace_bytes(int K, int R) { (void)R; return (size_t)K * 1184 * 3 * sizeof(float) + 16; }   // partial sums | ticket
 
 extern "C" int cnf_composite_loss_fwd(int K, int R, int S, const float* alpha, const float* color, const float* z,
                                       const float* gt_depth, const float* gt_color, const uint8_t* labels,
@@ -761,8 +779,12 @@ extern "C" int cnf_composite_loss_fwd(int K, int R, int S, const float* alpha, c
   if (S <= 32 && use_dense(S)) {
     nb = dense_blocks(R, S, false);
     if (int rc = dense_attr<0>(S)) return rc;
+    unsigned* ticket = reinterpret_cast<unsigned*>((float*)ws + (size_t)K * 1184 * 3);
+    CNF_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), as_stream(stream)));
     composite_dense_kernel<0><<<dim3(nb, K), TR, dense_smem_bytes(S, false), as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth,
-                                                                                                   counts, cs, os, nullptr, out_rays, (float*)ws, nullptr, nullptr);
+                                                                                                   counts, cs, os, nullptr, out_rays, (float*)ws, nullptr, nullptr,
+                                                                                                   ticket, out_loss);
+    return check_launch("cnf_composite_loss_fwd");
   } else if (S <= 32) {
     nb = tile_blocks(R);
     const int smem = tile_smem_floats(S, false) * 4;
@@ -789,7 +811,7 @@ extern "C" int cnf_composite_loss_bwd(int K, int R, int S, const float* alpha, c
   if (S <= 32 && use_dense(S)) {
     if (int rc = dense_attr<1>(S)) return rc;
     composite_dense_kernel<1><<<dim3(dense_blocks(R, S, true), K), TR, dense_smem_bytes(S, true), as_stream(stream)>>>(
-        K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth, counts, cs, os, g_loss, nullptr, nullptr, g_alpha, g_color);
+        K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth, counts, cs, os, g_loss, nullptr, nullptr, g_alpha, g_color, nullptr, nullptr);
     return check_launch("cnf_composite_loss_bwd");
   }
   if (S <= 32) {
@@ -819,9 +841,11 @@ extern "C" int cnf_composite_loss_fwd_bwd(int K, int R, int S, const float* alph
   if (use_dense(S)) {
     const int nbd = dense_blocks(R, S, true);
     if (int rc = dense_attr<2>(S)) return rc;
+    unsigned* ticket = reinterpret_cast<unsigned*>((float*)ws + (size_t)K * 1184 * 3);
+    CNF_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), as_stream(stream)));
     composite_dense_kernel<2><<<dim3(nbd, K), TR, dense_smem_bytes(S, true), as_stream(stream)>>>(K, R, S, alpha, color, z, gt_depth, gt_color, labels, mask_depth,
-                                                                                                   counts, cs, os, nullptr, out_rays, (float*)ws, g_alpha, g_color);
-    composite_finalize_kernel<<<1, nbd > 64 ? 1024 : 32, 0, as_stream(stream)>>>(K, nbd, (const float*)ws, counts, cs, os, out_loss);
+                                                                                                   counts, cs, os, nullptr, out_rays, (float*)ws, g_alpha, g_color,
+                                                                                                   ticket, out_loss);
     return check_launch("cnf_composite_loss_fwd_bwd");
   }
   const int nb = tile_blocks(R);

@@ -3,8 +3,8 @@
 // separately rounded (__fmul_rn/__fadd_rn/__fdiv_rn, no FMA contraction), linspace tables and random
 // draws are inputs, and rows of the random tensors are consumed by rank-within-case in ray order.
 //
-// HBM-bound.  Three launches: (A) per-block case counts + max depth, (B) per-category exclusive scan of
-// the block counts, (C) emit: thread-per-ray rank computation, then thread-per-sample coalesced writes.
+// HBM-bound.  Two launches (one for up to 4096 rays per category): (A) per-block case counts + max depth, whose last CTA per
+// category also (B) scans the block counts, (C) emit: one thread per ray (M <= 16 surface bins) or per sample (generic).
 #include "cnf_common.cuh"
 
 namespace cnf {
@@ -19,152 +19,161 @@ __device__ __forceinline__ int ray_case(float d, uint8_t label, float min_bound,
 }
 
 // (A) counts per 256-ray block: {nI, nO, nT} plus loss-mask counts {Nd, No, Ns} and block max depth.  One CTA covers COUNT_RB
-// consecutive ray blocks with all of a thread's loads in flight at once (one ray block per CTA made the kernel a chain of tiny
-// latency-bound CTAs: 770 GB/s); warp w counts the rays [32w, 32w + 32) of every ray block by ballots.
-constexpr int COUNT_RB = 8;
-__global__ void __launch_bounds__(SB)
+// consecutive ray blocks with all of a thread's loads in flight (one ray block per CTA made the kernel a chain of tiny
+// latency-bound CTAs: 770 GB/s); warp w counts the rays [32w, 32w + 32) of every ray block by ballots.  The CTA writes, per ray
+// block, the exclusive prefix of the case counts INSIDE the CTA, and its own totals.
+// (B) The LAST CTA of a category to finish (ticket counter) scans the CTA totals (nb / COUNT_RB entries: one round trip) into
+// cta_prefix and writes the category's stats row; an emit block's running counts are cta_prefix[b / COUNT_RB] + blk_counts[b].
+// A separate one-CTA scan launch over all ray blocks cost 15-20 us of a 150 us sampler at 1 Mi rays.
+constexpr int COUNT_RB = 8, SCAN_BATCH = 4;
+__global__ void __launch_bounds__(SB, 4)
 sample_count_kernel(int R, int nb, const uint8_t* __restrict__ rgbs, const float* __restrict__ depth,
-                    float min_bound, int this_obj, int* __restrict__ blk_counts, float* __restrict__ blk_max,
-                    int* __restrict__ sup /* [K][gridDim.x][8]: this CTA's totals {nI, nO, nT, Nd, No, Ns, bits(max depth), -} */) {
+                    float min_bound, int this_obj, int* __restrict__ blk_counts /* [K][nb][4] */,
+                    int4* __restrict__ cta_lo /* [K][gridDim.x] {nI, nO, nT, bits(max depth)} */,
+                    int4* __restrict__ cta_hi /* [K][gridDim.x] {Nd, No, Ns, -} */,
+                    int4* __restrict__ cta_prefix /* [K][gridDim.x] exclusive prefix of {nI, nO, nT} over the CTAs */,
+                    unsigned* __restrict__ ticket /* [K], zeroed by the host */, const float* __restrict__ max_override,
+                    int32_t* __restrict__ stats) {
   const int k = blockIdx.y, b0 = blockIdx.x * COUNT_RB;
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
   const uint32_t* px = reinterpret_cast<const uint32_t*>(rgbs);
-  float d[COUNT_RB];
-  uint32_t p[COUNT_RB];
-#pragma unroll
-  for (int j = 0; j < COUNT_RB; ++j) {
-    const int r = (b0 + j) * SB + threadIdx.x;
-    const bool in = r < R;
-    d[j] = in ? depth[(size_t)k * R + r] : 0.f;
-    p[j] = in ? px[(size_t)k * R + r] : 0u;
-  }
   __shared__ int s_c[COUNT_RB][SB / 32][6];
   __shared__ float s_m[COUNT_RB][SB / 32];
+  __shared__ int s_t[COUNT_RB][8];
+  {
+    float d[COUNT_RB];
+    uint32_t p[COUNT_RB];
 #pragma unroll
-  for (int j = 0; j < COUNT_RB; ++j) {
-    const int r = (b0 + j) * SB + threadIdx.x;
-    const bool in = r < R;
-    const uint8_t lab = (uint8_t)(p[j] >> 24);
-    const int c = in ? ray_case(d[j], lab, min_bound, this_obj) : 3;
-    const bool mo = in && lab != 0, ms = in && lab != 2;
-    const unsigned q0 = __ballot_sync(0xffffffffu, c == 0), q1 = __ballot_sync(0xffffffffu, c == 1), q2 = __ballot_sync(0xffffffffu, c == 2);
-    const unsigned q3 = __ballot_sync(0xffffffffu, c != 0 && mo), q4 = __ballot_sync(0xffffffffu, mo), q5 = __ballot_sync(0xffffffffu, ms);
-    const float mx = warp_max(in ? d[j] : -INFINITY);
-    if (l == 0) {
-      s_c[j][w][0] = __popc(q0); s_c[j][w][1] = __popc(q1); s_c[j][w][2] = __popc(q2);
-      s_c[j][w][3] = __popc(q3); s_c[j][w][4] = __popc(q4); s_c[j][w][5] = __popc(q5);
-      s_m[j][w] = mx;
+    for (int j = 0; j < COUNT_RB; ++j) {
+      const int r = (b0 + j) * SB + t;
+      const bool in = r < R;
+      d[j] = in ? depth[(size_t)k * R + r] : 0.f;
+      p[j] = in ? px[(size_t)k * R + r] : 0u;
     }
-  }
-  __syncthreads();
-  if (threadIdx.x < COUNT_RB * 8) {
-    const int j = threadIdx.x >> 3, cc = threadIdx.x & 7;
-    if (b0 + j < nb) {
-      if (cc < 6) {
-        int tt = 0;
 #pragma unroll
-        for (int i = 0; i < SB / 32; ++i) tt += s_c[j][i][cc];
-        blk_counts[((size_t)k * nb + b0 + j) * 8 + cc] = tt;
-      } else if (cc == 6) {
-        float m = s_m[j][0];
-#pragma unroll
-        for (int i = 1; i < SB / 32; ++i) m = fmaxf(m, s_m[j][i]);
-        blk_max[(size_t)k * nb + b0 + j] = m;
+    for (int j = 0; j < COUNT_RB; ++j) {
+      const int r = (b0 + j) * SB + t;
+      const bool in = r < R;
+      const uint8_t lab = (uint8_t)(p[j] >> 24);
+      const int c = in ? ray_case(d[j], lab, min_bound, this_obj) : 3;
+      const bool mo = in && lab != 0, ms = in && lab != 2;
+      const unsigned q0 = __ballot_sync(0xffffffffu, c == 0), q1 = __ballot_sync(0xffffffffu, c == 1), q2 = __ballot_sync(0xffffffffu, c == 2);
+      const unsigned q3 = __ballot_sync(0xffffffffu, c != 0 && mo), q4 = __ballot_sync(0xffffffffu, mo), q5 = __ballot_sync(0xffffffffu, ms);
+      const float mx = warp_max(in ? d[j] : -INFINITY);
+      if (l == 0) {
+        int* o = s_c[j][w];
+        o[0] = __popc(q0); o[1] = __popc(q1); o[2] = __popc(q2); o[3] = __popc(q3); o[4] = __popc(q4); o[5] = __popc(q5);
+        s_m[j][w] = mx;
       }
     }
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + 7) {           // totals of the CTA's COUNT_RB ray blocks (rays beyond R counted nothing)
-    const int cc = threadIdx.x - 64;
-    int* o = sup + ((size_t)k * gridDim.x + blockIdx.x) * 8;
+  __syncthreads();
+  if (t < COUNT_RB * 8) {                             // thread (j, cc): ray block j, counter cc (6 = max depth): totals of the ray block
+    const int j = t >> 3, cc = t & 7;
+    int tt = 0;
     if (cc < 6) {
-      int tt = 0;
 #pragma unroll
-      for (int j = 0; j < COUNT_RB; ++j)
+      for (int i = 0; i < SB / 32; ++i) tt += s_c[j][i][cc];
+    } else if (cc == 6) {
+      float m = s_m[j][0];
 #pragma unroll
-        for (int i = 0; i < SB / 32; ++i) tt += s_c[j][i][cc];
-      o[cc] = tt;
-    } else {
-      float m = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < COUNT_RB; ++j)
-#pragma unroll
-        for (int i = 0; i < SB / 32; ++i) m = fmaxf(m, s_m[j][i]);
-      o[6] = __float_as_int(m);
+      for (int i = 1; i < SB / 32; ++i) m = fmaxf(m, s_m[j][i]);
+      tt = __float_as_int(m);
     }
+    s_t[j][cc] = tt;
   }
-}
-
-// (B) one block (1024 threads) per category: exclusive scan of the block counts (in place, cols 0..2), totals -> stats.
-// Each thread owns a contiguous chunk of blocks, read as int4 pairs in batches of 8 blocks with every load of a batch in flight
-// at once (the serial load -> add chain of the first version cost 32 us at 4096 blocks); chunk sums are scanned with warp
-// shuffles + one smem hop.
-constexpr int SCAN_T = 1024;
-constexpr int SCAN_BATCH = 4;   // blocks per thread whose loads are in flight together (1024 threads x 4 = the 4096 blocks of 1 Mi rays)
-__global__ void __launch_bounds__(SCAN_T)
-sample_scan_kernel(int nb, int* __restrict__ blk_counts, const float* __restrict__ blk_max,
-                   const float* __restrict__ max_override, int32_t* __restrict__ stats) {
-  const int k = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  int4* bc4 = reinterpret_cast<int4*>(blk_counts + (size_t)k * nb * 8);       // block b: {nI, nO, nT, Nd} {No, Ns, -, -}
-  const float* bm = blk_max + (size_t)k * nb;
-  const int per = (nb + SCAN_T - 1) / SCAN_T;
-  const int b0 = min(nb, t * per), b1 = min(nb, b0 + per);
+  __syncthreads();
+  if (t < COUNT_RB) {                                 // ray block t: exclusive prefix of the case counts inside this CTA
+    int p0 = 0, p1 = 0, p2 = 0;
+    for (int j = 0; j < t; ++j) { p0 += s_t[j][0]; p1 += s_t[j][1]; p2 += s_t[j][2]; }
+    if (b0 + t < nb) reinterpret_cast<int4*>(blk_counts)[(size_t)k * nb + b0 + t] = make_int4(p0, p1, p2, 0);
+  } else if (t == 32) {                               // totals of the CTA (rays beyond R counted nothing)
+    int tot[6] = {0, 0, 0, 0, 0, 0};
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < COUNT_RB; ++j) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) tot[q] += s_t[j][q];
+      m = fmaxf(m, __int_as_float(s_t[j][6]));
+    }
+    cta_lo[(size_t)k * gridDim.x + blockIdx.x] = make_int4(tot[0], tot[1], tot[2], __float_as_int(m));
+    cta_hi[(size_t)k * gridDim.x + blockIdx.x] = make_int4(tot[3], tot[4], tot[5], 0);
+    __threadfence();
+  }
+  // ---- (B) last CTA of the category: exclusive scan of the CTA totals, category totals -> stats
+  __shared__ int s_last;
+  __syncthreads();
+  if (t == 0) s_last = atomicAdd(ticket + k, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int nc = gridDim.x;
+  const int4* lo4 = cta_lo + (size_t)k * nc;
+  const int4* hi4 = cta_hi + (size_t)k * nc;
+  int4* pre4 = cta_prefix + (size_t)k * nc;
+  const int per = (nc + SB - 1) / SB;
+  const int c0 = min(nc, t * per), c1 = min(nc, c0 + per);
   int sum[6] = {0, 0, 0, 0, 0, 0};
   float mx = -INFINITY;
-  for (int bb = b0; bb < b1; bb += SCAN_BATCH) {
+  for (int bb = c0; bb < c1; bb += SCAN_BATCH) {
     int4 lo[SCAN_BATCH], hi[SCAN_BATCH];
-    float m[SCAN_BATCH];
 #pragma unroll
     for (int j = 0; j < SCAN_BATCH; ++j) {
-      const bool in = bb + j < b1;
-      lo[j] = in ? bc4[(bb + j) * 2] : make_int4(0, 0, 0, 0);
-      hi[j] = in ? bc4[(bb + j) * 2 + 1] : make_int4(0, 0, 0, 0);
-      m[j] = in ? bm[bb + j] : -INFINITY;
+      const bool in = bb + j < c1;
+      lo[j] = in ? __ldcg(lo4 + bb + j) : make_int4(0, 0, 0, __float_as_int(-INFINITY));
+      hi[j] = in ? __ldcg(hi4 + bb + j) : make_int4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int j = 0; j < SCAN_BATCH; ++j) {
-      sum[0] += lo[j].x; sum[1] += lo[j].y; sum[2] += lo[j].z; sum[3] += lo[j].w; sum[4] += hi[j].x; sum[5] += hi[j].y;
-      mx = fmaxf(mx, m[j]);
+      sum[0] += lo[j].x; sum[1] += lo[j].y; sum[2] += lo[j].z; sum[3] += hi[j].x; sum[4] += hi[j].y; sum[5] += hi[j].z;
+      mx = fmaxf(mx, __int_as_float(lo[j].w));
     }
   }
-  __shared__ int s_w[SCAN_T / 32][6];
-  __shared__ float s_m[SCAN_T / 32];
-  int excl[6];
+  __shared__ int s_ws[SB / 32][6];
+  __shared__ float s_wm[SB / 32];
+  int excl[3];
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     int v = sum[c];
+    if (c < 3) {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += n; }
-    excl[c] = v - sum[c];
-    if (lane == 31) s_w[warp][c] = v;
+      for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, v, o); if (l >= o) v += n; }
+      excl[c] = v - sum[c];
+      if (l == 31) s_ws[w][c] = v;
+    } else {
+      v = warp_sum_i(v);
+      if (l == 0) s_ws[w][c] = v;
+    }
   }
   mx = warp_max(mx);
-  if (lane == 0) s_m[warp] = mx;
+  if (l == 0) s_wm[w] = mx;
   __syncthreads();
   int tot[6];
 #pragma unroll
   for (int c = 0; c < 6; ++c) {
     int before = 0, all = 0;
-    for (int w = 0; w < SCAN_T / 32; ++w) { const int v = s_w[w][c]; if (w < warp) before += v; all += v; }
-    excl[c] += before;
+#pragma unroll
+    for (int i = 0; i < SB / 32; ++i) { const int v = s_ws[i][c]; if (i < w) before += v; all += v; }
+    if (c < 3) excl[c] += before;
     tot[c] = all;
   }
   int run[3] = {excl[0], excl[1], excl[2]};
-  for (int bb = b0; bb < b1; bb += SCAN_BATCH) {
+  for (int bb = c0; bb < c1; bb += SCAN_BATCH) {
     int4 lo[SCAN_BATCH];
 #pragma unroll
-    for (int j = 0; j < SCAN_BATCH; ++j) lo[j] = (bb + j < b1) ? bc4[(bb + j) * 2] : make_int4(0, 0, 0, 0);
+    for (int j = 0; j < SCAN_BATCH; ++j) lo[j] = (bb + j < c1) ? __ldcg(lo4 + bb + j) : make_int4(0, 0, 0, 0);
 #pragma unroll
     for (int j = 0; j < SCAN_BATCH; ++j) {
-      if (bb + j < b1) {
-        const int4 v = lo[j];
-        bc4[(bb + j) * 2] = make_int4(run[0], run[1], run[2], v.w);
-        run[0] += v.x; run[1] += v.y; run[2] += v.z;
+      if (bb + j < c1) {
+        pre4[bb + j] = make_int4(run[0], run[1], run[2], 0);
+        run[0] += lo[j].x; run[1] += lo[j].y; run[2] += lo[j].z;
       }
     }
   }
   if (t == 0) {
-    float m = s_m[0];
-    for (int w = 1; w < SCAN_T / 32; ++w) m = fmaxf(m, s_m[w]);
+    float m = s_wm[0];
+#pragma unroll
+    for (int i = 1; i < SB / 32; ++i) m = fmaxf(m, s_wm[i]);
     int32_t* st = stats + k * 8;
     st[0] = tot[0];              // nI
     st[1] = tot[1] + tot[2];     // nV
@@ -311,15 +320,16 @@ sample_emit_kernel(int R, int N, int M, const uint8_t* __restrict__ rgbs, const 
                    const float* __restrict__ n_obj, const float* __restrict__ u_oth,
                    const float* __restrict__ lin_S, const float* __restrict__ lin_N, const float* __restrict__ lin_M,
                    float min_bound, float eps, float stop_eps, int this_obj,
-                   const int* __restrict__ blk_counts, const int32_t* __restrict__ stats,
+                   const int* __restrict__ blk_counts, const int4* __restrict__ cta_prefix, const int32_t* __restrict__ stats,
                    float* __restrict__ z, float* __restrict__ pcs, uint8_t* __restrict__ valid,
                    uint8_t* __restrict__ labels) {
   __shared__ EmitSmem sh;
   extern __shared__ float zbuf_dyn[];
   const int k = blockIdx.y, nb = gridDim.x, b = blockIdx.x;
-  const int* bc = blk_counts + ((size_t)k * nb + b) * 8;
+  const int4 pc = cta_prefix[(size_t)k * ((nb + COUNT_RB - 1) / COUNT_RB) + b / COUNT_RB];
+  const int4 pb = reinterpret_cast<const int4*>(blk_counts)[(size_t)k * nb + b];
   emit_block(sh, k, b, R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth, lin_S, lin_N, lin_M, min_bound, eps, stop_eps,
-             this_obj, bc[0], bc[1], bc[2], __int_as_float(stats[k * 8 + 7]), z, pcs, valid, labels, zbuf_dyn);
+             this_obj, pc.x + pb.x, pc.y + pb.y, pc.z + pb.z, __int_as_float(stats[k * 8 + 7]), z, pcs, valid, labels, zbuf_dyn);
 }
 
 // (C') emit, fast path for M <= 16 surface bins (every training / rendering shape of the reference except the 96-bin uncertainty
@@ -354,8 +364,7 @@ sample_emit_fast_kernel(int R, int N, const uint8_t* __restrict__ rgbs, const fl
                         const float* __restrict__ n_obj, const float* __restrict__ u_oth,
                         const float* __restrict__ lin_S, const float* __restrict__ lin_N, const float* __restrict__ lin_M,
                         float min_bound, float eps, float stop_eps, int this_obj,
-                        const int* __restrict__ blk_counts, int32_t* __restrict__ stats, const int* __restrict__ sup, int nsup,
-                        const float* __restrict__ max_override,
+                        const int* __restrict__ blk_counts, const int4* __restrict__ cta_prefix, const int32_t* __restrict__ stats,
                         float* __restrict__ z, float* __restrict__ pcs, uint8_t* __restrict__ valid, uint8_t* __restrict__ labels) {
   extern __shared__ __align__(16) float sm_f[];
   __shared__ int s_w[SB / 32][3];
@@ -368,68 +377,24 @@ sample_emit_fast_kernel(int R, int N, const uint8_t* __restrict__ rgbs, const fl
   const int r0 = b * SB, r = r0 + t, nrays = min(SB, R - r0);
   float* rbuf = sm_f;                         // [nrays * S]: random rows, then the block's z
   float* pbuf = sm_f + SB * S;                // [nrays * 3S]: the block's pcs
-  // ---- 0. running case counts before this block + the category's maximum depth.  sup == NULL: blk_counts was scanned by
-  //      sample_scan_kernel (exclusive prefixes) and stats holds the maximum.  Otherwise (R up to a few Mi rays) there is no scan
-  //      launch: every block sums the totals of the count kernel's CTAs in front of it (nsup x 32 B, L2-resident) and the raw counts
-  //      of the ray blocks of its own count CTA; block 0 also writes the category's stats row.
-  int base0, base1, base2;
-  float max_bound;
-  if (sup == nullptr) {
-    const int* bc = blk_counts + ((size_t)k * nb + b) * 8;
-    base0 = bc[0]; base1 = bc[1]; base2 = bc[2];
-    max_bound = __int_as_float(stats[k * 8 + 7]);
-  } else {
-    __shared__ int s_red[SB / 32][10];
-    const int4* sup4 = reinterpret_cast<const int4*>(sup + (size_t)k * nsup * 8);
-    const int my_sup = b / COUNT_RB;
-    int acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};        // prefix {nI, nO, nT}, totals {nI, nO, nT, Nd, No, Ns}
-    float mx = -INFINITY;
-    for (int i = t; i < nsup; i += SB) {
-      const int4 lo = sup4[i * 2], hi = sup4[i * 2 + 1];
-      if (i < my_sup) { acc[0] += lo.x; acc[1] += lo.y; acc[2] += lo.z; }
-      acc[3] += lo.x; acc[4] += lo.y; acc[5] += lo.z; acc[6] += lo.w; acc[7] += hi.x; acc[8] += hi.y;
-      mx = fmaxf(mx, __int_as_float(hi.z));
-    }
-    if (t < b - my_sup * COUNT_RB) {                 // earlier ray blocks of my count CTA (raw per-block counts)
-      const int* bc = blk_counts + ((size_t)k * nb + my_sup * COUNT_RB + t) * 8;
-      acc[0] += bc[0]; acc[1] += bc[1]; acc[2] += bc[2];
-    }
-    const bool first = (b == 0);                     // block 0 also needs the category totals (stats row)
-#pragma unroll
-    for (int q = 0; q < 9; ++q) if (q < 3 || first) acc[q] = warp_sum_i(acc[q]);
-    mx = warp_max(mx);
-    if (l == 0) {
-#pragma unroll
-      for (int q = 0; q < 9; ++q) if (q < 3 || first) s_red[w][q] = acc[q];
-      s_red[w][9] = __float_as_int(mx);
-    }
-    __syncthreads();
-    int tot[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    mx = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < SB / 32; ++i) {
-#pragma unroll
-      for (int q = 0; q < 9; ++q) if (q < 3 || first) tot[q] += s_red[i][q];
-      mx = fmaxf(mx, __int_as_float(s_red[i][9]));
-    }
-    base0 = tot[0]; base1 = tot[1]; base2 = tot[2];
-    max_bound = max_override ? max_override[k] : mx;
-    if (b == 0 && t == 0) {
-      int32_t* st = stats + k * 8;
-      st[0] = tot[3]; st[1] = tot[4] + tot[5]; st[2] = tot[4]; st[3] = tot[5];
-      st[4] = tot[6]; st[5] = tot[7]; st[6] = tot[8]; st[7] = __float_as_int(max_bound);
-    }
-  }
-
-  // ---- 1. ray data, case, rank inside the case (ray order)
-  int c = 3;
+  // ---- 1. ray data (issued first: the longest-latency loads of the block)
   float d = 0.f, o[3] = {0.f, 0.f, 0.f}, dr[3] = {0.f, 0.f, 0.f};
+  uint32_t px = 0;
   const size_t gi = (size_t)k * R + r;
   if (r < R) {
     d = depth[gi];
-    const uint32_t px = reinterpret_cast<const uint32_t*>(rgbs)[gi];
+    px = reinterpret_cast<const uint32_t*>(rgbs)[gi];
 #pragma unroll
     for (int j = 0; j < 3; ++j) { o[j] = origins[gi * 3 + j]; dr[j] = dirs[gi * 3 + j]; }
+  }
+  // running case counts before this block = prefix over the count kernel's CTAs + prefix inside its CTA; the category's maximum depth
+  const int4 pc = cta_prefix[(size_t)k * ((nb + COUNT_RB - 1) / COUNT_RB) + b / COUNT_RB];
+  const int4 pb = reinterpret_cast<const int4*>(blk_counts)[(size_t)k * nb + b];
+  const int base0 = pc.x + pb.x, base1 = pc.y + pb.y, base2 = pc.z + pb.z;
+  const float max_bound = __int_as_float(stats[k * 8 + 7]);
+  // case, rank inside the case (ray order)
+  int c = 3;
+  if (r < R) {
     const uint8_t lab = (uint8_t)(px >> 24);
     c = ray_case(d, lab, min_bound, this_obj);
     valid[gi] = (c != 0);
@@ -540,14 +505,13 @@ sample_emit_fast_kernel(int R, int N, const uint8_t* __restrict__ rgbs, const fl
 }
 
 typedef void (*emit_fast_fn)(int, int, const uint8_t*, const float*, const float*, const float*, const float*, const float*, const float*,
-                             const float*, const float*, const float*, const float*, float, float, float, int, const int*, int32_t*, const int*, int,
-                             const float*, float*, float*, uint8_t*, uint8_t*);
+                             const float*, const float*, const float*, const float*, float, float, float, int, const int*, const int4*,
+                             const int32_t*, float*, float*, uint8_t*, uint8_t*);
 template <int M> struct EmitFastTable {
   static void fill(emit_fast_fn* tab) { tab[M] = sample_emit_fast_kernel<M>; EmitFastTable<M - 1>::fill(tab); }
 };
 template <> struct EmitFastTable<0> { static void fill(emit_fast_fn*) {} };
 constexpr int EMIT_FAST_MAX_M = 16;
-constexpr int EMIT_FAST_MAX_SUP = 2048;
 
 // Single-launch sampler for small ray batches (R <= SAMPLE_SMALL_RAYS): grid (category, ray block).  Every CTA counts the cases /
 // loss masks and the maximum depth of its whole category (a few thousand rays: cheaper than a second launch), derives the running
@@ -748,9 +712,9 @@ extern "C" int cnf_pool_compose(int64_t n, const int32_t* perm_in, const int64_t
 
 extern "C" size_t cnf_sample_workspace_bytes(int n_cat, int n_rays) {
   const size_t nb = (size_t)(n_rays + SB - 1) / SB;
-  const size_t nsup = (nb + COUNT_RB - 1) / COUNT_RB;
-  return align_up((size_t)n_cat * nb * 8 * sizeof(int), 256) + align_up((size_t)n_cat * nb * sizeof(float), 256) +
-         align_up((size_t)n_cat * nsup * 8 * sizeof(int), 256);
+  const size_t nc = (nb + COUNT_RB - 1) / COUNT_RB;
+  return align_up((size_t)n_cat * nb * 4 * sizeof(int), 256) + 3 * align_up((size_t)n_cat * nc * 4 * sizeof(int), 256) +
+         align_up((size_t)n_cat * sizeof(unsigned), 256);            // block prefixes | CTA totals lo, hi | CTA prefixes | tickets
 }
 
 extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, const float* depth,
@@ -764,10 +728,14 @@ extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, c
   CNF_REQUIRE(u_inv && u_val && n_obj && u_oth && lin_S && lin_M && (N == 0 || lin_N), "cnf_sample_fwd: null random/linspace input");
   if (ws_bytes < cnf_sample_workspace_bytes(K, R)) { set_error("cnf_sample_fwd: workspace too small"); return CNF_ERR_WORKSPACE; }
   const int nb = (R + SB - 1) / SB;
-  int* blk_counts = reinterpret_cast<int*>(ws);
-  float* blk_max = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + align_up((size_t)K * nb * 8 * sizeof(int), 256));
-  const int nsup = (nb + COUNT_RB - 1) / COUNT_RB;
-  int* sup = reinterpret_cast<int*>(reinterpret_cast<char*>(blk_max) + align_up((size_t)K * nb * sizeof(float), 256));
+  const int nc = (nb + COUNT_RB - 1) / COUNT_RB;
+  char* w8 = reinterpret_cast<char*>(ws);
+  int* blk_counts = reinterpret_cast<int*>(w8);
+  const size_t cta_bytes = align_up((size_t)K * nc * 4 * sizeof(int), 256);
+  int4* cta_lo = reinterpret_cast<int4*>(w8 + align_up((size_t)K * nb * 4 * sizeof(int), 256));
+  int4* cta_hi = reinterpret_cast<int4*>(reinterpret_cast<char*>(cta_lo) + cta_bytes);
+  int4* cta_prefix = reinterpret_cast<int4*>(reinterpret_cast<char*>(cta_hi) + cta_bytes);
+  unsigned* ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(cta_prefix) + cta_bytes);
   cudaStream_t st = as_stream(stream);
   const size_t zbytes = (size_t)SB * (N + M) * sizeof(float);
   CNF_REQUIRE(N + M <= 96, "cnf_sample_fwd: more than 96 samples per ray");
@@ -782,11 +750,10 @@ extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, c
                                               eps, stop_eps, this_obj, max_depth_override, stats, z, pcs, valid, labels);
     return check_launch("cnf_sample_fwd");
   }
-  sample_count_kernel<<<dim3(nsup, K), SB, 0, st>>>(R, nb, rgbs, depth, min_bound, this_obj, blk_counts, blk_max, sup);
+  CNF_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned) * K, st));
+  sample_count_kernel<<<dim3(nc, K), SB, 0, st>>>(R, nb, rgbs, depth, min_bound, this_obj, blk_counts, cta_lo, cta_hi, cta_prefix, ticket,
+                                                  max_depth_override, stats);
   const bool fast = M <= EMIT_FAST_MAX_M && N + M <= 32;
-  // up to 2048 count CTAs per category (4 Mi rays) the fast emit kernel sums the count totals itself: no scan launch
-  const bool no_scan = fast && nsup <= EMIT_FAST_MAX_SUP;
-  if (!no_scan) sample_scan_kernel<<<K, SCAN_T, 0, st>>>(nb, blk_counts, blk_max, max_depth_override, stats);
   if (fast) {       // thread-per-ray fast path
     static emit_fast_fn tab[EMIT_FAST_MAX_M + 1] = {nullptr};
     if (!tab[1]) EmitFastTable<EMIT_FAST_MAX_M>::fill(tab);
@@ -798,13 +765,12 @@ extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, c
       fattr[M].done();
     }
     tab[M]<<<dim3(nb, K), SB, fbytes, st>>>(R, N, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth, lin_S, lin_N, lin_M, min_bound,
-                                             eps, stop_eps, this_obj, blk_counts, stats, no_scan ? sup : nullptr, nsup, max_depth_override, z, pcs, valid,
-                                             labels);
+                                             eps, stop_eps, this_obj, blk_counts, cta_prefix, stats, z, pcs, valid, labels);
     return check_launch("cnf_sample_fwd");
   }
   sample_emit_kernel<<<dim3(nb, K), EMIT_BIG_T, zbytes, st>>>(R, N, M, rgbs, depth, origins, dirs, u_inv, u_val, n_obj, u_oth,
                                                  lin_S, lin_N, lin_M, min_bound, eps, stop_eps, this_obj,
-                                                 blk_counts, stats, z, pcs, valid, labels);
+                                                 blk_counts, cta_prefix, stats, z, pcs, valid, labels);
   return check_launch("cnf_sample_fwd");
 }
 
