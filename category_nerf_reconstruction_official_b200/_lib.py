@@ -111,6 +111,7 @@ SIGNATURES = {
     "cnf_occmap_bwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, c_size_t, P, P, P]),
     "cnf_termination_fwd": (c_int, [c_int, c_int, P, P, P]),
     "cnf_termination_bwd": (c_int, [c_int, c_int, P, P, P, P]),
+    "cnf_ray_uncertainty": (c_int, [c_int, c_int, P, P, P]),
     "cnf_mask_counts": (c_int, [c_int, c_int, P, P, P, P]),
     "cnf_composite_workspace_bytes": (c_size_t, [c_int, c_int]),
     "cnf_composite_loss_fwd": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_float, c_float, P, P, P,

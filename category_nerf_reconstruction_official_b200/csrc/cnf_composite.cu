@@ -592,6 +592,24 @@ __global__ void termination_kernel(int n_rays, int S, const float* __restrict__ 
   }
 }
 
+// Uncertainty fields of the registration sweep (src/category_registration.py:152-162): from the termination weights of a ray,
+// entropy = sum_i -w_i log(w_i + 1e-10), mass = sum_i w_i and heuristic = mass * exp(-0.5 entropy).  One warp per ray (S = 96 there);
+// when `occ_in` is given the weights are composited on the fly from the occupancies (scan with a carry, as termination_kernel).
+__global__ void ray_uncertainty_kernel(int n_rays, int S, const float* __restrict__ w_in, float* __restrict__ out /* [n_rays,3] */) {
+  const int lane = threadIdx.x & 31, warps = (blockDim.x >> 5);
+  for (int r = blockIdx.x * warps + (threadIdx.x >> 5); r < n_rays; r += gridDim.x * warps) {
+    const float* w = w_in + (size_t)r * S;
+    float ent = 0.f, mass = 0.f;
+    for (int i = lane; i < S; i += 32) {
+      const float v = w[i];
+      ent -= v * logf(v + 1e-10f);
+      mass += v;
+    }
+    ent = warp_sum(ent); mass = warp_sum(mass);
+    if (lane == 0) { out[(size_t)r * 3] = ent; out[(size_t)r * 3 + 1] = mass; out[(size_t)r * 3 + 2] = mass * expf(-0.5f * ent); }
+  }
+}
+
 // Backward of occupancy_to_termination (src/render_rays.py:25-33 under autograd): w_i = occ_i T_i, T_i = prod_{j<i} f_j,
 // f_j = 1 - occ_j + 1e-10.  d occ_j = T_j (g_j - Q_j) with Q_j = sum_{i>j} g_i occ_i prod_{j<m<i} f_m, i.e. the reverse recurrence
 // Q_{j} = g_{j+1} occ_{j+1} + f_{j+1} Q_{j+1} -- division-free, so saturated samples (f = 1e-10) need no special case.  One thread
@@ -747,6 +765,14 @@ extern "C" int cnf_termination_fwd(int n_rays, int S, const float* occ, float* w
   if (n_rays == 0) return CNF_OK;
   termination_kernel<<<comp_blocks(n_rays, S), CT, 0, as_stream(stream)>>>(n_rays, S, occ, w);
   return check_launch("cnf_termination_fwd");
+}
+
+extern "C" int cnf_ray_uncertainty(int n_rays, int S, const float* w, float* out, cnf_stream_t stream) {
+  CNF_REQUIRE(n_rays >= 0 && S > 0 && w && out, "cnf_ray_uncertainty: bad arguments");
+  if (n_rays == 0) return CNF_OK;
+  int nb = (n_rays + 7) / 8; if (nb > 148 * 8) nb = 148 * 8;
+  ray_uncertainty_kernel<<<nb, 256, 0, as_stream(stream)>>>(n_rays, S, w, out);
+  return check_launch("cnf_ray_uncertainty");
 }
 
 extern "C" int cnf_termination_bwd(int n_rays, int S, const float* occ, const float* g_w, float* g_occ, cnf_stream_t stream) {

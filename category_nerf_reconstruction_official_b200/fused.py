@@ -327,3 +327,77 @@ class FusedCategoryTrainer:
     def opt_steps(self) -> int:
         """Optimizer steps taken so far (reads the device counter: synchronises)."""
         return 0 if self._opt_state is None else int(self._opt_state["t"][0])
+
+
+class HostStepPipeline:
+    """Feeds a FusedCategoryTrainer from HOST batches with the copies off the critical path (the reference uploads every step's
+    pool slices synchronously, scene_cateogries.py:421-431, and reads the loss back for logging, train.py:185-192).
+
+    Two slots.  Each slot owns one pinned host block + one device block holding a whole step's inputs (tensor views at 256-byte
+    aligned offsets) and a CUDA graph of the step over that device block.  ``submit(slot)`` enqueues the slot's host->device copy on
+    a copy stream (it overlaps the previous step's kernels), then the graph replay and the device->host copy of the loss terms on
+    the compute stream; ``result()`` waits for the OLDEST step in flight and returns its loss terms (pinned host tensor).  Keeping one
+    step in flight (submit i+1, then read i) hides the copies and the host-side launch work behind the GPU step.
+
+        pipe = HostStepPipeline(trainer, example_batch)          # dict of CPU tensors: rgbs, depth, origins, dirs, indices
+        for i, batch in enumerate(loader):
+            s = i & 1
+            for k, v in batch.items(): pipe.host[s][k].copy_(v)   # or let the loader write into pipe.host[s] directly
+            pipe.submit(s)
+            if i: loss_terms = pipe.result()
+        loss_terms = pipe.result()
+    """
+    KEYS = ("rgbs", "depth", "origins", "dirs", "indices")
+
+    def __init__(self, trainer: "FusedCategoryTrainer", example_batch: Dict[str, torch.Tensor], post=None):
+        self.tr = trainer
+        dev = trainer.device
+        offs, tot = {}, 0
+        for k in self.KEYS:
+            v = example_batch[k]
+            offs[k] = tot
+            tot += (v.numel() * v.element_size() + 255) // 256 * 256
+        self.bytes_per_step = sum(example_batch[k].numel() * example_batch[k].element_size() for k in self.KEYS)
+
+        def views(block):
+            return {k: block[offs[k]:offs[k] + example_batch[k].numel() * example_batch[k].element_size()]
+                    .view(example_batch[k].dtype).view(example_batch[k].shape) for k in self.KEYS}
+
+        self._host_block = [torch.empty(tot, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self._dev_block = [torch.empty(tot, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.host = [views(b) for b in self._host_block]
+        self.dev = [views(b) for b in self._dev_block]
+        for s in range(2):
+            for k in self.KEYS:
+                self.host[s][k].copy_(example_batch[k])
+            self._dev_block[s].copy_(self._host_block[s])
+        self.out_host = [torch.empty_like(trainer.out_loss, device="cpu").pin_memory() for _ in range(2)]
+        self._replay = [trainer.capture(d["rgbs"], d["depth"], d["origins"], d["dirs"], d["indices"], post=post) for d in self.dev]
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._ready = [torch.cuda.Event() for _ in range(2)]      # slot's inputs are on the device
+        self._free = [torch.cuda.Event() for _ in range(2)]       # slot's device block has been consumed
+        self._done = [torch.cuda.Event() for _ in range(2)]       # slot's loss terms are on the host
+        main = torch.cuda.current_stream(dev)
+        for e in self._free:
+            e.record(main)
+        self._inflight = []
+
+    def submit(self, slot: int):
+        main = torch.cuda.current_stream(self.tr.device)
+        cs = self._copy_stream
+        cs.wait_event(self._free[slot])
+        with torch.cuda.stream(cs):
+            self._dev_block[slot].copy_(self._host_block[slot], non_blocking=True)
+            self._ready[slot].record(cs)
+        main.wait_event(self._ready[slot])
+        self._replay[slot]()
+        self._free[slot].record(main)
+        self.out_host[slot].copy_(self.tr.out_loss, non_blocking=True)
+        self._done[slot].record(main)
+        self._inflight.append(slot)
+
+    def result(self) -> torch.Tensor:
+        """Loss terms (layout of ``FusedCategoryTrainer.out_loss``) of the oldest submitted step; blocks until they are on the host."""
+        slot = self._inflight.pop(0)
+        self._done[slot].synchronize()
+        return self.out_host[slot]

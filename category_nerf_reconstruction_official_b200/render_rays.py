@@ -29,6 +29,18 @@ def occupancy_to_termination(occupancy, is_batch=False):
     return _TerminationFn.apply(occupancy)
 
 
+def ray_uncertainty(termination):
+    """Uncertainty fields of category_registration.py:152-162 from termination weights [n_rays, S]:
+    (entropy [n_rays], termination mass [n_rays], heuristic = mass * exp(-0.5 entropy) [n_rays])."""
+    from ._lib import check, lib_for, ptr, stream
+    w = termination.detach().float().contiguous()
+    lib = lib_for(w)
+    n, S = w.shape
+    out = torch.empty(n, 3, device=w.device, dtype=torch.float32)
+    check(lib.cnf_ray_uncertainty(n, S, ptr(w), ptr(out), stream()))
+    return out[:, 0], out[:, 1], out[:, 2]
+
+
 def render(termination, vals, dim=-1):
     """Weighted sum of per-sample values along the sample axis (render_rays.py:46-50)."""
     return torch.sum(termination * vals, dim=dim)

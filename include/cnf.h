@@ -182,6 +182,9 @@ int cnf_occmap_tc_bwd(int n_pts, const float* params, const float* rgb, const fl
 int cnf_termination_fwd(int n_rays, int S, const float* occ, float* w, cnf_stream_t stream);
 /* its backward (the reference function is differentiable): g_w [n_rays,S] -> g_occ [n_rays,S]. */
 int cnf_termination_bwd(int n_rays, int S, const float* occ, const float* g_w, float* g_occ, cnf_stream_t stream);
+/* Uncertainty fields of a rendered ray bundle (src/category_registration.py:152-162): termination weights w [n_rays,S] ->
+ * out [n_rays,3] = {entropy = sum -w log(w + 1e-10), mass = sum w, heuristic = mass * exp(-0.5 entropy)}. */
+int cnf_ray_uncertainty(int n_rays, int S, const float* w, float* out, cnf_stream_t stream);
 /* mask counts for the loss denominators: labels u8 [K,R], mask_depth u8 [K,R] -> counts int32 [K,4]
  * = {N_depth&obj, N_obj, N_sem, 0}. */
 int cnf_mask_counts(int n_cat, int n_rays, const uint8_t* labels, const uint8_t* mask_depth,

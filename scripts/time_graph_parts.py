@@ -11,6 +11,8 @@ tr = FusedCategoryTrainer(wl["K"], wl["n_obj"], latent_dim=wl["L"], scale=wl["sc
 b = synth_batch(wl, seed=3, device=dev)
 rgbs, depth, org, dirs, idx = b["rgbs"], b["depth"], b["origins"], b["dirs"], b["indices"].contiguous()
 R = rgbs.shape[1]
+tr.operands_follow_optimizer = True          # as bench.py: the operand half of prepare runs with the optimizer step
+tr.refresh_operands(R)
 rand0 = sampling.draw_randoms(rgbs, depth, tr.N, tr.M, tr.eps)
 z0, _, valid0, _, stats0 = ops.sample_batched(rgbs, depth, org, dirs, tr.N, tr.M, tr.eps, tr.stop_eps, rand0, tr.min_bound, tr.this_obj, want_pcs=False)
 vm0 = valid0.view(torch.uint8)
@@ -19,6 +21,7 @@ def full(): tr.step(rgbs, depth, org, dirs, idx)
 def rng(): sampling.draw_randoms(rgbs, depth, tr.N, tr.M, tr.eps)
 def sampler(): ops.sample_batched(rgbs, depth, org, dirs, tr.N, tr.M, tr.eps, tr.stop_eps, rand0, tr.min_bound, tr.this_obj, want_pcs=False)
 def prepare(): tr.prepare(idx, R)
+def prepare_full(): tr.prepare(idx, R, what=3)
 def fused_fin(): tr.step_from_samples(org, dirs, z0, depth, rgbs, vm0, idx, stats0[:, 4:8], True, prepared=True)
 def all_inline():
     tr.prepare(idx, R)
@@ -27,7 +30,7 @@ def all_inline():
     tr.step_from_samples(org, dirs, z, depth, rgbs, valid.view(torch.uint8), idx, stats[:, 4:8], True, prepared=True)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for name, fn in (("full step (side-stream prepare)", full), ("full step, one stream", all_inline), ("rng only", rng), ("sampler only", sampler),
-                 ("prepare only", prepare), ("fused + finalize only", fused_fin)):
+                 ("prepare (input half) only", prepare), ("prepare (operands + inputs)", prepare_full), ("fused + finalize only", fused_fin)):
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):

@@ -65,3 +65,21 @@ def test_composite_loss_large_vs_oracle(K, R, S):
     for got, want in ((a1.grad.cpu(), a0.grad), (c1.grad.cpu(), c0.grad)):
         scale = float(want.abs().max())
         assert float((got - want).abs().max()) <= 2e-4 * scale + 1e-9, (float((got - want).abs().max()), scale)
+
+
+@pytest.mark.parametrize("n,S", [(10000, 96), (77, 14), (1, 1)])
+def test_ray_uncertainty_fields(n, S):
+    """Entropy / termination mass / heuristic of category_registration.py:152-162 (numpy formula of the reference, float64) from
+    termination weights produced by occupancy_to_termination."""
+    import numpy as np
+    from category_nerf_reconstruction_official_b200 import render_rays
+    g = torch.Generator().manual_seed(n + S)
+    occ = torch.sigmoid(torch.randn(n, S, generator=g) * 3 - 1)
+    term = render_rays.occupancy_to_termination(occ.to(DEV))
+    ent, mass, heur = (v.cpu().numpy() for v in render_rays.ray_uncertainty(term))
+    tp = O.termination(occ).double().numpy()                                  # the reference's weights (src/render_rays.py:25-33)
+    ent_ref = np.sum(-tp * np.log(tp + 1e-10), axis=-1)
+    mass_ref = np.sum(tp, axis=-1)
+    np.testing.assert_allclose(ent, ent_ref, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(mass, mass_ref, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(heur, mass_ref * np.exp(-0.5 * ent_ref), rtol=3e-5, atol=2e-6)
