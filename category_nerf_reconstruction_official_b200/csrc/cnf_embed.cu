@@ -56,8 +56,8 @@ embed_fwd_kernel(int P, const float* __restrict__ x, const float* __restrict__ B
 // Persistent CTAs, two stages: a tile's 64 x 129 upstream gradients (33 KB, contiguous) and its 64 points arrive by 1-D bulk copies
 // (TMA) on an mbarrier while the previous tile is reduced -- the first version's load loop (one LDG + STS per element, then a
 // barrier) held 60 % of the stall samples and kept the kernel at 63 % of the HBM roofline.  The 63 partial sums of g_B stay in
-// registers across the CTA's tiles (one atomic per output and CTA).  cos(pi 2^f proj) comes from ONE sincospi + the double-angle
-// recurrence (the exact argument reduction of sincospi is cheaper than libm sincosf's; |error| <= 4e-6 at the top octave).
+// registers across the CTA's tiles (one atomic per output and CTA).  cos(pi 2^f proj) comes from ONE hardware sin/cos after an exact
+// argument reduction + the double-angle recurrence (as in the fused kernels; the libm sincosf was 21 % of the instructions).
 constexpr int EB_STAGE_FLOATS = EP * CNF_EMB_DIM + EP * 3 + 4;        // g tile | x tile | pad (stage stays 16-byte aligned)
 __global__ void __launch_bounds__(ET)
 embed_bwd_kernel(int P, const float* __restrict__ x, const float* __restrict__ B, const float* __restrict__ scale,
@@ -113,18 +113,24 @@ embed_bwd_kernel(int P, const float* __restrict__ x, const float* __restrict__ B
         float proj = __fmul_rn(t0, s_B[d * 3 + 0]);
         proj = __fmaf_rn(t1, s_B[d * 3 + 1], proj);
         proj = __fmaf_rn(t2, s_B[d * 3 + 2], proj);
-        float sn, cs;
-        sincospif(proj, &sn, &cs);
+        // sin / cos(pi 2^f proj): exact reduction of 2^f proj to [-1, 1] (period 2), then the MUFU approximations (|error| <= 4e-7)
+        // at octaves 0 and 3, the double-angle recurrence for the two octaves after each (error x4: <= 2e-6 on any cosine)
         const float* gcol = s_g + p * CNF_EMB_DIM + 3 + d;
         float band = pi_f;
 #pragma unroll
-        for (int f = 0; f < CNF_N_FREQ; ++f) {
-          gp = fmaf(gcol[f * CNF_N_DIRS] * band, cs, gp);
-          const float tw = sn + sn;                 // sin 2a = 2 sin a cos a ; cos 2a = 1 - 2 sin^2 a
-          const float c2 = fmaf(-tw, sn, 1.0f);
-          sn = tw * cs;
-          cs = c2;
-          band *= 2.0f;
+        for (int h = 0; h < 2; ++h) {
+          const float pr = h ? 8.0f * proj : proj;
+          float sn, cs;
+          __sincosf(pi_f * (pr - 2.0f * rintf(0.5f * pr)), &sn, &cs);
+#pragma unroll
+          for (int f = 0; f < 3; ++f) {
+            gp = fmaf(gcol[(3 * h + f) * CNF_N_DIRS] * band, cs, gp);
+            const float tw = sn + sn;                 // sin 2a = 2 sin a cos a ; cos 2a = 1 - 2 sin^2 a
+            const float c2 = fmaf(-tw, sn, 1.0f);
+            sn = tw * cs;
+            cs = c2;
+            band *= 2.0f;
+          }
         }
       }
       s_gp[p][d] = gp;
