@@ -187,10 +187,18 @@ def main():
     ap.add_argument("--no-large", action="store_true", help="skip the extra large-batch (c4) roofline measurement")
     ap.add_argument("--with-optimizer", action="store_true", help="include the fused AdamW update in the timed step")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--categories", type=int, default=0, help="override the workload's categories per GPU (K); SURVEY 8(d): K is not derivable from the reference repo")
+    ap.add_argument("--instances", type=int, default=0, help="override the workload's instances per category (R stays 120 rays per instance)")
     ap.add_argument("--ray-split", action="store_true",
                     help="strong scaling: ONE copy of the workload, each rank takes R/N rays + NCCL all-reduce of counts/grads")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
+    if args.categories or args.instances:
+        rpi = wl["R"] // wl["n_obj"]
+        wl["K"] = args.categories or wl["K"]
+        wl["n_obj"] = args.instances or wl["n_obj"]
+        wl["R"] = rpi * wl["n_obj"]
+        wl["desc"] += " [overridden: %d categories x %d instances]" % (wl["K"], wl["n_obj"])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -349,14 +357,15 @@ def main():
     pts = K * R * S
     flops = pts * FLOP_PER_POINT
     ach = flops / (kern_ms * 1e-3) / 1e12
-    traffic = None                       # DRAM bytes of the fused kernel per launch, from the committed ncu capture of this workload
+    traffic, traffic_src = None, None    # DRAM bytes of the fused kernel per launch, from the committed ncu capture of this workload
     for tname in ("r02_traffic.json", "r01_traffic.json"):
         tpath = os.path.join(ROOT, "profiles", tname)
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and not (args.categories or args.instances):
             traffic = json.load(open(tpath)).get(args.workload, {}).get("bytes_per_launch")
+            traffic_src = "profiles/%s (ncu --set full capture of this workload; bench.py cannot run ncu itself)" % tname
             break
     roof = {"bound": "tensor", "kernel": "fused_step_kernel", "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
-            "frac": ach / pk["bf16_burst"], "traffic": traffic, "peak_source": pk["source"] + " (bf16 burst)",
+            "frac": ach / pk["bf16_burst"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["source"] + " (bf16 burst)",
             "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / step_ms,
             "algorithmic_flop_per_point": FLOP_PER_POINT, "points_per_launch": pts}
 

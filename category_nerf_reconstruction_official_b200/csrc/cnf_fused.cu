@@ -329,7 +329,7 @@ struct FusedWs {
     zlat = take(K * 4 * nom * NL * 4);
     raw = take(K * RAW_FLOATS * 4);          // raw and rawi are adjacent: one memset
     rawi = take(K * nom * 4 * 32 * 4);
-    done = take(256);                          // finalize completion counter (zeroed with raw / rawi)
+    done = take(256 + K * 4);                  // finalize completion counter | instance-sort tickets [K] at +256 (zeroed with raw / rawi)
     reg = take(K * 2 * 4);
     hist = take(K * nom * nblk * 4);
     base = take(K * nom * nblk * 4);
@@ -396,7 +396,8 @@ static int train_step_prepare(int K, int R, int S, int L, int nom, const float* 
     fused_prep_kernel<<<dim3(K, n_prep), 256, 0, st>>>(L, nom, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, prep, zlat, ctab);
   {
     sort_count_kernel<<<dim3(nblk, K), 256, nom * sizeof(int), st>>>(R, nom, nblk, inst, n_obj, hist);
-    sort_scan_kernel<<<K, SORT_SCAN_T, nom * sizeof(int), st>>>(nom, nblk, RPT, hist, base, seg_ray0, seg_tile0);
+    sort_scan_kernel<<<dim3(nom, K), SORT_SCAN_T, nom * sizeof(int), st>>>(nom, nblk, RPT, hist, base, seg_ray0, seg_tile0,
+                                                                           reinterpret_cast<unsigned*>(w8 + wl.done + 256));
     sort_scatter_kernel<<<dim3(nblk, K), 256, 0, st>>>(R, nom, nblk, inst, n_obj, base, seg_ray0, perm);
   }
   return check_launch("cnf_train_step_prepare");
