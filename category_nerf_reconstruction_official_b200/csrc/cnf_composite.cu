@@ -746,7 +746,7 @@ template <int MODE>
 static int dense_attr(int S) {
   static DeviceOnce once;
   if (once.pending()) {
-    CNF_CUDA(cudaFuncSetAttribute(composite_dense_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, dense_smem_bytes(30, MODE != 0)));
+    CNF_CUDA(cudaFuncSetAttribute(composite_dense_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, dense_smem_bytes(31, MODE != 0)));
     CNF_CUDA(cudaFuncSetAttribute(composite_dense_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     once.done();
   }

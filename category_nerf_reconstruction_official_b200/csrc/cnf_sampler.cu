@@ -269,9 +269,10 @@ emit_block(EmitSmem& sh, int k, int b, int R, int N, int M, const uint8_t* __res
   // ---- phase 2: thread per sample (coalesced z / pcs writes)
   const int nrays = min(SB, R - r0);
   const float fS = (float)S, fN = (float)N, fM = (float)M;
-  const unsigned invS = 0xFFFFFFFFu / (unsigned)S + 1u;      // e / S by multiplication (exact for e < SB * 32)
+  const unsigned invS = 0xFFFFFFFFu / (unsigned)S + 1u;      // e / S by multiplication (exact for e < SB * 32; S = 1 wraps to 0: see div_S)
+  auto div_S = [&](int e) { return S > 1 ? (int)__umulhi((unsigned)e, invS) : e; }; 
   for (int e = t; e < nrays * S; e += blockDim.x) {
-    const int rr = (int)__umulhi((unsigned)e, invS), i = e - rr * S;
+    const int rr = div_S(e), i = e - rr * S;
     const int cc = s_case[rr];
     const float dd = s_depth[rr];
     float zz;
@@ -307,7 +308,7 @@ emit_block(EmitSmem& sh, int k, int b, int R, int N, int M, const uint8_t* __res
   if (pcs) {
     for (int f = t; f < nz * 3; f += blockDim.x) {
       const int smp = (int)(__umulhi((unsigned)f, 0xAAAAAAABu) >> 1), a = f - 3 * smp;
-      const int rr = (int)__umulhi((unsigned)smp, invS);
+      const int rr = div_S(smp);
       pcs[g0 * 3 + f] = __fadd_rn(s_od[rr][a], __fmul_rn(s_od[rr][3 + a], zbuf[smp]));      // scene_cateogries.py:543-544
     }
   }
