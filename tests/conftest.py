@@ -33,3 +33,13 @@ def _seed_global_rng():
     import torch
     torch.manual_seed(1234)
     yield
+
+
+# hypothesis: the suite runs a FIXED set of examples (derandomize) so that results repeat; CNF_HYPOTHESIS=explore searches wider
+try:
+    from hypothesis import settings as _hs
+    _hs.register_profile("ci", derandomize=True, deadline=None)
+    _hs.register_profile("explore", max_examples=150, derandomize=False, deadline=None, print_blob=True)
+    _hs.load_profile(os.environ.get("CNF_HYPOTHESIS", "ci"))
+except ImportError:      # property tests are skipped at import time without hypothesis
+    pass

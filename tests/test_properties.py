@@ -21,7 +21,7 @@ def _case(seed, R, N, M, inv, p_this, p_other):
     return rgbs, depth, org, dirs, rand
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40)
 @given(seed=st.integers(0, 10 ** 6), R=st.integers(1, 300), N=st.integers(0, 6), M=st.integers(1, 12),
        inv=st.floats(0.0, 1.0), p_this=st.floats(0.0, 1.0), p_other=st.floats(0.0, 1.0))
 def test_oracle_sampler_invariants(seed, R, N, M, inv, p_this, p_other):
@@ -50,7 +50,7 @@ def test_oracle_sampler_invariants(seed, R, N, M, inv, p_this, p_other):
     torch.testing.assert_close(pcs, org[:, None, :] + dirs[:, None, :] * z[..., None], rtol=0, atol=0)
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40)
 @given(seed=st.integers(0, 10 ** 6), n=st.integers(1, 50), S=st.integers(1, 120))
 def test_oracle_termination_is_sub_probability(seed, n, S):
     g = torch.Generator().manual_seed(seed)
@@ -62,7 +62,7 @@ def test_oracle_termination_is_sub_probability(seed, n, S):
     torch.testing.assert_close(w[:, -1], occ[:, -1] * T_last, rtol=1e-5, atol=1e-7)
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25)
 @given(seed=st.integers(0, 10 ** 6), P=st.integers(40, 400), n=st.integers(1, 39))
 def test_oracle_pool_serves_each_row_once_per_epoch(seed, P, n):
     g = torch.Generator().manual_seed(seed)
@@ -82,7 +82,7 @@ def test_oracle_pool_serves_each_row_once_per_epoch(seed, P, n):
 
 # ------------------------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25)
 @given(seed=st.integers(0, 10 ** 6), K=st.integers(1, 3), R=st.integers(1, 9000), N=st.integers(0, 5), M=st.integers(1, 18),
        inv=st.floats(0.0, 1.0), p_this=st.floats(0.0, 1.0))
 def test_gpu_sampler_equals_oracle_on_random_shapes(seed, K, R, N, M, inv, p_this):
@@ -99,7 +99,7 @@ def test_gpu_sampler_equals_oracle_on_random_shapes(seed, K, R, N, M, inv, p_thi
 
 
 @pytest.mark.gpu
-@settings(max_examples=20, deadline=None)
+@settings(max_examples=20)
 @given(seed=st.integers(0, 10 ** 6), K=st.integers(1, 3), R=st.integers(1, 1500), S=st.integers(1, 40))
 def test_gpu_composite_loss_equals_oracle_on_random_shapes(seed, K, R, S):
     from category_nerf_reconstruction_official_b200 import loss
@@ -117,7 +117,7 @@ def test_gpu_composite_loss_equals_oracle_on_random_shapes(seed, K, R, S):
 
 
 @pytest.mark.gpu
-@settings(max_examples=15, deadline=None)
+@settings(max_examples=15)
 @given(seed=st.integers(0, 10 ** 6), P=st.integers(50, 3000), n=st.integers(1, 49))
 def test_gpu_pool_equals_oracle_pool_on_random_sizes(seed, P, n):
     from category_nerf_reconstruction_official_b200.pool import DeviceRayPools
@@ -134,3 +134,50 @@ def test_gpu_pool_equals_oracle_pool_on_random_sizes(seed, P, n):
         assert torch.equal(gr, r) and torch.equal(gd_, d) and torch.equal(gi, ix)
         torch.testing.assert_close(go, og, rtol=2e-5, atol=2e-6)
         torch.testing.assert_close(gdi, di, rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.gpu
+@settings(max_examples=14)
+@given(seed=st.integers(0, 10 ** 5), K=st.integers(1, 4), n_obj=st.integers(1, 9), R=st.integers(48, 700), N=st.integers(0, 5),
+       M=st.integers(5, 11), L=st.sampled_from([32, 64, 256]), inv=st.floats(0.0, 0.3))
+def test_gpu_fused_step_equals_oracle_on_random_shapes(seed, K, n_obj, R, N, M, L, inv):
+    """The fused tcgen05 step (sampler + CodeNeRF + compositing + losses, fwd + bwd) against the oracle on random shapes: any number
+    of rays from 48 (ragged tiles, fewer rays than a warp group), 5..16 samples per ray, instances without rays, invalid depths.
+    Bounds: loss 2e-3, whole MLP gradient of every category rel L2 <= 0.06 (worst of a 150-example search: 0.034 at 28 rays per
+    instance with half of the depths invalid; the fixtures of test_gpu_fused.py stay below 0.015), finite everywhere.  (Batches of a dozen valid rays with 2-4 samples are excluded: their depth term is weighted by 1/(sqrt(var)+1e-4)
+    with var -> 0, i.e. up to 1e4, which amplifies ANY forward rounding -- the fp32 reference's own included -- into O(1) errors.)"""
+    from category_nerf_reconstruction_official_b200.fused import FusedCategoryTrainer
+    S = N + M
+    g = torch.Generator().manual_seed(seed)
+    tr = FusedCategoryTrainer(K, n_obj, latent_dim=L, scale=2.0, device=DEV, n_bins_cam2surface=N, n_bins=M, generator=g)
+    cats = [O.synth_rays(R, n_obj, g, invalid_frac=inv) for _ in range(K)]
+    rgbs, depth, org, dirs, idx = (torch.stack([c[i] for c in cats]) for i in range(5))
+    rand = {"u_inv": torch.rand(K, R, S, generator=g), "u_val": torch.rand(K, R, N, generator=g),
+            "n_obj": torch.randn(K, R, M, generator=g) * (0.1 / 3), "u_oth": torch.rand(K, R, M, generator=g)}
+    loss = tr.step(rgbs.to(DEV), depth.to(DEV), org.to(DEV), dirs.to(DEV), idx.to(DEV), rand={k: v.to(DEV) for k, v in rand.items()})
+    torch.cuda.synchronize()
+    pcs, zz, valid, labels = [], [], [], []
+    for k in range(K):
+        _, _, v, lab, p, z = O.sample_points(rgbs[k], depth[k], org[k], dirs[k], N, M, 0.1, 0.05, {kk: vv[k] for kk, vv in rand.items()})
+        pcs.append(p); zz.append(z); valid.append(v); labels.append(lab)
+    sk = torch.stack
+    fc = [sk([tr.param_views(k)[i].cpu() for k in range(K)]) for i in range(28)]
+    try:
+        out = O.train_step(fc, tr.pe_B.cpu(), 2.0, [tr.shape_codes[k, :n_obj].cpu() for k in range(K)], [tr.tex_codes[k, :n_obj].cpu() for k in range(K)],
+                           sk(pcs), sk(zz), depth, rgbs[..., :3], sk(labels), sk(valid), idx)
+    except RuntimeError:
+        # every loss term zeroed by the empty-mask rule and no regulariser (single-instance categories): the reference's
+        # batch_loss.backward() (train.py:182) raises on a loss without graph; the fused step returns zero gradients
+        assert float(tr.g_params.abs().max()) == 0.0 and float(tr.g_B.abs().max()) == 0.0
+        return
+    assert torch.isfinite(tr.g_params).all() and torch.isfinite(tr.g_shape).all() and torch.isfinite(tr.g_B).all() and torch.isfinite(loss)
+    torch.testing.assert_close(loss.cpu(), out["loss"], rtol=2e-3, atol=2e-3)
+    for k in range(K):
+        want = torch.cat([out["g_fc"][i][k].flatten() for i in range(28)]).double()
+        got = tr.g_params[k].cpu().double()
+        if float(want.norm()) > 1e-6:
+            rel = float((got - want).norm() / want.norm())
+            assert rel <= 0.06, "category %d: whole MLP gradient rel L2 %.4f" % (k, rel)
+        want_c = out["g_shape"][k].double(); got_c = tr.g_shape[k, :n_obj].cpu().double()
+        if float(want_c.norm()) > 1e-6:
+            assert float((got_c - want_c).norm() / want_c.norm()) <= 0.05
