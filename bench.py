@@ -671,6 +671,10 @@ def ray_split_c4_block(make_trainer, dev, rank, world, flush, pk, steps=10, warm
     local_counts = ops.mask_counts(loc["rgbs"][..., 3].contiguous(), vm[:, sl].contiguous())
     counts_g, _ = rs.global_counts_and_max(local_counts, loc["depth"].max(dim=-1).values)
     counts_ok = bool(torch.equal(counts_g[:, :3], counts_full[:, :3]))
+    # the path RaySplitStep.step takes: the sampler's count pass on the local rays, all-gather of the stats rows, cnf_reduce_stats
+    counts_s, max_s = rs.global_stats(ops.sample_stats(loc["rgbs"], loc["depth"]))
+    counts_ok = counts_ok and bool(torch.equal(counts_s[:, :3], counts_full[:, :3])) and \
+        bool(torch.equal(max_s, full["depth"].max(dim=-1).values))
     tr.prepare(loc["indices"], loc["indices"].shape[1])
     rs.step_from_samples(loc["origins"], loc["dirs"], z[:, sl].contiguous(), loc["depth"], loc["rgbs"], vm[:, sl].contiguous(),
                          loc["indices"], counts_g, prepared=True)

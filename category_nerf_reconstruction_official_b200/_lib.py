@@ -95,6 +95,8 @@ SIGNATURES = {
     "cnf_sample_workspace_bytes": (c_size_t, [c_int, c_int]),
     "cnf_sample_fwd": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P,
                                c_float, c_float, c_float, c_int, P, P, P, P, P, P, P, c_size_t, P]),
+    "cnf_sample_stats": (c_int, [c_int, c_int, P, P, c_float, c_int, P, P, c_size_t, P]),
+    "cnf_reduce_stats": (c_int, [c_int, c_int, P, P, P, P]),
     "cnf_stratified_bins": (c_int, [c_int, c_int, P, c_int, P, c_int, P, P, P, P]),
     "cnf_pool_gather": (c_int, [c_int, c_int, c_int] + [P] * 15),
     "cnf_pool_compose": (c_int, [ctypes.c_int64, P, P, P, P]),

@@ -672,6 +672,22 @@ __global__ void pool_compose_kernel(int64_t n, const int32_t* __restrict__ perm_
   if (i < n) perm_out[i] = perm_in[idx[i]];
 }
 
+// Ray split across GPUs: sum the loss-mask counts and take the maximum depth over the ranks' stats rows (all-gathered).
+__global__ void reduce_stats_kernel(int world, int K, const int32_t* __restrict__ gathered /* [world][K][8] */,
+                                    int32_t* __restrict__ counts /* [K][4] */, float* __restrict__ max_depth /* [K] */) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  int c0 = 0, c1 = 0, c2 = 0;
+  float m = -INFINITY;
+  for (int r = 0; r < world; ++r) {
+    const int32_t* s = gathered + ((size_t)r * K + k) * 8;
+    c0 += s[4]; c1 += s[5]; c2 += s[6];
+    m = fmaxf(m, __int_as_float(s[7]));
+  }
+  counts[k * 4 + 0] = c0; counts[k * 4 + 1] = c1; counts[k * 4 + 2] = c2; counts[k * 4 + 3] = 0;
+  max_depth[k] = m;
+}
+
 }  // namespace cnf
 
 using namespace cnf;
@@ -716,6 +732,30 @@ extern "C" size_t cnf_sample_workspace_bytes(int n_cat, int n_rays) {
   const size_t nc = (nb + COUNT_RB - 1) / COUNT_RB;
   return align_up((size_t)n_cat * nb * 4 * sizeof(int), 256) + 3 * align_up((size_t)n_cat * nc * 4 * sizeof(int), 256) +
          align_up((size_t)n_cat * sizeof(unsigned), 256);            // block prefixes | CTA totals lo, hi | CTA prefixes | tickets
+}
+
+extern "C" int cnf_sample_stats(int K, int R, const uint8_t* rgbs, const float* depth, float min_bound, int this_obj, int32_t* stats,
+                                void* ws, size_t ws_bytes, cnf_stream_t stream) {
+  CNF_REQUIRE(K > 0 && R > 0 && rgbs && depth && stats && ws, "cnf_sample_stats: bad arguments");
+  if (ws_bytes < cnf_sample_workspace_bytes(K, R)) { set_error("cnf_sample_stats: workspace too small"); return CNF_ERR_WORKSPACE; }
+  const int nb = (R + SB - 1) / SB, nc = (nb + COUNT_RB - 1) / COUNT_RB;
+  char* w8 = reinterpret_cast<char*>(ws);
+  const size_t cta_bytes = align_up((size_t)K * nc * 4 * sizeof(int), 256);
+  int4* cta_lo = reinterpret_cast<int4*>(w8 + align_up((size_t)K * nb * 4 * sizeof(int), 256));
+  int4* cta_hi = reinterpret_cast<int4*>(reinterpret_cast<char*>(cta_lo) + cta_bytes);
+  int4* cta_prefix = reinterpret_cast<int4*>(reinterpret_cast<char*>(cta_hi) + cta_bytes);
+  unsigned* ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(cta_prefix) + cta_bytes);
+  cudaStream_t st = as_stream(stream);
+  CNF_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned) * K, st));
+  sample_count_kernel<<<dim3(nc, K), SB, 0, st>>>(R, nb, rgbs, depth, min_bound, this_obj, reinterpret_cast<int*>(w8), cta_lo, cta_hi, cta_prefix,
+                                                  ticket, nullptr, stats);
+  return check_launch("cnf_sample_stats");
+}
+
+extern "C" int cnf_reduce_stats(int world, int K, const int32_t* gathered, int32_t* counts, float* max_depth, cnf_stream_t stream) {
+  CNF_REQUIRE(world > 0 && K > 0 && gathered && counts && max_depth, "cnf_reduce_stats: bad arguments");
+  reduce_stats_kernel<<<(K + 127) / 128, 128, 0, as_stream(stream)>>>(world, K, gathered, counts, max_depth);
+  return check_launch("cnf_reduce_stats");
 }
 
 extern "C" int cnf_sample_fwd(int K, int R, int N, int M, const uint8_t* rgbs, const float* depth,

@@ -66,6 +66,28 @@ def sample_batched(rgbs, depth, origins, dirs, n_cam2surf: int, n_surf: int, eps
     return z, pcs, valid.view(torch.bool), labels, stats
 
 
+def sample_stats(rgbs, depth, min_bound: float = 0.0, this_obj: int = 1) -> torch.Tensor:
+    """The sampler's count pass alone: stats int32 [K,8] = {nI, nV, nO, nT, N_depth&obj, N_obj, N_sem, float_bits(max depth)}."""
+    lib = lib_for(depth)
+    K, R = depth.shape
+    rgbs = rgbs.contiguous(); depth = _f32c(depth)
+    stats = torch.empty(K, 8, device=depth.device, dtype=torch.int32)
+    ws_bytes = lib.cnf_sample_workspace_bytes(K, R)
+    ws = torch.empty(ws_bytes, device=depth.device, dtype=torch.uint8)
+    check(lib.cnf_sample_stats(K, R, ptr(rgbs), ptr(depth), float(min_bound), int(this_obj), ptr(stats), ptr(ws), ws_bytes, stream()))
+    return stats
+
+
+def reduce_stats(gathered: torch.Tensor):
+    """All-gathered stats rows int32 [world,K,8] -> (global mask counts int32 [K,4], global max depth fp32 [K])."""
+    lib = lib_for(gathered)
+    world, K, _ = gathered.shape
+    counts = torch.empty(K, 4, device=gathered.device, dtype=torch.int32)
+    max_depth = torch.empty(K, device=gathered.device, dtype=torch.float32)
+    check(lib.cnf_reduce_stats(world, K, ptr(gathered.contiguous()), ptr(counts), ptr(max_depth), stream()))
+    return counts, max_depth
+
+
 def stratified_bins_op(min_d, max_d, n_bins: int, u: torch.Tensor) -> torch.Tensor:
     lib = lib_for(u)
     n_rays = u.shape[0]

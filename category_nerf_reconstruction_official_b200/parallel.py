@@ -92,8 +92,9 @@ class RaySplitStep:
     """Ray-split training step of a FusedCategoryTrainer replica (BASELINE config 4): this rank's slice of every category's rays.
 
     Per step TWO collectives, both on the compute stream:
-      1. before the sampler, ONE all-gather of a [K,5] int32 message per rank: the three loss-mask counts (denominators
-         N_d, N_o, N_s, src/render_rays.py:86 -- functions of the inputs only) and the bit pattern of the local maximum depth
+      1. before the sampler, ONE all-gather of the rank's sampler stats rows ([K,8] int32, cnf_sample_stats): they hold the three
+         loss-mask counts (denominators N_d, N_o, N_s, src/render_rays.py:86 -- functions of the inputs only) and the bit pattern
+         of the local maximum depth
          (upper bound of the invalid-depth bins, src/scene_cateogries.py:486); every rank reduces the gathered messages itself
          (sum / max), so the sampler and the losses see the same globals as a single-GPU step over the whole batch;
       2. after the fused step, ONE all-reduce (sum) of the trainer's flat buffer {g_params | g_B | g_shape | g_tex | out_loss}
@@ -108,6 +109,7 @@ class RaySplitStep:
         self.world = dist.get_world_size(group)
         self._gathered = None
         self._graph = None
+        self._side = None
 
     # ---- collectives
     def global_counts_and_max(self, local_counts: torch.Tensor, local_max_depth: torch.Tensor):
@@ -130,20 +132,49 @@ class RaySplitStep:
         self.allreduce_outputs()
         return tr.out_loss[0]
 
+    def global_stats(self, local_stats: torch.Tensor):
+        """All-gather the ranks' sampler stats rows (int32 [K,8]) and reduce them on every rank: (counts [K,4], max depth [K])."""
+        from . import ops
+        K = local_stats.shape[0]
+        if self._gathered is None or self._gathered.shape != (self.world * K, 8):
+            self._gathered = torch.empty(self.world * K, 8, dtype=torch.int32, device=local_stats.device)
+        dist.all_gather_into_tensor(self._gathered, local_stats, group=self.group)
+        return ops.reduce_stats(self._gathered.view(self.world, K, 8))
+
     def step(self, rgbs, depth, origins, dirs, indices, rand: Optional[Dict[str, torch.Tensor]] = None):
-        """Inputs are THIS rank's rays ([K, R_local, ...]). Returns the global loss (identical on all ranks)."""
+        """Inputs are THIS rank's rays ([K, R_local, ...]). Returns the global loss (identical on all ranks).
+        Critical path: sampler count pass (cnf_sample_stats: local mask counts + max depth in ONE launch) -> all-gather ->
+        cnf_reduce_stats -> sampler -> fused step -> all-reduce; the instance sort / accumulator clear (prepare) and the random
+        draws run on side streams next to the first collective."""
         from . import ops, sampling
         tr = self.tr
+        dev = tr.device
         if indices.dtype != torch.int32:
             indices = indices.to(torch.int32)
+        indices = indices.contiguous()
+        main = torch.cuda.current_stream(dev)
+        if self._side is None:
+            self._side = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        tr._workspace(rgbs.shape[1])                                         # allocate on the main stream
+        self._side[0].wait_stream(main)
+        with torch.cuda.stream(self._side[0]):
+            tr.prepare(indices, rgbs.shape[1])
         if rand is None:
-            rand = sampling.draw_randoms(rgbs, depth, tr.N, tr.M, tr.eps, tr.min_bound, tr.this_obj)
-        valid = depth > tr.min_bound                                         # scene_cateogries.py:484 (inputs only)
-        local_counts = ops.mask_counts(rgbs[..., 3].contiguous(), valid.view(torch.uint8))
-        counts, max_depth = self.global_counts_and_max(local_counts, depth.max(dim=-1).values)
-        tr.prepare(indices, rgbs.shape[1])
+            self._side[1].wait_stream(main)
+            with torch.cuda.stream(self._side[1]):
+                # (allocated on the side stream; the next step's side-stream work starts with wait_stream(main), i.e. after
+                # this step's sampler has read them)
+                rand = sampling.draw_randoms(rgbs, depth, tr.N, tr.M, tr.eps, tr.min_bound, tr.this_obj)
+            drew = True
+        else:
+            drew = False
+        stats = ops.sample_stats(rgbs, depth, tr.min_bound, tr.this_obj)     # scene_cateogries.py:484-486, loss.py:33-36 (inputs only)
+        counts, max_depth = self.global_stats(stats)
+        if drew:
+            main.wait_stream(self._side[1])
         z, _, valid_s, _, _ = ops.sample_batched(rgbs, depth, origins, dirs, tr.N, tr.M, tr.eps, tr.stop_eps, rand,
                                                  tr.min_bound, tr.this_obj, want_pcs=False, max_depth=max_depth)
+        main.wait_stream(self._side[0])
         return self.step_from_samples(origins, dirs, z, depth, rgbs, valid_s.view(torch.uint8), indices, counts, prepared=True)
 
     def capture(self, rgbs, depth, origins, dirs, indices):

@@ -67,6 +67,15 @@ int cnf_sample_fwd(int n_cat, int n_rays, int n_cam2surf, int n_surf,
                    float* z, float* pcs, uint8_t* valid, uint8_t* labels, int32_t* stats,
                    void* ws, size_t ws_bytes, cnf_stream_t stream);
 
+/* Count pass of the sampler alone: stats [K,8] as cnf_sample_fwd writes them (case counts, loss-mask counts
+ * N_depth&obj / N_obj / N_sem = the denominators of src/render_rays.py:86, bits of the batch maximum depth,
+ * src/scene_cateogries.py:486).  When one category's rays are split across GPUs every rank all-gathers its rows and
+ * cnf_reduce_stats turns the gathered rows [world,K,8] into the GLOBAL counts int32 [K,4] (sum) and max depth [K] (max),
+ * which the sampler (max_depth_override) and the fused step (counts) then use.  ws as for cnf_sample_fwd. */
+int cnf_sample_stats(int n_cat, int n_rays, const uint8_t* rgbs, const float* depth, float min_bound, int this_obj,
+                     int32_t* stats, void* ws, size_t ws_bytes, cnf_stream_t stream);
+int cnf_reduce_stats(int world, int n_cat, const int32_t* gathered, int32_t* counts, float* max_depth, cnf_stream_t stream);
+
 /* stratified_bins(min, max, n_bins, n_rays) module-level function (src/scene_cateogries.py:51-81;
  * also called by src/category_registration.py:146).  min_d/max_d: [n_rays] or broadcast scalar
  * (stride 0 when *_is_scalar).  u [n_rays,n_bins], lin [n_bins+1] -> z [n_rays,n_bins]. */

@@ -1,3 +1,9 @@
 mkdir -p gpurun_out
-CNF_HYPOTHESIS=explore timeout 2400 python -m pytest tests/test_properties.py -m gpu -q -k fused 2>&1 | grep -E "Falsifying|seed=|K=|n_obj=|R=|N=|M=|L=|S=|P=|n=|inv=|p_this|Error|assert|passed|failed|rel L2" | head -60 > gpurun_out/tests.log
-cat gpurun_out/tests.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err
+tail -3 gpurun_out/bench_n8.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_n8.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','n_gpus')})
+print(d.get('ray_split_c4'))
+PY
