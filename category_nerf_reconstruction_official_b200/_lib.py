@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(CSRC, "libcnf_sm100.so")
 DEV_LIB_PATH = os.path.join(CSRC, "libcnf_sm100_dev.so")
 SOURCES = ["cnf_api.cu", "cnf_sampler.cu", "cnf_embed.cu", "cnf_composite.cu", "cnf_mlp_simt.cu", "cnf_fused.cu", "cnf_occmap_tc.cu"]
 DEV_SOURCES = SOURCES + ["cnf_selftest.cu"]
-HEADERS = ["cnf_common.cuh", "cnf_umma.cuh", "cnf_fused_a.inc", "cnf_fused_b.inc", "cnf_fused_c.inc", os.path.join("..", "..", "include", "cnf.h"),
+HEADERS = ["cnf_common.cuh", "cnf_umma.cuh", "cnf_sample_math.cuh", "cnf_fused_a.inc", "cnf_fused_b.inc", "cnf_fused_c.inc", os.path.join("..", "..", "include", "cnf.h"),
            os.path.join("..", "..", "include", "cnf_dev.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -123,6 +123,9 @@ SIGNATURES = {
     "cnf_train_step_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "cnf_train_step": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P, P,
                                c_float, c_float, c_float, c_int, P, P, P, P, P, P, c_size_t, P]),
+    "cnf_train_step_sampled_max_rays": (c_int, []),
+    "cnf_train_step_sampled": (c_int, [c_int] * 6 + [P] * 18 + [c_float, c_float, c_float, c_int, P, c_float, c_float, c_float, c_int]
+                               + [P] * 8 + [c_size_t, P]),
     "cnf_train_step_prepare": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, P, c_size_t, P]),
     "cnf_eval_points_workspace_bytes": (c_size_t, []),
     "cnf_eval_points": (c_int, [c_int, c_int, P, P, P, P, P, P, P, P, P, c_size_t, P]),

@@ -27,6 +27,7 @@
 // accumulators back to the reference's nn.Linear-shaped gradients (incl. latent layers, code tables, regulariser).
 #include "cnf_common.cuh"
 #include "cnf_umma.cuh"
+#include "cnf_sample_math.cuh"
 
 namespace cnf {
 using namespace umma;
@@ -318,7 +319,7 @@ fused_finalize_kernel(int L, int n_obj_max, const float* __restrict__ params, co
 }
 
 struct FusedWs {
-  size_t prep, ctab, zlat, raw, rawi, done, reg, hist, base, seg_ray0, seg_tile0, perm, total;
+  size_t prep, ctab, zlat, raw, rawi, done, reg, hist, base, seg_ray0, seg_tile0, perm, rec, rank_tmp, total;
   int nblk;
   FusedWs(size_t K, size_t R, size_t nom) {
     size_t o = 0;
@@ -336,6 +337,8 @@ struct FusedWs {
     seg_ray0 = take(K * (nom + 1) * 4);
     seg_tile0 = take(K * (nom + 1) * 4);
     perm = take(K * R * 4);
+    rec = take(K * R * 16);                    // in-kernel sampling: one record per sorted ray position (small batches)
+    rank_tmp = take(K * R * 8);
     total = o;
   }
 };
@@ -367,7 +370,8 @@ extern "C" size_t cnf_train_step_workspace_bytes(int K, int R, int S, int L, int
 // training loop refreshes them once per optimizer step), bit1 = input half (instance sort of this step's rays, accumulator clear).
 static int train_step_prepare(int K, int R, int S, int L, int nom, const float* params, const float* pe_B, const float* pe_scale,
                               const float* shape_codes, const float* tex_codes, const int32_t* n_obj, const int32_t* inst,
-                              uint8_t* w8, const FusedWs& wl, cudaStream_t st, int what = 3) {
+                              uint8_t* w8, const FusedWs& wl, cudaStream_t st, int what = 3, const SampleIn* si = nullptr,
+                              int32_t* stats = nullptr) {
   uint8_t* prep = w8 + wl.prep;
   float* ctab = reinterpret_cast<float*>(w8 + wl.ctab);
   float* zlat = reinterpret_cast<float*>(w8 + wl.zlat);
@@ -388,7 +392,8 @@ static int train_step_prepare(int K, int R, int S, int L, int nom, const float* 
     const int first = (what & 1) ? 0 : n_prep;             // input half only: skip the operand parts
     prepare_small_kernel<<<dim3(K, n_prep + 1 + PREP_ZERO_PARTS - first), 256, nom * sizeof(int), st>>>(
         L, nom, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, prep, zlat, ctab, R, RPT, inst, seg_ray0, seg_tile0, perm,
-        reinterpret_cast<uint4*>(raw), (wl.reg - wl.raw) / 16, first, g_dbg);
+        reinterpret_cast<uint4*>(raw), (wl.reg - wl.raw) / 16, first, si ? *si : SampleIn{}, reinterpret_cast<int4*>(w8 + wl.rec),
+        reinterpret_cast<int2*>(w8 + wl.rank_tmp), stats, g_dbg);
     return check_launch("cnf_train_step_prepare");
   }
   CNF_CUDA(cudaMemsetAsync(raw, 0, wl.reg - wl.raw, st));            // raw, rawi and the finalize completion counter
@@ -424,33 +429,23 @@ extern "C" int cnf_train_step_prepare(int K, int R, int S, int L, int n_obj_max,
                             reinterpret_cast<uint8_t*>(ws), wl, as_stream(stream), what);
 }
 
-extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const float* params, const float* pe_B,
-                              const float* pe_scale, const float* shape_codes, const float* tex_codes,
-                              const int32_t* n_obj, const float* origins, const float* dirs, const float* z,
-                              const float* gt_depth, const uint8_t* gt_rgb, const uint8_t* mask_depth,
-                              const int32_t* inst, const int32_t* counts, float cs, float os, float reg_scaling,
-                              int flags, float* g_params, float* g_B, float* g_shape, float* g_tex, float* out_loss,
-                              void* ws, size_t ws_bytes, cnf_stream_t stream) {
-  if (int e = check_step_sizes("cnf_train_step", K, R, S, L, n_obj_max)) return e;
-  CNF_REQUIRE(params && pe_B && pe_scale && shape_codes && tex_codes && n_obj && origins && dirs && z && gt_depth && gt_rgb &&
-                  mask_depth && inst && counts && g_params && g_B && g_shape && g_tex && out_loss && ws,
-              "cnf_train_step: null pointer");
-  const FusedWs wl(K, R, n_obj_max);
-  if (ws_bytes < wl.total) { set_error("cnf_train_step: workspace too small (%zu < %zu)", ws_bytes, wl.total); return CNF_ERR_WORKSPACE; }
-  cudaStream_t st = as_stream(stream);
-  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+// fused kernel + finalize (the prepare half has run): shared by cnf_train_step and cnf_train_step_sampled
+static int run_fused(int K, int R, int S, int L, int n_obj_max, const float* params, const float* pe_scale, const float* shape_codes,
+                     const float* tex_codes, const int32_t* n_obj, const float* origins, const float* dirs, const float* z,
+                     const float* gt_depth, const uint8_t* gt_rgb, const uint8_t* mask_depth, const int32_t* counts, float cs, float os,
+                     float reg_scaling, int flags, float* g_params, float* g_B, float* g_shape, float* g_tex, float* out_loss,
+                     uint8_t* w8, const FusedWs& wl, cudaStream_t st, const SampleIn* si) {
   const int nom = n_obj_max;
-  if (!(flags & 2)) {          // not prepared by cnf_train_step_prepare (e.g. on a side stream, overlapping the sampler)
-    if (int e = train_step_prepare(K, R, S, L, nom, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, inst, w8, wl, st)) return e;
-  }
   float* raw = reinterpret_cast<float*>(w8 + wl.raw);
   float* rawi = reinterpret_cast<float*>(w8 + wl.rawi);
   float* reg = reinterpret_cast<float*>(w8 + wl.reg);
   static DeviceOnce attr_set;
   if (attr_set.pending()) {
-    CNF_CUDA(cudaFuncSetAttribute(fused_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    CNF_CUDA(cudaFuncSetAttribute(fused_step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    CNF_CUDA(cudaFuncSetAttribute(fused_step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
 #ifdef CNF_DEV
-    CNF_CUDA(cudaFuncSetAttribute(fused_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    CNF_CUDA(cudaFuncSetAttribute(fused_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    CNF_CUDA(cudaFuncSetAttribute(fused_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
 #endif
     attr_set.done();
   }
@@ -468,12 +463,14 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
   const int cstride = ((flags >> 8) & 0xFF) ? ((flags >> 8) & 0xFF) : 4;
   fa.cstride = cstride;
   fa.cs = cs; fa.os = os; fa.raw = raw; fa.rawi = rawi; fa.dbg = g_dbg;
+  fa.si = si ? *si : SampleIn{}; fa.rec = reinterpret_cast<const int4*>(w8 + wl.rec);
   if (g_ev_start && g_ev_stop) CNF_CUDA(cudaEventRecord(g_ev_start, st));
 #ifdef CNF_DEV
-  if (g_dbg) fused_step_kernel<true><<<dim3(cpc, K), NT, SM_TOTAL, st>>>(fa);
+  if (g_dbg) { if (si) fused_step_kernel<true, true><<<dim3(cpc, K), NT, SM_TOTAL, st>>>(fa); else fused_step_kernel<true, false><<<dim3(cpc, K), NT, SM_TOTAL, st>>>(fa); }
   else
 #endif
-  fused_step_kernel<false><<<dim3(cpc, K), NT, SM_TOTAL, st>>>(fa);
+  if (si) fused_step_kernel<false, true><<<dim3(cpc, K), NT, SM_TOTAL, st>>>(fa);
+  else fused_step_kernel<false, false><<<dim3(cpc, K), NT, SM_TOTAL, st>>>(fa);
   if (g_ev_start && g_ev_stop) { CNF_CUDA(cudaEventRecord(g_ev_stop, st)); g_ev_start = g_ev_stop = nullptr; }
   int pm = (2 * n_sm) / (K * FIN_JOBS);                 // part multiplier: fill the machine when there are few categories
   if (pm < 1) pm = 1;
@@ -483,6 +480,65 @@ extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const f
                                                             g_shape, g_tex, reg, counts, cstride, cs, os, reinterpret_cast<int*>(w8 + wl.done), out_loss,
                                                             g_dbg);
   return check_launch("cnf_train_step");
+}
+
+extern "C" int cnf_train_step(int K, int R, int S, int L, int n_obj_max, const float* params, const float* pe_B,
+                              const float* pe_scale, const float* shape_codes, const float* tex_codes,
+                              const int32_t* n_obj, const float* origins, const float* dirs, const float* z,
+                              const float* gt_depth, const uint8_t* gt_rgb, const uint8_t* mask_depth,
+                              const int32_t* inst, const int32_t* counts, float cs, float os, float reg_scaling,
+                              int flags, float* g_params, float* g_B, float* g_shape, float* g_tex, float* out_loss,
+                              void* ws, size_t ws_bytes, cnf_stream_t stream) {
+  if (int e = check_step_sizes("cnf_train_step", K, R, S, L, n_obj_max)) return e;
+  CNF_REQUIRE(params && pe_B && pe_scale && shape_codes && tex_codes && n_obj && origins && dirs && z && gt_depth && gt_rgb &&
+                  mask_depth && inst && counts && g_params && g_B && g_shape && g_tex && out_loss && ws,
+              "cnf_train_step: null pointer");
+  const FusedWs wl(K, R, n_obj_max);
+  if (ws_bytes < wl.total) { set_error("cnf_train_step: workspace too small (%zu < %zu)", ws_bytes, wl.total); return CNF_ERR_WORKSPACE; }
+  cudaStream_t st = as_stream(stream);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  if (!(flags & 2)) {          // not prepared by cnf_train_step_prepare (e.g. on a side stream, overlapping the sampler)
+    if (int e = train_step_prepare(K, R, S, L, n_obj_max, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, inst, w8, wl, st)) return e;
+  }
+  return run_fused(K, R, S, L, n_obj_max, params, pe_scale, shape_codes, tex_codes, n_obj, origins, dirs, z, gt_depth, gt_rgb, mask_depth,
+                   counts, cs, os, reg_scaling, flags, g_params, g_B, g_shape, g_tex, out_loss, w8, wl, st, nullptr);
+}
+
+extern "C" int cnf_train_step_sampled_max_rays(void) { return SORT_SMALL_BLOCKS * 256; }
+
+extern "C" int cnf_train_step_sampled(int K, int R, int N, int M, int L, int n_obj_max, const float* params, const float* pe_B,
+                                      const float* pe_scale, const float* shape_codes, const float* tex_codes, const int32_t* n_obj,
+                                      const uint8_t* rgbs, const float* depth, const float* origins, const float* dirs, const int32_t* inst,
+                                      const float* u_inv, const float* u_val, const float* n_draws, const float* u_oth,
+                                      const float* lin_S, const float* lin_N, const float* lin_M, float min_bound, float eps, float stop_eps,
+                                      int this_obj, const float* max_depth_override, float cs, float os, float reg_scaling, int flags,
+                                      float* g_params, float* g_B, float* g_shape, float* g_tex, float* out_loss, int32_t* stats,
+                                      float* z_out, void* ws, size_t ws_bytes, cnf_stream_t stream) {
+  const int S = N + M;
+  if (int e = check_step_sizes("cnf_train_step_sampled", K, R, S, L, n_obj_max)) return e;
+  CNF_REQUIRE(N >= 0 && M >= 1, "cnf_train_step_sampled: bad bin counts N=%d M=%d", N, M);
+  CNF_REQUIRE(params && pe_B && pe_scale && shape_codes && tex_codes && n_obj && rgbs && depth && origins && dirs && inst && u_inv &&
+                  u_val && n_draws && u_oth && lin_S && lin_M && (N == 0 || lin_N) && g_params && g_B && g_shape && g_tex && out_loss &&
+                  stats && ws,
+              "cnf_train_step_sampled: null pointer");
+  const FusedWs wl(K, R, n_obj_max);
+  if (ws_bytes < wl.total) { set_error("cnf_train_step_sampled: workspace too small (%zu < %zu)", ws_bytes, wl.total); return CNF_ERR_WORKSPACE; }
+  if (wl.nblk > SORT_SMALL_BLOCKS) {
+    set_error("cnf_train_step_sampled: R=%d > %d rays per category (use cnf_sample_fwd + cnf_train_step)", R, SORT_SMALL_BLOCKS * 256);
+    return CNF_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = as_stream(stream);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(ws);
+  SampleIn si;
+  si.rgbs = rgbs; si.depth = depth; si.u_inv = u_inv; si.u_val = u_val; si.n_obj = n_draws; si.u_oth = u_oth;
+  si.lin_S = lin_S; si.lin_N = N ? lin_N : lin_S; si.lin_M = lin_M; si.max_override = max_depth_override;
+  si.min_bound = min_bound; si.eps = eps; si.stop_eps = stop_eps; si.this_obj = this_obj; si.N = N; si.M = M; si.z_out = z_out;
+  // flags bit3: the operand half (weight images, latent biases) is up to date (cnf_train_step_prepare(what = 1) after the optimizer)
+  if (int e = train_step_prepare(K, R, S, L, n_obj_max, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, inst, w8, wl, st,
+                                 (flags & 8) ? 2 : 3, &si, stats)) return e;
+  const int f2 = (flags & 5) | (8 << 8);                  // counts = stats + 4 with row stride 8 (stats[k][7] = max depth bits)
+  return run_fused(K, R, S, L, n_obj_max, params, pe_scale, shape_codes, tex_codes, n_obj, origins, dirs, nullptr, depth, rgbs, nullptr,
+                   stats + 4, cs, os, reg_scaling, f2, g_params, g_B, g_shape, g_tex, out_loss, w8, wl, st, &si);
 }
 
 static int eval_set_attrs() {

@@ -6,17 +6,11 @@
 // HBM-bound.  Two launches (one for up to 4096 rays per category): (A) per-block case counts + max depth, whose last CTA per
 // category also (B) scans the block counts, (C) emit: one thread per ray (M <= 16 surface bins) or per sample (generic).
 #include "cnf_common.cuh"
+#include "cnf_sample_math.cuh"
 
 namespace cnf {
 
 constexpr int SB = 256;  // rays per block
-
-struct SampleCase { int c; };  // 0 invalid, 1 valid&this-object, 2 valid&other
-
-__device__ __forceinline__ int ray_case(float d, uint8_t label, float min_bound, int this_obj) {
-  if (d <= min_bound) return 0;
-  return (label == this_obj) ? 1 : 2;
-}
 
 // (A) counts per 256-ray block: {nI, nO, nT} plus loss-mask counts {Nd, No, Ns} and block max depth.  One CTA covers COUNT_RB
 // consecutive ray blocks with all of a thread's loads in flight (one ray block per CTA made the kernel a chain of tiny
@@ -184,14 +178,6 @@ sample_count_kernel(int R, int nb, const uint8_t* __restrict__ rgbs, const float
     st[6] = tot[5];              // N_sem
     st[7] = __float_as_int(max_override ? max_override[k] : m);   // max depth bits
   }
-}
-
-// stratified z for bin k: (range*lin[k] + min) + u*(range/n)   -- scene_cateogries.py:62-77
-__device__ __forceinline__ float strat(float mn, float mxv, float lin_k, float u, float nf) {
-  const float range = __fsub_rn(mxv, mn);
-  const float lower = __fadd_rn(__fmul_rn(range, lin_k), mn);
-  const float len = __fdiv_rn(range, nf);
-  return __fadd_rn(lower, __fmul_rn(u, len));
 }
 
 

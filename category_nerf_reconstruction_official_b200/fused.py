@@ -86,6 +86,15 @@ class FusedCategoryTrainer:
         # True: they are rebuilt when the parameters change through this class (adamw_step, load_category, refresh_operands).
         self.operands_follow_optimizer = False
         self._operands_R = None
+        # Sampler inside the fused kernel for small batches (cnf_train_step_sampled): no sampler launch, no z round trip through HBM,
+        # depths bit-exact.  OFF by default: measured on the C2 batch it is SLOWER (0.098 vs 0.088 ms per step) -- the sampling
+        # arithmetic in both roles' tile prologues costs 5 us of kernel time, the prepare launch (sort + ranks) is serial with the
+        # kernel instead of parallel to the sampler, and the next step's random draws can no longer overlap the fused kernel
+        # (it reads them until it ends).  Set CNF_FUSED_SAMPLER=1 or this attribute to use it.
+        self.sample_in_kernel = os.environ.get("CNF_FUSED_SAMPLER") is not None
+        self.stats = torch.zeros(n_cat, 8, dtype=torch.int32, device=dev)     # sampler stats of the last step (fused-sampler path)
+        self.keep_z = False                     # verification: keep the depths the fused kernel used in self.z_used [K,R,S]
+        self.z_used = None
 
     # ------------------------------------------------------------------------------------------ state import
     def load_category(self, k: int, fc_params: Sequence[torch.Tensor], B: torch.Tensor, shape_codes: torch.Tensor,
@@ -188,6 +197,8 @@ class FusedCategoryTrainer:
         if indices.dtype != torch.int32:
             indices = indices.to(torch.int32)
         indices = indices.contiguous()
+        if self.sample_in_kernel and rgbs.shape[1] <= self._sampled_max_rays():
+            return self._step_sampled(rgbs, depth, origins, dirs, indices, rand, add_reg)
         main = torch.cuda.current_stream(self.device)
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
@@ -226,6 +237,58 @@ class FusedCategoryTrainer:
         if prefetch:
             main.wait_stream(self._side2)                    # join (a CUDA-graph capture needs every forked stream back)
         return loss
+
+    def _sampled_max_rays(self) -> int:
+        return lib_for(self.params).cnf_train_step_sampled_max_rays()
+
+    def _step_sampled(self, rgbs, depth, origins, dirs, indices, rand, add_reg=True, max_depth=None, secondary=False):
+        """Small batches: ONE call -- prepare launch (instance sort + sampling ranks + stats [+ operand images]), the fused kernel
+        with the sampler in its tile prologues, finalize.  The next step's random offsets are drawn on a side stream next to it."""
+        lib = lib_for(self.params)
+        K, R = depth.shape
+        N, M, S = self.N, self.M, self.S
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        ws = self._workspace(R)
+        prefetch = rand is None and os.environ.get("CNF_NO_RNG_PREFETCH") is None
+        if prefetch:
+            rand = self._prefetched_randoms(K, R)
+        elif rand is None:
+            rand = sampling.draw_randoms(rgbs, depth, N, M, self.eps, self.min_bound, self.this_obj)
+        f32c = lambda t: t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+        rgbs = rgbs.contiguous(); depth = f32c(depth); origins = f32c(origins); dirs = f32c(dirs)
+        u_inv, u_val, n_draws, u_oth = (f32c(rand[k]) for k in ("u_inv", "u_val", "n_obj", "u_oth"))
+        assert rgbs.dtype == torch.uint8 and rgbs.shape == (K, R, 4)
+        assert u_inv.shape == (K, R, S) and n_draws.shape == (K, R, M) and u_oth.shape == (K, R, M) and (N == 0 or u_val.shape == (K, R, N))
+        lin_S, lin_M = ops.linspace_table(S, dev), ops.linspace_table(M, dev)
+        lin_N = ops.linspace_table(N, dev) if N > 0 else lin_S
+        if N == 0:
+            u_val = u_inv
+        if self.keep_z:
+            self.z_used = torch.zeros(K, R, S, device=dev)
+        skip_ops = self.operands_follow_optimizer and self._operands_R == R
+        flags = (1 if add_reg else 0) | (4 if secondary else 0) | (8 if skip_ops else 0)
+        check(lib.cnf_train_step_sampled(K, R, N, M, self.L, self.n_obj_max, ptr(self.params), ptr(self.pe_B), ptr(self.pe_scale),
+                                         ptr(self.shape_codes), ptr(self.tex_codes), ptr(self.n_obj), ptr(rgbs), ptr(depth),
+                                         ptr(origins), ptr(dirs), ptr(indices), ptr(u_inv), ptr(u_val), ptr(n_draws), ptr(u_oth),
+                                         ptr(lin_S), ptr(lin_N), ptr(lin_M), float(self.min_bound), float(self.eps),
+                                         float(self.stop_eps), int(self.this_obj), ptr(max_depth), float(self.cs), float(self.os),
+                                         float(self.reg), flags, ptr(self.g_params), ptr(self.g_B), ptr(self.g_shape), ptr(self.g_tex),
+                                         ptr(self.out_loss), ptr(self.stats), ptr(self.z_used) if self.keep_z else None, ptr(ws),
+                                         ws.numel(), stream()))
+        if not skip_ops:
+            self._operands_R = R
+        self.launches_per_step = 3                           # prepare (sort | ranks | clear [| operands]), fused fwd+bwd, finalize
+        if prefetch:
+            # the NEXT step's offsets are drawn into the same buffers as soon as this step's kernels have read them: on a side
+            # stream that waits for the step (the draws then overlap whatever follows the step: optimizer, copies, the next H2D)
+            if self._side2 is None:
+                self._side2 = torch.cuda.Stream(device=dev)
+            self._side2.wait_stream(main)
+            with torch.cuda.stream(self._side2):
+                self._draw_randoms_into_buffers()
+            main.wait_stream(self._side2)
+        return self.out_loss[0]
 
     def _draw_randoms_into_buffers(self):
         self._rand_u.uniform_()

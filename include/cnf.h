@@ -267,6 +267,27 @@ int cnf_train_step(int n_cat, int n_rays, int S, int L, int n_obj_max,
                    float color_scaling, float opacity_scaling, float reg_scaling, int flags,
                    float* g_params, float* g_B, float* g_shape, float* g_tex, float* out_loss,
                    void* ws, size_t ws_bytes, cnf_stream_t stream);
+/* The whole step in one call WITH the sampler inside the fused kernel (north_star: "a fused sample -> embed -> MLP -> composite ->
+ * loss" step), for up to cnf_train_step_sampled_max_rays() rays per category (8192): no sampler launch and no z round trip through
+ * HBM.  The prepare launch (instance sort of the rays) also ranks every ray inside its sampling case in ray order -- the row of the
+ * random tensors the reference's boolean-mask assignment gives it (src/scene_cateogries.py:484-539) -- and writes the stats rows;
+ * each role of the fused kernel then derives a point's depth in its tile prologue with the arithmetic of cnf_sample_fwd (bit-exact;
+ * the sort of the M normal draws by warp shuffles).  Inputs as cnf_sample_fwd (rgbs, depth, origins, dirs, the four random tensors,
+ * linspace tables, min_bound / eps / stop_eps / this_obj, max_depth_override) + inst; gt_depth = depth, gt_rgb = rgbs, the depth mask
+ * is depth > min_bound (train.py:125-131).  Outputs as cnf_train_step + stats int32 [K,8] (as cnf_sample_fwd) and, if z_out != NULL,
+ * the depths z [K,R,S] the kernel used (verification).  flags: bit0 / bit2 as cnf_train_step; bit3 (8) = the operand half of the
+ * workspace is up to date (cnf_train_step_prepare(what = 1) has run since the last parameter change). */
+int cnf_train_step_sampled_max_rays(void);
+int cnf_train_step_sampled(int n_cat, int n_rays, int N, int M, int L, int n_obj_max,
+                           const float* params, const float* pe_B, const float* pe_scale,
+                           const float* shape_codes, const float* tex_codes, const int32_t* n_obj,
+                           const uint8_t* rgbs, const float* depth, const float* origins, const float* dirs, const int32_t* inst,
+                           const float* u_inv, const float* u_val, const float* n_draws, const float* u_oth,
+                           const float* lin_S, const float* lin_N, const float* lin_M,
+                           float min_bound, float eps, float stop_eps, int this_obj, const float* max_depth_override,
+                           float color_scaling, float opacity_scaling, float reg_scaling, int flags,
+                           float* g_params, float* g_B, float* g_shape, float* g_tex, float* out_loss, int32_t* stats,
+                           float* z_out, void* ws, size_t ws_bytes, cnf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (5b) Forward-only tensor-core evaluation of CodeNeRF (W=32) at arbitrary points with ONE instance's codes:

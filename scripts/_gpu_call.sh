@@ -1,9 +1,12 @@
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err
-tail -3 gpurun_out/bench_n8.err
+timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/tests.log
+cat gpurun_out/tests.log
+timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-large > gpurun_out/bench_q.json 2> gpurun_out/bench_q.err; tail -3 gpurun_out/bench_q.err
 python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/bench_n8.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','n_gpus')})
-print(d.get('ray_split_c4'))
+d=json.loads(open('gpurun_out/bench_q.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}); print(d['e2e']); print(d['roofline']['kernel_ms'], d.get('with_optimizer'))
 PY
+CNF_NO_FUSED_SAMPLER=1 timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-large 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('two-call path:', d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['kernel_ms'])"

@@ -306,3 +306,35 @@ def test_fused_step_shapes_vs_oracle(K, n_obj, R, N, M, L, empty_inst):
     if empty_inst is not None:      # an instance without rays only gets the regulariser gradient
         reg_only = 0.0005 * tr.shape_codes[:, empty_inst] / tr.shape_codes[:, empty_inst].norm(dim=-1, keepdim=True)
         torch.testing.assert_close(tr.g_shape[:, empty_inst], reg_only, rtol=1e-4, atol=1e-8)
+
+
+@pytest.mark.parametrize("K,n_obj,R,N,M,inv", [(3, 3, 360, 1, 9, 0.15), (2, 4, 333, 5, 9, 0.4), (1, 2, 97, 0, 12, 0.0), (2, 5, 2000, 3, 16, 0.3),
+                                               (1, 1, 8192, 1, 9, 0.15)])
+def test_fused_sampler_depths_bit_exact_and_same_step(K, n_obj, R, N, M, inv):
+    """cnf_train_step_sampled (sampler inside the fused kernel): the depths the kernel used (z_out) equal the oracle's sampler bit
+    for bit (src/scene_cateogries.py:453-546), the stats rows equal the standalone sampler's, and the step's loss / gradients equal
+    the two-call path (cnf_sample_fwd + cnf_train_step) on the same draws to fp32 accumulation-order noise."""
+    from category_nerf_reconstruction_official_b200 import ops
+    from category_nerf_reconstruction_official_b200.fused import FusedCategoryTrainer
+    g = torch.Generator().manual_seed(31 + R)
+    tr = FusedCategoryTrainer(K, n_obj, latent_dim=32, scale=2.0, device=DEV, n_bins_cam2surface=N, n_bins=M, generator=g)
+    cats = [O.synth_rays(R, n_obj, g, invalid_frac=inv) for _ in range(K)]
+    rgbs, depth, org, dirs, idx = (torch.stack([c[i] for c in cats]) for i in range(5))
+    rand = {"u_inv": torch.rand(K, R, N + M, generator=g), "u_val": torch.rand(K, R, N, generator=g),
+            "n_obj": torch.randn(K, R, M, generator=g) * (0.1 / 3), "u_oth": torch.rand(K, R, M, generator=g)}
+    dv = lambda t: t.to(DEV)
+    rd = {k: dv(v) for k, v in rand.items()}
+    tr.sample_in_kernel = True                      # (off by default: DESIGN 4)
+    assert R <= tr._sampled_max_rays()
+    tr.keep_z = True
+    loss1 = float(tr.step(dv(rgbs), dv(depth), dv(org), dv(dirs), dv(idx), rand=rd))
+    g1 = tr.grad_flat.clone(); z_used = tr.z_used.cpu(); stats1 = tr.stats.cpu()
+    for k in range(K):
+        _, _, v_o, l_o, _, z_o = O.sample_points(rgbs[k], depth[k], org[k], dirs[k], N, M, 0.1, 0.05, {kk: vv[k] for kk, vv in rand.items()})
+        assert torch.equal(z_used[k], z_o), "category %d: in-kernel depths differ from the reference sampler" % k
+    _, _, _, _, stats2 = ops.sample_batched(dv(rgbs), dv(depth), dv(org), dv(dirs), N, M, 0.1, 0.05, rd, want_pcs=False)
+    assert torch.equal(stats1, stats2.cpu())
+    tr.sample_in_kernel = False                     # the two-call path on the same draws
+    loss2 = float(tr.step(dv(rgbs), dv(depth), dv(org), dv(dirs), dv(idx), rand=rd))
+    assert abs(loss1 - loss2) <= 2e-6 * abs(loss2) + 1e-6
+    torch.testing.assert_close(g1, tr.grad_flat, rtol=1e-4, atol=1e-6 * float(tr.grad_flat.abs().max()) + 1e-9)
