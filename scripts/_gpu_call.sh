@@ -1,12 +1,11 @@
 mkdir -p gpurun_out
-timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/tests.log
+timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/tests.log
 cat gpurun_out/tests.log
-timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-large > gpurun_out/bench_q.json 2> gpurun_out/bench_q.err; tail -3 gpurun_out/bench_q.err
+timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+timeout 1200 python bench.py > gpurun_out/bench1.json 2> gpurun_out/bench1.err; tail -3 gpurun_out/bench1.err
+timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -2 gpurun_out/bench_ref.err; cut -c1-400 gpurun_out/bench_ref.json
 python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/bench_q.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}); print(d['e2e']); print(d['roofline']['kernel_ms'], d.get('with_optimizer'))
+d=json.loads(open('gpurun_out/bench1.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches','cpu_baseline')}); print(d['e2e']); print(d['roofline'])
 PY
-CNF_NO_FUSED_SAMPLER=1 timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-large 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('two-call path:', d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['kernel_ms'])"
