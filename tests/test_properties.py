@@ -181,3 +181,66 @@ def test_gpu_fused_step_equals_oracle_on_random_shapes(seed, K, n_obj, R, N, M, 
         want_c = out["g_shape"][k].double(); got_c = tr.g_shape[k, :n_obj].cpu().double()
         if float(want_c.norm()) > 1e-6:
             assert float((got_c - want_c).norm() / want_c.norm()) <= 0.05
+
+
+@pytest.mark.gpu
+@settings(max_examples=20)
+@given(seed=st.integers(0, 10 ** 6), K=st.integers(1, 3), P=st.integers(1, 3000), scale=st.sampled_from([2.0, 3.0, 5.0, 10.0]))
+def test_gpu_embedding_equals_oracle_on_random_shapes(seed, K, P, scale):
+    """UniDirsEmbed forward / backward (src/embedding.py:82-92) at random sizes: ragged last tile of the forward (64 points), bulk-copy
+    and fallback tiles of the double-buffered backward, categories whose offset is not 16-byte aligned."""
+    from category_nerf_reconstruction_official_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.rand(K, P, 3, generator=g) - 0.5) * 4
+    B = torch.randn(K, 21, 3, generator=g)
+    gout = torch.randn(K, P, 129, generator=g)
+    sc = torch.full((K,), scale)
+    xd = x.to(DEV).requires_grad_(True); Bd = B.to(DEV).requires_grad_(True)
+    emb = ops.EmbedFn.apply(xd, Bd, sc.to(DEV))
+    (emb * gout.to(DEV)).sum().backward()
+    for k in range(K):
+        xo = x[k].clone().requires_grad_(True); Bo = B[k].clone().requires_grad_(True)
+        eo = O.embed(xo, Bo, scale)
+        (eo * gout[k]).sum().backward()
+        torch.testing.assert_close(emb[k].detach().cpu(), eo.detach(), rtol=0, atol=3e-5)
+        tol = 2e-4 * float(Bo.grad.abs().max()) + 2e-3
+        assert float((Bd.grad[k].cpu() - Bo.grad).abs().max()) <= tol
+        assert float((xd.grad[k].cpu() - xo.grad).abs().max()) <= 2e-4 * float(xo.grad.abs().max()) + 2e-3
+
+
+@pytest.mark.gpu
+@settings(max_examples=25)
+@given(seed=st.integers(0, 10 ** 6), n=st.integers(1, 3000), S=st.integers(1, 130))
+def test_gpu_termination_and_uncertainty_on_random_shapes(seed, n, S):
+    from category_nerf_reconstruction_official_b200 import render_rays
+    g = torch.Generator().manual_seed(seed)
+    occ = torch.sigmoid(torch.randn(n, S, generator=g) * 3)
+    gw = torch.randn(n, S, generator=g)
+    od = occ.to(DEV).requires_grad_(True)
+    w = render_rays.occupancy_to_termination(od)
+    (w * gw.to(DEV)).sum().backward()
+    oo = occ.clone().requires_grad_(True)
+    wo = O.termination(oo)
+    (wo * gw).sum().backward()
+    torch.testing.assert_close(w.detach().cpu(), wo.detach(), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(od.grad.cpu(), oo.grad, rtol=1e-4, atol=1e-5)
+    ent, mass, _ = render_rays.ray_uncertainty(w.detach())
+    torch.testing.assert_close(mass.cpu(), wo.detach().sum(-1), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(ent.cpu(), -(wo.detach() * torch.log(wo.detach() + 1e-10)).sum(-1), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+@settings(max_examples=20)
+@given(seed=st.integers(0, 10 ** 6), n=st.integers(1, 5000), bins=st.integers(1, 100))
+def test_gpu_stratified_bins_and_origin_dirs_on_random_shapes(seed, n, bins):
+    from category_nerf_reconstruction_official_b200 import sampling
+    g = torch.Generator().manual_seed(seed)
+    u = torch.rand(n, bins, generator=g)
+    mx = torch.rand(n, generator=g) * 3 + 0.5
+    z = sampling.stratified_bins(0.1, mx.to(DEV), bins, n, u=u.to(DEV))
+    assert torch.equal(z.cpu(), O.stratified_bins(0.1, mx, bins, u))
+    pool = O.synth_pool(n, 3, 4, g)
+    og, di = sampling.origin_dirs_O(pool["poses"].to(DEV), pool["ray_dirs"].to(DEV))
+    og_o, di_o = O.origin_dirs(pool["poses"], pool["ray_dirs"], True)
+    torch.testing.assert_close(og.cpu(), og_o, rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(di.cpu(), di_o, rtol=2e-5, atol=2e-6)
