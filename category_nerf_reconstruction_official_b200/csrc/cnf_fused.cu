@@ -390,6 +390,11 @@ static int train_step_prepare(int K, int R, int S, int L, int nom, const float* 
   if (nblk <= SORT_SMALL_BLOCKS) {
     // one launch: [images + biases] | instance sort | clear of raw, rawi and the finalize completion counter (16-byte chunks)
     const int first = (what & 1) ? 0 : n_prep;             // input half only: skip the operand parts
+    static DeviceOnce pattr;
+    if (pattr.pending()) {
+      CNF_CUDA(cudaFuncSetAttribute(prepare_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, CNF_SMALL_STEP_CARVEOUT));
+      pattr.done();
+    }
     prepare_small_kernel<<<dim3(K, n_prep + 1 + PREP_ZERO_PARTS - first), 256, nom * sizeof(int), st>>>(
         L, nom, params, pe_B, pe_scale, shape_codes, tex_codes, n_obj, prep, zlat, ctab, R, RPT, inst, seg_ray0, seg_tile0, perm,
         reinterpret_cast<uint4*>(raw), (wl.reg - wl.raw) / 16, first, si ? *si : SampleIn{}, reinterpret_cast<int4*>(w8 + wl.rec),

@@ -1,4 +1,9 @@
 mkdir -p gpurun_out
-CNF_HYPOTHESIS=explore timeout 2400 python -m pytest tests/test_properties.py -m gpu -q 2>&1 | grep -E "Falsifying|seed=|K=|n_obj=|R=|N=|M=|L=|S=|P=|n=|bins=|scale=|inv=|p_this|Error|assert|passed|failed|Mismatch|Greatest" | head -60 > gpurun_out/tests.log
+timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/tests.log
 cat gpurun_out/tests.log
-timeout 2400 python -m pytest tests/test_properties.py -m gpu -q 2>&1 | tail -2
+timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_q.json 2> gpurun_out/bench_q.err; tail -3 gpurun_out/bench_q.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_q.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}); print(d['e2e']['ms_per_step']); print(d.get('background_step_1200x14')); print(d.get('iteration_objects_plus_background'))
+PY
