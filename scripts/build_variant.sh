@@ -9,9 +9,9 @@ work=/tmp/variant_$name/pkg/csrc
 rm -rf /tmp/variant_$name; mkdir -p $work /tmp/variant_$name/include $CS/variants $CS/build/$name
 cp $ROOT/include/cnf.h /tmp/variant_$name/include/
 cp $CS/cnf_common.cuh $work/
-for f in cnf_fused.cu cnf_fused_a.inc cnf_fused_b.inc cnf_umma.cuh; do cp $src/$f $work/; done
+for f in cnf_fused.cu cnf_fused_a.inc cnf_fused_b.inc cnf_fused_c.inc cnf_umma.cuh cnf_sample_math.cuh; do cp $src/$f $work/; done
 (cd $work && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v "$@" -c cnf_fused.cu -o cnf_fused.o 2>&1 | grep -A2 "fused_step_kernelILb0" | grep -E "spill" | sed "s/^/[$name] /")
-for f in cnf_api cnf_sampler cnf_embed cnf_composite cnf_mlp_simt cnf_selftest; do cp $CS/build/$f.o $CS/build/$name/; done
+for f in cnf_api cnf_sampler cnf_embed cnf_composite cnf_mlp_simt cnf_occmap_tc; do cp $CS/build/$f.o $CS/build/$name/; done
 cp $work/cnf_fused.o $CS/build/$name/
 nvcc -shared -o $CS/variants/libcnf_$name.so $CS/build/$name/*.o -cudart static 2>/dev/null
 echo "built variants/libcnf_$name.so"
