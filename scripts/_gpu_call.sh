@@ -1,2 +1,7 @@
 mkdir -p gpurun_out
-bash scripts/ab.sh base sleep20 sleep60 nohint 2>&1 | grep -v Warning > gpurun_out/ab.txt; cat gpurun_out/ab.txt
+timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/tests.log
+cat gpurun_out/tests.log
+timeout 600 python __graft_entry__.py smoke 2>&1 | tail -1
+timeout 900 python bench.py --steps 20 --warmup 5 --no-large 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['cpu_baseline']['ms_per_step'], d['gpu_launches'])"
